@@ -1,0 +1,458 @@
+// fp32 implicit-GEMM convolution on the CUDA cores (VSPW_PREC_FP32).
+//
+// This is the exact-fp32 arm of the conv path: it takes every geometry the reference uses
+// (3x3 stride-2 stem with Cin=3, 1x1 stride-2 downsample, dilated 3x3, Cout=124 classifiers,
+// s x s PPM maps) and is the cross-check for the tcgen05 arm in conv_tc.cu.
+//   fwd  : C[M = N*Ho*Wo][Cout]   = im2col(x)[M][K = kh*kw*Cin] * W_ohwi[Cout][K]^T   (+bias)
+//   dgrad: C[M = N*H*W][Cin]      = gather(dy)[M][K = kh*kw*Cout] * Wt[Cin][K]^T
+//   wgrad: dW[Cout][kh*kw*Cin]    = dy[M][Cout]^T * im2col(x)[M][kh*kw*Cin]   (split-K, fp32 atomics)
+// Tiles: 128x128x16, 256 threads, 8x8 outputs per thread, double-buffered shared memory.
+// Reference call sites: nn.Conv2d in models/resnet.py:61-66,100-106,130 and the head convs.
+#include "common.cuh"
+
+using namespace vspw;
+
+namespace {
+
+struct IGemmParams {
+  const float* A;     // gathered NHWC tensor [N][H][W][C]
+  const float* B;     // [Nout][K], K contiguous
+  const float* bias;  // [Nout] or null
+  float* Cmat;        // [M][Nout]
+  int N, H, W, C;     // dims of A
+  int OH, OW;         // row space (output pixels for fwd, input pixels for dgrad)
+  int KH, KW, stride, pad, dil;
+  int Nout, K, M;
+};
+
+constexpr int BM = 128, BN = 128, BK = 16, LDS = 132;
+
+// MODE 0: forward gather   ih = oh*stride - pad + r*dil
+// MODE 1: dgrad gather     ih = (oh + pad - r*dil)/stride, only when divisible
+template <int MODE>
+__device__ __forceinline__ bool tap_coord(const IGemmParams& p, int o, int t, int lim, int& i) {
+  if (MODE == 0) {
+    i = o * p.stride - p.pad + t * p.dil;
+    return i >= 0 && i < lim;
+  } else {
+    int num = o + p.pad - t * p.dil;
+    if (num < 0) return false;
+    if (p.stride == 1) {
+      i = num;
+    } else {
+      if (num % p.stride) return false;
+      i = num / p.stride;
+    }
+    return i < lim;
+  }
+}
+
+__device__ __forceinline__ void mma_8x8(float (&acc)[8][8], const float4& a0, const float4& a1, const float4& b0,
+                                        const float4& b1) {
+  float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+}
+
+template <int MODE, bool VEC>
+__global__ void __launch_bounds__(256, 2) igemm_kernel(IGemmParams p) {
+  __shared__ __align__(16) float As[2][BK][LDS];
+  __shared__ __align__(16) float Bs[2][BK][LDS];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int tx = tid & 15, ty = tid >> 4;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  const int nk = (p.K + BK - 1) / BK;
+
+  if (VEC) {
+    // each thread stages two float4 of A and two of B per k-step: rows lrow, lrow+64; k-chunk lchunk
+    const int lrow = tid >> 2, lchunk = tid & 3;
+    int a_n[2], a_oh[2], a_ow[2];
+    bool a_ok[2], b_ok[2];
+    const float* b_ptr[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      int m = m0 + lrow + 64 * i;
+      a_ok[i] = m < p.M;
+      int mm = a_ok[i] ? m : 0;
+      a_n[i] = mm / (p.OH * p.OW);
+      int rem = mm - a_n[i] * (p.OH * p.OW);
+      a_oh[i] = rem / p.OW;
+      a_ow[i] = rem - a_oh[i] * p.OW;
+      int n = n0 + lrow + 64 * i;
+      b_ok[i] = n < p.Nout;
+      b_ptr[i] = p.B + (size_t)(b_ok[i] ? n : 0) * p.K + lchunk * 4;
+    }
+    float4 ra[2], rb[2];
+    auto gload = [&](int k0) {
+      int tap = k0 / p.C;
+      int c0 = k0 - tap * p.C + lchunk * 4;
+      int r = tap / p.KW, s = tap - r * p.KW;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        int ih, iw;
+        bool ok = a_ok[i] && tap_coord<MODE>(p, a_oh[i], r, p.H, ih) && tap_coord<MODE>(p, a_ow[i], s, p.W, iw);
+        ra[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.A + (((size_t)a_n[i] * p.H + ih) * p.W + iw) * p.C + c0))
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        rb[i] = b_ok[i] ? __ldg(reinterpret_cast<const float4*>(b_ptr[i] + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        int row = lrow + 64 * i, kk = lchunk * 4;
+        As[buf][kk + 0][row] = ra[i].x; As[buf][kk + 1][row] = ra[i].y;
+        As[buf][kk + 2][row] = ra[i].z; As[buf][kk + 3][row] = ra[i].w;
+        Bs[buf][kk + 0][row] = rb[i].x; Bs[buf][kk + 1][row] = rb[i].y;
+        Bs[buf][kk + 2][row] = rb[i].z; Bs[buf][kk + 3][row] = rb[i].w;
+      }
+    };
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    int buf = 0;
+    for (int kt = 0; kt < nk; ++kt) {
+      if (kt + 1 < nk) gload((kt + 1) * BK);
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+        float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+        float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+        float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+        mma_8x8(acc, a0, a1, b0, b1);
+      }
+      if (kt + 1 < nk) sstore(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  } else {
+    // generic scalar staging: any Cin (stem Cin=3), any K tail
+    const int lk = tid & 15, lrow0 = tid >> 4;  // rows lrow0 + 16*j
+    float ra[8], rb[8];
+    auto gload = [&](int k0) {
+      int k = k0 + lk;
+      bool kok = k < p.K;
+      int tap = kok ? k / p.C : 0;
+      int c = k - tap * p.C;
+      int r = tap / p.KW, s = tap - r * p.KW;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int row = lrow0 + 16 * j;
+        int m = m0 + row;
+        float va = 0.f;
+        if (kok && m < p.M) {
+          int n = m / (p.OH * p.OW);
+          int rem = m - n * (p.OH * p.OW);
+          int oh = rem / p.OW, ow = rem - oh * p.OW;
+          int ih, iw;
+          if (tap_coord<MODE>(p, oh, r, p.H, ih) && tap_coord<MODE>(p, ow, s, p.W, iw))
+            va = __ldg(p.A + (((size_t)n * p.H + ih) * p.W + iw) * p.C + c);
+        }
+        ra[j] = va;
+        int nn = n0 + row;
+        rb[j] = (kok && nn < p.Nout) ? __ldg(p.B + (size_t)nn * p.K + k) : 0.f;
+      }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        As[buf][lk][lrow0 + 16 * j] = ra[j];
+        Bs[buf][lk][lrow0 + 16 * j] = rb[j];
+      }
+    };
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    int buf = 0;
+    for (int kt = 0; kt < nk; ++kt) {
+      if (kt + 1 < nk) gload((kt + 1) * BK);
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+        float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+        float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+        float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+        mma_8x8(acc, a0, a1, b0, b1);
+      }
+      if (kt + 1 < nk) sstore(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+
+  // epilogue: rows ty*4+i (+64), cols tx*4+j (+64)
+  const bool vec_out = (p.Nout % 4 == 0);
+#pragma unroll
+  for (int ih = 0; ih < 2; ++ih)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int m = m0 + ih * 64 + ty * 4 + i;
+      if (m >= p.M) continue;
+#pragma unroll
+      for (int jh = 0; jh < 2; ++jh) {
+        int n = n0 + jh * 64 + tx * 4;
+        if (n >= p.Nout) continue;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[j] = acc[ih * 4 + i][jh * 4 + j];
+          if (p.bias && n + j < p.Nout) v[j] += __ldg(p.bias + n + j);
+        }
+        float* dst = p.Cmat + (size_t)m * p.Nout + n;
+        if (vec_out && n + 3 < p.Nout) {
+          *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (n + j < p.Nout) dst[j] = v[j];
+        }
+      }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct WGradParams {
+  const float* X;   // [N][H][W][Cin]
+  const float* DY;  // [N][Ho][Wo][Cout]
+  float* DW;        // [Cout][KH*KW*Cin]
+  int N, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad, dil;
+  int M;            // N*Ho*Wo
+  int NW;           // KH*KW*Cin
+  int chunk;        // pixels per split-K slice (multiple of BK)
+};
+
+template <bool VEC>
+__global__ void __launch_bounds__(256, 2) wgrad_kernel(WGradParams p) {
+  __shared__ __align__(16) float As[2][BK][LDS];  // [pixel][cout]
+  __shared__ __align__(16) float Bs[2][BK][LDS];  // [pixel][tap*cin]
+  const int tid = threadIdx.x;
+  const int co0 = blockIdx.x * BM, col0 = blockIdx.y * BN;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int kbeg = blockIdx.z * p.chunk;
+  const int kend = min(p.M, kbeg + p.chunk);
+  if (kbeg >= kend) return;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  const int nk = (kend - kbeg + BK - 1) / BK;
+  const int HoWo = p.Ho * p.Wo;
+
+  if (VEC) {
+    const int lpix = tid >> 5;        // 0..7, pixels lpix and lpix+8
+    const int l4 = (tid & 31) * 4;    // column offset inside the tile
+    const int co = co0 + l4;
+    const bool co_ok = co < p.Cout;   // Cout%4==0 -> whole float4 valid
+    const int col = col0 + l4;
+    const bool col_ok = col < p.NW;
+    int tap = col_ok ? col / p.Cin : 0;
+    const int ci = col - tap * p.Cin;
+    const int r = tap / p.KW, s = tap - r * p.KW;
+    float4 ra[2], rb[2];
+    auto gload = [&](int kb) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        int m = kb + lpix + 8 * i;
+        bool mok = m < kend;
+        ra[i] = (mok && co_ok) ? __ldg(reinterpret_cast<const float4*>(p.DY + (size_t)m * p.Cout + co))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mok && col_ok) {
+          int n = m / HoWo;
+          int rem = m - n * HoWo;
+          int oh = rem / p.Wo, ow = rem - oh * p.Wo;
+          int ih = oh * p.stride - p.pad + r * p.dil, iw = ow * p.stride - p.pad + s * p.dil;
+          if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W)
+            v = __ldg(reinterpret_cast<const float4*>(p.X + (((size_t)n * p.H + ih) * p.W + iw) * p.Cin + ci));
+        }
+        rb[i] = v;
+      }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        *reinterpret_cast<float4*>(&As[buf][lpix + 8 * i][l4]) = ra[i];
+        *reinterpret_cast<float4*>(&Bs[buf][lpix + 8 * i][l4]) = rb[i];
+      }
+    };
+    gload(kbeg);
+    sstore(0);
+    __syncthreads();
+    int buf = 0;
+    for (int kt = 0; kt < nk; ++kt) {
+      if (kt + 1 < nk) gload(kbeg + (kt + 1) * BK);
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+        float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+        float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+        float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+        mma_8x8(acc, a0, a1, b0, b1);
+      }
+      if (kt + 1 < nk) sstore(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  } else {
+    // scalar staging: thread owns column lcol (0..127) of both tiles for pixels lp0, lp0+2, ...
+    const int lcol = tid & 127, lp0 = tid >> 7;  // 0..1
+    const int co = co0 + lcol;
+    const bool co_ok = co < p.Cout;
+    const int col = col0 + lcol;
+    const bool col_ok = col < p.NW;
+    int tap = col_ok ? col / p.Cin : 0;
+    const int ci = col - tap * p.Cin;
+    const int r = tap / p.KW, s = tap - r * p.KW;
+    float ra[8], rb[8];
+    auto gload = [&](int kb) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int m = kb + lp0 + 2 * j;
+        bool mok = m < kend;
+        ra[j] = (mok && co_ok) ? __ldg(p.DY + (size_t)m * p.Cout + co) : 0.f;
+        float v = 0.f;
+        if (mok && col_ok) {
+          int n = m / HoWo;
+          int rem = m - n * HoWo;
+          int oh = rem / p.Wo, ow = rem - oh * p.Wo;
+          int ih = oh * p.stride - p.pad + r * p.dil, iw = ow * p.stride - p.pad + s * p.dil;
+          if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W)
+            v = __ldg(p.X + (((size_t)n * p.H + ih) * p.W + iw) * p.Cin + ci);
+        }
+        rb[j] = v;
+      }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        As[buf][lp0 + 2 * j][lcol] = ra[j];
+        Bs[buf][lp0 + 2 * j][lcol] = rb[j];
+      }
+    };
+    gload(kbeg);
+    sstore(0);
+    __syncthreads();
+    int buf = 0;
+    for (int kt = 0; kt < nk; ++kt) {
+      if (kt + 1 < nk) gload(kbeg + (kt + 1) * BK);
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+        float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+        float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+        float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+        mma_8x8(acc, a0, a1, b0, b1);
+      }
+      if (kt + 1 < nk) sstore(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+
+#pragma unroll
+  for (int ih = 0; ih < 2; ++ih)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int co = co0 + ih * 64 + ty * 4 + i;
+      if (co >= p.Cout) continue;
+#pragma unroll
+      for (int jh = 0; jh < 2; ++jh)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int col = col0 + jh * 64 + tx * 4 + j;
+          if (col < p.NW) atomicAdd(p.DW + (size_t)co * p.NW + col, acc[ih * 4 + i][jh * 4 + j]);
+        }
+    }
+}
+
+int validate_desc(const vspw_conv_desc* d, const char* who) {
+  VSPW_REQUIRE(d, "%s: null descriptor", who);
+  VSPW_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0 && d->cin > 0 && d->cout > 0, "%s: non-positive dims", who);
+  VSPW_REQUIRE(d->kh > 0 && d->kw > 0 && d->stride > 0 && d->dil > 0 && d->pad >= 0, "%s: bad kernel geometry", who);
+  int ho = (d->h + 2 * d->pad - d->dil * (d->kh - 1) - 1) / d->stride + 1;
+  int wo = (d->w + 2 * d->pad - d->dil * (d->kw - 1) - 1) / d->stride + 1;
+  VSPW_REQUIRE(ho == d->ho && wo == d->wo, "%s: ho/wo (%d,%d) do not match geometry (%d,%d)", who, d->ho, d->wo, ho, wo);
+  VSPW_REQUIRE((long long)d->n * d->ho * d->wo < (1ll << 31) && (long long)d->n * d->h * d->w < (1ll << 31),
+               "%s: pixel count overflows int32", who);
+  return VSPW_OK;
+}
+
+}  // namespace
+
+extern "C" int vspw_conv2d_fwd(const vspw_conv_desc* d, const float* x, const float* w_ohwi, const float* bias, float* y,
+                               void* stream) {
+  int rc = validate_desc(d, "vspw_conv2d_fwd");
+  if (rc) return rc;
+  VSPW_REQUIRE(x && w_ohwi && y, "vspw_conv2d_fwd: null pointer");
+  IGemmParams p;
+  p.A = x; p.B = w_ohwi; p.bias = bias; p.Cmat = y;
+  p.N = d->n; p.H = d->h; p.W = d->w; p.C = d->cin;
+  p.OH = d->ho; p.OW = d->wo;
+  p.KH = d->kh; p.KW = d->kw; p.stride = d->stride; p.pad = d->pad; p.dil = d->dil;
+  p.Nout = d->cout; p.K = d->kh * d->kw * d->cin; p.M = d->n * d->ho * d->wo;
+  dim3 grid((p.M + BM - 1) / BM, (p.Nout + BN - 1) / BN);
+  bool vec = (d->cin % 16 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)w_ohwi % 16 == 0);
+  if (vec) igemm_kernel<0, true><<<grid, 256, 0, as_stream(stream)>>>(p);
+  else igemm_kernel<0, false><<<grid, 256, 0, as_stream(stream)>>>(p);
+  return check_launch("vspw_conv2d_fwd");
+}
+
+extern "C" int vspw_conv2d_dgrad(const vspw_conv_desc* d, const float* dy, const float* w_t_ihwo, float* dx, void* stream) {
+  int rc = validate_desc(d, "vspw_conv2d_dgrad");
+  if (rc) return rc;
+  VSPW_REQUIRE(dy && w_t_ihwo && dx, "vspw_conv2d_dgrad: null pointer");
+  IGemmParams p;
+  p.A = dy; p.B = w_t_ihwo; p.bias = nullptr; p.Cmat = dx;
+  p.N = d->n; p.H = d->ho; p.W = d->wo; p.C = d->cout;
+  p.OH = d->h; p.OW = d->w;
+  p.KH = d->kh; p.KW = d->kw; p.stride = d->stride; p.pad = d->pad; p.dil = d->dil;
+  p.Nout = d->cin; p.K = d->kh * d->kw * d->cout; p.M = d->n * d->h * d->w;
+  dim3 grid((p.M + BM - 1) / BM, (p.Nout + BN - 1) / BN);
+  bool vec = (d->cout % 16 == 0) && ((uintptr_t)dy % 16 == 0) && ((uintptr_t)w_t_ihwo % 16 == 0);
+  if (vec) igemm_kernel<1, true><<<grid, 256, 0, as_stream(stream)>>>(p);
+  else igemm_kernel<1, false><<<grid, 256, 0, as_stream(stream)>>>(p);
+  return check_launch("vspw_conv2d_dgrad");
+}
+
+extern "C" int vspw_conv2d_wgrad(const vspw_conv_desc* d, const float* x, const float* dy, float* dw_ohwi, void* stream) {
+  int rc = validate_desc(d, "vspw_conv2d_wgrad");
+  if (rc) return rc;
+  VSPW_REQUIRE(x && dy && dw_ohwi, "vspw_conv2d_wgrad: null pointer");
+  WGradParams p;
+  p.X = x; p.DY = dy; p.DW = dw_ohwi;
+  p.N = d->n; p.H = d->h; p.W = d->w; p.Cin = d->cin; p.Ho = d->ho; p.Wo = d->wo; p.Cout = d->cout;
+  p.KH = d->kh; p.KW = d->kw; p.stride = d->stride; p.pad = d->pad; p.dil = d->dil;
+  p.M = d->n * d->ho * d->wo;
+  p.NW = d->kh * d->kw * d->cin;
+  int tiles = ((p.Cout + BM - 1) / BM) * ((p.NW + BN - 1) / BN);
+  int want = (2 * kNumSMs + tiles - 1) / tiles;             // ~2 waves of CTAs
+  int max_split = (p.M + 8 * BK - 1) / (8 * BK);            // at least 8 k-steps per slice
+  int split = want < 1 ? 1 : (want > max_split ? max_split : want);
+  if (split > 65535) split = 65535;
+  int chunk = (p.M + split - 1) / split;
+  chunk = (chunk + BK - 1) / BK * BK;
+  split = (p.M + chunk - 1) / chunk;
+  p.chunk = chunk;
+  cudaError_t e = cudaMemsetAsync(dw_ohwi, 0, (size_t)p.Cout * p.NW * sizeof(float), as_stream(stream));
+  if (e != cudaSuccess) {
+    set_error("vspw_conv2d_wgrad: memset: %s", cudaGetErrorString(e));
+    return VSPW_ERR_CUDA;
+  }
+  dim3 grid((p.Cout + BM - 1) / BM, (p.NW + BN - 1) / BN, split);
+  bool vec = (d->cin % 4 == 0) && (d->cout % 4 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)dy % 16 == 0);
+  if (vec) wgrad_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(p);
+  else wgrad_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(p);
+  return check_launch("vspw_conv2d_wgrad");
+}

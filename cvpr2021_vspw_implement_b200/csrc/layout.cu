@@ -1,0 +1,196 @@
+// Layout / elementwise plumbing kernels: permute, fill, axpby, bf16 hi/lo split, channel-slice copy.
+// All HBM-bound; grid sized as a multiple of the 148 SMs with grid-stride loops.
+#include "common.cuh"
+#include <string.h>
+
+namespace vspw {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace vspw
+
+using namespace vspw;
+
+extern "C" const char* vspw_last_error(void) { return vspw::g_err; }
+extern "C" int vspw_version(void) { return 100; }
+
+// ---------------------------------------------------------------------------------------------
+struct Perm4 {
+  int od[4];        // output dims
+  long long ss[4];  // source stride (elements) of the dim that feeds output dim i
+};
+
+__global__ void permute4d_kernel(const float* __restrict__ src, float* __restrict__ dst, Perm4 p, size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t r = i;
+    int i3 = (int)(r % p.od[3]); r /= p.od[3];
+    int i2 = (int)(r % p.od[2]); r /= p.od[2];
+    int i1 = (int)(r % p.od[1]); r /= p.od[1];
+    int i0 = (int)r;
+    dst[i] = __ldg(src + i0 * p.ss[0] + i1 * p.ss[1] + i2 * p.ss[2] + i3 * p.ss[3]);
+  }
+}
+
+// Tiled transpose for the common [A][B][C] -> [A][C][B] case (NCHW<->NHWC, OIHW<->OHWI) so that
+// both the read and the write side are coalesced.
+__global__ void transpose_inner_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C) {
+  __shared__ float tile[32][33];
+  size_t a = blockIdx.z;
+  const float* s = src + a * (size_t)B * C;
+  float* d = dst + a * (size_t)B * C;
+  int c0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int b = b0 + j, c = c0 + threadIdx.x;
+    if (b < B && c < C) tile[j][threadIdx.x] = s[(size_t)b * C + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int c = c0 + j, b = b0 + threadIdx.x;
+    if (b < B && c < C) d[(size_t)c * B + b] = tile[threadIdx.x][j];
+  }
+}
+
+extern "C" int vspw_permute4d(const float* src, float* dst, const int32_t d[4], const int32_t perm[4], void* stream) {
+  VSPW_REQUIRE(src && dst && d && perm, "vspw_permute4d: null argument");
+  long long sstride[4];
+  sstride[3] = 1;
+  for (int i = 2; i >= 0; --i) sstride[i] = sstride[i + 1] * d[i + 1];
+  Perm4 p;
+  size_t total = 1;
+  int seen = 0;
+  for (int i = 0; i < 4; ++i) {
+    VSPW_REQUIRE(perm[i] >= 0 && perm[i] < 4, "vspw_permute4d: bad perm");
+    seen |= 1 << perm[i];
+    p.od[i] = d[perm[i]];
+    p.ss[i] = sstride[perm[i]];
+    total *= (size_t)d[i];
+  }
+  VSPW_REQUIRE(seen == 15, "vspw_permute4d: perm is not a permutation");
+  if (total == 0) return VSPW_OK;
+  // [0,2,3,1] : (A, B, C1, C2) -> (A, C1, C2, B)  == [A][B][C] -> [A][C][B] with C = C1*C2
+  // [0,3,1,2] : (A, C1, C2, B) -> (A, B, C1, C2)  == [A][C][B] -> [A][B][C]
+  if (perm[0] == 0 && perm[1] == 2 && perm[2] == 3 && perm[3] == 1) {
+    int B = d[1], C = d[2] * d[3];
+    if (d[0] <= 65535 && (C + 31) / 32 > 0 && (B + 31) / 32 <= 65535) {
+      dim3 grid((C + 31) / 32, (B + 31) / 32, d[0]);
+      transpose_inner_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(src, dst, B, C);
+      return check_launch("vspw_permute4d(transpose)");
+    }
+  }
+  if (perm[0] == 0 && perm[1] == 3 && perm[2] == 1 && perm[3] == 2) {
+    int B = d[1] * d[2], C = d[3];
+    if (d[0] <= 65535 && (B + 31) / 32 <= 65535) {
+      dim3 grid((C + 31) / 32, (B + 31) / 32, d[0]);
+      transpose_inner_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(src, dst, B, C);
+      return check_launch("vspw_permute4d(transpose)");
+    }
+  }
+  permute4d_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(src, dst, p, total);
+  return check_launch("vspw_permute4d");
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void fill_kernel(float* __restrict__ dst, float v, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = v;
+}
+extern "C" int vspw_fill(float* dst, float value, size_t n, void* stream) {
+  if (n == 0) return VSPW_OK;
+  VSPW_REQUIRE(dst, "vspw_fill: null dst");
+  fill_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(dst, value, n);
+  return check_launch("vspw_fill");
+}
+
+__global__ void axpby_kernel(const float* __restrict__ x, float* __restrict__ y, float a, float b, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = (b == 0.f) ? a * x[i] : fmaf(a, x[i], b * y[i]);
+}
+__global__ void axpby4_kernel(const float4* __restrict__ x, float4* __restrict__ y, float a, float b, size_t n4) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 xv = x[i], yv;
+    if (b == 0.f) {
+      yv = make_float4(a * xv.x, a * xv.y, a * xv.z, a * xv.w);
+    } else {
+      yv = y[i];
+      yv.x = fmaf(a, xv.x, b * yv.x); yv.y = fmaf(a, xv.y, b * yv.y);
+      yv.z = fmaf(a, xv.z, b * yv.z); yv.w = fmaf(a, xv.w, b * yv.w);
+    }
+    y[i] = yv;
+  }
+}
+extern "C" int vspw_axpby(const float* x, float* y, float a, float b, size_t n, void* stream) {
+  if (n == 0) return VSPW_OK;
+  VSPW_REQUIRE(x && y, "vspw_axpby: null argument");
+  if ((n % 4 == 0) && (((uintptr_t)x | (uintptr_t)y) % 16 == 0)) {
+    axpby4_kernel<<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>((const float4*)x, (float4*)y, a, b, n / 4);
+  } else {
+    axpby_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, y, a, b, n);
+  }
+  return check_launch("vspw_axpby");
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float v = x[i];
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+__global__ void split_bf16_vec_kernel(const float4* __restrict__ x, uint2* __restrict__ hi, uint2* __restrict__ lo, size_t n4) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = x[i];
+    __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+    float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+    uint2 ho;
+    ho.x = *reinterpret_cast<uint32_t*>(&h01);
+    ho.y = *reinterpret_cast<uint32_t*>(&h23);
+    hi[i] = ho;
+    if (lo) {
+      __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
+      __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+      uint2 lv;
+      lv.x = *reinterpret_cast<uint32_t*>(&l01);
+      lv.y = *reinterpret_cast<uint32_t*>(&l23);
+      lo[i] = lv;
+    }
+  }
+}
+extern "C" int vspw_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, size_t n, void* stream) {
+  if (n == 0) return VSPW_OK;
+  VSPW_REQUIRE(x && hi, "vspw_split_bf16: null argument");
+  if (n % 4 == 0 && (((uintptr_t)x) % 16 == 0) && (((uintptr_t)hi | (uintptr_t)lo) % 8 == 0)) {
+    split_bf16_vec_kernel<<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>((const float4*)x, (uint2*)hi, (uint2*)lo, n / 4);
+  } else {
+    split_bf16_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
+  }
+  return check_launch("vspw_split_bf16");
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void copy_channels_kernel(const float* __restrict__ src, int src_c, int src_off, float* __restrict__ dst,
+                                     int dst_c, int dst_off, int cc, size_t total, int accumulate) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t p = i / cc;
+    int c = (int)(i - p * cc);
+    float v = src[p * src_c + src_off + c];
+    float* d = dst + p * dst_c + dst_off + c;
+    *d = accumulate ? (*d + v) : v;
+  }
+}
+extern "C" int vspw_copy_channels(const float* src, int32_t src_c, int32_t src_off, float* dst, int32_t dst_c,
+                                  int32_t dst_off, int32_t cc, size_t pixels, int32_t accumulate, void* stream) {
+  VSPW_REQUIRE(src && dst, "vspw_copy_channels: null argument");
+  VSPW_REQUIRE(src_off >= 0 && dst_off >= 0 && src_off + cc <= src_c && dst_off + cc <= dst_c,
+               "vspw_copy_channels: slice out of range");
+  size_t total = pixels * (size_t)cc;
+  if (total == 0) return VSPW_OK;
+  copy_channels_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(src, src_c, src_off, dst, dst_c, dst_off, cc,
+                                                                           total, accumulate);
+  return check_launch("vspw_copy_channels");
+}

@@ -1,0 +1,198 @@
+/*
+ * vspw_b200.h — C ABI of the B200 (sm_100a) engine for the VSPW per-clip hot path.
+ *
+ * The reference (sssdddwww2/CVPR2021_VSPW_Implement) has no FFI of its own: its hot path is a
+ * Python nn.Module graph whose arithmetic is done by ATen/cuDNN calls.  Every entry point below
+ * replaces one such ATen call sequence; the reference call site it stands for is cited next to
+ * it (paths relative to the reference root).  The Python host mirror in
+ * cvpr2021_vspw_implement_b200/ binds these with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it says "host";
+ *   - activations are fp32, NHWC ("channels last"): x[n][h][w][c];
+ *   - weights cross the boundary in the reference's OIHW layout and are re-laid out by
+ *     vspw_permute4d into OHWI (forward / wgrad) or IHWO-flattened "HWOI" (dgrad);
+ *   - `stream` is a cudaStream_t passed as void* (the caller's current stream);
+ *   - every function returns 0 on success, <0 on error; vspw_last_error() gives the message
+ *     (thread local).  No function synchronises the device or allocates device memory.
+ */
+#ifndef VSPW_B200_H
+#define VSPW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSPW_OK 0
+#define VSPW_ERR_ARG (-1)
+#define VSPW_ERR_CUDA (-2)
+#define VSPW_ERR_UNSUPPORTED (-3)
+
+/* arithmetic mode of the implicit-GEMM convolutions */
+#define VSPW_PREC_FP32 0   /* fp32 FFMA (CUDA cores), exact fp32 semantics                      */
+#define VSPW_PREC_BF16X3 1 /* tcgen05 bf16 hi/lo split, 3 MMAs per product (~16 mantissa bits)  */
+#define VSPW_PREC_BF16 2   /* tcgen05 single-pass bf16 operands, fp32 accumulate                */
+
+typedef struct vspw_conv_desc {
+  int32_t n, h, w, cin;   /* input  x[n][h][w][cin]                                  */
+  int32_t cout, kh, kw;   /* weight w[cout][kh][kw][cin] (OHWI)                      */
+  int32_t stride, pad, dil;
+  int32_t ho, wo;         /* output y[n][ho][wo][cout]                               */
+  int32_t precision;      /* VSPW_PREC_*                                             */
+} vspw_conv_desc;
+
+const char* vspw_last_error(void);
+int vspw_version(void);
+/* 1 if the tcgen05 path can take this geometry (stride 1, cin%64==0, cout%64==0) */
+int vspw_conv2d_tc_supported(const vspw_conv_desc* d);
+
+/* ---- layout / elementwise plumbing ------------------------------------------------------ */
+/* dst = permute(src): src has dims d[0..3] (row-major); dst dim i is src dim perm[i].
+ * Used for NCHW<->NHWC at the API edge (models/models.py:752-767 returns NCHW maps) and for
+ * OIHW->OHWI / OIHW->HWOI weight re-layout. */
+int vspw_permute4d(const float* src, float* dst, const int32_t d[4], const int32_t perm[4], void* stream);
+int vspw_fill(float* dst, float value, size_t n, void* stream);
+/* y = a*x + b*y  (grad accumulation on fan-out; loss = loss + 0.4*loss_deepsup, clip_psp.py:215) */
+int vspw_axpby(const float* x, float* y, float a, float b, size_t n, void* stream);
+/* fp32 -> (hi, lo) bf16 planes, hi = bf16(x), lo = bf16(x - hi): operands of the tcgen05 path */
+int vspw_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, size_t n, void* stream);
+/* copy a channel slice: dst[p][dst_off + c] = src[p][src_off + c], c < cc   (torch.cat(dim=1),
+ * clip_psp.py:53, spatial_ocr_block.py:375; accumulate!=0 adds instead (backward of cat/split)) */
+int vspw_copy_channels(const float* src, int32_t src_c, int32_t src_off, float* dst, int32_t dst_c,
+                       int32_t dst_off, int32_t cc, size_t pixels, int32_t accumulate, void* stream);
+
+/* ---- convolution = implicit GEMM (nn.Conv2d, models/resnet.py:61-66,100-106,130;
+ *      clip_psp.py:28,35-41,74-79; clip_ocr.py:43,56-62; spatial_ocr_block.py:208-245,351) ---- */
+/* y = conv(x, w_ohwi) (+ bias[cout] if non-null).  For VSPW_PREC_BF16X3/BF16 the caller passes
+ * the bf16 planes of x and w (x_hi/x_lo: same NHWC shape; w_hi/w_lo: OHWI) instead of x/w. */
+int vspw_conv2d_fwd(const vspw_conv_desc* d, const float* x, const float* w_ohwi, const float* bias,
+                    float* y, void* stream);
+/* dx = conv_transpose(dy, w): w_hwoi[kh][kw][cout][cin] flattened so that row ci holds
+ * K = kh*kw*cout contiguous values, i.e. w_t[ci][r][s][co]. */
+int vspw_conv2d_dgrad(const vspw_conv_desc* d, const float* dy, const float* w_t_ihwo, float* dx,
+                      void* stream);
+/* dw_ohwi[cout][kh][kw][cin] = sum over pixels dy * x  (split-K with fp32 atomics; zeroed inside) */
+int vspw_conv2d_wgrad(const vspw_conv_desc* d, const float* x, const float* dy, float* dw_ohwi,
+                      void* stream);
+/* tcgen05 variants: operands as bf16 hi/lo planes (lo may be null when precision==VSPW_PREC_BF16).
+ * fwd and dgrad share one kernel (dgrad = conv of dy with flipped taps and transposed weights). */
+int vspw_conv2d_fwd_tc(const vspw_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo,
+                       const uint16_t* w_hi, const uint16_t* w_lo, const float* bias, float* y,
+                       void* stream);
+int vspw_conv2d_dgrad_tc(const vspw_conv_desc* d, const uint16_t* dy_hi, const uint16_t* dy_lo,
+                         const uint16_t* wt_hi, const uint16_t* wt_lo, float* dx, void* stream);
+int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo,
+                         const uint16_t* dy_hi, const uint16_t* dy_lo, float* dw_ohwi, void* stream);
+
+/* ---- batch norm (+ReLU, +residual, +Dropout2d channel mask)
+ *      models/sync_batchnorm/batchnorm.py:68-73 (F.batch_norm), :133-150; resnet.py:72-92 ---- */
+/* per-channel sum / sum of squares over `pixels` rows of C channels (double accumulators, caller
+ * zeroes them); also used for conv-bias gradients (column sums of dy). */
+int vspw_bn_stats(const float* y, size_t pixels, int32_t c, double* sum, double* sqsum, void* stream);
+/* train: mean/var from sums -> scale = gamma*invstd, shift = beta - mean*scale; running stats
+ * updated with momentum (unbiased variance), F.batch_norm semantics: invstd = 1/sqrt(var+eps).
+ * clamp_mode!=0 selects the DataParallel SyncBN form clamp(var,eps)^-1/2 (batchnorm.py:150). */
+int vspw_bn_finalize_train(const double* sum, const double* sqsum, double count, const float* gamma,
+                           const float* beta, float eps, float momentum, float* running_mean,
+                           float* running_var, float* mean, float* invstd, float* scale,
+                           float* shift, int32_t c, int32_t clamp_mode, void* stream);
+/* eval: scale/shift folded from the running statistics */
+int vspw_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean,
+                      const float* running_var, float eps, float* scale, float* shift, int32_t c,
+                      void* stream);
+/* out = relu?(y*scale + shift + residual?) * chan_scale?[n][c]; optional bf16 planes of out */
+int vspw_bn_act_fwd(const float* y, const float* scale, const float* shift, const float* residual,
+                    const float* chan_scale, int32_t relu, float* out, uint16_t* out_hi,
+                    uint16_t* out_lo, size_t pixels, int32_t c, size_t pixels_per_image,
+                    void* stream);
+/* backward pass 1: g = dout * chan_scale * [out>0]; dbeta = sum g; dgamma = sum g*xhat */
+int vspw_bn_bwd_reduce(const float* dout, const float* out, const float* y, const float* mean,
+                       const float* invstd, const float* chan_scale, int32_t relu, size_t pixels,
+                       int32_t c, size_t pixels_per_image, double* dbeta, double* dgamma,
+                       void* stream);
+/* backward pass 2: dy = gamma*invstd*(g - dbeta/P - xhat*dgamma/P); dres = g (if non-null);
+ * also converts the double sums to float dgamma_f/dbeta_f.  eval_mode!=0: dy = g*scale. */
+int vspw_bn_bwd_apply(const float* dout, const float* out, const float* y, const float* mean,
+                      const float* invstd, const float* gamma, const float* chan_scale, int32_t relu,
+                      const double* dbeta, const double* dgamma, float* dy, float* dres,
+                      float* dgamma_f, float* dbeta_f, size_t pixels, int32_t c,
+                      size_t pixels_per_image, int32_t eval_mode, void* stream);
+
+/* ---- pooling -------------------------------------------------------------------------- */
+/* nn.MaxPool2d(3, 2, 1) (models/resnet.py:109); idx saves the winning tap (0..8) per output */
+int vspw_maxpool3x3s2_fwd(const float* x, float* y, uint8_t* idx, int32_t n, int32_t h, int32_t w,
+                          int32_t c, int32_t ho, int32_t wo, void* stream);
+int vspw_maxpool3x3s2_bwd(const float* dy, const uint8_t* idx, float* dx, int32_t n, int32_t h,
+                          int32_t w, int32_t c, int32_t ho, int32_t wo, void* stream);
+/* Temporal pyramid pooling (the TCB step of Clip_PSP, models/clip_psp.py:154-188):
+ * feat[(t*n_clips+i)][h][w][c]  ->  pooled[i][bin][c], bins of all `n_scales` AdaptiveAvgPool2d
+ * scales concatenated (1,4,9,36 -> 50), averaged over the T frames; frame_w[t][i] (nullable)
+ * are the psp_weight softmax weights already permuted to the reference's list order.
+ * pooled must be zero-filled by the caller (fp32 atomics). */
+int vspw_tcb_pool_fwd(const float* feat, const float* frame_w, float* pooled, int32_t t_frames,
+                      int32_t n_clips, int32_t h, int32_t w, int32_t c, const int32_t* scales_host,
+                      int32_t n_scales, void* stream);
+/* dfeat (overwritten) from dpooled; dframe_w[t][i] (nullable, zeroed by the caller) */
+int vspw_tcb_pool_bwd(const float* dpooled, const float* frame_w, const float* feat, float* dfeat,
+                      float* dframe_w, int32_t t_frames, int32_t n_clips, int32_t h, int32_t w,
+                      int32_t c, const int32_t* scales_host, int32_t n_scales, void* stream);
+
+/* ---- bilinear (align_corners=False) up-sampling into a channel slice
+ *      (PPM_conv.forward, clip_psp.py:48-53; PPMDeepsup.forward models/models.py:975-981) ---- */
+int vspw_upsample_bilinear_fwd(const float* src, int32_t n, int32_t sh, int32_t sw, int32_t c,
+                               float* dst, int32_t dh, int32_t dw, int32_t dst_c, int32_t dst_off,
+                               void* stream);
+/* dsrc[n][sh][sw][c] (zeroed inside) += bilinear^T(ddst slice) */
+int vspw_upsample_bilinear_bwd(const float* ddst, int32_t dh, int32_t dw, int32_t dst_c,
+                               int32_t dst_off, float* dsrc, int32_t n, int32_t sh, int32_t sw,
+                               int32_t c, void* stream);
+
+/* ---- loss tail: log_softmax(dim=1) at h*w -> bilinear to H*W -> NLLLoss(ignore_index) and
+ *      pixel_acc (clip_psp.py:92-98,196-217; clip_ocr.py:180-198).  logits[n][h][w][k] NHWC,
+ *      labels[n][H][W] float (values 0..k-1 or ignore_index).  Outputs (double, zeroed inside):
+ *      acc[0]=sum of -logp over valid pixels, acc[1]=#valid (label!=ignore), acc[2]=#correct
+ *      (argmax==label, over label>=0), acc[3]=#(label>=0).  logp[n][h][w][k] is saved. ---- */
+int vspw_logsoftmax_up_nll_fwd(const float* logits, const float* labels, float* logp, double* acc,
+                               int32_t n, int32_t h, int32_t w, int32_t k, int32_t H, int32_t W,
+                               int32_t ignore_index, int32_t want_acc, void* stream);
+/* dlogits = d(loss)/d(logits) for loss = gscale_dev[0] * loss_scale * mean_valid(-logp_up[label]);
+ * gscale_dev is a device scalar (upstream grad), n_valid comes from acc[1] on device. */
+int vspw_logsoftmax_up_nll_bwd(const float* logp, const float* labels, const double* acc,
+                               const float* gscale_dev, float loss_scale, float* dlogits,
+                               float* scratch_g, int32_t n, int32_t h, int32_t w, int32_t k,
+                               int32_t H, int32_t W, int32_t ignore_index, void* stream);
+/* loss = acc0/acc1 (+ scale2 * acc2_0/acc2_1 if acc_b non-null), pixacc = acc[2]/(acc[3]+1e-10) */
+int vspw_loss_finalize(const double* acc_main, const double* acc_aux, float aux_scale, float* loss,
+                       float* pixacc, void* stream);
+/* inference tail: bilinear to segSize then softmax(dim=1), NCHW output probs[n][k][H][W]
+ * (clip_psp.py:190-194; clip_ocr.py:174-178); pred (nullable) = argmax as int32 [n][H][W] */
+int vspw_up_softmax_fwd(const float* logits, float* probs_nchw, int32_t* pred, int32_t n, int32_t h,
+                        int32_t w, int32_t k, int32_t H, int32_t W, void* stream);
+
+/* ---- OCR pieces (models/ocr_modules/spatial_ocr_block.py:97-109, 258-275) ---------------- */
+/* softmax along `len` for `rows` rows with arbitrary strides: out[r*row_stride + j*elem_stride] */
+int vspw_softmax_strided_fwd(const float* x, float* y, size_t rows, int32_t len, size_t row_stride,
+                             size_t elem_stride, int32_t rows_inner, size_t outer_stride, float scale,
+                             void* stream);
+/* dx = scale * y * (dy - sum_j dy_j*y_j) */
+int vspw_softmax_strided_bwd(const float* y, const float* dy, float* dx, size_t rows, int32_t len,
+                             size_t row_stride, size_t elem_stride, int32_t rows_inner,
+                             size_t outer_stride, float scale, void* stream);
+/* batched strided GEMM: C[b][i][j] = alpha * sum_k A[b][i][k]*B[b][k][j] + beta*C[b][i][j]
+ * with explicit element strides (torch.matmul call sites spatial_ocr_block.py:105,266,271) */
+int vspw_bgemm(const float* a, const float* b, float* c, int32_t batch, int32_t m, int32_t n,
+               int32_t k, int64_t a_bs, int64_t a_rs, int64_t a_cs, int64_t b_bs, int64_t b_rs,
+               int64_t b_cs, int64_t c_bs, int64_t c_rs, int64_t c_cs, float alpha, float beta,
+               void* stream);
+
+/* ---- evaluation (utils.py:55-107 Evaluator._generate_matrix): conf[gt][pred] += 1 ---------- */
+int vspw_confusion_add(const int32_t* pred, const float* labels, int64_t* conf, size_t pixels,
+                       int32_t num_class, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSPW_B200_H */
