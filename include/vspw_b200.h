@@ -128,8 +128,9 @@ int vspw_maxpool3x3s2_fwd(const float* x, float* y, uint8_t* idx, int32_t n, int
 int vspw_maxpool3x3s2_bwd(const float* dy, const uint8_t* idx, float* dx, int32_t n, int32_t h,
                           int32_t w, int32_t c, int32_t ho, int32_t wo, void* stream);
 /* Temporal pyramid pooling (the TCB step of Clip_PSP, models/clip_psp.py:154-188):
- * feat[(t*n_clips+i)][h][w][c]  ->  pooled[i][bin][c], bins of all `n_scales` AdaptiveAvgPool2d
- * scales concatenated (1,4,9,36 -> 50), averaged over the T frames; frame_w[t][i] (nullable)
+ * feat[(t*n_clips+i)][h][w][c]  ->  pooled = one block per `n_scales` AdaptiveAvgPool2d scale s,
+ * block s is a dense NHWC map [n_clips][s][s][c] stored at float offset n_clips*c*(sum of earlier
+ * s^2) (1,4,9,36 -> 50 bins per clip), averaged over the T frames; frame_w[t][i] (nullable)
  * are the psp_weight softmax weights already permuted to the reference's list order.
  * pooled must be zero-filled by the caller (fp32 atomics). */
 int vspw_tcb_pool_fwd(const float* feat, const float* frame_w, float* pooled, int32_t t_frames,
