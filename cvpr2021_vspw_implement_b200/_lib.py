@@ -1,0 +1,118 @@
+"""ctypes binding of ``csrc/libvspw_b200.so`` (the C ABI declared in ``include/vspw_b200.h``).
+
+The product path has no CPU or library fallback: if the shared library is missing and cannot be
+built, importing the engine raises.  Every call passes raw device pointers (``Tensor.data_ptr()``)
+and the caller's current CUDA stream.
+"""
+import ctypes
+import os
+import threading
+
+from . import build as _build
+
+_c_int = ctypes.c_int32
+_c_vp = ctypes.c_void_p
+_c_sz = ctypes.c_size_t
+_c_f = ctypes.c_float
+_c_d = ctypes.c_double
+_c_i64 = ctypes.c_int64
+
+PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
+
+
+class ConvDesc(ctypes.Structure):
+    """Mirror of ``vspw_conv_desc`` (include/vspw_b200.h)."""
+
+    _fields_ = [(k, _c_int) for k in ("n", "h", "w", "cin", "cout", "kh", "kw", "stride", "pad", "dil", "ho", "wo", "precision")]
+
+
+# name -> argtypes; every function returns int (0 = ok)
+_SIGNATURES = {
+    "vspw_conv2d_tc_supported": [ctypes.POINTER(ConvDesc)],
+    "vspw_permute4d": [_c_vp, _c_vp, ctypes.POINTER(_c_int * 4), ctypes.POINTER(_c_int * 4), _c_vp],
+    "vspw_fill": [_c_vp, _c_f, _c_sz, _c_vp],
+    "vspw_axpby": [_c_vp, _c_vp, _c_f, _c_f, _c_sz, _c_vp],
+    "vspw_split_bf16": [_c_vp, _c_vp, _c_vp, _c_sz, _c_vp],
+    "vspw_cast_f64_f32": [_c_vp, _c_vp, _c_sz, _c_vp],
+    "vspw_copy_channels": [_c_vp, _c_int, _c_int, _c_vp, _c_int, _c_int, _c_int, _c_sz, _c_int, _c_vp],
+    "vspw_conv2d_fwd": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
+    "vspw_conv2d_dgrad": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp],
+    "vspw_conv2d_wgrad": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp],
+    "vspw_conv2d_fwd_tc": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
+    "vspw_conv2d_dgrad_tc": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
+    "vspw_conv2d_wgrad_tc": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
+    "vspw_bn_stats": [_c_vp, _c_sz, _c_int, _c_vp, _c_vp, _c_vp],
+    "vspw_bn_finalize_train": [_c_vp, _c_vp, _c_d, _c_vp, _c_vp, _c_f, _c_f, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_vp],
+    "vspw_bn_fold_eval": [_c_vp, _c_vp, _c_vp, _c_vp, _c_f, _c_vp, _c_vp, _c_int, _c_vp],
+    "vspw_bn_act_fwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_vp],
+    "vspw_bn_bwd_reduce": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_sz, _c_vp, _c_vp, _c_vp],
+    "vspw_bn_bwd_apply": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_int, _c_vp],
+    "vspw_maxpool3x3s2_fwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp],
+    "vspw_maxpool3x3s2_bwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp],
+    "vspw_tcb_pool_fwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_int, _c_vp],
+    "vspw_tcb_pool_bwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_int, _c_vp],
+    "vspw_upsample_bilinear_fwd": [_c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp],
+    "vspw_upsample_bilinear_bwd": [_c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp],
+    "vspw_logsoftmax_up_nll_fwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp],
+    "vspw_logsoftmax_up_nll_bwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_f, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp],
+    "vspw_loss_finalize": [_c_vp, _c_vp, _c_f, _c_vp, _c_vp, _c_vp],
+    "vspw_up_softmax_fwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp],
+    "vspw_softmax_strided_fwd": [_c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_sz, _c_int, _c_sz, _c_f, _c_vp],
+    "vspw_softmax_strided_bwd": [_c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_sz, _c_int, _c_sz, _c_f, _c_vp],
+    "vspw_bgemm": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int] + [_c_i64] * 9 + [_c_f, _c_f, _c_vp],
+    "vspw_confusion_add": [_c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_vp],
+}
+
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["vspw_last_error", "vspw_version"])
+
+
+class VspwError(RuntimeError):
+    pass
+
+
+class _Lib:
+    def __init__(self):
+        self._dll = None
+        self._lock = threading.Lock()
+        self.launches = 0  # number of C-ABI compute calls issued (bench.py reports it)
+
+    def dll(self):
+        if self._dll is None:
+            with self._lock:
+                if self._dll is None:
+                    path = _build.LIB
+                    if not os.path.exists(path):
+                        path = _build.build_library()  # raises if nvcc is unavailable: no silent fallback
+                    dll = ctypes.CDLL(path)
+                    for name, argtypes in _SIGNATURES.items():
+                        fn = getattr(dll, name)
+                        fn.argtypes = argtypes
+                        fn.restype = ctypes.c_int
+                    dll.vspw_last_error.restype = ctypes.c_char_p
+                    dll.vspw_last_error.argtypes = []
+                    dll.vspw_version.restype = ctypes.c_int
+                    dll.vspw_version.argtypes = []
+                    self._dll = dll
+        return self._dll
+
+    def call(self, name, *args):
+        dll = self.dll()
+        rc = getattr(dll, name)(*args)
+        if rc != 0:
+            msg = dll.vspw_last_error().decode("utf-8", "replace")
+            raise VspwError(f"{name} failed ({rc}): {msg}")
+        self.launches += 1
+        return rc
+
+    def tc_supported(self, desc):
+        return bool(self.dll().vspw_conv2d_tc_supported(ctypes.byref(desc)))
+
+    def version(self):
+        return self.dll().vspw_version()
+
+
+lib = _Lib()
+
+
+def i4(*vals):
+    return ctypes.byref((_c_int * 4)(*vals))

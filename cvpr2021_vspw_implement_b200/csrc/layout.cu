@@ -194,3 +194,14 @@ extern "C" int vspw_copy_channels(const float* src, int32_t src_c, int32_t src_o
                                                                            total, accumulate);
   return check_launch("vspw_copy_channels");
 }
+
+// ---------------------------------------------------------------------------------------------
+__global__ void cast_f64_f32_kernel(const double* __restrict__ x, float* __restrict__ y, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = (float)x[i];
+}
+extern "C" int vspw_cast_f64_f32(const double* x, float* y, size_t n, void* stream) {
+  if (n == 0) return VSPW_OK;
+  VSPW_REQUIRE(x && y, "vspw_cast_f64_f32: null argument");
+  cast_f64_f32_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, y, n);
+  return check_launch("vspw_cast_f64_f32");
+}

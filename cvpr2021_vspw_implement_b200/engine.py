@@ -1,0 +1,762 @@
+"""Tape engine: explicit forward/backward of the per-clip hot path over the C-ABI kernels.
+
+Why a tape and not one ``autograd.Function`` per op: every activation buffer, every gradient
+accumulation and every kernel launch is ours — no ATen compute kernel runs inside the hot path, the
+fan-out sums (residual branches, layer4 -> pooling + decoder) use ``vspw_axpby`` and the whole step
+is one node in torch's autograd graph (``run_graph``), so ``loss.backward()`` at the caller
+(reference: train_clip2.py:97-104) works unchanged.
+
+Layout: activations are fp32 NHWC ``(N, H, W, C)`` torch tensors (torch = allocator + stream only).
+"""
+import ctypes
+import math
+from contextlib import contextmanager
+
+import torch
+
+from ._lib import ConvDesc, PREC_BF16, PREC_BF16X3, PREC_FP32, VspwError, i4, lib
+
+_PRECISION = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+_state = {"precision": "fp32", "syncbn_clamp": False}
+
+
+def set_precision(mode):
+    """'fp32' (CUDA-core FFMA), 'bf16x3' (tcgen05, 3-MMA split, parity mode) or 'bf16' (tcgen05 fast mode)."""
+    if mode not in _PRECISION:
+        raise ValueError(f"unknown precision {mode!r}; expected one of {sorted(_PRECISION)}")
+    _state["precision"] = mode
+
+
+def get_precision():
+    return _state["precision"]
+
+
+@contextmanager
+def precision(mode):
+    old = _state["precision"]
+    set_precision(mode)
+    try:
+        yield
+    finally:
+        _state["precision"] = old
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise VspwError(f"{what}: tensor must live on a CUDA device (the engine has no CPU path)")
+
+
+class Var:
+    """An activation (NHWC fp32) with an optional gradient slot and cached bf16 planes."""
+
+    __slots__ = ("data", "grad", "needs_grad", "planes")
+
+    def __init__(self, data, needs_grad=False):
+        self.data = data
+        self.grad = None
+        self.needs_grad = needs_grad
+        self.planes = None
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+    def add_grad(self, g):
+        """Accumulate ``g`` (takes ownership when the slot is empty)."""
+        if self.grad is None:
+            self.grad = g
+        else:
+            lib.call("vspw_axpby", _p(g), _p(self.grad), 1.0, 1.0, g.numel(), _stream())
+
+    def add_grad_rows(self, g, n0, n1):
+        """Accumulate into images [n0, n1) of the gradient (backward of a batch-axis slice)."""
+        if self.grad is None:
+            self.grad = torch.empty_like(self.data)
+            lib.call("vspw_fill", _p(self.grad), 0.0, self.grad.numel(), _stream())
+        dst = self.grad[n0:n1]
+        lib.call("vspw_axpby", _p(g), _p(dst), 1.0, 1.0, g.numel(), _stream())
+
+
+class PVar:
+    """A parameter seen by the tape: reference-layout data plus per-step derived layouts."""
+
+    __slots__ = ("param", "grad", "cache")
+
+    def __init__(self, param):
+        self.param = param
+        self.grad = None
+        self.cache = {}
+
+    @property
+    def data(self):
+        return self.param.data
+
+    @property
+    def needs_grad(self):
+        return self.param.requires_grad
+
+    def add_grad(self, g):
+        if self.grad is None:
+            self.grad = g
+        else:
+            lib.call("vspw_axpby", _p(g), _p(self.grad), 1.0, 1.0, g.numel(), _stream())
+
+
+class Tape:
+    def __init__(self, grad_enabled):
+        self.grad_enabled = grad_enabled
+        self._nodes = []
+        self._params = {}
+
+    def param(self, p):
+        if p is None:
+            return None
+        v = self._params.get(id(p))
+        if v is None:
+            v = self._params[id(p)] = PVar(p)
+        return v
+
+    def record(self, fn):
+        if self.grad_enabled:
+            self._nodes.append(fn)
+
+    def backward(self):
+        for fn in reversed(self._nodes):
+            fn()
+        self._nodes = []
+
+    def release(self):
+        self._nodes = []
+
+
+# ------------------------------------------------------------------------------------------------
+# layout helpers
+def permute4d(src, dst, dims, perm):
+    lib.call("vspw_permute4d", _p(src), _p(dst), i4(*dims), i4(*perm), _stream())
+
+
+def nchw_to_nhwc_into(src_nchw, dst_nhwc):
+    n, c, h, w = src_nchw.shape
+    permute4d(src_nchw, dst_nhwc, (n, c, h, w), (0, 2, 3, 1))
+
+
+def nhwc_to_nchw(x):
+    n, h, w, c = x.shape
+    out = torch.empty((n, c, h, w), device=x.device, dtype=torch.float32)
+    permute4d(x, out, (n, h, w, c), (0, 3, 1, 2))
+    return out
+
+
+def input_from_frames(frames):
+    """cat(frames, dim=0) + NCHW->NHWC in one pass per frame (clip_psp.py:142-143)."""
+    n, c, h, w = frames[0].shape
+    out = torch.empty((n * len(frames), h, w, c), device=frames[0].device, dtype=torch.float32)
+    for t, f in enumerate(frames):
+        _require_cuda(f, "input frame")
+        if f.shape != frames[0].shape:
+            raise VspwError("all frames of a clip must have the same shape")
+        f = f.contiguous() if not f.is_contiguous() else f
+        if f.dtype != torch.float32:
+            f = f.float()
+        nchw_to_nhwc_into(f, out[t * n:(t + 1) * n])
+    return out
+
+
+def _weight_ohwi(tape, wv):
+    """OIHW -> OHWI ([Cout][kh][kw][Cin], K contiguous); identity for 1x1."""
+    w = wv.data
+    co, ci, kh, kw = w.shape
+    if kh == 1 and kw == 1:
+        return w
+    t = wv.cache.get("ohwi")
+    if t is None:
+        t = torch.empty((co, kh, kw, ci), device=w.device, dtype=torch.float32)
+        permute4d(w, t, (co, ci, kh, kw), (0, 2, 3, 1))
+        wv.cache["ohwi"] = t
+    return t
+
+
+def _weight_ihwo(tape, wv):
+    """OIHW -> [Cin][kh][kw][Cout] (rows = Cin, K = taps*Cout contiguous) for dgrad."""
+    w = wv.data
+    co, ci, kh, kw = w.shape
+    t = wv.cache.get("ihwo")
+    if t is None:
+        t = torch.empty((ci, kh, kw, co), device=w.device, dtype=torch.float32)
+        # (co, ci*kh*kw) -> (ci*kh*kw, co): tiled transpose fast path
+        permute4d(w, t, (1, co, ci * kh * kw, 1), (0, 2, 3, 1))
+        wv.cache["ihwo"] = t
+    return t
+
+
+def _planes_of(t):
+    """(hi, lo) bf16 planes of an fp32 tensor (operands of the tcgen05 convs)."""
+    hi = torch.empty(t.shape, device=t.device, dtype=torch.bfloat16)
+    lo = torch.empty(t.shape, device=t.device, dtype=torch.bfloat16) if _state["precision"] == "bf16x3" else None
+    lib.call("vspw_split_bf16", _p(t), _p(hi), _p(lo), t.numel(), _stream())
+    return hi, lo
+
+
+def _var_planes(v):
+    if v.planes is None:
+        v.planes = _planes_of(v.data)
+    return v.planes
+
+
+def _weight_planes(wv, key, t):
+    pk = key + "_planes_" + _state["precision"]
+    pl = wv.cache.get(pk)
+    if pl is None:
+        pl = wv.cache[pk] = _planes_of(t)
+    return pl
+
+
+# ------------------------------------------------------------------------------------------------
+def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1):
+    """nn.Conv2d forward + recorded dgrad/wgrad (reference: models/resnet.py:61-66 etc.)."""
+    wv = tape.param(weight)
+    bv = tape.param(bias)
+    n, h, w, cin = x.shape
+    co, ci, kh, kw = wv.data.shape
+    if ci != cin:
+        raise VspwError(f"conv2d: input has {cin} channels, weight expects {ci}")
+    ho = (h + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+    wo = (w + 2 * pad - dil * (kw - 1) - 1) // stride + 1
+    prec = _PRECISION[_state["precision"]]
+    desc = ConvDesc(n, h, w, cin, co, kh, kw, stride, pad, dil, ho, wo, prec)
+    use_tc = prec != PREC_FP32 and lib.tc_supported(desc)
+    if not use_tc:
+        desc.precision = PREC_FP32
+    y = torch.empty((n, ho, wo, co), device=x.data.device, dtype=torch.float32)
+    w_ohwi = _weight_ohwi(tape, wv)
+    if use_tc:
+        xh, xl = _var_planes(x)
+        wh, wl = _weight_planes(wv, "ohwi", w_ohwi)
+        lib.call("vspw_conv2d_fwd_tc", ctypes.byref(desc), _p(xh), _p(xl), _p(wh), _p(wl), _p(bv.data if bv else None), _p(y), _stream())
+    else:
+        lib.call("vspw_conv2d_fwd", ctypes.byref(desc), _p(x.data), _p(w_ohwi), _p(bv.data if bv else None), _p(y), _stream())
+    out = Var(y, needs_grad=tape.grad_enabled and (x.needs_grad or wv.needs_grad))
+
+    def backward():
+        dy = out.grad
+        out.grad = None
+        if dy is None:
+            return
+        st = _stream()
+        dyp = None
+        if use_tc:
+            dyp = _planes_of(dy)
+        if wv.needs_grad:
+            dw = torch.empty((co, kh, kw, ci), device=dy.device, dtype=torch.float32)
+            if use_tc:
+                xh, xl = _var_planes(x)
+                lib.call("vspw_conv2d_wgrad_tc", ctypes.byref(desc), _p(xh), _p(xl), _p(dyp[0]), _p(dyp[1]), _p(dw), st)
+            else:
+                lib.call("vspw_conv2d_wgrad", ctypes.byref(desc), _p(x.data), _p(dy), _p(dw), st)
+            if kh == 1 and kw == 1:
+                wv.add_grad(dw.view(co, ci, 1, 1))
+            else:
+                dw_oihw = torch.empty((co, ci, kh, kw), device=dy.device, dtype=torch.float32)
+                permute4d(dw, dw_oihw, (co, kh, kw, ci), (0, 3, 1, 2))
+                wv.add_grad(dw_oihw)
+        if bv is not None and bv.needs_grad:
+            sums = torch.zeros(co, device=dy.device, dtype=torch.float64)
+            lib.call("vspw_bn_stats", _p(dy), n * ho * wo, co, _p(sums), None, st)
+            bv.add_grad(_double_to_float(sums))
+        if x.needs_grad:
+            dx = torch.empty((n, h, w, cin), device=dy.device, dtype=torch.float32)
+            w_t = _weight_ihwo(tape, wv)
+            if use_tc:
+                th, tl = _weight_planes(wv, "ihwo", w_t)
+                lib.call("vspw_conv2d_dgrad_tc", ctypes.byref(desc), _p(dyp[0]), _p(dyp[1]), _p(th), _p(tl), _p(dx), st)
+            else:
+                lib.call("vspw_conv2d_dgrad", ctypes.byref(desc), _p(dy), _p(w_t), _p(dx), st)
+            x.add_grad(dx)
+
+    tape.record(backward)
+    return out
+
+
+def _double_to_float(d):
+    """fp64 -> fp32 of a tiny per-channel vector (no ATen compute kernel in the path)."""
+    f = torch.empty(d.shape, device=d.device, dtype=torch.float32)
+    lib.call("vspw_cast_f64_f32", _p(d), _p(f), d.numel(), _stream())
+    return f
+
+
+def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, training=None):
+    """BN (train: batch stats, eval: running stats) [+ residual] [+ ReLU] [* Dropout2d mask].
+
+    Reference: SynchronizedBatchNorm2d.forward (sync_batchnorm/batchnorm.py:68-73) followed by
+    nn.ReLU / `out += residual` (resnet.py:72-92) / nn.Dropout2d (clip_psp.py:39).
+    """
+    n, h, w, c = y.shape
+    pixels = n * h * w
+    training = bn.training if training is None else training
+    gv, bv = tape.param(bn.weight), tape.param(bn.bias)
+    dev = y.data.device
+    st = _stream()
+    scale = torch.empty(c, device=dev, dtype=torch.float32)
+    shift = torch.empty(c, device=dev, dtype=torch.float32)
+    mean = invstd = None
+    if training:
+        if pixels <= 1:
+            raise ValueError(f"Expected more than 1 value per channel when training, got input size {[n, c, h, w]}")
+        sums = torch.zeros((2, c), device=dev, dtype=torch.float64)
+        lib.call("vspw_bn_stats", _p(y.data), pixels, c, _p(sums[0]), _p(sums[1]), st)
+        mean = torch.empty(c, device=dev, dtype=torch.float32)
+        invstd = torch.empty(c, device=dev, dtype=torch.float32)
+        lib.call("vspw_bn_finalize_train", _p(sums[0]), _p(sums[1]), float(pixels), _p(gv.data), _p(bv.data), float(bn.eps),
+                 float(bn.momentum), _p(bn.running_mean), _p(bn.running_var), _p(mean), _p(invstd), _p(scale), _p(shift), c,
+                 1 if _state["syncbn_clamp"] else 0, st)
+    else:
+        lib.call("vspw_bn_fold_eval", _p(gv.data), _p(bv.data), _p(bn.running_mean), _p(bn.running_var), float(bn.eps),
+                 _p(scale), _p(shift), c, st)
+    o = torch.empty_like(y.data)
+    want_planes = _state["precision"] != "fp32" and c % 64 == 0
+    hi = lo = None
+    if want_planes:
+        hi = torch.empty(o.shape, device=dev, dtype=torch.bfloat16)
+        lo = torch.empty(o.shape, device=dev, dtype=torch.bfloat16) if _state["precision"] == "bf16x3" else None
+    lib.call("vspw_bn_act_fwd", _p(y.data), _p(scale), _p(shift), _p(residual.data if residual is not None else None),
+             _p(chan_scale), 1 if relu else 0, _p(o), _p(hi), _p(lo), pixels, c, h * w, st)
+    needs = tape.grad_enabled and (y.needs_grad or gv.needs_grad or (residual is not None and residual.needs_grad))
+    out = Var(o, needs_grad=needs)
+    if want_planes:
+        out.planes = (hi, lo)
+
+    def backward():
+        dout = out.grad
+        out.grad = None
+        if dout is None:
+            return
+        st = _stream()
+        dy = torch.empty_like(dout)
+        dres = torch.empty_like(dout) if (residual is not None and residual.needs_grad) else None
+        if training:
+            dsum = torch.zeros((2, c), device=dev, dtype=torch.float64)
+            lib.call("vspw_bn_bwd_reduce", _p(dout), _p(o), _p(y.data), _p(mean), _p(invstd), _p(chan_scale), 1 if relu else 0,
+                     pixels, c, h * w, _p(dsum[0]), _p(dsum[1]), st)
+            dgam = torch.empty(c, device=dev, dtype=torch.float32)
+            dbet = torch.empty(c, device=dev, dtype=torch.float32)
+            lib.call("vspw_bn_bwd_apply", _p(dout), _p(o), _p(y.data), _p(mean), _p(invstd), _p(gv.data), _p(chan_scale),
+                     1 if relu else 0, _p(dsum[0]), _p(dsum[1]), _p(dy), _p(dres), _p(dgam), _p(dbet), pixels, c, h * w, 0, st)
+            if gv.needs_grad:
+                gv.add_grad(dgam)
+            if bv.needs_grad:
+                bv.add_grad(dbet)
+        else:
+            # frozen statistics: dy = g * gamma/sqrt(var+eps) = g * scale
+            lib.call("vspw_bn_bwd_apply", _p(dout), _p(o), None, None, _p(scale), None, _p(chan_scale), 1 if relu else 0, None,
+                     None, _p(dy), _p(dres), None, None, pixels, c, h * w, 1, st)
+        if y.needs_grad:
+            y.add_grad(dy)
+        if dres is not None:
+            residual.add_grad(dres)
+
+    tape.record(backward)
+    return out
+
+
+def maxpool3x3s2(tape, x):
+    n, h, w, c = x.shape
+    ho, wo = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+    y = torch.empty((n, ho, wo, c), device=x.data.device, dtype=torch.float32)
+    idx = torch.empty((n, ho, wo, c), device=x.data.device, dtype=torch.uint8) if tape.grad_enabled and x.needs_grad else None
+    lib.call("vspw_maxpool3x3s2_fwd", _p(x.data), _p(y), _p(idx), n, h, w, c, ho, wo, _stream())
+    out = Var(y, needs_grad=tape.grad_enabled and x.needs_grad)
+
+    def backward():
+        dy = out.grad
+        out.grad = None
+        if dy is None or not x.needs_grad:
+            return
+        dx = torch.empty_like(x.data)
+        lib.call("vspw_maxpool3x3s2_bwd", _p(dy), _p(idx), _p(dx), n, h, w, c, ho, wo, _stream())
+        x.add_grad(dx)
+
+    tape.record(backward)
+    return out
+
+
+def slice_images(tape, x, n0, n1):
+    """x[n0:n1] along the image axis (torch.split(dim=0), clip_psp.py:154-156)."""
+    out = Var(x.data[n0:n1], needs_grad=x.needs_grad)
+    if x.planes is not None:
+        out.planes = tuple(p[n0:n1] if p is not None else None for p in x.planes)
+
+    def backward():
+        g = out.grad
+        out.grad = None
+        if g is not None and x.needs_grad:
+            x.add_grad_rows(g, n0, n1)
+
+    tape.record(backward)
+    return out
+
+
+def tcb_pool(tape, feat, t_frames, n_clips, scales, frame_w=None):
+    """Temporal pyramid pooling: list of Vars (n_clips, s, s, C), one per scale (clip_psp.py:157-188)."""
+    N, h, w, c = feat.shape
+    assert N == t_frames * n_clips
+    dev = feat.data.device
+    total_bins = sum(s * s for s in scales)
+    pooled = torch.zeros(n_clips * total_bins * c, device=dev, dtype=torch.float32)
+    sc = (ctypes.c_int32 * len(scales))(*scales)
+    fw = frame_w.data if frame_w is not None else None
+    lib.call("vspw_tcb_pool_fwd", _p(feat.data), _p(fw), _p(pooled), t_frames, n_clips, h, w, c, sc, len(scales), _stream())
+    outs, off = [], 0
+    needs = tape.grad_enabled and (feat.needs_grad or (frame_w is not None and frame_w.needs_grad))
+    for s in scales:
+        cnt = n_clips * s * s * c
+        outs.append(Var(pooled[off:off + cnt].view(n_clips, s, s, c), needs_grad=needs))
+        off += cnt
+
+    def backward():
+        dp = torch.empty_like(pooled)
+        off = 0
+        any_grad = False
+        for s, o in zip(scales, outs):
+            cnt = n_clips * s * s * c
+            if o.grad is not None:
+                any_grad = True
+                lib.call("vspw_axpby", _p(o.grad), _p(dp[off:off + cnt]), 1.0, 0.0, cnt, _stream())
+            else:
+                lib.call("vspw_fill", _p(dp[off:off + cnt]), 0.0, cnt, _stream())
+            o.grad = None
+            off += cnt
+        if not any_grad:
+            return
+        dfeat = torch.empty_like(feat.data) if feat.needs_grad else None
+        dfw = None
+        if frame_w is not None and frame_w.needs_grad:
+            dfw = torch.zeros_like(frame_w.data)
+        if dfeat is None and dfw is None:
+            return
+        if dfeat is None:
+            dfeat = torch.empty_like(feat.data)
+        lib.call("vspw_tcb_pool_bwd", _p(dp), _p(fw), _p(feat.data), _p(dfeat), _p(dfw), t_frames, n_clips, h, w, c, sc,
+                 len(scales), _stream())
+        if feat.needs_grad:
+            feat.add_grad(dfeat)
+        if dfw is not None:
+            frame_w.add_grad(dfw)
+
+    tape.record(backward)
+    return outs
+
+
+def ppm_concat(tape, base, pyramids):
+    """cat([base] + [bilinear_up(p) for p in pyramids], channel axis) (clip_psp.py:45-53)."""
+    n, h, w, c0 = base.shape
+    ctot = c0 + sum(p.shape[3] for p in pyramids)
+    dev = base.data.device
+    cat = torch.empty((n, h, w, ctot), device=dev, dtype=torch.float32)
+    st = _stream()
+    lib.call("vspw_copy_channels", _p(base.data), c0, 0, _p(cat), ctot, 0, c0, n * h * w, 0, st)
+    offs, off = [], c0
+    for p in pyramids:
+        pn, sh, sw, pc = p.shape
+        lib.call("vspw_upsample_bilinear_fwd", _p(p.data), pn, sh, sw, pc, _p(cat), h, w, ctot, off, st)
+        offs.append(off)
+        off += pc
+    out = Var(cat, needs_grad=tape.grad_enabled and (base.needs_grad or any(p.needs_grad for p in pyramids)))
+
+    def backward():
+        g = out.grad
+        out.grad = None
+        if g is None:
+            return
+        st = _stream()
+        if base.needs_grad:
+            db = torch.empty_like(base.data)
+            lib.call("vspw_copy_channels", _p(g), ctot, 0, _p(db), c0, 0, c0, n * h * w, 0, st)
+            base.add_grad(db)
+        for p, o in zip(pyramids, offs):
+            if not p.needs_grad:
+                continue
+            pn, sh, sw, pc = p.shape
+            dp = torch.empty_like(p.data)
+            lib.call("vspw_upsample_bilinear_bwd", _p(g), h, w, ctot, o, _p(dp), pn, sh, sw, pc, st)
+            p.add_grad(dp)
+
+    tape.record(backward)
+    return out
+
+
+def concat_channels(tape, parts):
+    """torch.cat(parts, dim=1) in NHWC (spatial_ocr_block.py:375)."""
+    n, h, w, _ = parts[0].shape
+    ctot = sum(p.shape[3] for p in parts)
+    cat = torch.empty((n, h, w, ctot), device=parts[0].data.device, dtype=torch.float32)
+    st = _stream()
+    offs, off = [], 0
+    for p in parts:
+        pc = p.shape[3]
+        lib.call("vspw_copy_channels", _p(p.data), pc, 0, _p(cat), ctot, off, pc, n * h * w, 0, st)
+        offs.append(off)
+        off += pc
+    out = Var(cat, needs_grad=tape.grad_enabled and any(p.needs_grad for p in parts))
+
+    def backward():
+        g = out.grad
+        out.grad = None
+        if g is None:
+            return
+        for p, o in zip(parts, offs):
+            if not p.needs_grad:
+                continue
+            pc = p.shape[3]
+            dp = torch.empty_like(p.data)
+            lib.call("vspw_copy_channels", _p(g), ctot, o, _p(dp), pc, 0, pc, n * h * w, 0, _stream())
+            p.add_grad(dp)
+
+    tape.record(backward)
+    return out
+
+
+class LossTerm:
+    """One `crit(interpolate(log_softmax(logits)), label)` term; accumulators stay on the device."""
+
+    def __init__(self, logits, labels, ignore_index, want_acc):
+        self.logits, self.labels, self.ignore_index, self.want_acc = logits, labels, ignore_index, want_acc
+        self.acc = None
+        self.logp = None
+
+
+def nll_term(tape, logits, labels, ignore_index, want_acc):
+    """log_softmax -> bilinear up -> NLL (+pixel_acc) sums (clip_psp.py:196-217)."""
+    n, h, w, k = logits.shape
+    ln, lc, H, W = labels.shape
+    if ln != n or lc != 1:
+        raise VspwError(f"labels {tuple(labels.shape)} do not match logits batch {n}")
+    term = LossTerm(logits, labels, ignore_index, want_acc)
+    dev = logits.data.device
+    term.acc = torch.empty(4, device=dev, dtype=torch.float64)
+    term.logp = torch.empty_like(logits.data)
+    lib.call("vspw_logsoftmax_up_nll_fwd", _p(logits.data), _p(labels), _p(term.logp), _p(term.acc), n, h, w, k, H, W,
+             ignore_index, 1 if want_acc else 0, _stream())
+    return term
+
+
+def loss_combine(tape, main, aux, aux_scale):
+    """loss = main + aux_scale*aux, acc from main; returns (loss, acc) 0-d tensors and records backward."""
+    dev = main.logits.data.device
+    loss = torch.empty((), device=dev, dtype=torch.float32)
+    pixacc = torch.empty((), device=dev, dtype=torch.float32)
+    lib.call("vspw_loss_finalize", _p(main.acc), _p(aux.acc if aux is not None else None), float(aux_scale), _p(loss),
+             _p(pixacc), _stream())
+    gslot = {"g": None}
+
+    def backward():
+        g = gslot["g"]  # device scalar: upstream d/d(loss)
+        st = _stream()
+        for term, scale in ((main, 1.0), (aux, aux_scale)):
+            if term is None or not term.logits.needs_grad:
+                continue
+            n, h, w, k = term.logits.shape
+            H, W = term.labels.shape[2], term.labels.shape[3]
+            dl = torch.empty_like(term.logits.data)
+            scratch = torch.empty_like(term.logits.data)
+            lib.call("vspw_logsoftmax_up_nll_bwd", _p(term.logp), _p(term.labels), _p(term.acc), _p(g), float(scale), _p(dl),
+                     _p(scratch), n, h, w, k, H, W, term.ignore_index, st)
+            term.logits.add_grad(dl)
+
+    tape.record(backward)
+    return loss, pixacc, gslot
+
+
+def up_softmax(logits, H, W, want_pred=False):
+    """Inference tail: bilinear to (H, W) then softmax(dim=1); NCHW probabilities (clip_psp.py:190-194)."""
+    n, h, w, k = logits.shape
+    dev = logits.data.device
+    probs = torch.empty((n, k, H, W), device=dev, dtype=torch.float32)
+    pred = torch.empty((n, H, W), device=dev, dtype=torch.int32) if want_pred else None
+    lib.call("vspw_up_softmax_fwd", _p(logits.data), _p(probs), _p(pred), n, h, w, k, H, W, _stream())
+    return (probs, pred) if want_pred else probs
+
+
+# ------------------------------------------------------------------------------------------------
+# OCR ops
+def region_gather(tape, feats, dsn, t_frames, n_clips):
+    """SpatialTemporalGather_Module (spatial_ocr_block.py:97-109): per frame softmax over hw of the dsn
+    logits, probs[K x hw] . feats[hw x C], mean over the T frames -> context Var (n_clips, K, 1, C)."""
+    N, h, w, c = feats.shape
+    k = dsn.shape[3]
+    hw = h * w
+    dev = feats.data.device
+    st = _stream()
+    probs = torch.empty_like(dsn.data)  # [N][hw][K]
+    lib.call("vspw_softmax_strided_fwd", _p(dsn.data), _p(probs), N * k, hw, 1, k, k, hw * k, 1.0, st)
+    ctx = torch.empty((n_clips, k, 1, c), device=dev, dtype=torch.float32)
+    inv_t = 1.0 / t_frames
+    for t in range(t_frames):
+        pr = probs[t * n_clips:(t + 1) * n_clips]
+        ft = feats.data[t * n_clips:(t + 1) * n_clips]
+        # C[b][i=class][j=ch] = sum_p probs[b][p][i] * feats[b][p][j]
+        lib.call("vspw_bgemm", _p(pr), _p(ft), _p(ctx), n_clips, k, c, hw, hw * k, 1, k, hw * c, c, 1, k * c, c, 1, inv_t,
+                 0.0 if t == 0 else 1.0, st)
+    out = Var(ctx, needs_grad=tape.grad_enabled and (feats.needs_grad or dsn.needs_grad))
+
+    def backward():
+        g = out.grad
+        out.grad = None
+        if g is None:
+            return
+        st = _stream()
+        if feats.needs_grad:
+            df = torch.empty_like(feats.data)
+            for t in range(t_frames):
+                pr = probs[t * n_clips:(t + 1) * n_clips]
+                # dF[b][p][j] = (1/T) sum_i probs[b][p][i] * g[b][i][j]
+                lib.call("vspw_bgemm", _p(pr), _p(g), _p(df[t * n_clips:(t + 1) * n_clips]), n_clips, hw, c, k, hw * k, k, 1,
+                         k * c, c, 1, hw * c, c, 1, inv_t, 0.0, st)
+            feats.add_grad(df)
+        if dsn.needs_grad:
+            dprobs = torch.empty_like(probs)
+            for t in range(t_frames):
+                ft = feats.data[t * n_clips:(t + 1) * n_clips]
+                # dP[b][p][i] = (1/T) sum_j feats[b][p][j] * g[b][i][j]
+                lib.call("vspw_bgemm", _p(ft), _p(g), _p(dprobs[t * n_clips:(t + 1) * n_clips]), n_clips, hw, k, c, hw * c, c, 1,
+                         k * c, 1, c, hw * k, k, 1, inv_t, 0.0, st)
+            dd = torch.empty_like(dsn.data)
+            lib.call("vspw_softmax_strided_bwd", _p(probs), _p(dprobs), _p(dd), N * k, hw, 1, k, k, hw * k, 1.0, st)
+            dsn.add_grad(dd)
+
+    tape.record(backward)
+    return out
+
+
+def object_attention(tape, query, key, value, key_channels):
+    """sim = softmax(kc^-0.5 * Q.K^T) over regions; ctx = sim.V (spatial_ocr_block.py:258-275).
+    query (n,h,w,kc), key (n,K,1,kc), value (n,K,1,kc) -> (n,h,w,kc)."""
+    n, h, w, kc = query.shape
+    K = key.shape[1]
+    hw = h * w
+    dev = query.data.device
+    st = _stream()
+    raw = torch.empty((n, hw, K), device=dev, dtype=torch.float32)
+    # raw[b][p][i] = sum_c Q[b][p][c] * Key[b][i][c]
+    lib.call("vspw_bgemm", _p(query.data), _p(key.data), _p(raw), n, hw, K, kc, hw * kc, kc, 1, K * kc, 1, kc, hw * K, K, 1, 1.0,
+             0.0, st)
+    sim = torch.empty_like(raw)
+    scale = float(key_channels) ** -0.5
+    lib.call("vspw_softmax_strided_fwd", _p(raw), _p(sim), n * hw, K, K, 1, n * hw, 0, scale, st)
+    ctx = torch.empty((n, h, w, kc), device=dev, dtype=torch.float32)
+    lib.call("vspw_bgemm", _p(sim), _p(value.data), _p(ctx), n, hw, kc, K, hw * K, K, 1, K * kc, kc, 1, hw * kc, kc, 1, 1.0, 0.0,
+             st)
+    out = Var(ctx, needs_grad=tape.grad_enabled and (query.needs_grad or key.needs_grad or value.needs_grad))
+
+    def backward():
+        g = out.grad
+        out.grad = None
+        if g is None:
+            return
+        st = _stream()
+        if value.needs_grad:
+            dv = torch.empty_like(value.data)
+            # dV[b][i][c] = sum_p sim[b][p][i] * g[b][p][c]
+            lib.call("vspw_bgemm", _p(sim), _p(g), _p(dv), n, K, kc, hw, hw * K, 1, K, hw * kc, kc, 1, K * kc, kc, 1, 1.0, 0.0, st)
+            value.add_grad(dv)
+        if query.needs_grad or key.needs_grad:
+            dsim = torch.empty_like(sim)
+            # dsim[b][p][i] = sum_c g[b][p][c] * V[b][i][c]
+            lib.call("vspw_bgemm", _p(g), _p(value.data), _p(dsim), n, hw, K, kc, hw * kc, kc, 1, K * kc, 1, kc, hw * K, K, 1, 1.0,
+                     0.0, st)
+            draw = torch.empty_like(sim)
+            lib.call("vspw_softmax_strided_bwd", _p(sim), _p(dsim), _p(draw), n * hw, K, K, 1, n * hw, 0, scale, st)
+            if query.needs_grad:
+                dq = torch.empty_like(query.data)
+                # dQ[b][p][c] = sum_i draw[b][p][i] * Key[b][i][c]
+                lib.call("vspw_bgemm", _p(draw), _p(key.data), _p(dq), n, hw, kc, K, hw * K, K, 1, K * kc, kc, 1, hw * kc, kc, 1,
+                         1.0, 0.0, st)
+                query.add_grad(dq)
+            if key.needs_grad:
+                dk = torch.empty_like(key.data)
+                # dKey[b][i][c] = sum_p draw[b][p][i] * Q[b][p][c]
+                lib.call("vspw_bgemm", _p(draw), _p(query.data), _p(dk), n, K, kc, hw, hw * K, 1, K, hw * kc, kc, 1, K * kc, kc, 1,
+                         1.0, 0.0, st)
+                key.add_grad(dk)
+
+    tape.record(backward)
+    return out
+
+
+def mean_over_stack(tape, items):
+    """torch.mean(torch.cat(items, dim=0), dim=0) for equally shaped Vars (memory bank, :122-125)."""
+    out_t = torch.empty_like(items[0].data)
+    inv = 1.0 / len(items)
+    for i, it in enumerate(items):
+        lib.call("vspw_axpby", _p(it.data), _p(out_t), inv, 0.0 if i == 0 else 1.0, out_t.numel(), _stream())
+    out = Var(out_t, needs_grad=tape.grad_enabled and any(i.needs_grad for i in items))
+
+    def backward():
+        g = out.grad
+        out.grad = None
+        if g is None:
+            return
+        for it in items:
+            if it.needs_grad:
+                d = torch.empty_like(g)
+                lib.call("vspw_axpby", _p(g), _p(d), inv, 0.0, g.numel(), _stream())
+                it.add_grad(d)
+
+    tape.record(backward)
+    return out
+
+
+def dropout2d_mask(p, n, c, device, training):
+    """Per-(image, channel) keep mask scaled by 1/(1-p) (nn.Dropout2d); None when inactive.
+    The Bernoulli draw is host-side plumbing (torch RNG); it is applied inside vspw_bn_act_fwd."""
+    if not training or p <= 0.0:
+        return None
+    keep = torch.empty((n, c), device=device, dtype=torch.float32).bernoulli_(1.0 - p)
+    lib.call("vspw_axpby", _p(keep), _p(keep), 1.0 / (1.0 - p), 0.0, keep.numel(), _stream())
+    return keep
+
+
+# ------------------------------------------------------------------------------------------------
+class _GraphFunction(torch.autograd.Function):
+    """One autograd node for a whole tape: forward runs `runner(tape)`, backward replays the tape."""
+
+    @staticmethod
+    def forward(ctx, runner, params, grad_on, *param_tensors):
+        tape = Tape(grad_enabled=grad_on)
+        outs, seed = runner(tape)
+        ctx.tape = tape
+        ctx.seed = seed
+        ctx.params = params
+        ctx.mark_non_differentiable(*[o for o in outs[1:]])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        tape, params = ctx.tape, ctx.params
+        if tape is None or not tape.grad_enabled:
+            raise VspwError("backward called on a graph that was run without gradients (or twice)")
+        ctx.seed(gouts[0])
+        tape.backward()
+        grads = []
+        for p in params:
+            pv = tape._params.get(id(p))
+            g = pv.grad if pv is not None else None
+            if g is not None and g.shape != p.shape:
+                g = g.view(p.shape)
+            grads.append(g)
+        ctx.tape = None
+        return (None, None, None, *grads)
+
+
+def run_graph(module, runner):
+    """Execute `runner(tape) -> (outputs, seed_fn)` as a single autograd node over module's parameters."""
+    params = [p for p in module.parameters()]
+    grad_on = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    return _GraphFunction.apply(runner, params, grad_on, *params)

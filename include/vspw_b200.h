@@ -61,6 +61,8 @@ int vspw_axpby(const float* x, float* y, float a, float b, size_t n, void* strea
 int vspw_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, size_t n, void* stream);
 /* copy a channel slice: dst[p][dst_off + c] = src[p][src_off + c], c < cc   (torch.cat(dim=1),
  * clip_psp.py:53, spatial_ocr_block.py:375; accumulate!=0 adds instead (backward of cat/split)) */
+/* double accumulators (BN sums, bias gradients) -> fp32 parameter-gradient vectors */
+int vspw_cast_f64_f32(const double* x, float* y, size_t n, void* stream);
 int vspw_copy_channels(const float* src, int32_t src_c, int32_t src_off, float* dst, int32_t dst_c,
                        int32_t dst_off, int32_t cc, size_t pixels, int32_t accumulate, void* stream);
 
