@@ -1,0 +1,198 @@
+"""Generate tests/golden/*.npz by EXECUTING THE REFERENCE (read-only at /root/reference) on CPU.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python oracle/make_golden.py
+
+Every case is fully described by seeds: weights = the reference constructors under
+``torch.manual_seed(seed)`` (our mirror reproduces them bit-for-bit, tests/test_host.py checks that
+while the reference is mounted) + ``tcb_oracle.condition_weights``; inputs =
+``tcb_oracle.synthetic_clip``.  The fixtures hold only the reference's OUTPUTS, so they stay small.
+Dropout2d modules are put in eval mode (their masks come from torch's global RNG and are not part of
+the algorithm under test).
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.dont_write_bytecode = True
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+REF = os.environ.get("VSPW_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+sys.path.insert(1, os.path.join(REF, "RAFT_core"))
+
+import tcb_oracle as O  # noqa: E402
+
+OUT = os.path.join(HERE, "..", "tests", "golden")
+CASES = {
+    # name: (builder kind, arch, T, n, H, W, model seed, data seed)
+    "clip_psp": ("Clip_PSP", "resnet50dilated", 3, 2, 49, 65, 11, 304),
+    "clip_psp_pspw": ("Clip_PSP_pspw", "resnet50dilated", 3, 2, 49, 65, 12, 305),
+    "clip_ocr": ("ClipOCRNet", "resnet50dilated", 3, 2, 49, 65, 13, 306),
+    "segmodule_r18": ("SegmentationModule", "resnet18dilated", 1, 2, 49, 65, 14, 307),
+}
+NUM_CLASS = 124
+
+
+def ns(**kw):
+    base = dict(num_class=NUM_CLASS, psp_weight=False, use_memory=False, memory_num=8, clipocr_all=False)
+    base.update(kw)
+    return argparse.Namespace(**base)
+
+
+def build(ref, kind, arch, seed, **kw):
+    torch.manual_seed(seed)
+    crit = torch.nn.NLLLoss(ignore_index=255)
+    enc = ref.ModelBuilder.build_encoder(arch)
+    if kind == "Clip_PSP":
+        m = ref.Clip_PSP(enc, crit, ns(**kw), deep_sup_scale=0.4)
+    elif kind == "Clip_PSP_pspw":
+        m = ref.Clip_PSP(enc, crit, ns(psp_weight=True, **kw), deep_sup_scale=0.4)
+    elif kind == "ClipOCRNet":
+        m = ref.ClipOCRNet(enc, crit, ns(**kw), deep_sup_scale=0.4)
+    else:
+        dec = ref.ModelBuilder.build_decoder("ppm_deepsup", fc_dim=512, num_class=NUM_CLASS)
+        m = ref.SegmentationModule(enc, dec, crit, deep_sup_scale=0.4)
+    sd = m.state_dict()
+    O.condition_weights(sd)
+    m.load_state_dict(sd)
+    return m
+
+
+def no_dropout(m):
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout2d):
+            mod.eval()
+
+
+def grad_summary(model):
+    """Per-parameter gradient pins: L2 norm, sum, and the first 64 values (full tensor when small)."""
+    out = {}
+    for name, p in model.named_parameters():
+        if p.grad is None:
+            continue
+        g = p.grad.detach().float().reshape(-1)
+        out["gnorm/" + name] = np.float64(g.double().norm().item())
+        out["gsum/" + name] = np.float64(g.double().sum().item())
+        out["ghead/" + name] = g[:64].numpy().copy()
+    return out
+
+
+def feed(imgs, labs, train):
+    # reference convention (train_clip2.py:75-83): frame 0 of the sampled clip is "current"
+    d = {"img_data": imgs[0], "seg_label": labs[0], "clipimgs_data": list(imgs[1:]), "step": 1}
+    if train:
+        d["cliplabels_data"] = list(labs[1:])
+    return d
+
+
+def run_case(ref, name, spec):
+    kind, arch, T, n, H, W, mseed, dseed = spec
+    imgs, labs = O.synthetic_clip(T, n, H, W, NUM_CLASS, seed=dseed, block=16)
+    rec = {"meta": np.array([T, n, H, W, mseed, dseed])}
+    # ---- train step -------------------------------------------------------------------------------
+    m = build(ref, kind, arch, mseed)
+    m.train()
+    no_dropout(m)
+    captured = {}
+    hooks = []
+    if kind.startswith("Clip_PSP"):
+        hooks.append(m.ppm_conv.register_forward_hook(lambda mod, i, o: captured.__setitem__("logits", o.detach())))
+        hooks.append(m.deepsup.register_forward_hook(lambda mod, i, o: captured.__setitem__("logits_deepsup", o.detach())))
+    elif kind == "ClipOCRNet":
+        hooks.append(m.head.register_forward_hook(lambda mod, i, o: captured.__setitem__("logits", o.detach())))
+        hooks.append(m.dsn_head.register_forward_hook(lambda mod, i, o: captured.__setitem__("logits_deepsup", o.detach())))
+        hooks.append(m.spatial_context_head.register_forward_hook(lambda mod, i, o: captured.__setitem__("context", o.detach())))
+    else:
+        hooks.append(m.decoder.conv_last_.register_forward_hook(lambda mod, i, o: captured.__setitem__("logits", o.detach())))
+    loss, acc = m(feed(imgs, labs, True)) if kind != "SegmentationModule" else m({"img_data": imgs[0], "seg_label": labs[0]})
+    loss.backward()
+    for h in hooks:
+        h.remove()
+    rec["train/loss"] = np.float64(loss.item())
+    rec["train/acc"] = np.float64(acc.item())
+    for k, v in captured.items():
+        rec["train/" + k] = v.numpy().copy()
+    rec.update({"train/" + k: v for k, v in grad_summary(m).items()})
+    sd = m.state_dict()
+    for k in ("encoder.bn1.running_mean", "encoder.bn1.running_var", "encoder.layer4.0.bn2.running_mean",
+              "encoder.layer4.0.bn2.running_var"):
+        rec["train/after/" + k] = sd[k].numpy().copy()
+    # ---- eval forward -----------------------------------------------------------------------------
+    m = build(ref, kind, arch, mseed)
+    m.eval()
+    with torch.no_grad():
+        if kind == "SegmentationModule":
+            probs = m({"img_data": imgs[0], "seg_label": labs[0]}, segSize=(H, W))
+        else:
+            probs = m(feed(imgs, labs, False), segSize=(H, W))
+    pred = probs.argmax(1)
+    rec["eval/probs_sub"] = probs[:, :, ::4, ::4].numpy().copy()
+    rec["eval/pred"] = pred.numpy().astype(np.uint8)
+    ev = O.Evaluator(NUM_CLASS)
+    import utils as ref_utils  # the reference's own Evaluator (utils.py:55-107)
+    rev = ref_utils.Evaluator(NUM_CLASS)
+    gt = labs[0].squeeze(1).numpy()
+    rev.add_batch(gt, pred.numpy())
+    ev.add_batch(gt, pred.numpy())
+    rec["eval/miou"] = np.float64(rev.Mean_Intersection_over_Union())
+    rec["eval/pixacc"] = np.float64(rev.Pixel_Accuracy())
+    rec["eval/fwiou"] = np.float64(rev.Frequency_Weighted_Intersection_over_Union())
+    assert abs(ev.mean_iou() - rec["eval/miou"]) < 1e-12 and abs(ev.fw_iou() - rec["eval/fwiou"]) < 1e-12
+    # ---- OCR inference memory bank (quirk Q9): two consecutive calls of one "video" -----------------
+    if kind == "ClipOCRNet":
+        m = build(ref, kind, arch, mseed, use_memory=True, memory_num=2)
+        m.eval()
+        imgs2, _ = O.synthetic_clip(T, n, H, W, NUM_CLASS, seed=dseed + 1000, block=16)
+        with torch.no_grad():
+            d1 = feed(imgs, labs, False)
+            d1["is_clean_memory"] = True
+            p1 = m(d1, segSize=(H, W))
+            d2 = feed(imgs2, labs, False)
+            d2["is_clean_memory"] = False
+            p2 = m(d2, segSize=(H, W))
+        rec["mem/probs1_sub"] = p1[:, :, ::4, ::4].numpy().copy()
+        rec["mem/probs2_sub"] = p2[:, :, ::4, ::4].numpy().copy()
+        rec["mem/bank_len"] = np.array([len(m.memory)])
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **rec)
+    print(f"{name}: loss={rec['train/loss']:.6f} acc={rec['train/acc']:.6f} miou={rec['eval/miou']:.6f} "
+          f"-> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def bn_formula_pin():
+    """The one numeric pin the reference's own tests hold for this path
+    (lib/nn/modules/tests/test_numeric_batchnorm.py:29-52): train-mode BN = (x-mean)/sqrt(var_biased+eps),
+    running_var uses the unbiased variance.  Stored as a tiny fixture for the BN kernel tests."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 8, 5, 7, generator=g) * 3 + 1
+    w, b = torch.rand(8, generator=g) + 0.5, torch.randn(8, generator=g)
+    rm, rv = torch.zeros(8), torch.ones(8)
+    y = torch.nn.functional.batch_norm(x, rm, rv, w, b, True, 0.1, 1e-5)
+    mean = x.mean(dim=(0, 2, 3))
+    var_b = x.var(dim=(0, 2, 3), unbiased=False)
+    y_formula = (x - mean[None, :, None, None]) / torch.sqrt(var_b + 1e-5)[None, :, None, None] * w[None, :, None, None] + b[None, :, None, None]
+    assert torch.allclose(y, y_formula, atol=1e-5)
+    np.savez_compressed(os.path.join(OUT, "bn_formula.npz"), x=x.numpy(), w=w.numpy(), b=b.numpy(), y=y.numpy(),
+                        running_mean=rm.numpy(), running_var=rv.numpy())
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    import importlib
+    ref = importlib.import_module("models")
+    torch.set_num_threads(8)
+    only = sys.argv[1:]
+    for name, spec in CASES.items():
+        if only and name not in only:
+            continue
+        run_case(ref, name, spec)
+    bn_formula_pin()
+
+
+if __name__ == "__main__":
+    main()

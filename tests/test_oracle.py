@@ -1,0 +1,110 @@
+"""CPU: the oracle restatement (oracle/tcb_oracle.py) against the golden outputs of the reference."""
+import numpy as np
+import pytest
+import torch
+
+import cases as C
+import tcb_oracle as O
+
+
+def _oracle_train(name):
+    kind, arch, T, n, H, W, mseed, dseed = C.CASES[name]
+    m = C.build(kind, arch, mseed)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    params = {k for k, _ in m.named_parameters()}
+    for k in params:
+        sd[k].requires_grad_(True)
+    imgs, labs = C.clip_inputs(name)
+    if kind == "SegmentationModule":
+        out = O.segmentation_module_forward(sd, imgs[0], labs[0], train=True)
+    elif kind == "ClipOCRNet":
+        fr, lb = C.oracle_order(imgs, labs)
+        out = O.clip_ocr_forward(sd, fr, lb, train=True)
+    else:
+        fr, lb = C.oracle_order(imgs, labs)
+        out = O.clip_psp_forward(sd, fr, lb, args_psp_weight=(kind == "Clip_PSP_pspw"), train=True)
+    out["loss"].backward()
+    return out, sd, params
+
+
+@pytest.mark.parametrize("name", list(C.CASES))
+def test_oracle_train_matches_reference(name):
+    g = C.golden(name)
+    out, sd, params = _oracle_train(name)
+    assert abs(out["loss"].item() - float(g["train/loss"])) <= 1e-5 * abs(float(g["train/loss"]))
+    assert abs(out["acc"].item() - float(g["train/acc"])) <= 1e-6
+    assert C.rel_err(out["logits"].detach(), g["train/logits"]) <= 1e-4
+    if "train/logits_deepsup" in g:
+        assert C.rel_err(out["logits_deepsup"].detach(), g["train/logits_deepsup"]) <= 1e-4
+    if "train/context" in g:
+        assert C.rel_err(out["context"].detach(), g["train/context"]) <= 1e-4
+    checked = 0
+    for k in params:
+        key = "train/gnorm/" + k
+        if key not in g:
+            assert sd[k].grad is None or float(sd[k].grad.abs().max()) == 0.0, k
+            continue
+        gr = sd[k].grad
+        assert gr is not None, k
+        ref_norm = float(g[key])
+        assert abs(float(gr.double().norm()) - ref_norm) <= 2e-3 * max(ref_norm, 1e-12), k
+        assert C.rel_err(gr.reshape(-1)[:64], g["train/ghead/" + k]) <= 5e-3 or ref_norm < 1e-10, k
+        checked += 1
+    assert checked > 60
+    for k in ("encoder.bn1.running_mean", "encoder.bn1.running_var", "encoder.layer4.0.bn2.running_mean",
+              "encoder.layer4.0.bn2.running_var"):
+        assert C.rel_err(sd[k].detach(), g["train/after/" + k]) <= 1e-5, k
+
+
+@pytest.mark.parametrize("name", list(C.CASES))
+def test_oracle_eval_matches_reference(name):
+    kind, arch, T, n, H, W, mseed, dseed = C.CASES[name]
+    g = C.golden(name)
+    m = C.build(kind, arch, mseed)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    imgs, labs = C.clip_inputs(name)
+    with torch.no_grad():
+        if kind == "SegmentationModule":
+            out = O.segmentation_module_forward(sd, imgs[0], train=False, seg_size=(H, W))
+        elif kind == "ClipOCRNet":
+            out = O.clip_ocr_forward(sd, C.oracle_order(imgs, labs)[0], train=False, seg_size=(H, W))
+        else:
+            out = O.clip_psp_forward(sd, C.oracle_order(imgs, labs)[0], args_psp_weight=(kind == "Clip_PSP_pspw"),
+                                     train=False, seg_size=(H, W))
+    probs = out["probs"]
+    assert C.rel_err(probs[:, :, ::4, ::4], g["eval/probs_sub"]) <= 1e-4
+    pred = probs.argmax(1).numpy()
+    assert (pred == g["eval/pred"]).mean() >= 0.999
+    ev = O.Evaluator(C.NUM_CLASS)
+    ev.add_batch(labs[0].squeeze(1).numpy(), pred)
+    assert abs(ev.mean_iou() - float(g["eval/miou"])) <= 1e-6
+    assert abs(ev.pixel_accuracy() - float(g["eval/pixacc"])) <= 1e-6
+
+
+def test_oracle_memory_bank_quirk():
+    """Two consecutive inference calls with use_memory: the bank only grows on the first call (Q9)."""
+    kind, arch, T, n, H, W, mseed, dseed = C.CASES["clip_ocr"]
+    g = C.golden("clip_ocr")
+    m = C.build(kind, arch, mseed)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    imgs, labs = C.clip_inputs("clip_ocr")
+    imgs2, _ = O.synthetic_clip(T, n, H, W, C.NUM_CLASS, seed=dseed + 1000, block=16)
+    memory = []
+    with torch.no_grad():
+        p1 = O.clip_ocr_forward(sd, C.oracle_order(imgs, labs)[0], train=False, seg_size=(H, W), memory=memory, memory_num=2)
+        p2 = O.clip_ocr_forward(sd, C.oracle_order(imgs2, labs)[0], train=False, seg_size=(H, W), memory=memory, memory_num=2)
+    assert len(memory) == int(g["mem/bank_len"][0])
+    assert C.rel_err(p1["probs"][:, :, ::4, ::4], g["mem/probs1_sub"]) <= 1e-4
+    assert C.rel_err(p2["probs"][:, :, ::4, ::4], g["mem/probs2_sub"]) <= 1e-4
+
+
+def test_bn_formula_pin():
+    """The reference's own numeric BN test (lib/nn/modules/tests/test_numeric_batchnorm.py:29-52)."""
+    g = C.golden("bn_formula")
+    x = torch.from_numpy(g["x"])
+    sd = {"bn.weight": torch.from_numpy(g["w"]), "bn.bias": torch.from_numpy(g["b"]), "bn.running_mean": torch.zeros(8),
+          "bn.running_var": torch.ones(8)}
+    y = O.batch_norm(sd, "bn", x, True)
+    assert torch.allclose(y, torch.from_numpy(g["y"]), atol=1e-6)
+    assert torch.allclose(sd["bn.running_mean"], torch.from_numpy(g["running_mean"]), atol=1e-6)
+    assert torch.allclose(sd["bn.running_var"], torch.from_numpy(g["running_var"]), atol=1e-6)
