@@ -41,6 +41,25 @@ def precision(mode):
         _state["precision"] = old
 
 
+_capture = None
+
+
+@contextmanager
+def capturing():
+    """Test hook: collect named intermediate tensors (NHWC) that the graphs publish via ``publish``."""
+    global _capture
+    old, _capture = _capture, {}
+    try:
+        yield _capture
+    finally:
+        _capture = old
+
+
+def publish(name, var):
+    if _capture is not None:
+        _capture[name] = var.data
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 

@@ -67,7 +67,7 @@ class ClipOCRNet(nn.Module):
         maps = self.encoder.graph(tape, x)
         # dsn head on layer3 output of all N frames (reference :117)
         y = conv_op(tape, self.dsn_head[0], maps[-2])
-        mask = E.dropout2d_mask(self.dsn_head[3].p, y.shape[0], y.shape[3], y.data.device, training)
+        mask = E.dropout2d_mask(self.dsn_head[3].p, y.shape[0], y.shape[3], y.data.device, training and self.dsn_head[3].training)
         d = E.batchnorm_act(tape, y, self.dsn_head[1], relu=True, chan_scale=mask, training=training)
         x_dsn = conv_op(tape, self.dsn_head[4], d)
         feats = E.batchnorm_act(tape, conv_op(tape, self.conv_3x3[0], maps[-1]), self.conv_3x3[1], relu=True,
@@ -76,6 +76,7 @@ class ClipOCRNet(nn.Module):
             context = self.spatial_context_head.graph(tape, feats, x_dsn, t_frames - 1, memory, self.args.memory_num)
         else:
             context = self.spatial_context_head.graph(tape, feats, x_dsn, t_frames - 1)
+        E.publish("context", context)
         if self.args.clipocr_all:
             raise NotImplementedError("--clipocr_all True fails inside the reference itself (view of T*n pixels rows "
                                       "against an n-clip context, clip_ocr.py:136-137); the TCB scripts use False")
@@ -112,6 +113,8 @@ class ClipOCRNet(nn.Module):
 
         def runner(tape):
             logits, x_dsn = self._logits(tape, frames, training)
+            E.publish("logits", logits)
+            E.publish("logits_deepsup", x_dsn)
             main = E.nll_term(tape, logits, label, ignore, want_acc=True)
             all_lab = torch.empty((n * len(clip_labels), 1) + tuple(label.shape[2:]), device=label.device, dtype=torch.float32)
             for t, lab in enumerate(clip_labels):

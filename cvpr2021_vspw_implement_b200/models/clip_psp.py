@@ -35,7 +35,7 @@ class PPM_conv(nn.Module):
                for br, p in zip(self.ppm, pooled)]
         cat = E.ppm_concat(tape, x, pyr)
         y = conv_op(tape, self.conv_last_[0], cat)
-        mask = E.dropout2d_mask(self.conv_last_[3].p, y.shape[0], y.shape[3], y.data.device, training)
+        mask = E.dropout2d_mask(self.conv_last_[3].p, y.shape[0], y.shape[3], y.data.device, training and self.conv_last_[3].training)
         z = E.batchnorm_act(tape, y, self.conv_last_[1], relu=True, chan_scale=mask, training=training)
         return conv_op(tape, self.conv_last_[4], z)
 
@@ -132,6 +132,7 @@ class Clip_PSP(nn.Module):
 
         def runner(tape):
             logits, maps = self._logits(tape, frames, training)
+            E.publish("logits", logits)
             main = E.nll_term(tape, logits, label, ignore, want_acc=True)
             aux = None
             if self.deep_sup_scale is not None:
@@ -141,9 +142,11 @@ class Clip_PSP(nn.Module):
                     all_lab[t * n:(t + 1) * n].copy_(lab)  # D2D copy (torch.cat in the reference, :204)
                 conv4 = maps[-2]
                 y = conv_op(tape, self.deepsup[0], conv4)
-                mask = E.dropout2d_mask(self.deepsup[3].p, y.shape[0], y.shape[3], y.data.device, training)
+                mask = E.dropout2d_mask(self.deepsup[3].p, y.shape[0], y.shape[3], y.data.device, training and self.deepsup[3].training)
                 d = E.batchnorm_act(tape, y, self.deepsup[1], relu=True, chan_scale=mask, training=training)
-                aux = E.nll_term(tape, conv_op(tape, self.deepsup[4], d), all_lab, ignore, want_acc=False)
+                lds = conv_op(tape, self.deepsup[4], d)
+                E.publish("logits_deepsup", lds)
+                aux = E.nll_term(tape, lds, all_lab, ignore, want_acc=False)
             loss, acc, gslot = E.loss_combine(tape, main, aux, self.deep_sup_scale or 0.0)
             return (loss, acc), lambda g: gslot.__setitem__("g", g.contiguous())
 

@@ -61,6 +61,7 @@ class SegmentationModule(SegmentationModuleBase):
                 maps = self.encoder.graph(tape, x)
                 logits, logits_ds = self.decoder.graph(tape, maps, training=self.training,
                                                        want_deepsup=self.deep_sup_scale is not None)
+                E.publish("logits", logits)
                 main = E.nll_term(tape, logits, labels, ignore, want_acc=True)
                 aux = E.nll_term(tape, logits_ds, labels, ignore, want_acc=False) if logits_ds is not None else None
                 loss, acc, gslot = E.loss_combine(tape, main, aux, self.deep_sup_scale or 0.0)
@@ -172,14 +173,14 @@ class PPMDeepsup(nn.Module):
             pyr.append(E.batchnorm_act(tape, conv_op(tape, branch[1], p), branch[2], relu=True, training=training))
         cat = E.ppm_concat(tape, conv5, pyr)
         y = conv_op(tape, self.conv_last_[0], cat)
-        mask = E.dropout2d_mask(self.conv_last_[3].p, n, y.shape[3], y.data.device, training)
+        mask = E.dropout2d_mask(self.conv_last_[3].p, n, y.shape[3], y.data.device, training and self.conv_last_[3].training)
         x = E.batchnorm_act(tape, y, self.conv_last_[1], relu=True, chan_scale=mask, training=training)
         logits = conv_op(tape, self.conv_last_[4], x)
         if not want_deepsup:
             return logits, None
         conv4 = conv_out[-2]
         y = conv_op(tape, self.cbr_deepsup[0], conv4)
-        mask = E.dropout2d_mask(self.dropout_deepsup.p, n, y.shape[3], y.data.device, training)
+        mask = E.dropout2d_mask(self.dropout_deepsup.p, n, y.shape[3], y.data.device, training and self.dropout_deepsup.training)
         d = E.batchnorm_act(tape, y, self.cbr_deepsup[1], relu=True, chan_scale=mask, training=training)
         return logits, conv_op(tape, self.conv_last_deepsup_, d)
 

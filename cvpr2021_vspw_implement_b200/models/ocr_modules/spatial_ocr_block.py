@@ -102,5 +102,5 @@ class SpatialOCR_Module(nn.Module):
         context = self.object_context_block.graph(tape, feats, proxy_feats, training)
         cat = E.concat_channels(tape, [context, feats])
         y = conv_op(tape, self.conv_bn_dropout[0], cat)
-        mask = E.dropout2d_mask(self.conv_bn_dropout[3].p, y.shape[0], y.shape[3], y.data.device, training)
+        mask = E.dropout2d_mask(self.conv_bn_dropout[3].p, y.shape[0], y.shape[3], y.data.device, training and self.conv_bn_dropout[3].training)
         return E.batchnorm_act(tape, y, self.conv_bn_dropout[1], relu=True, chan_scale=mask, training=training)

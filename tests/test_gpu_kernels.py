@@ -1,0 +1,306 @@
+"""GPU: every C-ABI kernel family against the plain fp32 CPU op it replaces (through the ctypes boundary)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cases as C
+import tcb_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def E():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from cvpr2021_vspw_implement_b200 import engine
+    return engine
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+CONV_GEOMS = [
+    # n, cin, h, w, cout, k, stride, pad, dil, bias
+    (2, 3, 33, 45, 64, 3, 2, 1, 1, False),      # stem conv1 (scalar path)
+    (2, 64, 17, 23, 64, 3, 1, 1, 1, False),
+    (2, 128, 13, 19, 128, 3, 2, 1, 1, False),   # layer2 strided 3x3
+    (2, 256, 13, 19, 512, 1, 2, 0, 1, False),   # strided 1x1 downsample
+    (3, 256, 9, 13, 256, 3, 1, 2, 2, False),    # dilated d2
+    (2, 512, 9, 13, 512, 3, 1, 4, 4, False),    # dilated d4
+    (2, 1024, 7, 9, 256, 1, 1, 0, 1, False),
+    (2, 512, 7, 9, 124, 1, 1, 0, 1, True),      # classifier with bias, Cout not multiple of 128
+    (2, 2048, 6, 6, 1, 1, 1, 0, 1, False),      # pspweight conv, Cout=1
+    (2, 96, 5, 7, 40, 3, 1, 1, 1, True),        # odd channel counts
+    (2, 2048, 1, 1, 512, 1, 1, 0, 1, False),    # PPM scale-1 map
+]
+
+
+@pytest.mark.parametrize("geom", CONV_GEOMS)
+def test_conv2d_fwd_dgrad_wgrad(E, geom):
+    n, cin, h, w, cout, k, stride, pad, dil, has_bias = geom
+    g = torch.Generator().manual_seed(hash(geom) % 1000)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, generator=g) if has_bias else None
+    xr = x.clone().requires_grad_(True)
+    wr = wt.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True) if has_bias else None
+    yr = F.conv2d(xr, wr, br, stride=stride, padding=pad, dilation=dil)
+    gy = torch.randn(yr.shape, generator=g)
+    yr.backward(gy)
+
+    tape = E.Tape(True)
+    wp = torch.nn.Parameter(wt.cuda())
+    bp = torch.nn.Parameter(b.cuda()) if has_bias else None
+    xv = E.Var(nhwc(x).cuda(), needs_grad=True)
+    with E.precision("fp32"):
+        yv = E.conv2d(tape, xv, wp, bp, stride, pad, dil)
+        assert C.rel_err(nchw(yv.data.cpu()), yr.detach()) <= 2e-5
+        yv.grad = nhwc(gy).cuda()
+        tape.backward()
+    assert C.rel_err(nchw(xv.grad.cpu()), xr.grad) <= 2e-5
+    assert C.rel_err(tape.param(wp).grad.cpu(), wr.grad) <= 5e-5
+    if has_bias:
+        assert C.rel_err(tape.param(bp).grad.cpu(), br.grad) <= 2e-5
+
+
+@pytest.mark.parametrize("c,relu,res,drop,train", [(64, True, False, False, True), (256, True, True, False, True),
+                                                   (512, True, False, True, True), (128, False, False, False, True),
+                                                   (256, True, True, False, False), (2048, True, False, False, True)])
+def test_batchnorm_act(E, c, relu, res, drop, train):
+    g = torch.Generator().manual_seed(c + relu + 2 * res)
+    n, h, w = 3, 7, 9
+    y = torch.randn(n, c, h, w, generator=g) * 2 + 0.5
+    r = torch.randn(n, c, h, w, generator=g) if res else None
+    mask = ((torch.rand(n, c, generator=g) > 0.3).float() / 0.7) if drop else None
+    bn_ref = torch.nn.BatchNorm2d(c)
+    bn_ref.weight.data = torch.rand(c, generator=g) + 0.5
+    bn_ref.bias.data = torch.randn(c, generator=g)
+    bn_ref.running_mean.data = torch.randn(c, generator=g) * 0.1
+    bn_ref.running_var.data = torch.rand(c, generator=g) + 0.5
+    from cvpr2021_vspw_implement_b200.models.sync_batchnorm import BatchNorm2d
+    bn = BatchNorm2d(c)
+    bn.load_state_dict(bn_ref.state_dict())
+    bn = bn.cuda()
+    bn_ref.train(train)
+    yr = y.clone().requires_grad_(True)
+    rr = r.clone().requires_grad_(True) if res else None
+    o = bn_ref(yr)
+    if res:
+        o = o + rr
+    if relu:
+        o = F.relu(o)
+    if drop:
+        o = o * mask[:, :, None, None]
+    go = torch.randn(o.shape, generator=g)
+    o.backward(go)
+
+    tape = E.Tape(True)
+    yv = E.Var(nhwc(y).cuda(), needs_grad=True)
+    rv = E.Var(nhwc(r).cuda(), needs_grad=True) if res else None
+    ov = E.batchnorm_act(tape, yv, bn, relu=relu, residual=rv, chan_scale=mask.cuda() if drop else None, training=train)
+    assert C.rel_err(nchw(ov.data.cpu()), o.detach()) <= 1e-5
+    ov.grad = nhwc(go).cuda()
+    tape.backward()
+    assert C.rel_err(nchw(yv.grad.cpu()), yr.grad) <= 5e-5
+    if res:
+        assert C.rel_err(nchw(rv.grad.cpu()), rr.grad) <= 1e-6
+    if train:
+        assert C.rel_err(tape.param(bn.weight).grad.cpu(), bn_ref.weight.grad) <= 5e-5
+        assert C.rel_err(tape.param(bn.bias).grad.cpu(), bn_ref.bias.grad) <= 5e-5
+        assert C.rel_err(bn.running_mean.cpu(), bn_ref.running_mean) <= 1e-5
+        assert C.rel_err(bn.running_var.cpu(), bn_ref.running_var) <= 1e-5
+
+
+def test_bn_golden_formula(E):
+    """The reference's own BN numeric pin (tests/golden/bn_formula.npz) through the CUDA kernels."""
+    gd = C.golden("bn_formula")
+    from cvpr2021_vspw_implement_b200.models.sync_batchnorm import BatchNorm2d
+    bn = BatchNorm2d(8)
+    bn.weight.data = torch.from_numpy(gd["w"])
+    bn.bias.data = torch.from_numpy(gd["b"])
+    bn = bn.cuda().train()
+    tape = E.Tape(False)
+    out = E.batchnorm_act(tape, E.Var(nhwc(torch.from_numpy(gd["x"])).cuda()), bn, relu=False)
+    assert np.allclose(nchw(out.data.cpu()).numpy(), gd["y"], atol=1e-5)
+    assert np.allclose(bn.running_mean.cpu().numpy(), gd["running_mean"], atol=1e-6)
+    assert np.allclose(bn.running_var.cpu().numpy(), gd["running_var"], atol=1e-6)
+
+
+def test_bn_train_single_value_raises(E):
+    from cvpr2021_vspw_implement_b200.models.sync_batchnorm import BatchNorm2d
+    bn = BatchNorm2d(8).cuda().train()
+    with pytest.raises(ValueError):
+        E.batchnorm_act(E.Tape(False), E.Var(torch.zeros(1, 1, 1, 8, device="cuda")), bn)
+
+
+@pytest.mark.parametrize("h,w", [(33, 45), (32, 44), (7, 5)])
+def test_maxpool(E, h, w):
+    g = torch.Generator().manual_seed(h * w)
+    x = F.relu(torch.randn(2, 64, h, w, generator=g))
+    xr = x.clone().requires_grad_(True)
+    yr = F.max_pool2d(xr, 3, 2, 1)
+    gy = torch.randn(yr.shape, generator=g)
+    yr.backward(gy)
+    tape = E.Tape(True)
+    xv = E.Var(nhwc(x).cuda(), needs_grad=True)
+    yv = E.maxpool3x3s2(tape, xv)
+    assert torch.equal(nchw(yv.data.cpu()), yr.detach())
+    yv.grad = nhwc(gy).cuda()
+    tape.backward()
+    # ties (zeros after ReLU) may pick another element of the window; compare where the input is positive
+    pos = x > 0
+    assert C.rel_err(nchw(xv.grad.cpu())[pos], xr.grad[pos]) <= 1e-6
+
+
+@pytest.mark.parametrize("T,n,h,w,c", [(3, 2, 7, 9, 64), (5, 2, 13, 22, 128), (1, 3, 6, 6, 32), (2, 1, 60, 107, 16)])
+def test_tcb_pool(E, T, n, h, w, c):
+    g = torch.Generator().manual_seed(T * 100 + h)
+    feat = torch.randn(T * n, c, h, w, generator=g)
+    fr = feat.clone().requires_grad_(True)
+    scales = (1, 2, 3, 6)
+    refs = O.tcb_pool(list(torch.split(fr, n, dim=0)), scales)
+    gs = [torch.randn(r.shape, generator=g) for r in refs]
+    sum((r * gg).sum() for r, gg in zip(refs, gs)).backward()
+    tape = E.Tape(True)
+    fv = E.Var(nhwc(feat).cuda(), needs_grad=True)
+    outs = E.tcb_pool(tape, fv, T, n, scales)
+    for o, r, gg in zip(outs, refs, gs):
+        assert C.rel_err(nchw(o.data.cpu()), r.detach()) <= 2e-5
+        o.grad = nhwc(gg).cuda()
+    tape.backward()
+    assert C.rel_err(nchw(fv.grad.cpu()), fr.grad) <= 2e-5
+
+
+def test_ppm_concat(E):
+    g = torch.Generator().manual_seed(3)
+    n, h, w = 2, 13, 22
+    base = torch.randn(n, 64, h, w, generator=g)
+    pyr = [torch.randn(n, 32, s, s, generator=g) for s in (1, 2, 3, 6)]
+    br = base.clone().requires_grad_(True)
+    pr = [p.clone().requires_grad_(True) for p in pyr]
+    cat = torch.cat([br] + [F.interpolate(p, (h, w), mode="bilinear", align_corners=False) for p in pr], 1)
+    gc = torch.randn(cat.shape, generator=g)
+    cat.backward(gc)
+    tape = E.Tape(True)
+    bv = E.Var(nhwc(base).cuda(), needs_grad=True)
+    pv = [E.Var(nhwc(p).cuda(), needs_grad=True) for p in pyr]
+    cv = E.ppm_concat(tape, bv, pv)
+    assert C.rel_err(nchw(cv.data.cpu()), cat.detach()) <= 1e-5
+    cv.grad = nhwc(gc).cuda()
+    tape.backward()
+    assert C.rel_err(nchw(bv.grad.cpu()), br.grad) <= 1e-6
+    for a, b in zip(pv, pr):
+        assert C.rel_err(nchw(a.grad.cpu()), b.grad) <= 2e-5
+
+
+@pytest.mark.parametrize("n,h,w,H,W,k", [(2, 7, 9, 49, 65, 124), (3, 6, 11, 41, 83, 124), (1, 60, 107, 480, 854, 124), (2, 5, 5, 5, 5, 19)])
+def test_loss_tail(E, n, h, w, H, W, k):
+    g = torch.Generator().manual_seed(n * h)
+    logits = torch.randn(n, k, h, w, generator=g) * 3
+    _, labs = O.synthetic_clip(1, n, H, W, k, seed=h * w, block=8)
+    lab = labs[0]
+    lr = logits.clone().requires_grad_(True)
+    loss, lp, lb = O.nll_up(lr, lab, 255)
+    acc = O.pixel_acc(lp, lb)
+    (loss * 1.7).backward()
+    tape = E.Tape(True)
+    lv = E.Var(nhwc(logits).cuda(), needs_grad=True)
+    term = E.nll_term(tape, lv, lab.cuda(), 255, want_acc=True)
+    out_loss, out_acc, gslot = E.loss_combine(tape, term, None, 0.0)
+    assert abs(out_loss.item() - loss.item()) <= 2e-5 * abs(loss.item())
+    assert abs(out_acc.item() - acc.item()) <= 2e-5
+    gslot["g"] = torch.tensor(1.7, device="cuda")
+    tape.backward()
+    assert C.rel_err(nchw(lv.grad.cpu()), lr.grad) <= 5e-5
+    # aux-only (thread-per-pixel kernel) must agree with the warp-per-pixel one
+    term2 = E.nll_term(E.Tape(False), E.Var(nhwc(logits).cuda()), lab.cuda(), 255, want_acc=False)
+    torch.cuda.synchronize()
+    assert abs(float(term2.acc[0] / term2.acc[1]) - loss.item()) <= 2e-5 * abs(loss.item())
+
+
+def test_loss_all_ignored_is_nan(E):
+    lv = E.Var(torch.randn(1, 4, 4, 8, device="cuda"))
+    lab = torch.full((1, 1, 16, 16), 255.0, device="cuda")
+    term = E.nll_term(E.Tape(False), lv, lab, 255, want_acc=True)
+    loss, acc, _ = E.loss_combine(E.Tape(False), term, None, 0.0)
+    assert torch.isnan(loss).item() and acc.item() == 0.0
+
+
+@pytest.mark.parametrize("n,h,w,H,W,k", [(2, 7, 9, 49, 65, 124), (1, 9, 14, 70, 107, 124), (2, 4, 4, 33, 31, 150)])
+def test_up_softmax(E, n, h, w, H, W, k):
+    g = torch.Generator().manual_seed(H)
+    logits = torch.randn(n, k, h, w, generator=g) * 3
+    ref = F.softmax(F.interpolate(logits, (H, W), mode="bilinear", align_corners=False), dim=1)
+    probs, pred = E.up_softmax(E.Var(nhwc(logits).cuda()), H, W, want_pred=True)
+    assert C.rel_err(probs.cpu(), ref) <= 1e-5
+    assert (pred.cpu() == ref.argmax(1)).float().mean().item() >= 0.9999
+
+
+def test_region_gather_and_attention(E):
+    g = torch.Generator().manual_seed(9)
+    T, n, h, w, c, K, kc = 3, 2, 7, 9, 64, 24, 32
+    feats = torch.randn(T * n, c, h, w, generator=g)
+    dsn = torch.randn(T * n, K, h, w, generator=g) * 2
+    fr, dr = feats.clone().requires_grad_(True), dsn.clone().requires_grad_(True)
+    ctx = O.region_gather(fr, dr, T)  # (n, c, K, 1)
+    gc = torch.randn(ctx.shape, generator=g)
+    ctx.backward(gc)
+    tape = E.Tape(True)
+    fv, dv = E.Var(nhwc(feats).cuda(), needs_grad=True), E.Var(nhwc(dsn).cuda(), needs_grad=True)
+    cv = E.region_gather(tape, fv, dv, T, n)
+    assert C.rel_err(nchw(cv.data.cpu()), ctx.detach()) <= 2e-5
+    cv.grad = nhwc(gc).cuda()
+    tape.backward()
+    assert C.rel_err(nchw(fv.grad.cpu()), fr.grad) <= 5e-5
+    assert C.rel_err(nchw(dv.grad.cpu()), dr.grad) <= 5e-5
+
+    q = torch.randn(n, kc, h, w, generator=g)
+    key = torch.randn(n, kc, K, 1, generator=g)
+    val = torch.randn(n, kc, K, 1, generator=g)
+    qr, kr, vr = (t.clone().requires_grad_(True) for t in (q, key, val))
+    sim = F.softmax(kc ** -0.5 * torch.matmul(qr.reshape(n, kc, -1).permute(0, 2, 1), kr.reshape(n, kc, -1)), dim=-1)
+    out = torch.matmul(sim, vr.reshape(n, kc, -1).permute(0, 2, 1)).permute(0, 2, 1).reshape(n, kc, h, w)
+    go = torch.randn(out.shape, generator=g)
+    out.backward(go)
+    tape = E.Tape(True)
+    qv, kv, vv = (E.Var(nhwc(t).cuda(), needs_grad=True) for t in (q, key, val))
+    ov = E.object_attention(tape, qv, kv, vv, kc)
+    assert C.rel_err(nchw(ov.data.cpu()), out.detach()) <= 2e-5
+    ov.grad = nhwc(go).cuda()
+    tape.backward()
+    for a, b in ((qv, qr), (kv, kr), (vv, vr)):
+        assert C.rel_err(nchw(a.grad.cpu()), b.grad) <= 5e-5
+
+
+def test_permute_and_layout(E):
+    x = torch.randn(3, 5, 7, 11)
+    out = torch.empty(3, 7, 11, 5, device="cuda")
+    E.permute4d(x.cuda(), out, (3, 5, 7, 11), (0, 2, 3, 1))
+    assert torch.equal(out.cpu(), x.permute(0, 2, 3, 1))
+    back = E.nhwc_to_nchw(out)
+    assert torch.equal(back.cpu(), x)
+    out2 = torch.empty(11, 3, 7, 5, device="cuda")
+    E.permute4d(x.cuda(), out2, (3, 5, 7, 11), (3, 0, 2, 1))
+    assert torch.equal(out2.cpu(), x.permute(3, 0, 2, 1))
+
+
+def test_confusion_matrix_matches_evaluator(E):
+    import ctypes
+    from cvpr2021_vspw_implement_b200._lib import lib
+    g = torch.Generator().manual_seed(1)
+    pred = torch.randint(0, 124, (2, 33, 41), generator=g, dtype=torch.int32)
+    _, labs = O.synthetic_clip(1, 2, 33, 41, 124, seed=2, block=8)
+    conf = torch.zeros(124, 124, dtype=torch.int64, device="cuda")
+    lib.call("vspw_confusion_add", ctypes.c_void_p(pred.cuda().data_ptr()), ctypes.c_void_p(labs[0].cuda().data_ptr()),
+             ctypes.c_void_p(conf.data_ptr()), pred.numel(), 124, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    ev = O.Evaluator(124)
+    ev.add_batch(labs[0].squeeze(1).numpy(), pred.numpy())
+    assert np.array_equal(conf.cpu().numpy(), ev.confusion_matrix.astype(np.int64))

@@ -1,0 +1,155 @@
+"""GPU: the drop-in modules (through the C ABI) against the golden outputs of the reference and the oracle.
+
+Tolerances (north_star: "within 1e-3 relative fp32 tolerance"): logits / probabilities
+max|d|/max|ref| <= 1e-3, loss and acc relative 1e-3, gradient L2 norms relative 1e-3 (2e-3 for the tiny
+fixtures whose PPM scale-1 BN sees two values per channel), argmax agreement >= 99.9 %, mIoU |d| <= 1e-3.
+"""
+import numpy as np
+import pytest
+import torch
+
+import cases as C
+import tcb_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def E():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from cvpr2021_vspw_implement_b200 import engine
+    return engine
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+def _train_step(E, name, prec):
+    kind, arch, T, n, H, W, mseed, dseed = C.CASES[name]
+    m = C.no_dropout(C.build(kind, arch, mseed)).cuda().train()
+    imgs, labs = C.clip_inputs(name)
+    with E.precision(prec), E.capturing() as cap:
+        if kind == "SegmentationModule":
+            loss, acc = m({"img_data": imgs[0].cuda(), "seg_label": labs[0].cuda()})
+        else:
+            loss, acc = m(C.feed(imgs, labs, True, "cuda"))
+        loss.backward()
+    torch.cuda.synchronize()
+    return m, loss, acc, cap
+
+
+@pytest.mark.parametrize("name", ["clip_psp", "clip_ocr", "segmodule_r18"])
+@pytest.mark.parametrize("prec", ["fp32"])
+def test_train_step_matches_reference(E, name, prec):
+    g = C.golden(name)
+    m, loss, acc, cap = _train_step(E, name, prec)
+    assert abs(loss.item() - float(g["train/loss"])) <= TOL * abs(float(g["train/loss"]))
+    assert abs(acc.item() - float(g["train/acc"])) <= TOL
+    assert C.rel_err(nchw(cap["logits"].cpu()), g["train/logits"]) <= TOL
+    if "train/logits_deepsup" in g and "logits_deepsup" in cap:
+        assert C.rel_err(nchw(cap["logits_deepsup"].cpu()), g["train/logits_deepsup"]) <= TOL
+    if "train/context" in g:
+        assert C.rel_err(nchw(cap["context"].cpu()), g["train/context"]) <= TOL
+    worst = 0.0
+    checked = 0
+    for k, p in m.named_parameters():
+        key = "train/gnorm/" + k
+        if key not in g:
+            continue
+        assert p.grad is not None, k
+        ref_norm = float(g[key])
+        if ref_norm < 1e-9:
+            continue
+        err = abs(float(p.grad.double().norm()) - ref_norm) / ref_norm
+        worst = max(worst, err)
+        assert err <= 2 * TOL, (k, err)
+        assert C.rel_err(p.grad.reshape(-1)[:64].cpu(), g["train/ghead/" + k]) <= 5 * TOL, k
+        checked += 1
+    assert checked > 60
+    sd = m.state_dict()
+    for k in ("encoder.bn1.running_mean", "encoder.bn1.running_var", "encoder.layer4.0.bn2.running_mean",
+              "encoder.layer4.0.bn2.running_var"):
+        assert C.rel_err(sd[k].cpu(), g["train/after/" + k]) <= TOL, k
+    print(f"{name}/{prec}: worst grad-norm rel err {worst:.2e}")
+
+
+@pytest.mark.parametrize("name", ["clip_psp", "clip_ocr", "segmodule_r18"])
+def test_eval_matches_reference(E, name):
+    kind, arch, T, n, H, W, mseed, dseed = C.CASES[name]
+    g = C.golden(name)
+    m = C.build(kind, arch, mseed).cuda().eval()
+    imgs, labs = C.clip_inputs(name)
+    with torch.no_grad():
+        if kind == "SegmentationModule":
+            probs = m({"img_data": imgs[0].cuda(), "seg_label": labs[0].cuda()}, segSize=(H, W))
+        else:
+            probs = m(C.feed(imgs, labs, False, "cuda"), segSize=(H, W))
+    assert tuple(probs.shape) == (n, C.NUM_CLASS, H, W)
+    assert C.rel_err(probs[:, :, ::4, ::4].cpu(), g["eval/probs_sub"]) <= TOL
+    pred = probs.argmax(1).cpu().numpy()
+    assert (pred == g["eval/pred"]).mean() >= 0.999
+    # mIoU parity on labels that agree with the reference prediction on ~half of the 8x8 tiles
+    rng = np.random.RandomState(0)
+    gt = g["eval/pred"].astype(np.int64).copy()
+    tiles = rng.rand(n, (H + 7) // 8, (W + 7) // 8) < 0.5
+    noise = rng.randint(0, C.NUM_CLASS, size=tiles.shape)
+    up = lambda a: np.repeat(np.repeat(a, 8, axis=1), 8, axis=2)[:, :H, :W]
+    gt = np.where(up(tiles), up(noise), gt)
+    ev_ref, ev_new = O.Evaluator(C.NUM_CLASS), O.Evaluator(C.NUM_CLASS)
+    ev_ref.add_batch(gt, g["eval/pred"].astype(np.int64))
+    ev_new.add_batch(gt, pred)
+    assert abs(ev_ref.mean_iou() - ev_new.mean_iou()) <= TOL
+    assert ev_ref.mean_iou() > 0.2
+
+
+def test_ocr_memory_bank_quirk(E):
+    kind, arch, T, n, H, W, mseed, dseed = C.CASES["clip_ocr"]
+    g = C.golden("clip_ocr")
+    m = C.build(kind, arch, mseed, use_memory=True, memory_num=2).cuda().eval()
+    imgs, labs = C.clip_inputs("clip_ocr")
+    imgs2, _ = O.synthetic_clip(T, n, H, W, C.NUM_CLASS, seed=dseed + 1000, block=16)
+    with torch.no_grad():
+        d1 = C.feed(imgs, labs, False, "cuda"); d1["is_clean_memory"] = True
+        p1 = m(d1, segSize=(H, W))
+        d2 = C.feed(imgs2, labs, False, "cuda"); d2["is_clean_memory"] = False
+        p2 = m(d2, segSize=(H, W))
+    assert len(m.memory) == int(g["mem/bank_len"][0])
+    assert C.rel_err(p1[:, :, ::4, ::4].cpu(), g["mem/probs1_sub"]) <= TOL
+    assert C.rel_err(p2[:, :, ::4, ::4].cpu(), g["mem/probs2_sub"]) <= TOL
+
+
+def test_forward_mutates_caller_lists_like_reference(E):
+    kind, arch, T, n, H, W, mseed, dseed = C.CASES["clip_psp"]
+    m = C.no_dropout(C.build(kind, arch, mseed)).cuda().train()
+    imgs, labs = C.clip_inputs("clip_psp")
+    d = C.feed(imgs, labs, True, "cuda")
+    m(d)
+    assert len(d["clipimgs_data"]) == T and len(d["cliplabels_data"]) == T
+
+
+def test_clip_psp_train_needs_two_clips(E):
+    """Reference quirk Q12: n=1 per device fails in the scale-1 PPM branch's train-mode BN."""
+    kind, arch, T, n, H, W, mseed, dseed = C.CASES["clip_psp"]
+    m = C.no_dropout(C.build(kind, arch, mseed)).cuda().train()
+    imgs, labs = O.synthetic_clip(T, 1, H, W, C.NUM_CLASS, seed=1, block=16)
+    with pytest.raises(ValueError, match="more than 1 value per channel"):
+        m(C.feed(imgs, labs, True, "cuda"))
+
+
+def test_encoder_api_returns_nchw_maps(E):
+    from cvpr2021_vspw_implement_b200 import models as M
+    torch.manual_seed(0)
+    enc = M.ModelBuilder.build_encoder("resnet18dilated").cuda().eval()
+    x = torch.randn(1, 3, 49, 65)
+    sd = {"encoder." + k: v.cpu() for k, v in enc.state_dict().items()}
+    with torch.no_grad():
+        maps = enc(x.cuda(), return_feature_maps=True)
+        ref = O.resnet_forward(sd, "encoder.", x, False)
+    assert [tuple(m.shape) for m in maps] == [tuple(r.shape) for r in ref]
+    for a, b in zip(maps, ref):
+        assert C.rel_err(a.cpu(), b) <= TOL
+    with torch.no_grad():
+        assert len(enc(x.cuda())) == 1
