@@ -15,45 +15,51 @@ namespace {
 constexpr int kStatThreads = 256;
 constexpr int kPixPerThread = 32;
 
-template <typename F>
+struct D4 { double x, y, z, w; };
+
+// SQUARE=true: elem yields v, and the second accumulator is sum(v*v) with the product formed in fp64
+// (exact for fp32 inputs).  E[x^2]-E[x]^2 on fp32 products loses the variance when |mean| >> std, which
+// happens on the s x s PPM maps of near-identical clips (2..72 values per channel).
+template <bool SQUARE, typename F>
 __device__ __forceinline__ void stats_block(size_t pixels, int c, double* out_a, double* out_b, F&& elem) {
-  extern __shared__ float4 sh[];  // [2][kStatThreads]
+  extern __shared__ D4 sh[];  // [2][kStatThreads]
   const int c4 = c >> 2;
   const int G = c4 < kStatThreads ? c4 : kStatThreads;  // channel groups handled in parallel
   const int PL = kStatThreads / G;                      // pixel lanes
   const int g = threadIdx.x % G, pl = threadIdx.x / G;
   const size_t pix_per_block = (size_t)PL * kPixPerThread;
   const size_t p0 = (size_t)blockIdx.x * pix_per_block;
-  if (pl >= PL) {  // threads beyond PL*G idle (G does not divide 256)
-    // still must reach the barriers below
-  }
   for (int cg = g; cg < c4; cg += G) {
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    if (pl < PL) {
+    D4 a = {0, 0, 0, 0}, b = {0, 0, 0, 0};
+    if (pl < PL) {  // threads beyond PL*G idle (G need not divide 256) but still reach the barriers
       for (int i = 0; i < kPixPerThread; ++i) {
         size_t p = p0 + (size_t)i * PL + pl;
         if (p >= pixels) break;
         float4 va, vb;
         elem(p, cg, va, vb);
         a.x += va.x; a.y += va.y; a.z += va.z; a.w += va.w;
-        b.x += vb.x; b.y += vb.y; b.z += vb.z; b.w += vb.w;
+        if (SQUARE) {
+          b.x += (double)va.x * va.x; b.y += (double)va.y * va.y; b.z += (double)va.z * va.z; b.w += (double)va.w * va.w;
+        } else {
+          b.x += vb.x; b.y += vb.y; b.z += vb.z; b.w += vb.w;
+        }
       }
     }
     sh[threadIdx.x] = a;
     sh[kStatThreads + threadIdx.x] = b;
     __syncthreads();
     if (pl == 0) {
-      double ax = 0, ay = 0, az = 0, aw = 0, bx = 0, by = 0, bz = 0, bw = 0;
-      for (int l = 0; l < PL; ++l) {
-        float4 u = sh[l * G + g], v = sh[kStatThreads + l * G + g];
-        ax += u.x; ay += u.y; az += u.z; aw += u.w;
-        bx += v.x; by += v.y; bz += v.z; bw += v.w;
+      D4 u = sh[g], v = sh[kStatThreads + g];
+      for (int l = 1; l < PL; ++l) {
+        D4 u2 = sh[l * G + g], v2 = sh[kStatThreads + l * G + g];
+        u.x += u2.x; u.y += u2.y; u.z += u2.z; u.w += u2.w;
+        v.x += v2.x; v.y += v2.y; v.z += v2.z; v.w += v2.w;
       }
-      atomicAdd(out_a + cg * 4 + 0, ax); atomicAdd(out_a + cg * 4 + 1, ay);
-      atomicAdd(out_a + cg * 4 + 2, az); atomicAdd(out_a + cg * 4 + 3, aw);
+      atomicAdd(out_a + cg * 4 + 0, u.x); atomicAdd(out_a + cg * 4 + 1, u.y);
+      atomicAdd(out_a + cg * 4 + 2, u.z); atomicAdd(out_a + cg * 4 + 3, u.w);
       if (out_b) {
-        atomicAdd(out_b + cg * 4 + 0, bx); atomicAdd(out_b + cg * 4 + 1, by);
-        atomicAdd(out_b + cg * 4 + 2, bz); atomicAdd(out_b + cg * 4 + 3, bw);
+        atomicAdd(out_b + cg * 4 + 0, v.x); atomicAdd(out_b + cg * 4 + 1, v.y);
+        atomicAdd(out_b + cg * 4 + 2, v.z); atomicAdd(out_b + cg * 4 + 3, v.w);
       }
     }
     __syncthreads();
@@ -72,10 +78,8 @@ __global__ void __launch_bounds__(kStatThreads) bn_stats_kernel(const float* __r
                                                                  double* sum, double* sqsum) {
   const float4* y4 = reinterpret_cast<const float4*>(y);
   const int c4 = c >> 2;
-  stats_block(pixels, c, sum, sqsum, [&](size_t p, int cg, float4& a, float4& b) {
-    float4 v = __ldg(y4 + p * c4 + cg);
-    a = v;
-    b = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
+  stats_block<true>(pixels, c, sum, sqsum, [&](size_t p, int cg, float4& a, float4& b) {
+    a = __ldg(y4 + p * c4 + cg);
   });
 }
 
@@ -140,6 +144,8 @@ __device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d)
 
 __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float4* __restrict__ y, const float4* __restrict__ scale,
                                                           const float4* __restrict__ shift,
+                                                          const float4* __restrict__ mean,
+                                                          const float4* __restrict__ beta,
                                                           const float4* __restrict__ residual,
                                                           const float4* __restrict__ chan_scale, int relu,
                                                           float4* __restrict__ out, uint2* __restrict__ out_hi,
@@ -148,9 +154,16 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float4* __restric
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
     size_t p = i / c4;
     int cg = (int)(i - p * c4);
-    float4 v = y[i], sc = __ldg(scale + cg), sh = __ldg(shift + cg);
-    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
-    v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+    float4 v = y[i], sc = __ldg(scale + cg);
+    if (mean) {  // centred form (x-mean)*scale+beta: no cancellation when |mean| >> std
+      float4 m = __ldg(mean + cg), b = beta ? __ldg(beta + cg) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v.x = fmaf(v.x - m.x, sc.x, b.x); v.y = fmaf(v.y - m.y, sc.y, b.y);
+      v.z = fmaf(v.z - m.z, sc.z, b.z); v.w = fmaf(v.w - m.w, sc.w, b.w);
+    } else {
+      float4 sh = __ldg(shift + cg);
+      v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+      v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+    }
     if (residual) {
       float4 r = residual[i];
       v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
@@ -204,7 +217,7 @@ __global__ void __launch_bounds__(kStatThreads) bn_bwd_reduce_kernel(
   const float4* m4 = reinterpret_cast<const float4*>(mean);
   const float4* s4 = reinterpret_cast<const float4*>(invstd);
   const float4* cs4 = reinterpret_cast<const float4*>(chan_scale);
-  stats_block(pixels, c, dbeta, dgamma, [&](size_t p, int cg, float4& a, float4& b) {
+  stats_block<false>(pixels, c, dbeta, dgamma, [&](size_t p, int cg, float4& a, float4& b) {
     size_t i = p * c4 + cg;
     float4 g = masked_grad(d4, o4, cs4, relu, i, p, cg, c4, pix_per_img);
     float4 yv = __ldg(y4 + i), m = __ldg(m4 + cg), is = __ldg(s4 + cg);
@@ -261,7 +274,7 @@ extern "C" int vspw_bn_stats(const float* y, size_t pixels, int32_t c, double* s
   VSPW_REQUIRE(c > 0, "vspw_bn_stats: c must be positive");
   if (pixels == 0) return VSPW_OK;
   if (c % 4 == 0 && (uintptr_t)y % 16 == 0) {
-    bn_stats_kernel<<<stats_grid(pixels, c), kStatThreads, 2 * kStatThreads * sizeof(float4), as_stream(stream)>>>(
+    bn_stats_kernel<<<stats_grid(pixels, c), kStatThreads, 2 * kStatThreads * sizeof(D4), as_stream(stream)>>>(
         y, pixels, c, sum, sqsum);
   } else {
     unsigned gy = (unsigned)((pixels + 256 * 64 - 1) / (256 * 64));
@@ -290,16 +303,18 @@ extern "C" int vspw_bn_fold_eval(const float* gamma, const float* beta, const fl
   return check_launch("vspw_bn_fold_eval");
 }
 
-extern "C" int vspw_bn_act_fwd(const float* y, const float* scale, const float* shift, const float* residual,
+extern "C" int vspw_bn_act_fwd(const float* y, const float* scale, const float* shift, const float* mean,
+                               const float* beta, const float* residual,
                                const float* chan_scale, int32_t relu, float* out, uint16_t* out_hi, uint16_t* out_lo,
                                size_t pixels, int32_t c, size_t pixels_per_image, void* stream) {
-  VSPW_REQUIRE(y && scale && shift && out, "vspw_bn_act_fwd: null pointer");
+  VSPW_REQUIRE(y && scale && (shift || mean) && out, "vspw_bn_act_fwd: null pointer");
   VSPW_REQUIRE(c > 0 && c % 4 == 0, "vspw_bn_act_fwd: channels must be a multiple of 4 (got %d)", c);
   VSPW_REQUIRE(pixels_per_image > 0, "vspw_bn_act_fwd: pixels_per_image must be positive");
   size_t total4 = pixels * (size_t)(c / 4);
   if (total4 == 0) return VSPW_OK;
   bn_act_fwd_kernel<<<grid_for(total4, 256), 256, 0, as_stream(stream)>>>(
-      (const float4*)y, (const float4*)scale, (const float4*)shift, (const float4*)residual, (const float4*)chan_scale,
+      (const float4*)y, (const float4*)scale, (const float4*)shift, (const float4*)mean, (const float4*)beta,
+      (const float4*)residual, (const float4*)chan_scale,
       relu, (float4*)out, (uint2*)out_hi, (uint2*)out_lo, total4, c / 4, pixels_per_image);
   return check_launch("vspw_bn_act_fwd");
 }
@@ -311,7 +326,7 @@ extern "C" int vspw_bn_bwd_reduce(const float* dout, const float* out, const flo
   VSPW_REQUIRE(!relu || out, "vspw_bn_bwd_reduce: relu mask needs the forward output");
   VSPW_REQUIRE(c > 0 && c % 4 == 0, "vspw_bn_bwd_reduce: channels must be a multiple of 4 (got %d)", c);
   if (pixels == 0) return VSPW_OK;
-  bn_bwd_reduce_kernel<<<stats_grid(pixels, c), kStatThreads, 2 * kStatThreads * sizeof(float4), as_stream(stream)>>>(
+  bn_bwd_reduce_kernel<<<stats_grid(pixels, c), kStatThreads, 2 * kStatThreads * sizeof(D4), as_stream(stream)>>>(
       dout, out, y, mean, invstd, chan_scale, relu, pixels, c, pixels_per_image, dbeta, dgamma);
   return check_launch("vspw_bn_bwd_reduce");
 }

@@ -345,7 +345,9 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
     if want_planes:
         hi = torch.empty(o.shape, device=dev, dtype=torch.bfloat16)
         lo = torch.empty(o.shape, device=dev, dtype=torch.bfloat16) if _state["precision"] == "bf16x3" else None
-    lib.call("vspw_bn_act_fwd", _p(y.data), _p(scale), _p(shift), _p(residual.data if residual is not None else None),
+    center = mean if training else bn.running_mean
+    lib.call("vspw_bn_act_fwd", _p(y.data), _p(scale), _p(shift), _p(center), _p(bv.data),
+             _p(residual.data if residual is not None else None),
              _p(chan_scale), 1 if relu else 0, _p(o), _p(hi), _p(lo), pixels, c, h * w, st)
     needs = tape.grad_enabled and (y.needs_grad or gv.needs_grad or (residual is not None and residual.needs_grad))
     out = Var(o, needs_grad=needs)

@@ -105,8 +105,10 @@ int vspw_bn_finalize_train(const double* sum, const double* sqsum, double count,
 int vspw_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean,
                       const float* running_var, float eps, float* scale, float* shift, int32_t c,
                       void* stream);
-/* out = relu?(y*scale + shift + residual?) * chan_scale?[n][c]; optional bf16 planes of out */
-int vspw_bn_act_fwd(const float* y, const float* scale, const float* shift, const float* residual,
+/* out = relu?(bn(y) + residual?) * chan_scale?[n][c]; bn(y) = (y-mean)*scale + beta when mean is
+ * non-null (centred, F.batch_norm's form), else y*scale + shift; optional bf16 planes of out */
+int vspw_bn_act_fwd(const float* y, const float* scale, const float* shift, const float* mean,
+                    const float* beta, const float* residual,
                     const float* chan_scale, int32_t relu, float* out, uint16_t* out_hi,
                     uint16_t* out_lo, size_t pixels, int32_t c, size_t pixels_per_image,
                     void* stream);

@@ -299,7 +299,8 @@ def test_confusion_matrix_matches_evaluator(E):
     pred = torch.randint(0, 124, (2, 33, 41), generator=g, dtype=torch.int32)
     _, labs = O.synthetic_clip(1, 2, 33, 41, 124, seed=2, block=8)
     conf = torch.zeros(124, 124, dtype=torch.int64, device="cuda")
-    lib.call("vspw_confusion_add", ctypes.c_void_p(pred.cuda().data_ptr()), ctypes.c_void_p(labs[0].cuda().data_ptr()),
+    pred_d, lab_d = pred.cuda(), labs[0].cuda()
+    lib.call("vspw_confusion_add", ctypes.c_void_p(pred_d.data_ptr()), ctypes.c_void_p(lab_d.data_ptr()),
              ctypes.c_void_p(conf.data_ptr()), pred.numel(), 124, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     ev = O.Evaluator(124)
     ev.add_batch(labs[0].squeeze(1).numpy(), pred.numpy())
