@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Benchmark of the VSPW per-clip hot path: TCB-PSP ResNet101-dilated, T=5 synthetic 480p clips, train fwd+bwd.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|bf16x3|bf16]
+
+One JSON line on stdout (rank 0).  `value` = clip-frames/s with the clip already resident in HBM, `e2e` = the same
+step driven through the reference-facing module call from pinned HOST buffers (H2D of images+labels and D2H of
+the loss inside the timed region).  `roofline` = the dominant kernel family (implicit-GEMM convolutions) timed with
+CUDA events on the launching stream inside the timed steps.  `cpu_baseline` / `--impl reference` time the CPU
+oracle (oracle/tcb_oracle.py = the reference's PyTorch-CPU path restated) on the box's host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+METRIC = "clip-frames/sec @480p T=5 ResNet101-TCB-PSP"
+UNIT = "clip-frames/s"
+T_FRAMES, N_CLIPS, H, W, NUM_CLASS = 5, 2, 480, 854, 124
+# algorithmic FLOPs (2*MAC, conv+matmul) of one TCB-PSP train step at this config, BASELINE.md section 3
+STEP_TFLOP = 20.631
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("VSPW_PRECISION", "fp32"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--syncbn", action="store_true", help="all-reduce BN statistics across ranks (reference multi-GPU semantics)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-run", action="store_true", help="for ncu captures only: honour --warmup below 3, skip e2e/cpu legs")
+    ap.add_argument("--cpu-sample", default="240x427", help="HxW of the bounded CPU sample")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# --------------------------------------------------------------------------------------------------
+def build_model(device, seed=0):
+    from cvpr2021_vspw_implement_b200 import models as M
+    torch.manual_seed(seed)
+    ns = argparse.Namespace(num_class=NUM_CLASS, psp_weight=False, use_memory=False, memory_num=8, clipocr_all=False)
+    enc = M.ModelBuilder.build_encoder("resnet101dilated")
+    m = M.Clip_PSP(enc, torch.nn.NLLLoss(ignore_index=255), ns, deep_sup_scale=0.4)
+    return m.to(device).train()
+
+
+def make_optimizer(m, lr=0.002):
+    """create_optimizers of the reference (train_clip2.py:215-236): SGD momentum .9, 4 param groups.  The duplicate
+    yields of the generators (quirk Q10) are de-duplicated here because torch >= 2 rejects duplicate parameters."""
+    def uniq(gen, seen):
+        out = []
+        for p in gen:
+            if id(p) not in seen:
+                seen.add(id(p))
+                out.append(p)
+        return out
+    seen = set()
+    groups = [
+        {"params": uniq(m.get_1x_lr_params(), seen), "lr": lr * 0.1, "weight_decay": 1e-4},
+        {"params": uniq(m.get_10x_lr_params(), seen), "lr": lr, "weight_decay": 1e-4},
+        {"params": uniq(m.get_1x_lr_params_bias(), seen), "lr": lr * 0.1, "weight_decay": 0.0},
+        {"params": uniq(m.get_10x_lr_params_bias(), seen), "lr": lr, "weight_decay": 0.0},
+    ]
+    return torch.optim.SGD([g for g in groups if g["params"]], lr=lr, momentum=0.9)
+
+
+def feed_from(imgs, labs):
+    return {"img_data": imgs[0], "seg_label": labs[0], "clipimgs_data": list(imgs[1:]), "cliplabels_data": list(labs[1:]), "step": 1}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def all_reduce_grads(params, world):
+    """DDP-style gradient averaging: one flat bucket, one NCCL all-reduce over NVLink."""
+    import torch.distributed as dist
+    grads = [p.grad for p in params if p.grad is not None]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.mul_(1.0 / world)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from cvpr2021_vspw_implement_b200 import engine as E
+    from cvpr2021_vspw_implement_b200._lib import lib
+    import tcb_oracle as O
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    E.set_precision(args.precision)
+    if args.syncbn:
+        E.set_syncbn(True)
+
+    model = build_model(dev, seed=0)
+    params = [p for p in model.parameters()]
+    opt = make_optimizer(model)
+    imgs_h, labs_h = O.synthetic_clip(T_FRAMES, N_CLIPS, H, W, NUM_CLASS, seed=304 + rank)
+    imgs_h = [t.pin_memory() for t in imgs_h]
+    labs_h = [t.pin_memory() for t in labs_h]
+    imgs_d = [t.to(dev) for t in imgs_h]
+    labs_d = [t.to(dev) for t in labs_h]
+    h2d_bytes = sum(t.numel() * 4 for t in imgs_h + labs_h)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+
+    def step(imgs, labs):
+        opt.zero_grad(set_to_none=True)
+        loss, acc = model(feed_from(imgs, labs))
+        loss.backward()
+        if world > 1:
+            all_reduce_grads(params, world)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ------------------------------------------------------------------------------------------------
+    n_warm = args.warmup if args.profile_run else max(args.warmup, 3)
+    for _ in range(n_warm):
+        step(imgs_d, labs_d)
+    barrier()
+
+    # ---- timed: device-resident inputs ------------------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    E.conv_profile_begin()
+    l0 = lib.launches
+    evs = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(0.0)  # L2 flush between timed steps (outside the event pair)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss = step(imgs_d, labs_d)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    launches = (lib.launches - l0) // max(args.steps, 1)
+    conv_prof = E.conv_profile_end()
+    clocks = sampler.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    ms_per_step = dev_ms / args.steps
+    frames_per_step = T_FRAMES * N_CLIPS * world
+    value = frames_per_step / (ms_per_step / 1e3)
+    final_loss = float(loss.item())
+
+    # ---- timed: end to end from pinned host buffers ---------------------------------------------------------------
+    e2e_steps = 0 if args.profile_run else max(2, min(args.steps, 5))
+    barrier()
+    evs = []
+    for _ in range(e2e_steps):
+        flush.fill_(0.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        imgs = [t.to(dev, non_blocking=True) for t in imgs_h]
+        labs = [t.to(dev, non_blocking=True) for t in labs_h]
+        loss = step(imgs, labs)
+        _ = loss.item()  # D2H read of the step's result
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = frames_per_step / (float(t.item()) / e2e_steps / 1e3) if e2e_steps else 0.0
+
+    pk = peaks()
+    roof = None
+    if conv_prof["launches"]:
+        ach = conv_prof["tflop"] / (conv_prof["ms"] / 1e3)
+        peak = pk["bf16_tflops_sustained"]
+        roof = {"bound": "tensor", "kernel": conv_prof["kernel"], "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s",
+                "frac": round(ach / peak, 4), "traffic": None, "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                "launches_per_step": conv_prof["launches"] // args.steps, "ms_per_step": round(conv_prof["ms"] / args.steps, 3),
+                "algorithmic_tflop_per_step": round(conv_prof["tflop"] / args.steps, 3),
+                "note": {"fp32": "CUDA-core FFMA arm: tensor pipe idle, frac is vs the tensor roofline the tcgen05 arm is judged on",
+                         "bf16x3": "each algorithmic FLOP costs 3 tensor FLOPs (hi/lo split): algorithmic ceiling = peak/3",
+                         "bf16": "single-pass bf16 operands"}[args.precision]}
+
+    out = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
+           "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (bf16 hi+lo operands, f32 accumulate)", "bf16": "bf16"}[args.precision],
+           "data": "synthetic", "impl": "ours",
+           "config": {"workload": "TCB-PSP ResNet101-dilated train fwd+bwd+SGD, T=5, n=2 clips/GPU, 480x854, K=124 (BASELINE configs[1])",
+                      "frames_per_step_per_gpu": T_FRAMES * N_CLIPS, "parallelism": f"dp{world}", "precision_mode": args.precision,
+                      "syncbn": bool(args.syncbn), "l2_flush": "256 MiB write between timed steps",
+                      "optimizer": "torch.optim.SGD as the reference (train_clip2.py:215-236), outside the CUDA hot path",
+                      "loss": round(final_loss, 5), "wall_s_timed_region": round(wall, 3)},
+           "clocks": clocks, "gpu_launches": int(launches),
+           "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4, "steps": e2e_steps},
+           "roofline": roof}
+    if rank == 0 and not args.no_cpu_baseline and not args.profile_run and world == 1:
+        out["cpu_baseline"] = cpu_baseline(args)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------
+def _cpu_step(sd, imgs, labs):
+    import tcb_oracle as O
+    for v in sd.values():
+        if v.grad is not None:
+            v.grad = None
+    fr, lb = list(imgs[1:]) + [imgs[0]], list(labs[1:]) + [labs[0]]
+    out = O.clip_psp_forward(sd, fr, lb, train=True)
+    out["loss"].backward()
+    return float(out["loss"].item())
+
+
+def _cpu_setup(hs, ws):
+    import tcb_oracle as O
+    from cvpr2021_vspw_implement_b200 import models as M  # parameter containers only (CPU), no kernels involved
+    torch.manual_seed(0)
+    ns = argparse.Namespace(num_class=NUM_CLASS, psp_weight=False, use_memory=False, memory_num=8, clipocr_all=False)
+    m = M.Clip_PSP(M.ModelBuilder.build_encoder("resnet101dilated"), torch.nn.NLLLoss(ignore_index=255), ns, deep_sup_scale=0.4)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    for k, _ in m.named_parameters():
+        sd[k].requires_grad_(True)
+    imgs, labs = O.synthetic_clip(T_FRAMES, N_CLIPS, hs, ws, NUM_CLASS, seed=304)
+    return sd, imgs, labs
+
+
+def cpu_baseline(args):
+    """The CPU oracle (reference path restated in PyTorch-CPU fp32) on a bounded sample: the same T=5, n=2 train step at
+    `--cpu-sample` resolution, throughput scaled by the pixel ratio to the 480x854 workload (conv cost is linear in pixels)."""
+    hs, ws = (int(x) for x in args.cpu_sample.lower().split("x"))
+    sd, imgs, labs = _cpu_setup(hs, ws)
+    t0 = time.perf_counter()
+    _cpu_step(sd, imgs, labs)
+    dt = time.perf_counter() - t0
+    raw = T_FRAMES * N_CLIPS / dt
+    scaled = raw * (hs * ws) / (H * W)
+    return {"value": round(scaled, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"one TCB-PSP R101 train fwd+bwd step, T=5 n=2 at {hs}x{ws} ({dt:.1f} s, {raw:.3f} clip-frames/s at that size), "
+                      f"scaled by the pixel ratio {hs * ws}/{H * W} to 480x854; host has {os.cpu_count()} logical CPUs"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    hs, ws = (int(x) for x in args.cpu_sample.lower().split("x"))
+    sd, imgs, labs = _cpu_setup(hs, ws)
+    steps = max(1, min(args.steps, 2))
+    warm = 1 if args.warmup > 0 else 0
+    for _ in range(warm):
+        _cpu_step(sd, imgs, labs)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _cpu_step(sd, imgs, labs)
+    dt = (time.perf_counter() - t0) / steps
+    raw = T_FRAMES * N_CLIPS / dt
+    scaled = raw * (hs * ws) / (H * W)
+    sample = (f"{steps} TCB-PSP R101 train fwd+bwd step(s) after {warm} warm-up, T=5 n=2 at {hs}x{ws} ({dt:.1f} s/step, {raw:.3f} clip-frames/s "
+              f"at that size) scaled by the pixel ratio {hs * ws}/{H * W} to 480x854; PyTorch-CPU fp32 (oneDNN), {torch.get_num_threads()} threads of "
+              f"{os.cpu_count()} logical CPUs")
+    out = {"metric": METRIC, "value": round(scaled, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+           "ms_per_step": round(dt * 1e3 * (H * W) / (hs * ws), 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "impl": "reference",
+           "config": {"workload": "TCB-PSP ResNet101-dilated train fwd+bwd, T=5, n=2 clips, 480x854, K=124 (BASELINE configs[1])", "sample": sample},
+           "cpu_baseline": {"value": round(scaled, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+           "e2e": {"value": round(scaled, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

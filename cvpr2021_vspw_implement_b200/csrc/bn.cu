@@ -344,7 +344,7 @@ extern "C" int vspw_bn_bwd_apply(const float* dout, const float* out, const floa
   bn_bwd_apply_kernel<<<grid_for(total4, 256), 256, 0, as_stream(stream)>>>(
       (const float4*)dout, (const float4*)out, (const float4*)y, (const float4*)mean, (const float4*)invstd,
       (const float4*)gamma, (const float4*)chan_scale, relu, dbeta, dgamma, (float4*)dy, (float4*)dres, total4, c / 4,
-      pixels_per_image, 1.0 / (double)pixels, eval_mode);
+      pixels_per_image, 1.0 / count, eval_mode);
   int rc = check_launch("vspw_bn_bwd_apply");
   if (rc) return rc;
   if ((dgamma_f || dbeta_f) && dbeta && dgamma) {

@@ -17,7 +17,7 @@ import torch
 from ._lib import ConvDesc, PREC_BF16, PREC_BF16X3, PREC_FP32, VspwError, i4, lib
 
 _PRECISION = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
-_state = {"precision": "fp32", "syncbn_clamp": False}
+_state = {"precision": "fp32", "syncbn_clamp": False, "syncbn": False}
 
 
 def set_precision(mode):
@@ -42,6 +42,65 @@ def precision(mode):
 
 
 _capture = None
+_prof = None  # live conv-kernel profile: list of (start_event, stop_event, flops, used_tc)
+
+
+def conv_profile_begin():
+    """Start timing every implicit-GEMM conv launch (fwd/dgrad/wgrad) with CUDA events on the launching stream."""
+    global _prof
+    _prof = []
+
+
+def conv_profile_end():
+    """Stop; returns {'launches', 'ms', 'tflop', 'kernel'} summed over the profiled launches (synchronises)."""
+    global _prof
+    rec, _prof = _prof or [], None
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b, _, _ in rec)
+    tc = sum(1 for r in rec if r[3])
+    kern = "conv_tc_kernel (tcgen05 implicit GEMM)" if tc * 2 > len(rec) else "igemm_kernel/wgrad_kernel (fp32 FFMA implicit GEMM)"
+    return {"launches": len(rec), "ms": ms, "tflop": sum(r[2] for r in rec) / 1e12, "kernel": kern, "tc_launches": tc}
+
+
+class _ConvTimer:
+    __slots__ = ("e0", "flops", "tc")
+
+    def __init__(self, flops, tc):
+        self.flops, self.tc = flops, tc
+        self.e0 = None
+
+    def __enter__(self):
+        if _prof is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.e0 is not None and _prof is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _prof.append((self.e0, e1, self.flops, self.tc))
+        return False
+
+
+def set_syncbn(on, clamp=None):
+    """Cross-rank BN statistics (reference multi-GPU semantics, sync_batchnorm/batchnorm.py:110-150): the per-channel
+    sum / sum-of-squares (and the two backward sums) are all-reduced over torch.distributed's default group."""
+    _state["syncbn"] = bool(on)
+    if clamp is not None:
+        _state["syncbn_clamp"] = bool(clamp)
+
+
+def _syncbn_world():
+    if not _state.get("syncbn"):
+        return 1
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def _allreduce_sums(t):
+    import torch.distributed as dist
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
 
 @contextmanager
@@ -256,12 +315,15 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1):
         desc.precision = PREC_FP32
     y = torch.empty((n, ho, wo, co), device=x.data.device, dtype=torch.float32)
     w_ohwi = _weight_ohwi(tape, wv)
+    flops = 2.0 * n * ho * wo * co * kh * kw * ci
     if use_tc:
         xh, xl = _var_planes(x)
         wh, wl = _weight_planes(wv, "ohwi", w_ohwi)
-        lib.call("vspw_conv2d_fwd_tc", ctypes.byref(desc), _p(xh), _p(xl), _p(wh), _p(wl), _p(bv.data if bv else None), _p(y), _stream())
+        with _ConvTimer(flops, True):
+            lib.call("vspw_conv2d_fwd_tc", ctypes.byref(desc), _p(xh), _p(xl), _p(wh), _p(wl), _p(bv.data if bv else None), _p(y), _stream())
     else:
-        lib.call("vspw_conv2d_fwd", ctypes.byref(desc), _p(x.data), _p(w_ohwi), _p(bv.data if bv else None), _p(y), _stream())
+        with _ConvTimer(flops, False):
+            lib.call("vspw_conv2d_fwd", ctypes.byref(desc), _p(x.data), _p(w_ohwi), _p(bv.data if bv else None), _p(y), _stream())
     out = Var(y, needs_grad=tape.grad_enabled and (x.needs_grad or wv.needs_grad))
 
     def backward():
@@ -277,9 +339,11 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1):
             dw = torch.empty((co, kh, kw, ci), device=dy.device, dtype=torch.float32)
             if use_tc:
                 xh, xl = _var_planes(x)
-                lib.call("vspw_conv2d_wgrad_tc", ctypes.byref(desc), _p(xh), _p(xl), _p(dyp[0]), _p(dyp[1]), _p(dw), st)
+                with _ConvTimer(flops, True):
+                    lib.call("vspw_conv2d_wgrad_tc", ctypes.byref(desc), _p(xh), _p(xl), _p(dyp[0]), _p(dyp[1]), _p(dw), st)
             else:
-                lib.call("vspw_conv2d_wgrad", ctypes.byref(desc), _p(x.data), _p(dy), _p(dw), st)
+                with _ConvTimer(flops, False):
+                    lib.call("vspw_conv2d_wgrad", ctypes.byref(desc), _p(x.data), _p(dy), _p(dw), st)
             if kh == 1 and kw == 1:
                 wv.add_grad(dw.view(co, ci, 1, 1))
             else:
@@ -295,9 +359,11 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1):
             w_t = _weight_ihwo(tape, wv)
             if use_tc:
                 th, tl = _weight_planes(wv, "ihwo", w_t)
-                lib.call("vspw_conv2d_dgrad_tc", ctypes.byref(desc), _p(dyp[0]), _p(dyp[1]), _p(th), _p(tl), _p(dx), st)
+                with _ConvTimer(flops, True):
+                    lib.call("vspw_conv2d_dgrad_tc", ctypes.byref(desc), _p(dyp[0]), _p(dyp[1]), _p(th), _p(tl), _p(dx), st)
             else:
-                lib.call("vspw_conv2d_dgrad", ctypes.byref(desc), _p(dy), _p(w_t), _p(dx), st)
+                with _ConvTimer(flops, False):
+                    lib.call("vspw_conv2d_dgrad", ctypes.byref(desc), _p(dy), _p(w_t), _p(dx), st)
             x.add_grad(dx)
 
     tape.record(backward)
@@ -331,9 +397,13 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
             raise ValueError(f"Expected more than 1 value per channel when training, got input size {[n, c, h, w]}")
         sums = torch.zeros((2, c), device=dev, dtype=torch.float64)
         lib.call("vspw_bn_stats", _p(y.data), pixels, c, _p(sums[0]), _p(sums[1]), st)
+        world = _syncbn_world()
+        if world > 1:
+            _allreduce_sums(sums)
+        count = float(pixels * world)
         mean = torch.empty(c, device=dev, dtype=torch.float32)
         invstd = torch.empty(c, device=dev, dtype=torch.float32)
-        lib.call("vspw_bn_finalize_train", _p(sums[0]), _p(sums[1]), float(pixels), _p(gv.data), _p(bv.data), float(bn.eps),
+        lib.call("vspw_bn_finalize_train", _p(sums[0]), _p(sums[1]), count, _p(gv.data), _p(bv.data), float(bn.eps),
                  float(bn.momentum), _p(bn.running_mean), _p(bn.running_var), _p(mean), _p(invstd), _p(scale), _p(shift), c,
                  1 if _state["syncbn_clamp"] else 0, st)
     else:
@@ -366,10 +436,13 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
             dsum = torch.zeros((2, c), device=dev, dtype=torch.float64)
             lib.call("vspw_bn_bwd_reduce", _p(dout), _p(o), _p(y.data), _p(mean), _p(invstd), _p(chan_scale), 1 if relu else 0,
                      pixels, c, h * w, _p(dsum[0]), _p(dsum[1]), st)
+            if world > 1:
+                _allreduce_sums(dsum)
             dgam = torch.empty(c, device=dev, dtype=torch.float32)
             dbet = torch.empty(c, device=dev, dtype=torch.float32)
             lib.call("vspw_bn_bwd_apply", _p(dout), _p(o), _p(y.data), _p(mean), _p(invstd), _p(gv.data), _p(chan_scale),
-                     1 if relu else 0, _p(dsum[0]), _p(dsum[1]), _p(dy), _p(dres), _p(dgam), _p(dbet), pixels, c, h * w, 0, st)
+                     1 if relu else 0, _p(dsum[0]), _p(dsum[1]), _p(dy), _p(dres), _p(dgam), _p(dbet), pixels, c, h * w, 0,
+                     float(pixels * world), st)
             if gv.needs_grad:
                 gv.add_grad(dgam)
             if bv.needs_grad:
@@ -377,7 +450,7 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
         else:
             # frozen statistics: dy = g * gamma/sqrt(var+eps) = g * scale
             lib.call("vspw_bn_bwd_apply", _p(dout), _p(o), None, None, _p(scale), None, _p(chan_scale), 1 if relu else 0, None,
-                     None, _p(dy), _p(dres), None, None, pixels, c, h * w, 1, st)
+                     None, _p(dy), _p(dres), None, None, pixels, c, h * w, 1, float(pixels), st)
         if y.needs_grad:
             y.add_grad(dy)
         if dres is not None:

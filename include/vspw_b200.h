@@ -118,12 +118,14 @@ int vspw_bn_bwd_reduce(const float* dout, const float* out, const float* y, cons
                        int32_t c, size_t pixels_per_image, double* dbeta, double* dgamma,
                        void* stream);
 /* backward pass 2: dy = gamma*invstd*(g - dbeta/P - xhat*dgamma/P); dres = g (if non-null);
- * also converts the double sums to float dgamma_f/dbeta_f.  eval_mode!=0: dy = g*scale. */
+ * also converts the double sums to float dgamma_f/dbeta_f.  eval_mode!=0: dy = g*scale.
+ * P = `count` = number of values per channel the statistics were taken over (pixels, or the
+ * all-rank total when the sums were all-reduced for SyncBN). */
 int vspw_bn_bwd_apply(const float* dout, const float* out, const float* y, const float* mean,
                       const float* invstd, const float* gamma, const float* chan_scale, int32_t relu,
                       const double* dbeta, const double* dgamma, float* dy, float* dres,
                       float* dgamma_f, float* dbeta_f, size_t pixels, int32_t c,
-                      size_t pixels_per_image, int32_t eval_mode, void* stream);
+                      size_t pixels_per_image, int32_t eval_mode, double count, void* stream);
 
 /* ---- pooling -------------------------------------------------------------------------- */
 /* nn.MaxPool2d(3, 2, 1) (models/resnet.py:109); idx saves the winning tap (0..8) per output */
