@@ -80,9 +80,8 @@ class _Lib:
         if self._dll is None:
             with self._lock:
                 if self._dll is None:
-                    path = _build.LIB
-                    if not os.path.exists(path):
-                        path = _build.build_library()  # raises if nvcc is unavailable: no silent fallback
+                    # (re)build when the sources are newer than the .so; raises if nvcc fails: no silent fallback
+                    path = _build.build_library()
                     dll = ctypes.CDLL(path)
                     for name, argtypes in _SIGNATURES.items():
                         fn = getattr(dll, name)

@@ -335,8 +335,9 @@ extern "C" int vspw_bn_bwd_apply(const float* dout, const float* out, const floa
                                  const float* invstd, const float* gamma, const float* chan_scale, int32_t relu,
                                  const double* dbeta, const double* dgamma, float* dy, float* dres, float* dgamma_f,
                                  float* dbeta_f, size_t pixels, int32_t c, size_t pixels_per_image, int32_t eval_mode,
-                                 void* stream) {
+                                 double count, void* stream) {
   VSPW_REQUIRE(dout && invstd && dy, "vspw_bn_bwd_apply: null pointer");
+  VSPW_REQUIRE(count >= 1.0, "vspw_bn_bwd_apply: count must be >= 1");
   VSPW_REQUIRE(eval_mode || (y && mean && dbeta && dgamma), "vspw_bn_bwd_apply: train mode needs y/mean/sums");
   VSPW_REQUIRE(c > 0 && c % 4 == 0, "vspw_bn_bwd_apply: channels must be a multiple of 4 (got %d)", c);
   size_t total4 = pixels * (size_t)(c / 4);
