@@ -29,6 +29,7 @@ class ConvDesc(ctypes.Structure):
 # name -> argtypes; every function returns int (0 = ok)
 _SIGNATURES = {
     "vspw_conv2d_tc_supported": [ctypes.POINTER(ConvDesc)],
+    "vspw_conv2d_wgrad_tc_supported": [ctypes.POINTER(ConvDesc)],
     "vspw_permute4d": [_c_vp, _c_vp, ctypes.POINTER(_c_int * 4), ctypes.POINTER(_c_int * 4), _c_vp],
     "vspw_fill": [_c_vp, _c_f, _c_sz, _c_vp],
     "vspw_axpby": [_c_vp, _c_vp, _c_f, _c_f, _c_sz, _c_vp],
@@ -105,6 +106,9 @@ class _Lib:
 
     def tc_supported(self, desc):
         return bool(self.dll().vspw_conv2d_tc_supported(ctypes.byref(desc)))
+
+    def wgrad_tc_supported(self, desc):
+        return bool(self.dll().vspw_conv2d_wgrad_tc_supported(ctypes.byref(desc)))
 
     def version(self):
         return self.dll().vspw_version()

@@ -1,7 +1,455 @@
-// placeholder, replaced by the tcgen05 implementation
+// tcgen05 implicit-GEMM convolution for sm_100a (VSPW_PREC_BF16X3 / VSPW_PREC_BF16).
+//
+//   out[pixel][n] = sum_{tap, c} A[pixel + off(tap)][c] * B[n][tap][c]          (stride-1 convs)
+//
+//   * forward : A = x planes (NHWC bf16 hi/lo), B = OHWI weight planes, off(tap) = -pad + tap*dil
+//   * dgrad   : A = dy planes,                 B = [Cin][kh][kw][Cout] planes, off(tap) = +pad - tap*dil
+//   * wgrad   : dW[co][tap][ci] = sum_pixel dy[pixel][co] * x[pixel + off(tap)][ci]   (second kernel below)
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0 / lane 0 : TMA producer.  The activation tile is a BW x BH pixel patch of one image fetched with a
+//                     4-D tiled tensor map (C, W, H, N) at coordinates shifted by the filter tap — im2col is
+//                     folded into the TMA coordinates and the zero padding into TMA's out-of-bounds fill.  The box
+//                     lands in shared memory as 128 rows x 128 B with the 128-byte swizzle, which is exactly the
+//                     K-major SWIZZLE_128B operand layout tcgen05.mma reads.
+//   warp 1 / lane 0 : MMA issuer.  UMMA 128 x BN x 16 (bf16 in, fp32 accumulate in TMEM).  In BF16X3 mode every
+//                     k-step issues hi*hi + hi*lo + lo*hi (3 MMAs) for ~16 mantissa bits per operand.
+//   warps 2..5      : epilogue.  tcgen05.ld of the 128 x BN fp32 accumulator (one TMEM lane = one pixel),
+//                     bias add, 16-byte stores to the NHWC fp32 output.  Two TMEM accumulator stages let the
+//                     epilogue of tile i overlap the main loop of tile i+1.
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA), tmem full/empty mbarriers (MMA <-> epilogue).
+// Reference call sites replaced: the stride-1 nn.Conv2d of models/resnet.py:61-66 (layer1..4), the PPM / deepsup /
+// OCR head convs (clip_psp.py:35-41,74-79; clip_ocr.py:43,56-62) and their autograd backward.
 #include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+
 using namespace vspw;
-extern "C" int vspw_conv2d_tc_supported(const vspw_conv_desc* d) { (void)d; return 0; }
-extern "C" int vspw_conv2d_fwd_tc(const vspw_conv_desc*, const uint16_t*, const uint16_t*, const uint16_t*, const uint16_t*, const float*, float*, void*) { set_error("tc path not built"); return VSPW_ERR_UNSUPPORTED; }
-extern "C" int vspw_conv2d_dgrad_tc(const vspw_conv_desc*, const uint16_t*, const uint16_t*, const uint16_t*, const uint16_t*, float*, void*) { set_error("tc path not built"); return VSPW_ERR_UNSUPPORTED; }
-extern "C" int vspw_conv2d_wgrad_tc(const vspw_conv_desc*, const uint16_t*, const uint16_t*, const uint16_t*, const uint16_t*, float*, void*) { set_error("tc path not built"); return VSPW_ERR_UNSUPPORTED; }
+
+namespace {
+
+constexpr int BM = 128;        // pixels per tile (UMMA M)
+constexpr int BK = 64;         // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 192;  // 6 warps
+constexpr uint32_t kSpinLimit = 1u << 27;
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (spin > kSpinLimit) __trap();  // a protocol bug must fail loudly instead of hanging the GPU
+  }
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint64_t desc_a, uint64_t desc_b, uint32_t tmem_d, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory operand descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4, [16,30) LBO >> 4 (=1, unused for swizzled K-major), [32,46) SBO >> 4 (8 rows x 128 B
+//   = 1024 B), [46,48) version = 1 (Blackwell), [61,64) layout type = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// MN-major, SWIZZLE_128B: rows of 64 MN-elements (128 B), 8 K-rows per 1024-B atom.
+//   LBO = byte distance between 64-element MN blocks, SBO = byte distance between 8-row K groups (1024 B).
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// cute::UMMA::InstrDescriptor for kind::f16: c_format F32 (1) @4, a/b format BF16 (1) @7/@10, a/b major @15/@16
+// (0 = K-major, 1 = MN-major), N>>3 @17, M>>4 @24.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+struct ConvTcParams {
+  float* out;          // [N][H][W][Nout] fp32
+  const float* bias;   // [Nout] or null
+  int N, H, W, C;      // activation tensor (rows of the GEMM are its pixels; stride-1 conv keeps H x W)
+  int Nout;
+  int taps_h, taps_w;
+  int off0, step;      // tap offset = off0 + tap*step (both axes)
+  int bw, bh;          // pixel patch, bw*bh == 128
+  int tiles_x, tiles_y, tiles_n;
+  int x3;              // 1: hi/lo planes, 3 MMAs per k-step
+};
+
+template <int BN, int STAGES>
+struct ConvSmem {
+  static constexpr int kATile = BM * BK * 2;  // 16 KB
+  static constexpr int kBTile = BN * BK * 2;
+  static constexpr int kStage = 2 * kATile + 2 * kBTile;  // hi+lo of A and B
+  static constexpr int kBytes = STAGES * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, ConvTcParams p) {
+  using S = ConvSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStage);
+  uint64_t* full_bar = bars;                    // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.N * p.tiles_y * p.tiles_x * p.tiles_n;
+  const int kblocks_per_tap = p.C / BK;
+  const int num_k = p.taps_h * p.taps_w * kblocks_per_tap;
+  const uint32_t stage_bytes = (uint32_t)(S::kATile + S::kBTile) * (p.x3 ? 2u : 1u);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi);
+    tma_prefetch_desc(&map_b_hi);
+    if (p.x3) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_b_lo); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int tn = tile % p.tiles_n;
+      int tm = tile / p.tiles_n;
+      int tx = tm % p.tiles_x; tm /= p.tiles_x;
+      int ty = tm % p.tiles_y;
+      int img = tm / p.tiles_y;
+      const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * BN;
+      for (int r = 0; r < p.taps_h; ++r)
+        for (int s = 0; s < p.taps_w; ++s)
+          for (int kb = 0; kb < kblocks_per_tap; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + stage * S::kStage;
+            mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+            const int cx = x0 + p.off0 + s * p.step, cy = y0 + p.off0 + r * p.step;
+            const int kcol = ((r * p.taps_w + s) * kblocks_per_tap + kb) * BK;
+            tma_load_4d(st, &map_a_hi, &full_bar[stage], kb * BK, cx, cy, img);
+            tma_load_2d(st + 2 * S::kATile, &map_b_hi, &full_bar[stage], kcol, n0);
+            if (p.x3) {
+              tma_load_4d(st + S::kATile, &map_a_lo, &full_bar[stage], kb * BK, cx, cy, img);
+              tma_load_2d(st + 2 * S::kATile + S::kBTile, &map_b_lo, &full_bar[stage], kcol, n0);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+      for (int k = 0; k < num_k; ++k) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        const uint32_t a_hi = smem_u32(smem + stage * S::kStage);
+        const uint32_t a_lo = a_hi + S::kATile;
+        const uint32_t b_hi = a_hi + 2 * S::kATile;
+        const uint32_t b_lo = b_hi + S::kBTile;
+#pragma unroll
+        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+          const uint32_t koff = kk * UMMA_K * 2;  // bytes inside the 128-byte swizzle row
+          const uint64_t da_hi = make_kmajor_sw128_desc(a_hi + koff), db_hi = make_kmajor_sw128_desc(b_hi + koff);
+          umma_bf16(da_hi, db_hi, tmem_d, idesc, (k | kk) != 0);
+          if (p.x3) {
+            const uint64_t da_lo = make_kmajor_sw128_desc(a_lo + koff), db_lo = make_kmajor_sw128_desc(b_lo + koff);
+            umma_bf16(da_hi, db_lo, tmem_d, idesc, 1);
+            umma_bf16(da_lo, db_hi, tmem_d, idesc, 1);
+          }
+        }
+        umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 2) {
+    // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int tn = tile % p.tiles_n;
+      int tm = tile / p.tiles_n;
+      int tx = tm % p.tiles_x; tm /= p.tiles_x;
+      int ty = tm % p.tiles_y;
+      int img = tm / p.tiles_y;
+      const int px = tx * p.bw + row % p.bw, py = ty * p.bh + row / p.bw, n0 = tn * BN;
+      const bool ok = px < p.W && py < p.H;
+      float* dst = p.out + (((size_t)img * p.H + py) * p.W + px) * p.Nout + n0;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c0, v);
+        tmem_ld_wait();
+        if (ok && n0 + c0 < p.Nout) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                   __uint_as_float(v[j + 3]));
+            if (p.bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            *reinterpret_cast<float4*>(dst + c0 + j) = o;
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 2) tmem_dealloc<2 * BN>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side: tensor maps through the driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// bf16 NHWC activation planes: dims (C, W, H, N), box (64, bw, bh, 1), 128-byte swizzle, zero OOB fill
+int make_act_map(CUtensorMap* m, const void* base, int n, int h, int w, int c, int bw, int bh, const char* who) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("%s: cuTensorMapEncodeTiled entry point unavailable", who); return VSPW_ERR_CUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(activation) failed with %d", who, (int)r); return VSPW_ERR_CUDA; }
+  return VSPW_OK;
+}
+
+// bf16 row-major matrix [rows][cols] (cols contiguous): dims (cols, rows), box (box_cols, box_rows)
+int make_mat_map(CUtensorMap* m, const void* base, long long rows, long long cols, int box_cols, int box_rows, const char* who) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("%s: cuTensorMapEncodeTiled entry point unavailable", who); return VSPW_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(matrix) failed with %d", who, (int)r); return VSPW_ERR_CUDA; }
+  return VSPW_OK;
+}
+
+// pixel patch bw x bh (bw*bh == 128) with the least padding waste on an h x w map
+void pick_patch(int h, int w, int& bw, int& bh) {
+  const int cand[8][2] = {{16, 8}, {8, 16}, {32, 4}, {4, 32}, {64, 2}, {2, 64}, {128, 1}, {1, 128}};
+  long long best = -1;
+  for (auto& c : cand) {
+    long long cover = (long long)((w + c[0] - 1) / c[0]) * c[0] * ((h + c[1] - 1) / c[1]) * c[1];
+    if (best < 0 || cover < best) { best = cover; bw = c[0]; bh = c[1]; }
+  }
+}
+
+bool geometry_ok(const vspw_conv_desc* d) {
+  if (!d) return false;
+  if (d->stride != 1) return false;
+  if (d->cin % 64 || d->cout % 64) return false;
+  if (d->ho != d->h || d->wo != d->w) return false;              // "same" convs only (pad == dil*(k-1)/2)
+  if (d->kh != d->kw || (d->kh != 1 && d->kh != 3)) return false;
+  if ((long long)d->n * d->h * d->w < 2048) return false;        // tiny maps (PPM s x s) stay on the CUDA-core arm
+  return true;
+}
+
+constexpr int kBN = 128, kStages = 3;
+
+int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int taps, int off0, int step, const uint16_t* a_hi,
+                   const uint16_t* a_lo, const uint16_t* b_hi, const uint16_t* b_lo, const float* bias, float* out, int x3,
+                   cudaStream_t stream) {
+  VSPW_REQUIRE(a_hi && b_hi && out, "%s: null pointer", who);
+  VSPW_REQUIRE(!x3 || (a_lo && b_lo), "%s: BF16X3 needs the lo planes", who);
+  ConvTcParams p;
+  p.out = out; p.bias = bias; p.N = n; p.H = h; p.W = w; p.C = c; p.Nout = nout;
+  p.taps_h = taps; p.taps_w = taps; p.off0 = off0; p.step = step; p.x3 = x3;
+  pick_patch(h, w, p.bw, p.bh);
+  p.tiles_x = (w + p.bw - 1) / p.bw;
+  p.tiles_y = (h + p.bh - 1) / p.bh;
+  p.tiles_n = (nout + kBN - 1) / kBN;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
+  if ((rc = make_act_map(&ma_hi, a_hi, n, h, w, c, p.bw, p.bh, who))) return rc;
+  if ((rc = make_act_map(&ma_lo, x3 ? a_lo : a_hi, n, h, w, c, p.bw, p.bh, who))) return rc;
+  const long long kdim = (long long)taps * taps * c;
+  if ((rc = make_mat_map(&mb_hi, b_hi, nout, kdim, BK, kBN, who))) return rc;
+  if ((rc = make_mat_map(&mb_lo, x3 ? b_lo : b_hi, nout, kdim, BK, kBN, who))) return rc;
+  using S = ConvSmem<kBN, kStages>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel<kBN, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes);
+  });
+  if (attr_err != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(attr_err)); return VSPW_ERR_CUDA; }
+  long long tiles = (long long)n * p.tiles_y * p.tiles_x * p.tiles_n;
+  int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+  conv_tc_kernel<kBN, kStages><<<grid, kThreads, S::kBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  return check_launch(who);
+}
+
+}  // namespace
+
+extern "C" int vspw_conv2d_tc_supported(const vspw_conv_desc* d) { return geometry_ok(d) ? 1 : 0; }
+extern "C" int vspw_conv2d_wgrad_tc_supported(const vspw_conv_desc* d) { (void)d; return 0; }
+
+extern "C" int vspw_conv2d_fwd_tc(const vspw_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi,
+                                  const uint16_t* w_lo, const float* bias, float* y, void* stream) {
+  VSPW_REQUIRE(geometry_ok(d), "vspw_conv2d_fwd_tc: geometry not supported by the tcgen05 path");
+  VSPW_REQUIRE(d->precision == VSPW_PREC_BF16X3 || d->precision == VSPW_PREC_BF16, "vspw_conv2d_fwd_tc: precision must be BF16X3 or BF16");
+  return launch_conv_tc("vspw_conv2d_fwd_tc", d->n, d->h, d->w, d->cin, d->cout, d->kh, -d->pad, d->dil, x_hi, x_lo, w_hi, w_lo,
+                        bias, y, d->precision == VSPW_PREC_BF16X3, as_stream(stream));
+}
+
+extern "C" int vspw_conv2d_dgrad_tc(const vspw_conv_desc* d, const uint16_t* dy_hi, const uint16_t* dy_lo, const uint16_t* wt_hi,
+                                    const uint16_t* wt_lo, float* dx, void* stream) {
+  VSPW_REQUIRE(geometry_ok(d), "vspw_conv2d_dgrad_tc: geometry not supported by the tcgen05 path");
+  VSPW_REQUIRE(d->precision == VSPW_PREC_BF16X3 || d->precision == VSPW_PREC_BF16, "vspw_conv2d_dgrad_tc: precision must be BF16X3 or BF16");
+  // dx[p][ci] = sum_{tap,co} dy[p + pad - tap*dil][co] * Wt[ci][tap][co]
+  return launch_conv_tc("vspw_conv2d_dgrad_tc", d->n, d->h, d->w, d->cout, d->cin, d->kh, d->pad, -d->dil, dy_hi, dy_lo, wt_hi,
+                        wt_lo, nullptr, dx, d->precision == VSPW_PREC_BF16X3, as_stream(stream));
+}
+
+extern "C" int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* dy_hi,
+                                    const uint16_t* dy_lo, float* dw_ohwi, void* stream) {
+  (void)d; (void)x_hi; (void)x_lo; (void)dy_hi; (void)dy_lo; (void)dw_ohwi; (void)stream;
+  set_error("vspw_conv2d_wgrad_tc: not built yet (the engine uses the fp32 wgrad kernel)");
+  return VSPW_ERR_UNSUPPORTED;
+}

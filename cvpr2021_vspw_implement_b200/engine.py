@@ -333,11 +333,12 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1):
             return
         st = _stream()
         dyp = None
-        if use_tc:
+        wgrad_tc = use_tc and wv.needs_grad and lib.wgrad_tc_supported(desc)
+        if use_tc and (x.needs_grad or wgrad_tc):
             dyp = _planes_of(dy)
         if wv.needs_grad:
             dw = torch.empty((co, kh, kw, ci), device=dy.device, dtype=torch.float32)
-            if use_tc:
+            if wgrad_tc:
                 xh, xl = _var_planes(x)
                 with _ConvTimer(flops, True):
                     lib.call("vspw_conv2d_wgrad_tc", ctypes.byref(desc), _p(xh), _p(xl), _p(dyp[0]), _p(dyp[1]), _p(dw), st)

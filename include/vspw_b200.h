@@ -48,6 +48,8 @@ const char* vspw_last_error(void);
 int vspw_version(void);
 /* 1 if the tcgen05 path can take this geometry (stride 1, cin%64==0, cout%64==0) */
 int vspw_conv2d_tc_supported(const vspw_conv_desc* d);
+/* 1 if vspw_conv2d_wgrad_tc can take this geometry (otherwise the fp32 wgrad kernel is used) */
+int vspw_conv2d_wgrad_tc_supported(const vspw_conv_desc* d);
 
 /* ---- layout / elementwise plumbing ------------------------------------------------------ */
 /* dst = permute(src): src has dims d[0..3] (row-major); dst dim i is src dim perm[i].

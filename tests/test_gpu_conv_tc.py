@@ -1,0 +1,85 @@
+"""GPU: the tcgen05 implicit-GEMM convolution (conv_tc.cu) against fp32 F.conv2d on the CPU and against the
+exact-fp32 CUDA-core arm.  bf16x3 (parity mode) must sit far inside the 1e-3 north-star tolerance; single-pass
+bf16 (fast mode) is reported and loosely gated."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cases as C
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def E():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from cvpr2021_vspw_implement_b200 import engine
+    return engine
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+TC_GEOMS = [
+    # n, cin, h, w, cout, k, pad, dil, bias
+    (2, 64, 40, 56, 64, 1, 0, 1, False),       # single k-block, Cout < BN (tile wider than the matrix)
+    (2, 256, 30, 53, 256, 3, 2, 2, False),     # layer3-style dilated 3x3, ragged patch edges (53 = 3*16+5)
+    (3, 512, 24, 40, 128, 1, 0, 1, True),      # 1x1 with bias
+    (2, 128, 33, 47, 192, 3, 1, 1, False),     # Cout = 1.5 tiles
+    (1, 512, 60, 107, 512, 3, 4, 4, False),    # layer4 geometry at the real 480p map size
+    (10, 256, 12, 20, 1024, 1, 0, 1, False),   # many images, 8 n-tiles
+]
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 1e-4), ("bf16", 2e-2)])
+@pytest.mark.parametrize("geom", TC_GEOMS)
+def test_conv_tc_fwd_dgrad(E, geom, prec, tol):
+    from cvpr2021_vspw_implement_b200._lib import ConvDesc, lib, PREC_BF16X3
+    n, cin, h, w, cout, k, pad, dil, has_bias = geom
+    assert lib.tc_supported(ConvDesc(n, h, w, cin, cout, k, k, 1, pad, dil, h, w, PREC_BF16X3))
+    g = torch.Generator().manual_seed(abs(hash(geom)) % 1000)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, generator=g) if has_bias else None
+    xr = x.clone().requires_grad_(True)
+    wr = wt.clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, b, stride=1, padding=pad, dilation=dil)
+    gy = torch.randn(yr.shape, generator=g)
+    yr.backward(gy)
+
+    tape = E.Tape(True)
+    wp = torch.nn.Parameter(wt.cuda())
+    bp = torch.nn.Parameter(b.cuda()) if has_bias else None
+    xv = E.Var(nhwc(x).cuda(), needs_grad=True)
+    with E.precision(prec):
+        E.conv_profile_begin()
+        yv = E.conv2d(tape, xv, wp, bp, 1, pad, dil)
+        yv.grad = nhwc(gy).cuda()
+        tape.backward()
+        prof = E.conv_profile_end()
+    assert prof["tc_launches"] >= 2, "the tcgen05 kernel must be the one that ran (fwd + dgrad)"
+    e_fwd = C.rel_err(nchw(yv.data.cpu()), yr.detach())
+    e_dx = C.rel_err(nchw(xv.grad.cpu()), xr.grad)
+    e_dw = C.rel_err(tape.param(wp).grad.cpu(), wr.grad)
+    print(f"{prec} {geom}: fwd {e_fwd:.2e} dgrad {e_dx:.2e} wgrad {e_dw:.2e}")
+    assert e_fwd <= tol and e_dx <= tol
+    assert e_dw <= max(tol, 5e-5)
+
+
+def test_conv_tc_zero_padding_is_exact(E):
+    """All-ones input and weights: every output equals the number of in-bounds taps times Cin (exact in bf16),
+    so any error in the TMA out-of-bounds fill or the tap offsets shows up as an integer mismatch."""
+    n, c, h, w = 1, 64, 37, 61
+    x = torch.ones(n, c, h, w)
+    wt = torch.ones(64, c, 3, 3)
+    ref = F.conv2d(x, wt, None, 1, 4, 4)
+    tape = E.Tape(False)
+    with E.precision("bf16x3"):
+        y = E.conv2d(tape, E.Var(nhwc(x).cuda()), torch.nn.Parameter(wt.cuda()), None, 1, 4, 4)
+    assert torch.equal(nchw(y.data.cpu()), ref)
