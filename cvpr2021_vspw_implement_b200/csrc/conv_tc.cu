@@ -425,10 +425,164 @@ int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int ta
   return check_launch(who);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// wgrad: dW[co][tap][ci] = sum_pixels dy[pixel][co] * x[pixel + off(tap)][ci]
+//   GEMM D[M = 128 co][N = 128 ci] += A^T B with K = pixels: both operands are MN-major (channels contiguous),
+//   fetched as [64 pixels][64 channels] boxes (128-byte swizzle) -> MN-major SWIZZLE_128B UMMA operands:
+//   LBO = distance between 64-channel blocks (8 KB), SBO = distance between 8-pixel groups (1 KB).
+//   One CTA = one (co tile, ci tile, tap, pixel-range split); partial sums are added with red.global.add.v4.f32.
+constexpr int WG_PIX = 64;                   // pixels (GEMM K) per stage
+constexpr int WG_BLK = WG_PIX * 64 * 2;      // one [64 px][64 ch] bf16 box = 8 KB
+constexpr int WG_STAGES = 3;
+constexpr int WG_STAGE_BYTES = 8 * WG_BLK;   // dy: 2 ch-blocks x (hi,lo); x: 2 ch-blocks x (hi,lo)
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
+
+struct WgradTcParams {
+  float* dw;          // [Cout][taps][Cin] fp32, zero-initialised
+  int N, H, W, Cin, Cout;
+  int taps_w, off0, step;   // x pixel = dy pixel + off0 + tap*step
+  int bw, bh;         // pixel patch, bw*bh == 64
+  int tiles_x, tiles_y;
+  int tiles_co, tiles_ci, splits, chunk;  // chunk = patches per split
+  int x3;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy_hi, const __grid_constant__ CUtensorMap map_dy_lo,
+                const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo, WgradTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + WG_STAGES;
+  uint64_t* done_bar = bars + 2 * WG_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_STAGES + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int t = blockIdx.x;
+  const int split = t % p.splits; t /= p.splits;
+  const int tco = t % p.tiles_co; t /= p.tiles_co;
+  const int tci = t % p.tiles_ci; t /= p.tiles_ci;
+  const int tap = t;
+  const int tr = tap / p.taps_w, ts = tap - tr * p.taps_w;
+  const int dxo = p.off0 + ts * p.step, dyo = p.off0 + tr * p.step;
+  const int total_patches = p.N * p.tiles_y * p.tiles_x;
+  const int pbeg = split * p.chunk;
+  const int pend = min(total_patches, pbeg + p.chunk);
+  const int num_k = pend - pbeg;  // host guarantees >= 1
+  const uint32_t stage_bytes = (uint32_t)(4 * WG_BLK) * (p.x3 ? 2u : 1u);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_dy_hi);
+    tma_prefetch_desc(&map_x_hi);
+    if (p.x3) { tma_prefetch_desc(&map_dy_lo); tma_prefetch_desc(&map_x_lo); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<128>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int pi = pbeg; pi < pend; ++pi) {
+      int q = pi;
+      const int tx = q % p.tiles_x; q /= p.tiles_x;
+      const int ty = q % p.tiles_y;
+      const int img = q / p.tiles_y;
+      const int x0 = tx * p.bw, y0 = ty * p.bh;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* st = smem + stage * WG_STAGE_BYTES;
+      mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+      // layout of a stage: [dy_hi c0][dy_hi c1][x_hi c0][x_hi c1][dy_lo c0][dy_lo c1][x_lo c0][x_lo c1]
+      tma_load_4d(st + 0 * WG_BLK, &map_dy_hi, &full_bar[stage], tco * 128, x0, y0, img);
+      tma_load_4d(st + 1 * WG_BLK, &map_dy_hi, &full_bar[stage], tco * 128 + 64, x0, y0, img);
+      tma_load_4d(st + 2 * WG_BLK, &map_x_hi, &full_bar[stage], tci * 128, x0 + dxo, y0 + dyo, img);
+      tma_load_4d(st + 3 * WG_BLK, &map_x_hi, &full_bar[stage], tci * 128 + 64, x0 + dxo, y0 + dyo, img);
+      if (p.x3) {
+        tma_load_4d(st + 4 * WG_BLK, &map_dy_lo, &full_bar[stage], tco * 128, x0, y0, img);
+        tma_load_4d(st + 5 * WG_BLK, &map_dy_lo, &full_bar[stage], tco * 128 + 64, x0, y0, img);
+        tma_load_4d(st + 6 * WG_BLK, &map_x_lo, &full_bar[stage], tci * 128, x0 + dxo, y0 + dyo, img);
+        tma_load_4d(st + 7 * WG_BLK, &map_x_lo, &full_bar[stage], tci * 128 + 64, x0 + dxo, y0 + dyo, img);
+      }
+      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc = make_idesc(128, 128, 1, 1);  // both operands MN-major
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int k = 0; k < num_k; ++k) {
+      mbar_wait(&full_bar[stage], phase);
+      tcgen05_fence_after();
+      const uint32_t base = smem_u32(smem + stage * WG_STAGE_BYTES);
+#pragma unroll
+      for (int kk = 0; kk < WG_PIX / UMMA_K; ++kk) {
+        const uint32_t koff = kk * UMMA_K * 128;  // 16 pixel rows of 128 B
+        const uint64_t a_hi = make_mnmajor_sw128_desc(base + 0 * WG_BLK + koff, WG_BLK);
+        const uint64_t b_hi = make_mnmajor_sw128_desc(base + 2 * WG_BLK + koff, WG_BLK);
+        umma_bf16(a_hi, b_hi, tmem_d, idesc, (k | kk) != 0);
+        if (p.x3) {
+          const uint64_t a_lo = make_mnmajor_sw128_desc(base + 4 * WG_BLK + koff, WG_BLK);
+          const uint64_t b_lo = make_mnmajor_sw128_desc(base + 6 * WG_BLK + koff, WG_BLK);
+          umma_bf16(a_hi, b_lo, tmem_d, idesc, 1);
+          umma_bf16(a_lo, b_hi, tmem_d, idesc, 1);
+        }
+      }
+      umma_commit(&empty_bar[stage]);
+      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+    }
+    umma_commit(done_bar);
+  } else if (warp >= 2) {
+    const int q = warp & 3;
+    const int co = tco * 128 + q * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tcgen05_fence_after();
+    const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
+    const int taps = p.taps_w * p.taps_w;
+    float* dst = p.dw + ((size_t)co * taps + tap) * p.Cin + tci * 128;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(taddr + c0, v);
+      tmem_ld_wait();
+      if (co < p.Cout && tci * 128 + c0 < p.Cin) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          red_add_v4(dst + c0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                     __uint_as_float(v[j + 3]));
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 2) tmem_dealloc<128>(tmem_d);
+}
+
+void pick_patch64(int h, int w, int& bw, int& bh) {
+  const int cand[7][2] = {{16, 4}, {8, 8}, {32, 2}, {4, 16}, {64, 1}, {2, 32}, {1, 64}};
+  long long best = -1;
+  for (auto& c : cand) {
+    long long cover = (long long)((w + c[0] - 1) / c[0]) * c[0] * ((h + c[1] - 1) / c[1]) * c[1];
+    if (best < 0 || cover < best) { best = cover; bw = c[0]; bh = c[1]; }
+  }
+}
+
 }  // namespace
 
 extern "C" int vspw_conv2d_tc_supported(const vspw_conv_desc* d) { return geometry_ok(d) ? 1 : 0; }
-extern "C" int vspw_conv2d_wgrad_tc_supported(const vspw_conv_desc* d) { (void)d; return 0; }
+extern "C" int vspw_conv2d_wgrad_tc_supported(const vspw_conv_desc* d) { return geometry_ok(d) ? 1 : 0; }
 
 extern "C" int vspw_conv2d_fwd_tc(const vspw_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi,
                                   const uint16_t* w_lo, const float* bias, float* y, void* stream) {
@@ -449,7 +603,42 @@ extern "C" int vspw_conv2d_dgrad_tc(const vspw_conv_desc* d, const uint16_t* dy_
 
 extern "C" int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* dy_hi,
                                     const uint16_t* dy_lo, float* dw_ohwi, void* stream) {
-  (void)d; (void)x_hi; (void)x_lo; (void)dy_hi; (void)dy_lo; (void)dw_ohwi; (void)stream;
-  set_error("vspw_conv2d_wgrad_tc: not built yet (the engine uses the fp32 wgrad kernel)");
-  return VSPW_ERR_UNSUPPORTED;
+  const char* who = "vspw_conv2d_wgrad_tc";
+  VSPW_REQUIRE(geometry_ok(d), "%s: geometry not supported by the tcgen05 path", who);
+  VSPW_REQUIRE(d->precision == VSPW_PREC_BF16X3 || d->precision == VSPW_PREC_BF16, "%s: precision must be BF16X3 or BF16", who);
+  const int x3 = d->precision == VSPW_PREC_BF16X3;
+  VSPW_REQUIRE(x_hi && dy_hi && dw_ohwi && (!x3 || (x_lo && dy_lo)), "%s: null pointer", who);
+  cudaStream_t st = as_stream(stream);
+  WgradTcParams p;
+  p.dw = dw_ohwi; p.N = d->n; p.H = d->h; p.W = d->w; p.Cin = d->cin; p.Cout = d->cout;
+  p.taps_w = d->kw; p.off0 = -d->pad; p.step = d->dil; p.x3 = x3;
+  pick_patch64(d->h, d->w, p.bw, p.bh);
+  p.tiles_x = (d->w + p.bw - 1) / p.bw;
+  p.tiles_y = (d->h + p.bh - 1) / p.bh;
+  p.tiles_co = (d->cout + 127) / 128;
+  p.tiles_ci = (d->cin + 127) / 128;
+  const int taps = d->kh * d->kw;
+  const long long tiles = (long long)p.tiles_co * p.tiles_ci * taps;
+  const int total_patches = d->n * p.tiles_y * p.tiles_x;
+  int splits = (int)((2 * kNumSMs) / tiles);  // ~2 CTAs per SM's worth of work items; one resident at a time
+  if (splits < 1) splits = 1;
+  if (splits > total_patches) splits = total_patches;
+  p.chunk = (total_patches + splits - 1) / splits;
+  p.splits = (total_patches + p.chunk - 1) / p.chunk;
+  cudaError_t e = cudaMemsetAsync(dw_ohwi, 0, (size_t)d->cout * taps * d->cin * sizeof(float), st);
+  if (e != cudaSuccess) { set_error("%s: memset: %s", who, cudaGetErrorString(e)); return VSPW_ERR_CUDA; }
+  CUtensorMap mdy_hi, mdy_lo, mx_hi, mx_lo;
+  int rc;
+  if ((rc = make_act_map(&mdy_hi, dy_hi, d->n, d->h, d->w, d->cout, p.bw, p.bh, who))) return rc;
+  if ((rc = make_act_map(&mdy_lo, x3 ? dy_lo : dy_hi, d->n, d->h, d->w, d->cout, p.bw, p.bh, who))) return rc;
+  if ((rc = make_act_map(&mx_hi, x_hi, d->n, d->h, d->w, d->cin, p.bw, p.bh, who))) return rc;
+  if ((rc = make_act_map(&mx_lo, x3 ? x_lo : x_hi, d->n, d->h, d->w, d->cin, p.bw, p.bh, who))) return rc;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM); });
+  if (attr_err != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(attr_err)); return VSPW_ERR_CUDA; }
+  const long long grid = tiles * p.splits;
+  VSPW_REQUIRE(grid < (1ll << 31), "%s: grid too large", who);
+  wgrad_tc_kernel<<<(unsigned)grid, kThreads, WG_SMEM, st>>>(mdy_hi, mdy_lo, mx_hi, mx_lo, p);
+  return check_launch(who);
 }

@@ -122,6 +122,15 @@ def run_case(ref, name, spec):
     for k in ("encoder.bn1.running_mean", "encoder.bn1.running_var", "encoder.layer4.0.bn2.running_mean",
               "encoder.layer4.0.bn2.running_var"):
         rec["train/after/" + k] = sd[k].numpy().copy()
+    # ---- frozen-BN step (cfg.TRAIN.fix_bn -> module.train(False), train_clip2.py:33): loss + gradients with
+    #      running statistics; the network is not chaotic in this mode, so gradients pin tightly ----------
+    m = build(ref, kind, arch, mseed)
+    m.eval()
+    loss, acc = m(feed(imgs, labs, True)) if kind != "SegmentationModule" else m({"img_data": imgs[0], "seg_label": labs[0]})
+    loss.backward()
+    rec["fixbn/loss"] = np.float64(loss.item())
+    rec["fixbn/acc"] = np.float64(acc.item())
+    rec.update({"fixbn/" + k: v for k, v in grad_summary(m).items()})
     # ---- eval forward -----------------------------------------------------------------------------
     m = build(ref, kind, arch, mseed)
     m.eval()

@@ -57,6 +57,37 @@ def test_oracle_train_matches_reference(name):
 
 
 @pytest.mark.parametrize("name", list(C.CASES))
+def test_oracle_frozen_bn_step_matches_reference(name):
+    """loss + gradients with BN in eval mode (cfg.TRAIN.fix_bn): non-chaotic, so gradients pin at 1e-4."""
+    kind, arch, T, n, H, W, mseed, dseed = C.CASES[name]
+    g = C.golden(name)
+    m = C.build(kind, arch, mseed)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    params = [k for k, _ in m.named_parameters()]
+    for k in params:
+        sd[k].requires_grad_(True)
+    imgs, labs = C.clip_inputs(name)
+    if kind == "SegmentationModule":
+        out = O.segmentation_module_forward(sd, imgs[0], labs[0], train=False)
+    elif kind == "ClipOCRNet":
+        out = O.clip_ocr_forward(sd, *C.oracle_order(imgs, labs), train=False)
+    else:
+        out = O.clip_psp_forward(sd, *C.oracle_order(imgs, labs), args_psp_weight=(kind == "Clip_PSP_pspw"), train=False)
+    out["loss"].backward()
+    assert abs(out["loss"].item() - float(g["fixbn/loss"])) <= 1e-5 * abs(float(g["fixbn/loss"]))
+    checked = 0
+    for k in params:
+        key = "fixbn/gnorm/" + k
+        if key not in g or float(g[key]) < 1e-10:
+            continue
+        ref_norm = float(g[key])
+        assert abs(float(sd[k].grad.double().norm()) - ref_norm) <= 1e-4 * ref_norm, k
+        assert C.rel_err(sd[k].grad.reshape(-1)[:64], g["fixbn/ghead/" + k]) <= 1e-3, k
+        checked += 1
+    assert checked > 60
+
+
+@pytest.mark.parametrize("name", list(C.CASES))
 def test_oracle_eval_matches_reference(name):
     kind, arch, T, n, H, W, mseed, dseed = C.CASES[name]
     g = C.golden(name)
