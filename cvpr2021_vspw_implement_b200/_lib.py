@@ -44,7 +44,7 @@ _SIGNATURES = {
     "vspw_conv2d_wgrad_tc": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
     "vspw_bn_stats": [_c_vp, _c_sz, _c_int, _c_vp, _c_vp, _c_vp],
     "vspw_bn_finalize_train": [_c_vp, _c_vp, _c_d, _c_vp, _c_vp, _c_f, _c_f, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_vp],
-    "vspw_bn_fold_eval": [_c_vp, _c_vp, _c_vp, _c_vp, _c_f, _c_vp, _c_vp, _c_int, _c_vp],
+    "vspw_bn_fold_eval": [_c_vp, _c_vp, _c_vp, _c_vp, _c_f, _c_vp, _c_vp, _c_vp, _c_int, _c_vp],
     "vspw_bn_act_fwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_vp],
     "vspw_bn_bwd_reduce": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_sz, _c_vp, _c_vp, _c_vp],
     "vspw_bn_bwd_apply": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_int, _c_d, _c_vp],

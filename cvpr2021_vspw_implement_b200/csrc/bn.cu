@@ -125,10 +125,11 @@ __global__ void bn_finalize_train_kernel(const double* sum, const double* sqsum,
 }
 
 __global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
-                                    float* scale, float* shift, int c) {
+                                    float* scale, float* shift, float* invstd, int c) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c) return;
   float is = 1.f / sqrtf(rv[i] + eps);
+  if (invstd) invstd[i] = is;
   float sc = (gamma ? gamma[i] : 1.f) * is;
   scale[i] = sc;
   shift[i] = (beta ? beta[i] : 0.f) - rm[i] * sc;
@@ -296,10 +297,10 @@ extern "C" int vspw_bn_finalize_train(const double* sum, const double* sqsum, do
 }
 
 extern "C" int vspw_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
-                                 float eps, float* scale, float* shift, int32_t c, void* stream) {
+                                 float eps, float* scale, float* shift, float* invstd, int32_t c, void* stream) {
   VSPW_REQUIRE(running_mean && running_var && scale && shift, "vspw_bn_fold_eval: null pointer");
   bn_fold_eval_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(gamma, beta, running_mean, running_var, eps, scale,
-                                                                      shift, c);
+                                                                      shift, invstd, c);
   return check_launch("vspw_bn_fold_eval");
 }
 

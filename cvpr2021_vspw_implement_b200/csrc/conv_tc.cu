@@ -387,7 +387,7 @@ bool geometry_ok(const vspw_conv_desc* d) {
   if (d->cin % 64 || d->cout % 64) return false;
   if (d->ho != d->h || d->wo != d->w) return false;              // "same" convs only (pad == dil*(k-1)/2)
   if (d->kh != d->kw || (d->kh != 1 && d->kh != 3)) return false;
-  if ((long long)d->n * d->h * d->w < 2048) return false;        // tiny maps (PPM s x s) stay on the CUDA-core arm
+  if ((long long)d->n * d->h * d->w < 256) return false;         // tiny maps (PPM s x s, <= 72 px) stay on the CUDA-core arm
   return true;
 }
 

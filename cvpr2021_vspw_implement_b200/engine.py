@@ -408,8 +408,9 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
                  float(bn.momentum), _p(bn.running_mean), _p(bn.running_var), _p(mean), _p(invstd), _p(scale), _p(shift), c,
                  1 if _state["syncbn_clamp"] else 0, st)
     else:
+        invstd = torch.empty(c, device=dev, dtype=torch.float32)
         lib.call("vspw_bn_fold_eval", _p(gv.data), _p(bv.data), _p(bn.running_mean), _p(bn.running_var), float(bn.eps),
-                 _p(scale), _p(shift), c, st)
+                 _p(scale), _p(shift), _p(invstd), c, st)
     o = torch.empty_like(y.data)
     want_planes = _state["precision"] != "fp32" and c % 64 == 0
     hi = lo = None
@@ -449,9 +450,23 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
             if bv.needs_grad:
                 bv.add_grad(dbet)
         else:
-            # frozen statistics: dy = g * gamma/sqrt(var+eps) = g * scale
-            lib.call("vspw_bn_bwd_apply", _p(dout), _p(o), None, None, _p(scale), None, _p(chan_scale), 1 if relu else 0, None,
-                     None, _p(dy), _p(dres), None, None, pixels, c, h * w, 1, float(pixels), st)
+            # frozen statistics (cfg.TRAIN.fix_bn): dy = g * gamma/sqrt(var+eps) = g * scale; gamma/beta still learn:
+            # dbeta = sum g, dgamma = sum g * (y - running_mean) * invstd
+            dsum = dgam = dbet = None
+            if gv.needs_grad or bv.needs_grad:
+                dsum = torch.zeros((2, c), device=dev, dtype=torch.float64)
+                lib.call("vspw_bn_bwd_reduce", _p(dout), _p(o), _p(y.data), _p(bn.running_mean), _p(invstd), _p(chan_scale),
+                         1 if relu else 0, pixels, c, h * w, _p(dsum[0]), _p(dsum[1]), st)
+                dgam = torch.empty(c, device=dev, dtype=torch.float32)
+                dbet = torch.empty(c, device=dev, dtype=torch.float32)
+            lib.call("vspw_bn_bwd_apply", _p(dout), _p(o), None, None, _p(scale), None, _p(chan_scale), 1 if relu else 0,
+                     _p(dsum[0]) if dsum is not None else None, _p(dsum[1]) if dsum is not None else None, _p(dy), _p(dres),
+                     _p(dgam), _p(dbet), pixels, c, h * w, 1, float(pixels), st)
+            if dsum is not None:
+                if gv.needs_grad:
+                    gv.add_grad(dgam)
+                if bv.needs_grad:
+                    bv.add_grad(dbet)
         if y.needs_grad:
             y.add_grad(dy)
         if dres is not None:

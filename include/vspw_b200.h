@@ -103,10 +103,11 @@ int vspw_bn_finalize_train(const double* sum, const double* sqsum, double count,
                            const float* beta, float eps, float momentum, float* running_mean,
                            float* running_var, float* mean, float* invstd, float* scale,
                            float* shift, int32_t c, int32_t clamp_mode, void* stream);
-/* eval: scale/shift folded from the running statistics */
+/* eval: scale/shift folded from the running statistics; invstd (nullable) = 1/sqrt(running_var+eps),
+ * needed by the frozen-BN backward (cfg.TRAIN.fix_bn, train_clip2.py:33) for dgamma */
 int vspw_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean,
-                      const float* running_var, float eps, float* scale, float* shift, int32_t c,
-                      void* stream);
+                      const float* running_var, float eps, float* scale, float* shift, float* invstd,
+                      int32_t c, void* stream);
 /* out = relu?(bn(y) + residual?) * chan_scale?[n][c]; bn(y) = (y-mean)*scale + beta when mean is
  * non-null (centred, F.batch_norm's form), else y*scale + shift; optional bf16 planes of out */
 int vspw_bn_act_fwd(const float* y, const float* scale, const float* shift, const float* mean,
