@@ -1,0 +1,62 @@
+"""Synthetic stand-ins for the VSPW clip datasets, with the reference datasets' OUTPUT CONTRACT
+(dataset2.py: BaseDataset_longclip :852-1048 for training, TestDataset_longclip :344-490 for inference).
+
+JPEG/PNG decoding and augmentation are outside the hot path; what the hot path needs
+from a loader is the batch layout, which these reproduce exactly so the entry points run end to end without the
+VSPW files:
+
+  train item : (clip_imgs, clip_gts) = T tensors (3, H, W) float32 ImageNet-normalised, T tensors (1, H, W) float
+               with values in {0..num_class-1, 255}; the default collate turns them into lists of (n, 3, H, W) /
+               (n, 1, H, W) batches.  Frame 0 is the "current" frame (train_clip2.py:75-83).
+  test item  : (img, gt, clip_imgs, clip_gts, gt_name) per frame of a video (test_clip2.py:33).
+"""
+import torch
+from torch.utils.data import Dataset
+
+
+def synthetic_frame(gen, h, w, num_class, block=32, ignore_frac=0.05, ignore_index=255):
+    img = torch.randn(3, h, w, generator=gen)
+    bh, bw = (h + block - 1) // block, (w + block - 1) // block
+    tiles = torch.randint(0, num_class, (1, bh, bw), generator=gen).float()
+    tiles[torch.rand(1, bh, bw, generator=gen) < ignore_frac] = float(ignore_index)
+    lab = tiles.repeat_interleave(block, dim=1).repeat_interleave(block, dim=2)[:, :h, :w].contiguous()
+    return img, lab
+
+
+class SyntheticClipTrain(Dataset):
+    """`length` random clips of `clip_num` frames at (height, width); deterministic per index."""
+
+    def __init__(self, args, length=64, height=None, width=None, seed=304):
+        self.t = int(args.clip_num)
+        self.h = int(height or getattr(args, "cropsize", 480))
+        self.w = int(width or getattr(args, "cropsize", 480))
+        self.k = int(args.num_class)
+        self.length, self.seed = int(length), int(seed)
+
+    def __len__(self):
+        return self.length
+
+    def __getitem__(self, i):
+        gen = torch.Generator().manual_seed(self.seed * 100003 + i)
+        frames = [synthetic_frame(gen, self.h, self.w, self.k) for _ in range(self.t)]
+        return [f[0] for f in frames], [f[1] for f in frames]
+
+
+class SyntheticClipTest(Dataset):
+    """One synthetic 'video' of `frames` frames; item i = frame i plus its clip_num-1 neighbour frames."""
+
+    def __init__(self, args, video="synthetic_000", frames=12, height=480, width=854, seed=304):
+        self.t, self.k = int(args.clip_num), int(args.num_class)
+        gen = torch.Generator().manual_seed(seed + sum(map(ord, video)))
+        self.frames = [synthetic_frame(gen, height, width, self.k) for _ in range(frames)]
+        self.video = video
+        self.offsets = [int(x) for x in str(args.dilation2).split(",")] if self.t > 1 else []
+        assert len(self.offsets) + 1 == self.t  # dataset2.py:357
+
+    def __len__(self):
+        return len(self.frames)
+
+    def __getitem__(self, i):
+        img, gt = self.frames[i]
+        nb = [self.frames[max(0, i - o)] for o in self.offsets]  # earlier frames, clamped at the start of the video
+        return img, gt, [f[0] for f in nb], [f[1] for f in nb], f"{i:08d}.png"

@@ -1,0 +1,170 @@
+#!/usr/bin/env python
+"""Video inference / evaluation entry point on the B200 engine — same CLI as the reference's test_clip2.py (flags
+:349-405; per-video loop :280-321; metrics :323-331) for ``--method clip_psp`` and ``--method clip_ocr``.
+
+Per batch: ``scores = module(batch_data, segSize=(H, W))`` -> argmax -> Evaluator (global + per video) -> VC metric,
+exactly the reference's sequence (test_clip2.py:28-89).  ``--synthetic True`` evaluates seeded synthetic videos
+(the VSPW loader is outside the hot path); ``--load`` may be empty with ``--synthetic`` (random weights).
+Replicas only: videos are independent and the OCR memory bank is per-video state, so multi-GPU inference is one
+process per GPU over disjoint video lists.
+"""
+import argparse
+import os
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from cvpr2021_vspw_implement_b200 import engine as E
+from cvpr2021_vspw_implement_b200.config import cfg
+from cvpr2021_vspw_implement_b200.data import SyntheticClipTest
+from cvpr2021_vspw_implement_b200.models import Clip_PSP, ClipOCRNet, ModelBuilder
+from cvpr2021_vspw_implement_b200.utils import Evaluator, get_common, setup_logger
+from train_clip2 import OTHER_METHODS, str2bool
+
+
+def vspw_palette():
+    """The reference's palette (test_clip2.py:24): 22 VOC-style colours, then grey levels i,i,i for i >= 22."""
+    voc = [0, 0, 0, 128, 0, 0, 0, 128, 0, 128, 128, 0, 0, 0, 128, 128, 0, 128, 0, 128, 128, 128, 128, 128, 64, 0, 0, 191, 0, 0,
+           64, 128, 0, 191, 128, 0, 64, 0, 128, 191, 0, 128, 64, 128, 128, 191, 128, 128, 0, 64, 0, 128, 64, 0, 0, 191, 0,
+           128, 191, 0, 0, 64, 128, 128, 64, 128]
+    return voc + [c for i in range(22, 256) for c in (i, i, i)]
+
+
+def test(segmentation_module, loader, gpu, args, evaluator, eval_video, video):
+    segmentation_module.eval()
+    gtlist_, predlist_ = [], []
+    h = w = 0
+    for i, data in enumerate(loader):
+        imgs, gts, clip_imgs, _, gtnames = data
+        _, _, h, w = imgs.size()
+        dev = torch.device("cuda", args.start_gpu)
+        imgs, gts = imgs.to(dev), gts.to(dev)
+        batch_data = {'img_data': imgs, 'seg_label': gts, 'clipimgs_data': [c.to(dev) for c in clip_imgs]}
+        if args.use_memory:
+            batch_data['is_clean_memory'] = (i == 0)
+        with torch.no_grad():
+            scores = segmentation_module(batch_data, segSize=(imgs.size(2), imgs.size(3)))
+            pred = torch.argmax(scores, dim=1).cpu().numpy()
+        target = gts.squeeze(1).cpu().numpy()
+        evaluator.add_batch(target, pred)
+        eval_video.add_batch(target, pred)
+        for jj in range(pred.shape[0]):
+            predlist_.append(pred[jj])
+            gtlist_.append(target[jj])
+        if args.is_save:
+            from PIL import Image
+            os.makedirs(os.path.join(args.saveroot, video), exist_ok=True)
+            for j in range(pred.shape[0]):
+                im = Image.fromarray(pred[j].astype('uint8')).convert('P')
+                im.putpalette(vspw_palette())
+                im.save(os.path.join(args.saveroot, video, gtnames[j].split('.')[0] + '.png'))
+    return gtlist_, predlist_, h, w
+
+
+def build_module(cfg, args, num_class):
+    net_encoder = ModelBuilder.build_encoder(arch=cfg.MODEL.arch_encoder, fc_dim=cfg.MODEL.fc_dim, weights='')
+    crit = nn.NLLLoss(ignore_index=-1)
+    if args.method == 'clip_psp':
+        return Clip_PSP(net_encoder, crit, args)
+    if args.method == 'clip_ocr':
+        return ClipOCRNet(net_encoder, crit, args)
+    raise NotImplementedError(f"--method {args.method!r}: only clip_psp / clip_ocr run on the B200 engine")
+
+
+def main(cfg, gpu, args):
+    num_class = 42 if args.lesslabel else args.num_class
+    torch.cuda.set_device(gpu)
+    E.set_precision(args.precision)
+    torch.manual_seed(cfg.TRAIN.seed)
+    segmentation_module = build_module(cfg, args, num_class)
+    segmentation_module.cuda(args.start_gpu)
+    if args.load:
+        to_load = torch.load(args.load, map_location=torch.device("cuda:" + str(args.start_gpu)))
+        segmentation_module.load_state_dict(OrderedDict((k[7:], v) for k, v in to_load.items()))  # strip 'module.' (:267-271)
+    elif not args.synthetic:
+        raise ValueError("--load is required (a model_epoch_E.pth written by train_clip2.py)")
+    if args.gpu_num > 1:
+        raise NotImplementedError("multi-GPU inference = one test_clip2.py process per GPU over disjoint --split lists")
+    if args.synthetic:
+        videolists = [f"synthetic_{i:03d}" for i in range(args.synthetic_videos)]
+    else:
+        with open(os.path.join(args.dataroot, args.split + '.txt')) as f:
+            videolists = [line[:-1] for line in f.readlines()]
+    evaluator, eval_video = Evaluator(num_class), Evaluator(num_class)
+    total_vmIOU = total_vfwIOU = 0.0
+    total_VC_acc = []
+    for video in videolists:
+        eval_video.reset()
+        if args.synthetic:
+            h, w = (int(x) for x in args.synthetic_size.lower().split("x"))
+            test_dataset = SyntheticClipTest(args, video, frames=args.synthetic_frames, height=h, width=w, seed=cfg.TRAIN.seed)
+        else:
+            try:
+                from dataset2 import TestDataset_longclip  # the caller's VSPW loader (reference dataset2.py:344-490)
+            except ImportError as e:
+                raise RuntimeError("the VSPW JPEG/PNG loader is outside this engine's scope: put the reference's dataset2.py "
+                                   "on PYTHONPATH, or run with --synthetic True") from e
+            test_dataset = TestDataset_longclip(args.dataroot, video, args, is_train=False)
+        loader_test = torch.utils.data.DataLoader(test_dataset, batch_size=args.batchsize, shuffle=False, num_workers=0, drop_last=False)
+        gtlist_, predlist_, h, w = test(segmentation_module, loader_test, gpu, args, evaluator, eval_video, video)
+        accs = get_common(gtlist_, predlist_, args.vc_clip_num, h, w)
+        if accs:
+            print(sum(accs) / len(accs))
+        total_VC_acc.extend(accs)
+        v_mIOU = eval_video.Mean_Intersection_over_Union()
+        total_vmIOU += v_mIOU
+        total_vfwIOU += eval_video.Frequency_Weighted_Intersection_over_Union()
+        print(video, v_mIOU)
+    total_vmIOU /= len(videolists)
+    total_vfwIOU /= len(videolists)
+    Acc, Acc_class = evaluator.Pixel_Accuracy(), evaluator.Pixel_Accuracy_Class()
+    mIoU, FWIoU = evaluator.Mean_Intersection_over_Union(), evaluator.Frequency_Weighted_Intersection_over_Union()
+    print("Acc:{}, Acc_class:{}, mIoU:{}, fwIoU: {}, video mIOU: {}, video fwIOU: {}".format(Acc, Acc_class, mIoU, FWIoU, total_vmIOU, total_vfwIOU))
+    VC_Acc = np.nanmean(np.array(total_VC_acc)) if total_VC_acc else float("nan")
+    print("Video Consistency num :{} acc:{}".format(args.vc_clip_num, VC_Acc))
+    print('Inference done!')
+    return {"Acc": Acc, "Acc_class": Acc_class, "mIoU": mIoU, "fwIoU": FWIoU, "video_mIoU": total_vmIOU, "VC": VC_Acc}
+
+
+def make_parser():
+    parser = argparse.ArgumentParser(description="PyTorch Semantic Segmentation Testing (B200 engine)")
+    parser.add_argument("--cfg", default="config/vsp-resnet101dilated-ppm_deepsup_clip.yaml", metavar="FILE", type=str)
+    for name, typ, default in (("num_class", int, 124), ("start_gpu", int, 0), ("dataroot", str, ''), ("saveroot", str, ''),
+                               ("load_en", str, ''), ("load_de", str, ''), ("load", str, ''), ("batchsize", int, 4), ("split", str, 'val'),
+                               ("is_save", str2bool, False), ("lesslabel", str2bool, False), ("use_720p", str2bool, False),
+                               ("clip_num", int, 5), ("dilation_num", int, 0), ("gpu_num", int, 1), ("propclip2", str2bool, False),
+                               ("early_usecat", str2bool, False), ("earlyfuse", str2bool, False), ("allsup", str2bool, False),
+                               ("allsup_scale", float, 0.3), ("deepsup_scale", float, 0.0), ("linear_combine", str2bool, False),
+                               ("distsoftmax", str2bool, False), ("distnearest", str2bool, False), ("temp", float, 3),
+                               ("max_distances", str, '10'), ("clipocr_all", str2bool, False), ("dilation2", str, "2,5,9"),
+                               ("use_memory", str2bool, False), ("memory_num", int, 8), ("vc_clip_num", int, 8),
+                               ("psp_weight", str2bool, False)):
+        parser.add_argument("--" + name, type=typ, default=default)
+    parser.add_argument("--method", type=str, default='', choices=['clip_psp', 'clip_ocr'] + OTHER_METHODS)
+    parser.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32"])
+    parser.add_argument("--synthetic", type=str2bool, default=False)
+    parser.add_argument("--synthetic_size", type=str, default="480x854")
+    parser.add_argument("--synthetic_videos", type=int, default=2)
+    parser.add_argument("--synthetic_frames", type=int, default=12)
+    parser.add_argument("opts", help="Modify config options using the command-line", default=None, nargs=argparse.REMAINDER)
+    return parser
+
+
+if __name__ == '__main__':
+    args = make_parser().parse_args()
+    args.max_distances = [int(dd) for dd in args.max_distances.split(',')]
+    cfg.merge_from_file(args.cfg)
+    cfg.merge_from_list(args.opts)
+    logger = setup_logger(distributed_rank=0)
+    logger.info("Loaded configuration file {}".format(args.cfg))
+    logger.info("Running with config:\n{}".format(cfg))
+    cfg.MODEL.arch_encoder = cfg.MODEL.arch_encoder.lower()
+    cfg.MODEL.arch_decoder = cfg.MODEL.arch_decoder.lower()
+    cfg.MODEL.weights_encoder = args.load_en
+    cfg.MODEL.weights_decoder = args.load_de
+    if args.saveroot:
+        os.makedirs(args.saveroot, exist_ok=True)
+    main(cfg, args.start_gpu, args)
+    print(args)

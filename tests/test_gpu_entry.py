@@ -1,0 +1,55 @@
+"""GPU: the train_clip2.py / test_clip2.py entry points end to end on synthetic clips (reference call stacks
+SURVEY.md 3.1 / 3.4): training steps lower the loss, checkpoints round-trip through the 'module.'-prefix convention,
+and the inference entry reports the reference's metrics."""
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+@pytest.fixture(scope="module")
+def need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+@pytest.mark.parametrize("method", ["clip_psp", "clip_ocr"])
+def test_train_then_test_entry_points(need_gpu, method, tmp_path, monkeypatch):
+    import train_clip2
+    import test_clip2
+    from cvpr2021_vspw_implement_b200.config import cfg, get_defaults
+    monkeypatch.chdir(tmp_path)
+    cfg.clear()
+    cfg.update(get_defaults())
+    yaml = os.path.join(ROOT, "config", "vsp-resnet101dilated-ppm_deepsup_clip.yaml")
+    save = str(tmp_path / "ckpt")
+    argv = ["--cfg", yaml, "--method", method, "--clip_num", "3", "--dilation2", "3,6", "--batchsize", "2", "--gpu_num", "1",
+            "--lr", "0.002", "--totalepoch", "1", "--synthetic", "True", "--synthetic_size", "64x96", "--synthetic_clips", "8",
+            "--saveroot", save, "--checkpoint_every", "1", "--precision", "bf16x3",
+            "MODEL.arch_encoder", "resnet50dilated", "TRAIN.seed", "5"]
+    args = train_clip2.make_parser().parse_args(argv)
+    train_clip2.configure(args)
+    hist = train_clip2.main(cfg, args)
+    losses = hist["train"]["loss"]
+    assert len(losses) == 4 and all(l == l and l < 20 for l in losses)
+    assert losses[-1] < losses[0]  # SGD on the same 124-class problem: the loss must move down
+    ck = os.path.join(save, "model_epoch_1.pth")
+    sd = torch.load(ck, map_location="cpu")
+    assert all(k.startswith("module.") for k in sd) and os.path.exists(os.path.join(save, "opt_epoch_1.pth"))
+
+    targv = ["--cfg", yaml, "--method", method, "--clip_num", "3", "--dilation2", "3,6", "--batchsize", "2", "--load", ck,
+             "--synthetic", "True", "--synthetic_size", "64x96", "--synthetic_videos", "1", "--synthetic_frames", "6",
+             "--vc_clip_num", "2", "--use_memory", "True" if method == "clip_ocr" else "False", "--saveroot", str(tmp_path / "pred"),
+             "--is_save", "True", "MODEL.arch_encoder", "resnet50dilated"]
+    targs = test_clip2.make_parser().parse_args(targv)
+    targs.max_distances = [10]
+    cfg.merge_from_list(targs.opts)
+    res = test_clip2.main(cfg, 0, targs)
+    assert 0.0 <= res["mIoU"] <= 1.0 and 0.0 <= res["Acc"] <= 1.0 and res["VC"] == res["VC"]
+    assert len(os.listdir(tmp_path / "pred" / "synthetic_000")) == 6
