@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-run", action="store_true", help="for ncu captures only: honour --warmup below 3, skip e2e/cpu legs")
     ap.add_argument("--cpu-sample", default="240x427", help="HxW of the bounded CPU sample")
+    ap.add_argument("--kernel-profile", default="", help="write a per-entry-point CUDA-event breakdown of 2 extra steps to this file")
     return ap.parse_args()
 
 
@@ -244,6 +245,24 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = frames_per_step / (float(t.item()) / e2e_steps / 1e3) if e2e_steps else 0.0
+
+    if args.kernel_profile and rank == 0:
+        lib.profile_begin()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(2):
+            step(imgs_d, labs_d)
+        e1.record()
+        prof = lib.profile_end()
+        tot = e0.elapsed_time(e1) / 2
+        with open(args.kernel_profile, "w") as f:
+            f.write(f"# per-entry-point CUDA-event time inside 2 real steps ({args.precision}); step = {tot:.2f} ms\n")
+            f.write("| entry point | calls/step | ms/step | share |\n|---|---|---|---|\n")
+            acc = 0.0
+            for name, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+                f.write(f"| `{name}` | {n // 2} | {ms / 2:.2f} | {100 * ms / 2 / tot:.1f}% |\n")
+                acc += ms / 2
+            f.write(f"| (outside the C ABI: optimizer, allocator fills, gaps) | | {tot - acc:.2f} | {100 * (tot - acc) / tot:.1f}% |\n")
 
     pk = peaks()
     roof = None

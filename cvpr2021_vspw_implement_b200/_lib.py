@@ -39,15 +39,15 @@ _SIGNATURES = {
     "vspw_conv2d_fwd": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
     "vspw_conv2d_dgrad": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp],
     "vspw_conv2d_wgrad": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp],
-    "vspw_conv2d_fwd_tc": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
+    "vspw_conv2d_fwd_tc": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
     "vspw_conv2d_dgrad_tc": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
     "vspw_conv2d_wgrad_tc": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
     "vspw_bn_stats": [_c_vp, _c_sz, _c_int, _c_vp, _c_vp, _c_vp],
     "vspw_bn_finalize_train": [_c_vp, _c_vp, _c_d, _c_vp, _c_vp, _c_f, _c_f, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_vp],
     "vspw_bn_fold_eval": [_c_vp, _c_vp, _c_vp, _c_vp, _c_f, _c_vp, _c_vp, _c_vp, _c_int, _c_vp],
     "vspw_bn_act_fwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_vp],
-    "vspw_bn_bwd_reduce": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_sz, _c_vp, _c_vp, _c_vp],
-    "vspw_bn_bwd_apply": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_int, _c_d, _c_vp],
+    "vspw_bn_bwd_reduce": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_sz, _c_vp, _c_vp, _c_vp],
+    "vspw_bn_bwd_apply": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_int, _c_d, _c_vp],
     "vspw_maxpool3x3s2_fwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp],
     "vspw_maxpool3x3s2_bwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp],
     "vspw_tcb_pool_fwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_int, _c_vp],
@@ -76,6 +76,7 @@ class _Lib:
         self._dll = None
         self._lock = threading.Lock()
         self.launches = 0  # number of C-ABI compute calls issued (bench.py reports it)
+        self._prof = None  # live per-entry-point timing: list of (name, start_event, stop_event)
 
     def dll(self):
         if self._dll is None:
@@ -95,9 +96,32 @@ class _Lib:
                     self._dll = dll
         return self._dll
 
+    def profile_begin(self):
+        """Time every C-ABI call with CUDA events on the current stream (inside a real step, at real clocks)."""
+        self._prof = []
+
+    def profile_end(self):
+        """-> {entry point: (calls, total ms)}; synchronises the device."""
+        import torch
+        rec, self._prof = self._prof or [], None
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in rec:
+            n, ms = out.get(name, (0, 0.0))
+            out[name] = (n + 1, ms + e0.elapsed_time(e1))
+        return out
+
     def call(self, name, *args):
         dll = self.dll()
-        rc = getattr(dll, name)(*args)
+        if self._prof is not None:
+            import torch
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = getattr(dll, name)(*args)
+            e1.record()
+            self._prof.append((name, e0, e1))
+        else:
+            rc = getattr(dll, name)(*args)
         if rc != 0:
             msg = dll.vspw_last_error().decode("utf-8", "replace")
             raise VspwError(f"{name} failed ({rc}): {msg}")

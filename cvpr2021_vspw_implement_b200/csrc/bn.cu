@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float4* __restric
       float4 cs = __ldg(chan_scale + img * c4 + cg);
       v.x *= cs.x; v.y *= cs.y; v.z *= cs.z; v.w *= cs.w;
     }
-    out[i] = v;
+    if (out) out[i] = v;
     if (out_hi) {
       uint2 h = pack_bf16x4(v.x, v.y, v.z, v.w);
       out_hi[i] = h;
@@ -190,8 +190,9 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float4* __restric
   }
 }
 
-__device__ __forceinline__ float4 masked_grad(const float4* dout, const float4* out, const float4* chan_scale, int relu,
-                                              size_t i, size_t p, int cg, int c4, size_t pix_per_img) {
+__device__ __forceinline__ float4 masked_grad(const float4* dout, const float4* out, const uint2* out_hi,
+                                              const float4* chan_scale, int relu, size_t i, size_t p, int cg, int c4,
+                                              size_t pix_per_img) {
   float4 g = dout[i];
   if (chan_scale) {
     size_t img = p / pix_per_img;
@@ -199,28 +200,37 @@ __device__ __forceinline__ float4 masked_grad(const float4* dout, const float4* 
     g.x *= cs.x; g.y *= cs.y; g.z *= cs.z; g.w *= cs.w;
   }
   if (relu) {
-    float4 o = out[i];
     // out = relu(.)*chan_scale; a dropped channel (scale 0) already has g == 0
-    g.x = o.x != 0.f ? g.x : 0.f; g.y = o.y != 0.f ? g.y : 0.f;
-    g.z = o.z != 0.f ? g.z : 0.f; g.w = o.w != 0.f ? g.w : 0.f;
+    if (out) {
+      float4 o = out[i];
+      g.x = o.x != 0.f ? g.x : 0.f; g.y = o.y != 0.f ? g.y : 0.f;
+      g.z = o.z != 0.f ? g.z : 0.f; g.w = o.w != 0.f ? g.w : 0.f;
+    } else {
+      // the bf16 hi plane of the output: bf16_rn(x) is non-zero exactly when the (normal) fp32 x is
+      uint2 h = out_hi[i];
+      g.x = (h.x & 0x7fffu) ? g.x : 0.f; g.y = (h.x & 0x7fff0000u) ? g.y : 0.f;
+      g.z = (h.y & 0x7fffu) ? g.z : 0.f; g.w = (h.y & 0x7fff0000u) ? g.w : 0.f;
+    }
   }
   return g;
 }
 
 __global__ void __launch_bounds__(kStatThreads) bn_bwd_reduce_kernel(
-    const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ y,
+    const float* __restrict__ dout, const float* __restrict__ out, const uint16_t* __restrict__ out_hi,
+    const float* __restrict__ y,
     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ chan_scale, int relu,
     size_t pixels, int c, size_t pix_per_img, double* dbeta, double* dgamma) {
   const int c4 = c >> 2;
   const float4* d4 = reinterpret_cast<const float4*>(dout);
   const float4* o4 = reinterpret_cast<const float4*>(out);
+  const uint2* h4 = reinterpret_cast<const uint2*>(out_hi);
   const float4* y4 = reinterpret_cast<const float4*>(y);
   const float4* m4 = reinterpret_cast<const float4*>(mean);
   const float4* s4 = reinterpret_cast<const float4*>(invstd);
   const float4* cs4 = reinterpret_cast<const float4*>(chan_scale);
   stats_block<false>(pixels, c, dbeta, dgamma, [&](size_t p, int cg, float4& a, float4& b) {
     size_t i = p * c4 + cg;
-    float4 g = masked_grad(d4, o4, cs4, relu, i, p, cg, c4, pix_per_img);
+    float4 g = masked_grad(d4, o4, h4, cs4, relu, i, p, cg, c4, pix_per_img);
     float4 yv = __ldg(y4 + i), m = __ldg(m4 + cg), is = __ldg(s4 + cg);
     a = g;
     b = make_float4(g.x * (yv.x - m.x) * is.x, g.y * (yv.y - m.y) * is.y, g.z * (yv.z - m.z) * is.z,
@@ -229,15 +239,16 @@ __global__ void __launch_bounds__(kStatThreads) bn_bwd_reduce_kernel(
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
-    const float4* __restrict__ dout, const float4* __restrict__ out, const float4* __restrict__ y,
+    const float4* __restrict__ dout, const float4* __restrict__ out, const uint2* __restrict__ out_hi,
+    const float4* __restrict__ y,
     const float4* __restrict__ mean, const float4* __restrict__ invstd, const float4* __restrict__ gamma,
     const float4* __restrict__ chan_scale, int relu, const double* __restrict__ dbeta, const double* __restrict__ dgamma,
-    float4* __restrict__ dy, float4* __restrict__ dres, size_t total4, int c4, size_t pix_per_img, double inv_count,
-    int eval_mode) {
+    float4* __restrict__ dy, uint2* __restrict__ dy_hi, uint2* __restrict__ dy_lo, float4* __restrict__ dres, size_t total4,
+    int c4, size_t pix_per_img, double inv_count, int eval_mode) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
     size_t p = i / c4;
     int cg = (int)(i - p * c4);
-    float4 g = masked_grad(dout, out, chan_scale, relu, i, p, cg, c4, pix_per_img);
+    float4 g = masked_grad(dout, out, out_hi, chan_scale, relu, i, p, cg, c4, pix_per_img);
     if (dres) dres[i] = g;
     float4 is = __ldg(invstd + cg);
     float4 gm = gamma ? __ldg(gamma + cg) : make_float4(1.f, 1.f, 1.f, 1.f);
@@ -257,7 +268,16 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
       r.z = gm.z * is.z * (g.z - db[2] - (yv.z - m.z) * is.z * dg[2]);
       r.w = gm.w * is.w * (g.w - db[3] - (yv.w - m.w) * is.w * dg[3]);
     }
-    dy[i] = r;
+    if (dy) dy[i] = r;
+    if (dy_hi) {  // the consumer is a tcgen05 dgrad/wgrad: hand it the bf16 planes directly (no separate split pass)
+      uint2 h = pack_bf16x4(r.x, r.y, r.z, r.w);
+      dy_hi[i] = h;
+      if (dy_lo) {
+        __nv_bfloat162 h0 = *reinterpret_cast<__nv_bfloat162*>(&h.x), h1 = *reinterpret_cast<__nv_bfloat162*>(&h.y);
+        float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+        dy_lo[i] = pack_bf16x4(r.x - f0.x, r.y - f0.y, r.z - f1.x, r.w - f1.y);
+      }
+    }
   }
 }
 
@@ -308,7 +328,7 @@ extern "C" int vspw_bn_act_fwd(const float* y, const float* scale, const float* 
                                const float* beta, const float* residual,
                                const float* chan_scale, int32_t relu, float* out, uint16_t* out_hi, uint16_t* out_lo,
                                size_t pixels, int32_t c, size_t pixels_per_image, void* stream) {
-  VSPW_REQUIRE(y && scale && (shift || mean) && out, "vspw_bn_act_fwd: null pointer");
+  VSPW_REQUIRE(y && scale && (shift || mean) && (out || out_hi), "vspw_bn_act_fwd: null pointer");
   VSPW_REQUIRE(c > 0 && c % 4 == 0, "vspw_bn_act_fwd: channels must be a multiple of 4 (got %d)", c);
   VSPW_REQUIRE(pixels_per_image > 0, "vspw_bn_act_fwd: pixels_per_image must be positive");
   size_t total4 = pixels * (size_t)(c / 4);
@@ -320,33 +340,36 @@ extern "C" int vspw_bn_act_fwd(const float* y, const float* scale, const float* 
   return check_launch("vspw_bn_act_fwd");
 }
 
-extern "C" int vspw_bn_bwd_reduce(const float* dout, const float* out, const float* y, const float* mean,
-                                  const float* invstd, const float* chan_scale, int32_t relu, size_t pixels, int32_t c,
-                                  size_t pixels_per_image, double* dbeta, double* dgamma, void* stream) {
+extern "C" int vspw_bn_bwd_reduce(const float* dout, const float* out, const uint16_t* out_hi, const float* y,
+                                  const float* mean, const float* invstd, const float* chan_scale, int32_t relu,
+                                  size_t pixels, int32_t c, size_t pixels_per_image, double* dbeta, double* dgamma,
+                                  void* stream) {
   VSPW_REQUIRE(dout && y && mean && invstd && dbeta && dgamma, "vspw_bn_bwd_reduce: null pointer");
-  VSPW_REQUIRE(!relu || out, "vspw_bn_bwd_reduce: relu mask needs the forward output");
+  VSPW_REQUIRE(!relu || out || out_hi, "vspw_bn_bwd_reduce: relu mask needs the forward output (fp32 or bf16 hi plane)");
   VSPW_REQUIRE(c > 0 && c % 4 == 0, "vspw_bn_bwd_reduce: channels must be a multiple of 4 (got %d)", c);
   if (pixels == 0) return VSPW_OK;
   bn_bwd_reduce_kernel<<<stats_grid(pixels, c), kStatThreads, 2 * kStatThreads * sizeof(D4), as_stream(stream)>>>(
-      dout, out, y, mean, invstd, chan_scale, relu, pixels, c, pixels_per_image, dbeta, dgamma);
+      dout, out, out_hi, y, mean, invstd, chan_scale, relu, pixels, c, pixels_per_image, dbeta, dgamma);
   return check_launch("vspw_bn_bwd_reduce");
 }
 
-extern "C" int vspw_bn_bwd_apply(const float* dout, const float* out, const float* y, const float* mean,
-                                 const float* invstd, const float* gamma, const float* chan_scale, int32_t relu,
-                                 const double* dbeta, const double* dgamma, float* dy, float* dres, float* dgamma_f,
-                                 float* dbeta_f, size_t pixels, int32_t c, size_t pixels_per_image, int32_t eval_mode,
-                                 double count, void* stream) {
-  VSPW_REQUIRE(dout && invstd && dy, "vspw_bn_bwd_apply: null pointer");
+extern "C" int vspw_bn_bwd_apply(const float* dout, const float* out, const uint16_t* out_hi, const float* y,
+                                 const float* mean, const float* invstd, const float* gamma, const float* chan_scale,
+                                 int32_t relu, const double* dbeta, const double* dgamma, float* dy, uint16_t* dy_hi,
+                                 uint16_t* dy_lo, float* dres, float* dgamma_f, float* dbeta_f, size_t pixels, int32_t c,
+                                 size_t pixels_per_image, int32_t eval_mode, double count, void* stream) {
+  VSPW_REQUIRE(dout && invstd && (dy || dy_hi), "vspw_bn_bwd_apply: null pointer");
+  VSPW_REQUIRE(!relu || out || out_hi, "vspw_bn_bwd_apply: relu mask needs the forward output (fp32 or bf16 hi plane)");
+  VSPW_REQUIRE(!dy_lo || dy_hi, "vspw_bn_bwd_apply: dy_lo without dy_hi");
   VSPW_REQUIRE(count >= 1.0, "vspw_bn_bwd_apply: count must be >= 1");
   VSPW_REQUIRE(eval_mode || (y && mean && dbeta && dgamma), "vspw_bn_bwd_apply: train mode needs y/mean/sums");
   VSPW_REQUIRE(c > 0 && c % 4 == 0, "vspw_bn_bwd_apply: channels must be a multiple of 4 (got %d)", c);
   size_t total4 = pixels * (size_t)(c / 4);
   if (total4 == 0) return VSPW_OK;
   bn_bwd_apply_kernel<<<grid_for(total4, 256), 256, 0, as_stream(stream)>>>(
-      (const float4*)dout, (const float4*)out, (const float4*)y, (const float4*)mean, (const float4*)invstd,
-      (const float4*)gamma, (const float4*)chan_scale, relu, dbeta, dgamma, (float4*)dy, (float4*)dres, total4, c / 4,
-      pixels_per_image, 1.0 / count, eval_mode);
+      (const float4*)dout, (const float4*)out, (const uint2*)out_hi, (const float4*)y, (const float4*)mean,
+      (const float4*)invstd, (const float4*)gamma, (const float4*)chan_scale, relu, dbeta, dgamma, (float4*)dy,
+      (uint2*)dy_hi, (uint2*)dy_lo, (float4*)dres, total4, c / 4, pixels_per_image, 1.0 / count, eval_mode);
   int rc = check_launch("vspw_bn_bwd_apply");
   if (rc) return rc;
   if ((dgamma_f || dbeta_f) && dbeta && dgamma) {

@@ -164,6 +164,8 @@ struct ConvTcParams {
   int bw, bh;          // pixel patch, bw*bh == 128
   int tiles_x, tiles_y, tiles_n;
   int x3;              // 1: hi/lo planes, 3 MMAs per k-step
+  double* ch_sum;      // [Nout] per-channel sum of the outputs (train-mode BN statistics), or null
+  double* ch_sqsum;    // [Nout] per-channel sum of squares
 };
 
 template <int BN, int STAGES>
@@ -171,8 +173,25 @@ struct ConvSmem {
   static constexpr int kATile = BM * BK * 2;  // 16 KB
   static constexpr int kBTile = BN * BK * 2;
   static constexpr int kStage = 2 * kATile + 2 * kBTile;  // hi+lo of A and B
-  static constexpr int kBytes = STAGES * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int kStatBytes = 2 /*buffers*/ * 2 /*sum, sqsum*/ * BN * 4;
+  static constexpr int kBytes = STAGES * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/ + kStatBytes;
 };
+
+// Column sums over a warp's 32 rows: every lane enters with 32 column values v[0..31] of ITS row and leaves with the
+// sum over the 32 lanes of column `lane` in v[0] (recursive halving: 16+8+4+2+1 = 31 shuffles instead of 32*5).
+__device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float keep = upper ? v[i + off] : v[i];
+      const float send = upper ? v[i] : v[i + off];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -187,6 +206,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* stat_s = reinterpret_cast<float*>(smem + STAGES * S::kStage + 256);  // [2 buffers][sum | sqsum][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.N * p.tiles_y * p.tiles_x * p.tiles_n;
@@ -205,6 +225,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
+  if (p.ch_sum) for (int i = threadIdx.x; i < 4 * BN; i += kThreads) stat_s[i] = 0.f;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -306,12 +327,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
             }
             *reinterpret_cast<float4*>(dst + c0 + j) = o;
+            v[j] = __float_as_uint(o.x); v[j + 1] = __float_as_uint(o.y);
+            v[j + 2] = __float_as_uint(o.z); v[j + 3] = __float_as_uint(o.w);
           }
+        }
+        if (p.ch_sum && n0 + c0 < p.Nout) {
+          // fused train-mode BN statistics (replaces a full re-read of the output by vspw_bn_stats): column sums of
+          // this warp's 32 rows by shuffles, the 4 epilogue warps meet in shared memory, one fp64 atomic per channel
+          float a[32], b[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            a[j] = ok ? __uint_as_float(v[j]) : 0.f;
+            b[j] = a[j] * a[j];
+          }
+          const float sa = warp_column_sums(a, lane), sb = warp_column_sums(b, lane);
+          float* buf = stat_s + acc * 2 * BN;
+          atomicAdd(buf + c0 + lane, sa);
+          atomicAdd(buf + BN + c0 + lane, sb);
         }
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (p.ch_sum) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps have added their rows of this tile
+        const int col = (warp - 2) * 32 + lane;         // 128 threads <-> BN = 128 columns
+        float* buf = stat_s + acc * 2 * BN;
+        if (col < BN && n0 + col < p.Nout) {
+          atomicAdd(p.ch_sum + n0 + col, (double)buf[col]);
+          atomicAdd(p.ch_sqsum + n0 + col, (double)buf[BN + col]);
+        }
+        if (col < BN) { buf[col] = 0.f; buf[BN + col] = 0.f; }
+        // buffer `acc` is next written two tiles later, after the bar.sync of the tile in between
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -395,12 +443,21 @@ constexpr int kBN = 128, kStages = 3;
 
 int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int taps, int off0, int step, const uint16_t* a_hi,
                    const uint16_t* a_lo, const uint16_t* b_hi, const uint16_t* b_lo, const float* bias, float* out, int x3,
-                   cudaStream_t stream) {
+                   double* ch_sum, double* ch_sqsum, cudaStream_t stream) {
   VSPW_REQUIRE(a_hi && b_hi && out, "%s: null pointer", who);
   VSPW_REQUIRE(!x3 || (a_lo && b_lo), "%s: BF16X3 needs the lo planes", who);
+  if (taps == 1) {
+    // 1x1: no halo, so the N*H*W pixels are one flat row of a plain GEMM -> 128-pixel tiles with no patch padding
+    // (a 60x107 map covered by 16x8 patches wastes 10.4 % of every tile; the flat view wastes < 0.1 %)
+    const long long pix = (long long)n * h * w;
+    VSPW_REQUIRE(pix < (1ll << 31), "%s: too many pixels", who);
+    w = (int)pix; h = 1; n = 1;
+  }
   ConvTcParams p;
   p.out = out; p.bias = bias; p.N = n; p.H = h; p.W = w; p.C = c; p.Nout = nout;
   p.taps_h = taps; p.taps_w = taps; p.off0 = off0; p.step = step; p.x3 = x3;
+  VSPW_REQUIRE((ch_sum == nullptr) == (ch_sqsum == nullptr), "%s: ch_sum and ch_sqsum go together", who);
+  p.ch_sum = ch_sum; p.ch_sqsum = ch_sqsum;
   pick_patch(h, w, p.bw, p.bh);
   p.tiles_x = (w + p.bw - 1) / p.bw;
   p.tiles_y = (h + p.bh - 1) / p.bh;
@@ -585,11 +642,12 @@ extern "C" int vspw_conv2d_tc_supported(const vspw_conv_desc* d) { return geomet
 extern "C" int vspw_conv2d_wgrad_tc_supported(const vspw_conv_desc* d) { return geometry_ok(d) ? 1 : 0; }
 
 extern "C" int vspw_conv2d_fwd_tc(const vspw_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi,
-                                  const uint16_t* w_lo, const float* bias, float* y, void* stream) {
+                                  const uint16_t* w_lo, const float* bias, float* y, double* ch_sum, double* ch_sqsum,
+                                  void* stream) {
   VSPW_REQUIRE(geometry_ok(d), "vspw_conv2d_fwd_tc: geometry not supported by the tcgen05 path");
   VSPW_REQUIRE(d->precision == VSPW_PREC_BF16X3 || d->precision == VSPW_PREC_BF16, "vspw_conv2d_fwd_tc: precision must be BF16X3 or BF16");
   return launch_conv_tc("vspw_conv2d_fwd_tc", d->n, d->h, d->w, d->cin, d->cout, d->kh, -d->pad, d->dil, x_hi, x_lo, w_hi, w_lo,
-                        bias, y, d->precision == VSPW_PREC_BF16X3, as_stream(stream));
+                        bias, y, d->precision == VSPW_PREC_BF16X3, ch_sum, ch_sqsum, as_stream(stream));
 }
 
 extern "C" int vspw_conv2d_dgrad_tc(const vspw_conv_desc* d, const uint16_t* dy_hi, const uint16_t* dy_lo, const uint16_t* wt_hi,
@@ -598,7 +656,7 @@ extern "C" int vspw_conv2d_dgrad_tc(const vspw_conv_desc* d, const uint16_t* dy_
   VSPW_REQUIRE(d->precision == VSPW_PREC_BF16X3 || d->precision == VSPW_PREC_BF16, "vspw_conv2d_dgrad_tc: precision must be BF16X3 or BF16");
   // dx[p][ci] = sum_{tap,co} dy[p + pad - tap*dil][co] * Wt[ci][tap][co]
   return launch_conv_tc("vspw_conv2d_dgrad_tc", d->n, d->h, d->w, d->cout, d->cin, d->kh, d->pad, -d->dil, dy_hi, dy_lo, wt_hi,
-                        wt_lo, nullptr, dx, d->precision == VSPW_PREC_BF16X3, as_stream(stream));
+                        wt_lo, nullptr, dx, d->precision == VSPW_PREC_BF16X3, nullptr, nullptr, as_stream(stream));
 }
 
 extern "C" int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* dy_hi,
@@ -612,14 +670,17 @@ extern "C" int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_h
   WgradTcParams p;
   p.dw = dw_ohwi; p.N = d->n; p.H = d->h; p.W = d->w; p.Cin = d->cin; p.Cout = d->cout;
   p.taps_w = d->kw; p.off0 = -d->pad; p.step = d->dil; p.x3 = x3;
-  pick_patch64(d->h, d->w, p.bw, p.bh);
-  p.tiles_x = (d->w + p.bw - 1) / p.bw;
-  p.tiles_y = (d->h + p.bh - 1) / p.bh;
+  if (d->kh == 1) {  // 1x1: flat pixel axis, no patch padding (see launch_conv_tc)
+    p.N = 1; p.H = 1; p.W = d->n * d->h * d->w;
+  }
+  pick_patch64(p.H, p.W, p.bw, p.bh);
+  p.tiles_x = (p.W + p.bw - 1) / p.bw;
+  p.tiles_y = (p.H + p.bh - 1) / p.bh;
   p.tiles_co = (d->cout + 127) / 128;
   p.tiles_ci = (d->cin + 127) / 128;
   const int taps = d->kh * d->kw;
   const long long tiles = (long long)p.tiles_co * p.tiles_ci * taps;
-  const int total_patches = d->n * p.tiles_y * p.tiles_x;
+  const int total_patches = p.N * p.tiles_y * p.tiles_x;
   int splits = (int)((2 * kNumSMs) / tiles);  // ~2 CTAs per SM's worth of work items; one resident at a time
   if (splits < 1) splits = 1;
   if (splits > total_patches) splits = total_patches;
@@ -629,10 +690,10 @@ extern "C" int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_h
   if (e != cudaSuccess) { set_error("%s: memset: %s", who, cudaGetErrorString(e)); return VSPW_ERR_CUDA; }
   CUtensorMap mdy_hi, mdy_lo, mx_hi, mx_lo;
   int rc;
-  if ((rc = make_act_map(&mdy_hi, dy_hi, d->n, d->h, d->w, d->cout, p.bw, p.bh, who))) return rc;
-  if ((rc = make_act_map(&mdy_lo, x3 ? dy_lo : dy_hi, d->n, d->h, d->w, d->cout, p.bw, p.bh, who))) return rc;
-  if ((rc = make_act_map(&mx_hi, x_hi, d->n, d->h, d->w, d->cin, p.bw, p.bh, who))) return rc;
-  if ((rc = make_act_map(&mx_lo, x3 ? x_lo : x_hi, d->n, d->h, d->w, d->cin, p.bw, p.bh, who))) return rc;
+  if ((rc = make_act_map(&mdy_hi, dy_hi, p.N, p.H, p.W, d->cout, p.bw, p.bh, who))) return rc;
+  if ((rc = make_act_map(&mdy_lo, x3 ? dy_lo : dy_hi, p.N, p.H, p.W, d->cout, p.bw, p.bh, who))) return rc;
+  if ((rc = make_act_map(&mx_hi, x_hi, p.N, p.H, p.W, d->cin, p.bw, p.bh, who))) return rc;
+  if ((rc = make_act_map(&mx_lo, x3 ? x_lo : x_hi, p.N, p.H, p.W, d->cin, p.bw, p.bh, who))) return rc;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] { attr_err = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM); });

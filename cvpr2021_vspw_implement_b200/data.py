@@ -48,7 +48,9 @@ class SyntheticClipTest(Dataset):
     def __init__(self, args, video="synthetic_000", frames=12, height=480, width=854, seed=304):
         self.t, self.k = int(args.clip_num), int(args.num_class)
         gen = torch.Generator().manual_seed(seed + sum(map(ord, video)))
-        self.frames = [synthetic_frame(gen, height, width, self.k) for _ in range(frames)]
+        base, lab = synthetic_frame(gen, height, width, self.k)
+        # a static scene seen through per-frame noise: labels are constant over the video so the VC metric is defined
+        self.frames = [(base + 0.1 * torch.randn(3, height, width, generator=gen), lab) for _ in range(frames)]
         self.video = video
         self.offsets = [int(x) for x in str(args.dilation2).split(",")] if self.t > 1 else []
         assert len(self.offsets) + 1 == self.t  # dataset2.py:357

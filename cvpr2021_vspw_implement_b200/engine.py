@@ -135,17 +135,21 @@ def _require_cuda(t, what):
 class Var:
     """An activation (NHWC fp32) with an optional gradient slot and cached bf16 planes."""
 
-    __slots__ = ("data", "grad", "needs_grad", "planes")
+    __slots__ = ("data", "grad", "needs_grad", "planes", "stats", "grad_planes", "wants_grad_planes", "wants_grad_fp32")
 
     def __init__(self, data, needs_grad=False):
-        self.data = data
+        self.data = data          # fp32 NHWC tensor; None when only the bf16 planes were materialised
         self.grad = None
         self.needs_grad = needs_grad
         self.planes = None
+        self.grad_planes = None         # bf16 (hi, lo) planes of the COMPLETE gradient, written by the consumer's backward
+        self.wants_grad_planes = False  # set by a tcgen05 conv on its output: its backward reads planes
+        self.wants_grad_fp32 = True     # ... and whether it needs the fp32 gradient as well (bias gradient)
+        self.stats = None  # (2, C) fp64 per-channel [sum, sum of squares] when the producing conv's epilogue computed them
 
     @property
     def shape(self):
-        return self.data.shape
+        return self.data.shape if self.data is not None else self.planes[0].shape
 
     def add_grad(self, g):
         """Accumulate ``g`` (takes ownership when the slot is empty)."""
@@ -298,11 +302,13 @@ def _weight_planes(wv, key, t):
 
 
 # ------------------------------------------------------------------------------------------------
-def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1):
-    """nn.Conv2d forward + recorded dgrad/wgrad (reference: models/resnet.py:61-66 etc.)."""
+def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1, want_stats=False):
+    """nn.Conv2d forward + recorded dgrad/wgrad (reference: models/resnet.py:61-66 etc.).
+    want_stats: the output feeds a train-mode BN; the tcgen05 epilogue then also emits the per-channel sums."""
     wv = tape.param(weight)
     bv = tape.param(bias)
     n, h, w, cin = x.shape
+    dev = x.data.device if x.data is not None else x.planes[0].device
     co, ci, kh, kw = wv.data.shape
     if ci != cin:
         raise VspwError(f"conv2d: input has {cin} channels, weight expects {ci}")
@@ -313,31 +319,41 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1):
     use_tc = prec != PREC_FP32 and lib.tc_supported(desc)
     if not use_tc:
         desc.precision = PREC_FP32
-    y = torch.empty((n, ho, wo, co), device=x.data.device, dtype=torch.float32)
+    if not use_tc and x.data is None:
+        raise VspwError("conv2d: the input was materialised as bf16 planes only but this geometry runs on the fp32 arm")
+    y = torch.empty((n, ho, wo, co), device=dev, dtype=torch.float32)
     w_ohwi = _weight_ohwi(tape, wv)
     flops = 2.0 * n * ho * wo * co * kh * kw * ci
+    stats = None
     if use_tc:
         xh, xl = _var_planes(x)
         wh, wl = _weight_planes(wv, "ohwi", w_ohwi)
+        if want_stats:
+            stats = torch.zeros((2, co), device=y.device, dtype=torch.float64)
         with _ConvTimer(flops, True):
-            lib.call("vspw_conv2d_fwd_tc", ctypes.byref(desc), _p(xh), _p(xl), _p(wh), _p(wl), _p(bv.data if bv else None), _p(y), _stream())
+            lib.call("vspw_conv2d_fwd_tc", ctypes.byref(desc), _p(xh), _p(xl), _p(wh), _p(wl), _p(bv.data if bv else None), _p(y),
+                     _p(stats[0]) if stats is not None else None, _p(stats[1]) if stats is not None else None, _stream())
     else:
         with _ConvTimer(flops, False):
             lib.call("vspw_conv2d_fwd", ctypes.byref(desc), _p(x.data), _p(w_ohwi), _p(bv.data if bv else None), _p(y), _stream())
     out = Var(y, needs_grad=tape.grad_enabled and (x.needs_grad or wv.needs_grad))
+    out.stats = stats
+    wgrad_tc_ok = use_tc and lib.wgrad_tc_supported(desc)
+    if use_tc:
+        out.wants_grad_planes = True
+        out.wants_grad_fp32 = (bv is not None and bv.needs_grad) or (wv.needs_grad and not wgrad_tc_ok)
 
     def backward():
-        dy = out.grad
-        out.grad = None
-        if dy is None:
+        dy, dyp = out.grad, out.grad_planes
+        out.grad = out.grad_planes = None
+        if dy is None and dyp is None:
             return
         st = _stream()
-        dyp = None
-        wgrad_tc = use_tc and wv.needs_grad and lib.wgrad_tc_supported(desc)
-        if use_tc and (x.needs_grad or wgrad_tc):
+        wgrad_tc = wgrad_tc_ok and wv.needs_grad
+        if dyp is None and use_tc and (x.needs_grad or wgrad_tc):
             dyp = _planes_of(dy)
         if wv.needs_grad:
-            dw = torch.empty((co, kh, kw, ci), device=dy.device, dtype=torch.float32)
+            dw = torch.empty((co, kh, kw, ci), device=dev, dtype=torch.float32)
             if wgrad_tc:
                 xh, xl = _var_planes(x)
                 with _ConvTimer(flops, True):
@@ -348,15 +364,15 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1):
             if kh == 1 and kw == 1:
                 wv.add_grad(dw.view(co, ci, 1, 1))
             else:
-                dw_oihw = torch.empty((co, ci, kh, kw), device=dy.device, dtype=torch.float32)
+                dw_oihw = torch.empty((co, ci, kh, kw), device=dev, dtype=torch.float32)
                 permute4d(dw, dw_oihw, (co, kh, kw, ci), (0, 3, 1, 2))
                 wv.add_grad(dw_oihw)
         if bv is not None and bv.needs_grad:
-            sums = torch.zeros(co, device=dy.device, dtype=torch.float64)
+            sums = torch.zeros(co, device=dev, dtype=torch.float64)
             lib.call("vspw_bn_stats", _p(dy), n * ho * wo, co, _p(sums), None, st)
             bv.add_grad(_double_to_float(sums))
         if x.needs_grad:
-            dx = torch.empty((n, h, w, cin), device=dy.device, dtype=torch.float32)
+            dx = torch.empty((n, h, w, cin), device=dev, dtype=torch.float32)
             w_t = _weight_ihwo(tape, wv)
             if use_tc:
                 th, tl = _weight_planes(wv, "ihwo", w_t)
@@ -371,6 +387,19 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1):
     return out
 
 
+def conv_will_use_tc(x_shape, weight_shape, stride, pad, dil):
+    """True when conv2d would take the tcgen05 path for an NHWC input of `x_shape` in the current precision mode
+    (lets a producer skip materialising the fp32 copy of an activation that only tensor-core convs read)."""
+    prec = _PRECISION[_state["precision"]]
+    if prec == PREC_FP32:
+        return False
+    n, h, w, cin = x_shape
+    co, ci, kh, kw = weight_shape
+    ho = (h + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+    wo = (w + 2 * pad - dil * (kw - 1) - 1) // stride + 1
+    return bool(lib.tc_supported(ConvDesc(n, h, w, cin, co, kh, kw, stride, pad, dil, ho, wo, prec)))
+
+
 def _double_to_float(d):
     """fp64 -> fp32 of a tiny per-channel vector (no ATen compute kernel in the path)."""
     f = torch.empty(d.shape, device=d.device, dtype=torch.float32)
@@ -378,11 +407,13 @@ def _double_to_float(d):
     return f
 
 
-def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, training=None):
+def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, training=None, fp32_out=True):
     """BN (train: batch stats, eval: running stats) [+ residual] [+ ReLU] [* Dropout2d mask].
 
     Reference: SynchronizedBatchNorm2d.forward (sync_batchnorm/batchnorm.py:68-73) followed by
     nn.ReLU / `out += residual` (resnet.py:72-92) / nn.Dropout2d (clip_psp.py:39).
+    fp32_out=False: the caller guarantees every consumer is a tcgen05 conv, so only the bf16 planes are written
+    (and the backward ReLU mask is read from the hi plane); ignored when no planes are produced.
     """
     n, h, w, c = y.shape
     pixels = n * h * w
@@ -396,8 +427,10 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
     if training:
         if pixels <= 1:
             raise ValueError(f"Expected more than 1 value per channel when training, got input size {[n, c, h, w]}")
-        sums = torch.zeros((2, c), device=dev, dtype=torch.float64)
-        lib.call("vspw_bn_stats", _p(y.data), pixels, c, _p(sums[0]), _p(sums[1]), st)
+        sums = y.stats
+        if sums is None:
+            sums = torch.zeros((2, c), device=dev, dtype=torch.float64)
+            lib.call("vspw_bn_stats", _p(y.data), pixels, c, _p(sums[0]), _p(sums[1]), st)
         world = _syncbn_world()
         if world > 1:
             _allreduce_sums(sums)
@@ -411,12 +444,12 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
         invstd = torch.empty(c, device=dev, dtype=torch.float32)
         lib.call("vspw_bn_fold_eval", _p(gv.data), _p(bv.data), _p(bn.running_mean), _p(bn.running_var), float(bn.eps),
                  _p(scale), _p(shift), _p(invstd), c, st)
-    o = torch.empty_like(y.data)
     want_planes = _state["precision"] != "fp32" and c % 64 == 0
     hi = lo = None
     if want_planes:
-        hi = torch.empty(o.shape, device=dev, dtype=torch.bfloat16)
-        lo = torch.empty(o.shape, device=dev, dtype=torch.bfloat16) if _state["precision"] == "bf16x3" else None
+        hi = torch.empty(y.shape, device=dev, dtype=torch.bfloat16)
+        lo = torch.empty(y.shape, device=dev, dtype=torch.bfloat16) if _state["precision"] == "bf16x3" else None
+    o = torch.empty_like(y.data) if (fp32_out or not want_planes) else None
     center = mean if training else bn.running_mean
     lib.call("vspw_bn_act_fwd", _p(y.data), _p(scale), _p(shift), _p(center), _p(bv.data),
              _p(residual.data if residual is not None else None),
@@ -425,6 +458,7 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
     out = Var(o, needs_grad=needs)
     if want_planes:
         out.planes = (hi, lo)
+    mask_hi = hi if o is None else None  # ReLU mask source in the backward: fp32 output, else its bf16 hi plane
 
     def backward():
         dout = out.grad
@@ -432,19 +466,26 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
         if dout is None:
             return
         st = _stream()
-        dy = torch.empty_like(dout)
+        # the consumer of dy is the producing conv's dgrad/wgrad: tcgen05 kernels read bf16 planes, so write those
+        # here instead of an fp32 dy plus a separate split pass (fp32 dy only if someone else needs it)
+        dy = dy_hi = dy_lo = None
+        if y.wants_grad_planes and y.grad is None:
+            dy_hi = torch.empty(dout.shape, device=dev, dtype=torch.bfloat16)
+            dy_lo = torch.empty(dout.shape, device=dev, dtype=torch.bfloat16) if _state["precision"] == "bf16x3" else None
+        if dy_hi is None or y.wants_grad_fp32:
+            dy = torch.empty_like(dout)
         dres = torch.empty_like(dout) if (residual is not None and residual.needs_grad) else None
         if training:
             dsum = torch.zeros((2, c), device=dev, dtype=torch.float64)
-            lib.call("vspw_bn_bwd_reduce", _p(dout), _p(o), _p(y.data), _p(mean), _p(invstd), _p(chan_scale), 1 if relu else 0,
-                     pixels, c, h * w, _p(dsum[0]), _p(dsum[1]), st)
+            lib.call("vspw_bn_bwd_reduce", _p(dout), _p(o), _p(mask_hi), _p(y.data), _p(mean), _p(invstd), _p(chan_scale),
+                     1 if relu else 0, pixels, c, h * w, _p(dsum[0]), _p(dsum[1]), st)
             if world > 1:
                 _allreduce_sums(dsum)
             dgam = torch.empty(c, device=dev, dtype=torch.float32)
             dbet = torch.empty(c, device=dev, dtype=torch.float32)
-            lib.call("vspw_bn_bwd_apply", _p(dout), _p(o), _p(y.data), _p(mean), _p(invstd), _p(gv.data), _p(chan_scale),
-                     1 if relu else 0, _p(dsum[0]), _p(dsum[1]), _p(dy), _p(dres), _p(dgam), _p(dbet), pixels, c, h * w, 0,
-                     float(pixels * world), st)
+            lib.call("vspw_bn_bwd_apply", _p(dout), _p(o), _p(mask_hi), _p(y.data), _p(mean), _p(invstd), _p(gv.data),
+                     _p(chan_scale), 1 if relu else 0, _p(dsum[0]), _p(dsum[1]), _p(dy), _p(dy_hi), _p(dy_lo), _p(dres), _p(dgam),
+                     _p(dbet), pixels, c, h * w, 0, float(pixels * world), st)
             if gv.needs_grad:
                 gv.add_grad(dgam)
             if bv.needs_grad:
@@ -455,20 +496,23 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
             dsum = dgam = dbet = None
             if gv.needs_grad or bv.needs_grad:
                 dsum = torch.zeros((2, c), device=dev, dtype=torch.float64)
-                lib.call("vspw_bn_bwd_reduce", _p(dout), _p(o), _p(y.data), _p(bn.running_mean), _p(invstd), _p(chan_scale),
-                         1 if relu else 0, pixels, c, h * w, _p(dsum[0]), _p(dsum[1]), st)
+                lib.call("vspw_bn_bwd_reduce", _p(dout), _p(o), _p(mask_hi), _p(y.data), _p(bn.running_mean), _p(invstd),
+                         _p(chan_scale), 1 if relu else 0, pixels, c, h * w, _p(dsum[0]), _p(dsum[1]), st)
                 dgam = torch.empty(c, device=dev, dtype=torch.float32)
                 dbet = torch.empty(c, device=dev, dtype=torch.float32)
-            lib.call("vspw_bn_bwd_apply", _p(dout), _p(o), None, None, _p(scale), None, _p(chan_scale), 1 if relu else 0,
-                     _p(dsum[0]) if dsum is not None else None, _p(dsum[1]) if dsum is not None else None, _p(dy), _p(dres),
-                     _p(dgam), _p(dbet), pixels, c, h * w, 1, float(pixels), st)
+            lib.call("vspw_bn_bwd_apply", _p(dout), _p(o), _p(mask_hi), None, None, _p(scale), None, _p(chan_scale),
+                     1 if relu else 0, _p(dsum[0]) if dsum is not None else None, _p(dsum[1]) if dsum is not None else None,
+                     _p(dy), _p(dy_hi), _p(dy_lo), _p(dres), _p(dgam), _p(dbet), pixels, c, h * w, 1, float(pixels), st)
             if dsum is not None:
                 if gv.needs_grad:
                     gv.add_grad(dgam)
                 if bv.needs_grad:
                     bv.add_grad(dbet)
         if y.needs_grad:
-            y.add_grad(dy)
+            if dy_hi is not None:
+                y.grad_planes = (dy_hi, dy_lo)
+            if dy is not None:
+                y.add_grad(dy)
         if dres is not None:
             residual.add_grad(dres)
 

@@ -66,11 +66,11 @@ class ClipOCRNet(nn.Module):
         x = E.Var(E.input_from_frames(frames))
         maps = self.encoder.graph(tape, x)
         # dsn head on layer3 output of all N frames (reference :117)
-        y = conv_op(tape, self.dsn_head[0], maps[-2])
+        y = conv_op(tape, self.dsn_head[0], maps[-2], self.dsn_head[1])
         mask = E.dropout2d_mask(self.dsn_head[3].p, y.shape[0], y.shape[3], y.data.device, training and self.dsn_head[3].training)
         d = E.batchnorm_act(tape, y, self.dsn_head[1], relu=True, chan_scale=mask, training=training)
         x_dsn = conv_op(tape, self.dsn_head[4], d)
-        feats = E.batchnorm_act(tape, conv_op(tape, self.conv_3x3[0], maps[-1]), self.conv_3x3[1], relu=True,
+        feats = E.batchnorm_act(tape, conv_op(tape, self.conv_3x3[0], maps[-1], self.conv_3x3[1]), self.conv_3x3[1], relu=True,
                                 training=training)
         if memory is not None:
             context = self.spatial_context_head.graph(tape, feats, x_dsn, t_frames - 1, memory, self.args.memory_num)

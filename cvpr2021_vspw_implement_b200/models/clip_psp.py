@@ -31,10 +31,10 @@ class PPM_conv(nn.Module):
 
     def graph(self, tape, x, pooled, training):
         """x: current-frame layer4 map (n,h,w,2048); pooled: per-scale temporal means (n,s,s,2048)."""
-        pyr = [E.batchnorm_act(tape, conv_op(tape, br[0], p), br[1], relu=True, training=training)
+        pyr = [E.batchnorm_act(tape, conv_op(tape, br[0], p, br[1]), br[1], relu=True, training=training)
                for br, p in zip(self.ppm, pooled)]
         cat = E.ppm_concat(tape, x, pyr)
-        y = conv_op(tape, self.conv_last_[0], cat)
+        y = conv_op(tape, self.conv_last_[0], cat, self.conv_last_[1])
         mask = E.dropout2d_mask(self.conv_last_[3].p, y.shape[0], y.shape[3], y.data.device, training and self.conv_last_[3].training)
         z = E.batchnorm_act(tape, y, self.conv_last_[1], relu=True, chan_scale=mask, training=training)
         return conv_op(tape, self.conv_last_[4], z)
@@ -141,7 +141,7 @@ class Clip_PSP(nn.Module):
                 for t, lab in enumerate(clip_labels):
                     all_lab[t * n:(t + 1) * n].copy_(lab)  # D2D copy (torch.cat in the reference, :204)
                 conv4 = maps[-2]
-                y = conv_op(tape, self.deepsup[0], conv4)
+                y = conv_op(tape, self.deepsup[0], conv4, self.deepsup[1])
                 mask = E.dropout2d_mask(self.deepsup[3].p, y.shape[0], y.shape[3], y.data.device, training and self.deepsup[3].training)
                 d = E.batchnorm_act(tape, y, self.deepsup[1], relu=True, chan_scale=mask, training=training)
                 lds = conv_op(tape, self.deepsup[4], d)

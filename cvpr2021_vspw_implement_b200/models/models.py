@@ -170,16 +170,16 @@ class PPMDeepsup(nn.Module):
         pooled = E.tcb_pool(tape, conv5, 1, n, self.pool_scales)
         pyr = []
         for branch, p in zip(self.ppm, pooled):
-            pyr.append(E.batchnorm_act(tape, conv_op(tape, branch[1], p), branch[2], relu=True, training=training))
+            pyr.append(E.batchnorm_act(tape, conv_op(tape, branch[1], p, branch[2]), branch[2], relu=True, training=training))
         cat = E.ppm_concat(tape, conv5, pyr)
-        y = conv_op(tape, self.conv_last_[0], cat)
+        y = conv_op(tape, self.conv_last_[0], cat, self.conv_last_[1])
         mask = E.dropout2d_mask(self.conv_last_[3].p, n, y.shape[3], y.data.device, training and self.conv_last_[3].training)
         x = E.batchnorm_act(tape, y, self.conv_last_[1], relu=True, chan_scale=mask, training=training)
         logits = conv_op(tape, self.conv_last_[4], x)
         if not want_deepsup:
             return logits, None
         conv4 = conv_out[-2]
-        y = conv_op(tape, self.cbr_deepsup[0], conv4)
+        y = conv_op(tape, self.cbr_deepsup[0], conv4, self.cbr_deepsup[1])
         mask = E.dropout2d_mask(self.dropout_deepsup.p, n, y.shape[3], y.data.device, training and self.dropout_deepsup.training)
         d = E.batchnorm_act(tape, y, self.cbr_deepsup[1], relu=True, chan_scale=mask, training=training)
         return logits, conv_op(tape, self.conv_last_deepsup_, d)

@@ -58,7 +58,7 @@ def _cbr(cin, cout):
 def _run_cbr_chain(tape, seq, x, training):
     mods = list(seq)
     for i in range(0, len(mods), 3):
-        x = E.batchnorm_act(tape, conv_op(tape, mods[i], x), mods[i + 1], relu=True, training=training)
+        x = E.batchnorm_act(tape, conv_op(tape, mods[i], x, mods[i + 1]), mods[i + 1], relu=True, training=training)
     return x
 
 
@@ -101,6 +101,6 @@ class SpatialOCR_Module(nn.Module):
     def graph(self, tape, feats, proxy_feats, training):
         context = self.object_context_block.graph(tape, feats, proxy_feats, training)
         cat = E.concat_channels(tape, [context, feats])
-        y = conv_op(tape, self.conv_bn_dropout[0], cat)
+        y = conv_op(tape, self.conv_bn_dropout[0], cat, self.conv_bn_dropout[1])
         mask = E.dropout2d_mask(self.conv_bn_dropout[3].p, y.shape[0], y.shape[3], y.data.device, training and self.conv_bn_dropout[3].training)
         return E.batchnorm_act(tape, y, self.conv_bn_dropout[1], relu=True, chan_scale=mask, training=training)

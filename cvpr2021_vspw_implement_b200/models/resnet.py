@@ -19,14 +19,21 @@ def _conv(cin, cout, k, stride=1):
     return nn.Conv2d(cin, cout, kernel_size=k, stride=stride, padding=(k - 1) // 2, bias=False)
 
 
-def conv_op(tape, conv, x):
+def conv_op(tape, conv, x, bn=None):
     """Run an nn.Conv2d container through the engine, honouring stride/padding/dilation edits
-    made by ResnetDilated._nostride_dilate (reference models/models.py:737-750)."""
+    made by ResnetDilated._nostride_dilate (reference models/models.py:737-750).  `bn`: the BatchNorm module the
+    output feeds; in train mode its statistics are taken in the conv epilogue."""
     if conv.stride[0] != conv.stride[1] or conv.padding[0] != conv.padding[1] or conv.dilation[0] != conv.dilation[1]:
         raise NotImplementedError("anisotropic conv geometry is not on the VSPW hot path")
     if conv.groups != 1:
         raise NotImplementedError("grouped convolutions are not on the VSPW hot path")
-    return E.conv2d(tape, x, conv.weight, conv.bias, conv.stride[0], conv.padding[0], conv.dilation[0])
+    return E.conv2d(tape, x, conv.weight, conv.bias, conv.stride[0], conv.padding[0], conv.dilation[0],
+                    want_stats=bn is not None and bn.training)
+
+
+def _planes_only_ok(conv, x_shape):
+    """The activation feeding `conv` can skip its fp32 copy when that conv is its only reader and runs on tcgen05."""
+    return E.conv_will_use_tc(tuple(x_shape), tuple(conv.weight.shape), conv.stride[0], conv.padding[0], conv.dilation[0])
 
 
 class BasicBlock(nn.Module):
@@ -43,11 +50,12 @@ class BasicBlock(nn.Module):
         self.stride = stride
 
     def graph(self, tape, x):
-        out = E.batchnorm_act(tape, conv_op(tape, self.conv1, x), self.bn1, relu=True)
-        y2 = conv_op(tape, self.conv2, out)
+        y1 = conv_op(tape, self.conv1, x, self.bn1)
+        out = E.batchnorm_act(tape, y1, self.bn1, relu=True, fp32_out=not _planes_only_ok(self.conv2, y1.shape))
+        y2 = conv_op(tape, self.conv2, out, self.bn2)
         res = x
         if self.downsample is not None:
-            res = E.batchnorm_act(tape, conv_op(tape, self.downsample[0], x), self.downsample[1], relu=False)
+            res = E.batchnorm_act(tape, conv_op(tape, self.downsample[0], x, self.downsample[1]), self.downsample[1], relu=False)
         return E.batchnorm_act(tape, y2, self.bn2, relu=True, residual=res)
 
 
@@ -67,12 +75,15 @@ class Bottleneck(nn.Module):
         self.stride = stride
 
     def graph(self, tape, x):
-        out = E.batchnorm_act(tape, conv_op(tape, self.conv1, x), self.bn1, relu=True)
-        out = E.batchnorm_act(tape, conv_op(tape, self.conv2, out), self.bn2, relu=True)
-        y3 = conv_op(tape, self.conv3, out)
+        # the outputs of bn1 and bn2 are read by the next conv only: bf16 planes suffice when that conv is a tcgen05 one
+        y1 = conv_op(tape, self.conv1, x, self.bn1)
+        out = E.batchnorm_act(tape, y1, self.bn1, relu=True, fp32_out=not _planes_only_ok(self.conv2, y1.shape))
+        y2 = conv_op(tape, self.conv2, out, self.bn2)
+        out = E.batchnorm_act(tape, y2, self.bn2, relu=True, fp32_out=not _planes_only_ok(self.conv3, y2.shape))
+        y3 = conv_op(tape, self.conv3, out, self.bn3)
         res = x
         if self.downsample is not None:
-            res = E.batchnorm_act(tape, conv_op(tape, self.downsample[0], x), self.downsample[1], relu=False)
+            res = E.batchnorm_act(tape, conv_op(tape, self.downsample[0], x, self.downsample[1]), self.downsample[1], relu=False)
         # bn3 -> (+residual) -> relu fused in one pass
         return E.batchnorm_act(tape, y3, self.bn3, relu=True, residual=res)
 
@@ -122,9 +133,9 @@ class ResNet(nn.Module):
 def stem_and_layers_graph(tape, net, x):
     """conv1..conv3 (+BN+ReLU) -> maxpool -> layer1..4; returns the four stage outputs
     (reference ResnetDilated.forward, models/models.py:752-767)."""
-    x = E.batchnorm_act(tape, conv_op(tape, net.conv1, x), net.bn1, relu=True)
-    x = E.batchnorm_act(tape, conv_op(tape, net.conv2, x), net.bn2, relu=True)
-    x = E.batchnorm_act(tape, conv_op(tape, net.conv3, x), net.bn3, relu=True)
+    x = E.batchnorm_act(tape, conv_op(tape, net.conv1, x, net.bn1), net.bn1, relu=True)
+    x = E.batchnorm_act(tape, conv_op(tape, net.conv2, x, net.bn2), net.bn2, relu=True)
+    x = E.batchnorm_act(tape, conv_op(tape, net.conv3, x, net.bn3), net.bn3, relu=True)
     x = E.maxpool3x3s2(tape, x)
     outs = []
     for layer in (net.layer1, net.layer2, net.layer3, net.layer4):

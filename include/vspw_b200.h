@@ -83,9 +83,11 @@ int vspw_conv2d_wgrad(const vspw_conv_desc* d, const float* x, const float* dy, 
                       void* stream);
 /* tcgen05 variants: operands as bf16 hi/lo planes (lo may be null when precision==VSPW_PREC_BF16).
  * fwd and dgrad share one kernel (dgrad = conv of dy with flipped taps and transposed weights). */
+/* ch_sum / ch_sqsum (both nullable, [cout] doubles, ACCUMULATED into: the caller zeroes them): per-channel sum and
+ * sum of squares of y, produced by the epilogue so that train-mode BN needs no second pass over y */
 int vspw_conv2d_fwd_tc(const vspw_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo,
                        const uint16_t* w_hi, const uint16_t* w_lo, const float* bias, float* y,
-                       void* stream);
+                       double* ch_sum, double* ch_sqsum, void* stream);
 int vspw_conv2d_dgrad_tc(const vspw_conv_desc* d, const uint16_t* dy_hi, const uint16_t* dy_lo,
                          const uint16_t* wt_hi, const uint16_t* wt_lo, float* dx, void* stream);
 int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo,
@@ -109,25 +111,28 @@ int vspw_bn_fold_eval(const float* gamma, const float* beta, const float* runnin
                       const float* running_var, float eps, float* scale, float* shift, float* invstd,
                       int32_t c, void* stream);
 /* out = relu?(bn(y) + residual?) * chan_scale?[n][c]; bn(y) = (y-mean)*scale + beta when mean is
- * non-null (centred, F.batch_norm's form), else y*scale + shift; optional bf16 planes of out */
+ * non-null (centred, F.batch_norm's form), else y*scale + shift.  Outputs: fp32 `out` and/or the bf16 (hi, lo)
+ * planes the tcgen05 convs consume; `out` may be null when every consumer reads the planes */
 int vspw_bn_act_fwd(const float* y, const float* scale, const float* shift, const float* mean,
                     const float* beta, const float* residual,
                     const float* chan_scale, int32_t relu, float* out, uint16_t* out_hi,
                     uint16_t* out_lo, size_t pixels, int32_t c, size_t pixels_per_image,
                     void* stream);
-/* backward pass 1: g = dout * chan_scale * [out>0]; dbeta = sum g; dgamma = sum g*xhat */
-int vspw_bn_bwd_reduce(const float* dout, const float* out, const float* y, const float* mean,
-                       const float* invstd, const float* chan_scale, int32_t relu, size_t pixels,
-                       int32_t c, size_t pixels_per_image, double* dbeta, double* dgamma,
+/* backward pass 1: g = dout * chan_scale * [out>0]; dbeta = sum g; dgamma = sum g*xhat.  The ReLU mask is read from
+ * the fp32 output `out` or, when that is null, from its bf16 hi plane `out_hi` */
+int vspw_bn_bwd_reduce(const float* dout, const float* out, const uint16_t* out_hi, const float* y,
+                       const float* mean, const float* invstd, const float* chan_scale, int32_t relu,
+                       size_t pixels, int32_t c, size_t pixels_per_image, double* dbeta, double* dgamma,
                        void* stream);
 /* backward pass 2: dy = gamma*invstd*(g - dbeta/P - xhat*dgamma/P); dres = g (if non-null);
  * also converts the double sums to float dgamma_f/dbeta_f.  eval_mode!=0: dy = g*scale.
  * P = `count` = number of values per channel the statistics were taken over (pixels, or the
- * all-rank total when the sums were all-reduced for SyncBN). */
-int vspw_bn_bwd_apply(const float* dout, const float* out, const float* y, const float* mean,
-                      const float* invstd, const float* gamma, const float* chan_scale, int32_t relu,
-                      const double* dbeta, const double* dgamma, float* dy, float* dres,
-                      float* dgamma_f, float* dbeta_f, size_t pixels, int32_t c,
+ * all-rank total when the sums were all-reduced for SyncBN).  dy goes out as fp32 (`dy`) and/or as the bf16
+ * (hi, lo) planes the tcgen05 dgrad/wgrad kernels read (`dy_hi`, `dy_lo`; any of the three may be null). */
+int vspw_bn_bwd_apply(const float* dout, const float* out, const uint16_t* out_hi, const float* y,
+                      const float* mean, const float* invstd, const float* gamma, const float* chan_scale,
+                      int32_t relu, const double* dbeta, const double* dgamma, float* dy, uint16_t* dy_hi,
+                      uint16_t* dy_lo, float* dres, float* dgamma_f, float* dbeta_f, size_t pixels, int32_t c,
                       size_t pixels_per_image, int32_t eval_mode, double count, void* stream);
 
 /* ---- pooling -------------------------------------------------------------------------- */
