@@ -34,13 +34,14 @@ _SIGNATURES = {
     "vspw_fill": [_c_vp, _c_f, _c_sz, _c_vp],
     "vspw_axpby": [_c_vp, _c_vp, _c_f, _c_f, _c_sz, _c_vp],
     "vspw_split_bf16": [_c_vp, _c_vp, _c_vp, _c_sz, _c_vp],
+    "vspw_zero_insert2_bf16": [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp],
     "vspw_cast_f64_f32": [_c_vp, _c_vp, _c_sz, _c_vp],
     "vspw_copy_channels": [_c_vp, _c_int, _c_int, _c_vp, _c_int, _c_int, _c_int, _c_sz, _c_int, _c_vp],
     "vspw_conv2d_fwd": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
     "vspw_conv2d_dgrad": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp],
     "vspw_conv2d_wgrad": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp],
     "vspw_conv2d_fwd_tc": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
-    "vspw_conv2d_dgrad_tc": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
+    "vspw_conv2d_dgrad_tc": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp],
     "vspw_conv2d_wgrad_tc": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
     "vspw_bn_stats": [_c_vp, _c_sz, _c_int, _c_vp, _c_vp, _c_vp],
     "vspw_bn_finalize_train": [_c_vp, _c_vp, _c_d, _c_vp, _c_vp, _c_f, _c_f, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_vp],

@@ -143,139 +143,246 @@ __device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d)
   return r;
 }
 
-__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float4* __restrict__ y, const float4* __restrict__ scale,
-                                                          const float4* __restrict__ shift,
-                                                          const float4* __restrict__ mean,
-                                                          const float4* __restrict__ beta,
-                                                          const float4* __restrict__ residual,
-                                                          const float4* __restrict__ chan_scale, int relu,
-                                                          float4* __restrict__ out, uint2* __restrict__ out_hi,
-                                                          uint2* __restrict__ out_lo, size_t total4, int c4,
-                                                          size_t pix_per_img) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
-    size_t p = i / c4;
-    int cg = (int)(i - p * c4);
-    float4 v = y[i], sc = __ldg(scale + cg);
-    if (mean) {  // centred form (x-mean)*scale+beta: no cancellation when |mean| >> std
-      float4 m = __ldg(mean + cg), b = beta ? __ldg(beta + cg) : make_float4(0.f, 0.f, 0.f, 0.f);
-      v.x = fmaf(v.x - m.x, sc.x, b.x); v.y = fmaf(v.y - m.y, sc.y, b.y);
-      v.z = fmaf(v.z - m.z, sc.z, b.z); v.w = fmaf(v.w - m.w, sc.w, b.w);
-    } else {
-      float4 sh = __ldg(shift + cg);
-      v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
-      v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+// Streaming layout shared by the element-wise BN kernels: a thread owns ONE group of 4 channels (its per-channel
+// coefficients live in registers for the whole kernel) and walks over pixels, kUnroll independent 16-byte loads in
+// flight per stream.  G = min(C/4, 256) channel groups side by side, 256/G pixel lanes, grid.y = channel slabs.
+constexpr int kEwThreads = 256;
+constexpr int kUnroll = 4;
+
+struct EwMap {
+  int cg;          // channel group of this thread (float4 index inside a pixel), -1 = idle thread
+  size_t p0, dp;   // first pixel and pixel stride
+};
+__device__ __forceinline__ EwMap ew_map(int c4) {
+  const int G = c4 < kEwThreads ? c4 : kEwThreads;
+  const int PL = kEwThreads / G;
+  const int g = threadIdx.x % G, pl = threadIdx.x / G;
+  EwMap m;
+  m.cg = blockIdx.y * G + g;
+  if (pl >= PL || m.cg >= c4) m.cg = -1;
+  m.p0 = (size_t)blockIdx.x * PL + pl;
+  m.dp = (size_t)gridDim.x * PL;
+  return m;
+}
+inline dim3 ew_grid(size_t pixels, int c4) {
+  const int G = c4 < kEwThreads ? c4 : kEwThreads;
+  const int PL = kEwThreads / G;
+  const unsigned gy = (unsigned)((c4 + G - 1) / G);
+  size_t bx = (pixels + (size_t)PL * kUnroll - 1) / ((size_t)PL * kUnroll);
+  size_t cap = (size_t)kNumSMs * 8 / gy;
+  if (cap < 1) cap = 1;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  return dim3((unsigned)bx, gy, 1);
+}
+
+__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ uint2 ld_stream(const uint2* p) { return __ldcs(p); }
+
+__global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(
+    const float4* __restrict__ y, const float4* __restrict__ scale, const float4* __restrict__ shift,
+    const float4* __restrict__ mean, const float4* __restrict__ beta, const float4* __restrict__ residual,
+    const float4* __restrict__ chan_scale, int relu, float4* __restrict__ out, uint2* __restrict__ out_hi,
+    uint2* __restrict__ out_lo, size_t pixels, int c4, size_t pix_per_img) {
+  const EwMap m = ew_map(c4);
+  if (m.cg < 0) return;
+  const float4 sc = __ldg(scale + m.cg);
+  // centred form (x-mean)*scale+beta (no cancellation when |mean| >> std) or folded x*scale+shift
+  const float4 mu = mean ? __ldg(mean + m.cg) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 add = mean ? (beta ? __ldg(beta + m.cg) : make_float4(0.f, 0.f, 0.f, 0.f)) : __ldg(shift + m.cg);
+  for (size_t p = m.p0; p < pixels; p += m.dp * kUnroll) {
+    float4 v[kUnroll], r[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t q = p + u * m.dp;
+      if (q < pixels) {
+        v[u] = ld_stream(y + q * c4 + m.cg);
+        if (residual) r[u] = ld_stream(residual + q * c4 + m.cg);
+      }
     }
-    if (residual) {
-      float4 r = residual[i];
-      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-    }
-    if (relu) {
-      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-    }
-    if (chan_scale) {
-      size_t img = p / pix_per_img;
-      float4 cs = __ldg(chan_scale + img * c4 + cg);
-      v.x *= cs.x; v.y *= cs.y; v.z *= cs.z; v.w *= cs.w;
-    }
-    if (out) out[i] = v;
-    if (out_hi) {
-      uint2 h = pack_bf16x4(v.x, v.y, v.z, v.w);
-      out_hi[i] = h;
-      if (out_lo) {
-        __nv_bfloat162 h0 = *reinterpret_cast<__nv_bfloat162*>(&h.x), h1 = *reinterpret_cast<__nv_bfloat162*>(&h.y);
-        float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-        out_lo[i] = pack_bf16x4(v.x - f0.x, v.y - f0.y, v.z - f1.x, v.w - f1.y);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t q = p + u * m.dp;
+      if (q >= pixels) break;
+      const size_t i = q * c4 + m.cg;
+      float4 t = v[u];
+      t.x = fmaf(t.x - mu.x, sc.x, add.x); t.y = fmaf(t.y - mu.y, sc.y, add.y);
+      t.z = fmaf(t.z - mu.z, sc.z, add.z); t.w = fmaf(t.w - mu.w, sc.w, add.w);
+      if (residual) { t.x += r[u].x; t.y += r[u].y; t.z += r[u].z; t.w += r[u].w; }
+      if (relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+      if (chan_scale) {
+        const float4 cs = __ldg(chan_scale + (q / pix_per_img) * c4 + m.cg);
+        t.x *= cs.x; t.y *= cs.y; t.z *= cs.z; t.w *= cs.w;
+      }
+      if (out) out[i] = t;
+      if (out_hi) {
+        const uint2 h = pack_bf16x4(t.x, t.y, t.z, t.w);
+        out_hi[i] = h;
+        if (out_lo) {
+          const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&h.x), h1 = *reinterpret_cast<const __nv_bfloat162*>(&h.y);
+          const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+          out_lo[i] = pack_bf16x4(t.x - f0.x, t.y - f0.y, t.z - f1.x, t.w - f1.y);
+        }
       }
     }
   }
 }
 
-__device__ __forceinline__ float4 masked_grad(const float4* dout, const float4* out, const uint2* out_hi,
-                                              const float4* chan_scale, int relu, size_t i, size_t p, int cg, int c4,
-                                              size_t pix_per_img) {
-  float4 g = dout[i];
-  if (chan_scale) {
-    size_t img = p / pix_per_img;
-    float4 cs = __ldg(chan_scale + img * c4 + cg);
-    g.x *= cs.x; g.y *= cs.y; g.z *= cs.z; g.w *= cs.w;
-  }
-  if (relu) {
-    // out = relu(.)*chan_scale; a dropped channel (scale 0) already has g == 0
-    if (out) {
-      float4 o = out[i];
-      g.x = o.x != 0.f ? g.x : 0.f; g.y = o.y != 0.f ? g.y : 0.f;
-      g.z = o.z != 0.f ? g.z : 0.f; g.w = o.w != 0.f ? g.w : 0.f;
-    } else {
-      // the bf16 hi plane of the output: bf16_rn(x) is non-zero exactly when the (normal) fp32 x is
-      uint2 h = out_hi[i];
-      g.x = (h.x & 0x7fffu) ? g.x : 0.f; g.y = (h.x & 0x7fff0000u) ? g.y : 0.f;
-      g.z = (h.y & 0x7fffu) ? g.z : 0.f; g.w = (h.y & 0x7fff0000u) ? g.w : 0.f;
-    }
+// g = dout * chan_scale * [out > 0]; the ReLU mask comes from the fp32 output or from its bf16 hi plane
+// (bf16_rn(x) is non-zero exactly when the normal fp32 x is); a dropped channel (scale 0) already has g == 0.
+__device__ __forceinline__ float4 apply_mask(float4 g, bool has_o, float4 o, bool has_h, uint2 h) {
+  if (has_o) {
+    g.x = o.x != 0.f ? g.x : 0.f; g.y = o.y != 0.f ? g.y : 0.f;
+    g.z = o.z != 0.f ? g.z : 0.f; g.w = o.w != 0.f ? g.w : 0.f;
+  } else if (has_h) {
+    g.x = (h.x & 0x7fffu) ? g.x : 0.f; g.y = (h.x & 0x7fff0000u) ? g.y : 0.f;
+    g.z = (h.y & 0x7fffu) ? g.z : 0.f; g.w = (h.y & 0x7fff0000u) ? g.w : 0.f;
   }
   return g;
 }
 
-__global__ void __launch_bounds__(kStatThreads) bn_bwd_reduce_kernel(
-    const float* __restrict__ dout, const float* __restrict__ out, const uint16_t* __restrict__ out_hi,
-    const float* __restrict__ y,
-    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ chan_scale, int relu,
-    size_t pixels, int c, size_t pix_per_img, double* dbeta, double* dgamma) {
-  const int c4 = c >> 2;
-  const float4* d4 = reinterpret_cast<const float4*>(dout);
-  const float4* o4 = reinterpret_cast<const float4*>(out);
-  const uint2* h4 = reinterpret_cast<const uint2*>(out_hi);
-  const float4* y4 = reinterpret_cast<const float4*>(y);
-  const float4* m4 = reinterpret_cast<const float4*>(mean);
-  const float4* s4 = reinterpret_cast<const float4*>(invstd);
-  const float4* cs4 = reinterpret_cast<const float4*>(chan_scale);
-  stats_block<false>(pixels, c, dbeta, dgamma, [&](size_t p, int cg, float4& a, float4& b) {
-    size_t i = p * c4 + cg;
-    float4 g = masked_grad(d4, o4, h4, cs4, relu, i, p, cg, c4, pix_per_img);
-    float4 yv = __ldg(y4 + i), m = __ldg(m4 + cg), is = __ldg(s4 + cg);
-    a = g;
-    b = make_float4(g.x * (yv.x - m.x) * is.x, g.y * (yv.y - m.y) * is.y, g.z * (yv.z - m.z) * is.z,
-                    g.w * (yv.w - m.w) * is.w);
-  });
+// backward pass 1: per-channel dbeta = sum g, dgamma = sum g * xhat.  fp32 partials over <= kRedPix pixels per
+// thread (kUnroll independent streams), lanes meet in shared memory, one fp64 atomic per channel per block.
+constexpr int kRedPix = 64;
+
+__global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(
+    const float4* __restrict__ dout, const float4* __restrict__ out, const uint2* __restrict__ out_hi,
+    const float4* __restrict__ y, const float4* __restrict__ mean, const float4* __restrict__ invstd,
+    const float4* __restrict__ chan_scale, int relu, size_t pixels, int c4, size_t pix_per_img, double* dbeta,
+    double* dgamma) {
+  __shared__ float4 sh[2][kEwThreads];
+  const int G = c4 < kEwThreads ? c4 : kEwThreads;
+  const int PL = kEwThreads / G;
+  const int g = threadIdx.x % G, pl = threadIdx.x / G;
+  const int cg = blockIdx.y * G + g;
+  const bool active = pl < PL && cg < c4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  if (active) {
+    const float4 mu = __ldg(mean + cg), is = __ldg(invstd + cg);
+    const bool has_o = relu && out, has_h = relu && !out;
+    const size_t pbeg = (size_t)blockIdx.x * PL * kRedPix + pl;
+    const size_t pend = min(pixels, (size_t)(blockIdx.x + 1) * PL * kRedPix);
+    for (size_t p = pbeg; p < pend; p += (size_t)PL * kUnroll) {
+      float4 d[kUnroll], yv[kUnroll], o[kUnroll];
+      uint2 h[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const size_t q = p + (size_t)u * PL;
+        if (q < pend) {
+          const size_t i = q * c4 + cg;
+          d[u] = ld_stream(dout + i);
+          yv[u] = __ldg(y + i);
+          if (has_o) o[u] = __ldg(out + i);
+          if (has_h) h[u] = __ldg(out_hi + i);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const size_t q = p + (size_t)u * PL;
+        if (q >= pend) break;
+        float4 gg = d[u];
+        if (chan_scale) {
+          const float4 cs = __ldg(chan_scale + (q / pix_per_img) * c4 + cg);
+          gg.x *= cs.x; gg.y *= cs.y; gg.z *= cs.z; gg.w *= cs.w;
+        }
+        gg = apply_mask(gg, has_o, o[u], has_h, h[u]);
+        a.x += gg.x; a.y += gg.y; a.z += gg.z; a.w += gg.w;
+        b.x = fmaf(gg.x, (yv[u].x - mu.x) * is.x, b.x); b.y = fmaf(gg.y, (yv[u].y - mu.y) * is.y, b.y);
+        b.z = fmaf(gg.z, (yv[u].z - mu.z) * is.z, b.z); b.w = fmaf(gg.w, (yv[u].w - mu.w) * is.w, b.w);
+      }
+    }
+  }
+  sh[0][threadIdx.x] = a;
+  sh[1][threadIdx.x] = b;
+  __syncthreads();
+  if (active && pl == 0) {
+    double u0 = a.x, u1 = a.y, u2 = a.z, u3 = a.w, v0 = b.x, v1 = b.y, v2 = b.z, v3 = b.w;
+    for (int l = 1; l < PL; ++l) {
+      const float4 a2 = sh[0][l * G + g], b2 = sh[1][l * G + g];
+      u0 += a2.x; u1 += a2.y; u2 += a2.z; u3 += a2.w;
+      v0 += b2.x; v1 += b2.y; v2 += b2.z; v3 += b2.w;
+    }
+    atomicAdd(dbeta + cg * 4 + 0, u0); atomicAdd(dbeta + cg * 4 + 1, u1);
+    atomicAdd(dbeta + cg * 4 + 2, u2); atomicAdd(dbeta + cg * 4 + 3, u3);
+    atomicAdd(dgamma + cg * 4 + 0, v0); atomicAdd(dgamma + cg * 4 + 1, v1);
+    atomicAdd(dgamma + cg * 4 + 2, v2); atomicAdd(dgamma + cg * 4 + 3, v3);
+  }
+}
+inline dim3 red_grid(size_t pixels, int c4) {
+  const int G = c4 < kEwThreads ? c4 : kEwThreads;
+  const int PL = kEwThreads / G;
+  const size_t per_block = (size_t)PL * kRedPix;
+  return dim3((unsigned)((pixels + per_block - 1) / per_block), (unsigned)((c4 + G - 1) / G), 1);
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
+// backward pass 2: dy = gamma*invstd*(g - dbeta/P - xhat*dgamma/P)  (eval_mode: dy = g*scale), dres = g
+__global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(
     const float4* __restrict__ dout, const float4* __restrict__ out, const uint2* __restrict__ out_hi,
-    const float4* __restrict__ y,
-    const float4* __restrict__ mean, const float4* __restrict__ invstd, const float4* __restrict__ gamma,
-    const float4* __restrict__ chan_scale, int relu, const double* __restrict__ dbeta, const double* __restrict__ dgamma,
-    float4* __restrict__ dy, uint2* __restrict__ dy_hi, uint2* __restrict__ dy_lo, float4* __restrict__ dres, size_t total4,
-    int c4, size_t pix_per_img, double inv_count, int eval_mode) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
-    size_t p = i / c4;
-    int cg = (int)(i - p * c4);
-    float4 g = masked_grad(dout, out, out_hi, chan_scale, relu, i, p, cg, c4, pix_per_img);
-    if (dres) dres[i] = g;
-    float4 is = __ldg(invstd + cg);
-    float4 gm = gamma ? __ldg(gamma + cg) : make_float4(1.f, 1.f, 1.f, 1.f);
-    float4 r;
-    if (eval_mode) {
-      r = make_float4(g.x * gm.x * is.x, g.y * gm.y * is.y, g.z * gm.z * is.z, g.w * gm.w * is.w);
-    } else {
-      float4 yv = y[i], m = __ldg(mean + cg);
-      float db[4], dg[4];
+    const float4* __restrict__ y, const float4* __restrict__ mean, const float4* __restrict__ invstd,
+    const float4* __restrict__ gamma, const float4* __restrict__ chan_scale, int relu, const double* __restrict__ dbeta,
+    const double* __restrict__ dgamma, float4* __restrict__ dy, uint2* __restrict__ dy_hi, uint2* __restrict__ dy_lo,
+    float4* __restrict__ dres, size_t pixels, int c4, size_t pix_per_img, double inv_count, int eval_mode) {
+  const EwMap m = ew_map(c4);
+  if (m.cg < 0) return;
+  // dy = ka*g - kb - kc*(y - mean)
+  const float4 is = __ldg(invstd + m.cg);
+  const float4 gm = gamma ? __ldg(gamma + m.cg) : make_float4(1.f, 1.f, 1.f, 1.f);
+  const float4 ka = make_float4(gm.x * is.x, gm.y * is.y, gm.z * is.z, gm.w * is.w);
+  float4 kb = make_float4(0.f, 0.f, 0.f, 0.f), kc = kb, mu = kb;
+  if (!eval_mode) {
+    mu = __ldg(mean + m.cg);
+    const double* db = dbeta + (size_t)m.cg * 4;
+    const double* dg = dgamma + (size_t)m.cg * 4;
+    kb = make_float4(ka.x * (float)(db[0] * inv_count), ka.y * (float)(db[1] * inv_count), ka.z * (float)(db[2] * inv_count),
+                     ka.w * (float)(db[3] * inv_count));
+    kc = make_float4(ka.x * is.x * (float)(dg[0] * inv_count), ka.y * is.y * (float)(dg[1] * inv_count),
+                     ka.z * is.z * (float)(dg[2] * inv_count), ka.w * is.w * (float)(dg[3] * inv_count));
+  }
+  const bool has_o = relu && out, has_h = relu && !out;
+  for (size_t p = m.p0; p < pixels; p += m.dp * kUnroll) {
+    float4 d[kUnroll], yv[kUnroll], o[kUnroll];
+    uint2 h[kUnroll];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        db[j] = (float)(dbeta[cg * 4 + j] * inv_count);
-        dg[j] = (float)(dgamma[cg * 4 + j] * inv_count);
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t q = p + u * m.dp;
+      if (q < pixels) {
+        const size_t i = q * c4 + m.cg;
+        d[u] = ld_stream(dout + i);
+        if (!eval_mode) yv[u] = ld_stream(y + i);
+        if (has_o) o[u] = ld_stream(out + i);
+        if (has_h) h[u] = ld_stream(out_hi + i);
       }
-      r.x = gm.x * is.x * (g.x - db[0] - (yv.x - m.x) * is.x * dg[0]);
-      r.y = gm.y * is.y * (g.y - db[1] - (yv.y - m.y) * is.y * dg[1]);
-      r.z = gm.z * is.z * (g.z - db[2] - (yv.z - m.z) * is.z * dg[2]);
-      r.w = gm.w * is.w * (g.w - db[3] - (yv.w - m.w) * is.w * dg[3]);
     }
-    if (dy) dy[i] = r;
-    if (dy_hi) {  // the consumer is a tcgen05 dgrad/wgrad: hand it the bf16 planes directly (no separate split pass)
-      uint2 h = pack_bf16x4(r.x, r.y, r.z, r.w);
-      dy_hi[i] = h;
-      if (dy_lo) {
-        __nv_bfloat162 h0 = *reinterpret_cast<__nv_bfloat162*>(&h.x), h1 = *reinterpret_cast<__nv_bfloat162*>(&h.y);
-        float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-        dy_lo[i] = pack_bf16x4(r.x - f0.x, r.y - f0.y, r.z - f1.x, r.w - f1.y);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t q = p + u * m.dp;
+      if (q >= pixels) break;
+      const size_t i = q * c4 + m.cg;
+      float4 g = d[u];
+      if (chan_scale) {
+        const float4 cs = __ldg(chan_scale + (q / pix_per_img) * c4 + m.cg);
+        g.x *= cs.x; g.y *= cs.y; g.z *= cs.z; g.w *= cs.w;
+      }
+      g = apply_mask(g, has_o, o[u], has_h, h[u]);
+      if (dres) dres[i] = g;
+      float4 r;
+      if (eval_mode) {
+        r = make_float4(g.x * ka.x, g.y * ka.y, g.z * ka.z, g.w * ka.w);
+      } else {
+        r.x = fmaf(ka.x, g.x, -kb.x) - kc.x * (yv[u].x - mu.x);
+        r.y = fmaf(ka.y, g.y, -kb.y) - kc.y * (yv[u].y - mu.y);
+        r.z = fmaf(ka.z, g.z, -kb.z) - kc.z * (yv[u].z - mu.z);
+        r.w = fmaf(ka.w, g.w, -kb.w) - kc.w * (yv[u].w - mu.w);
+      }
+      if (dy) dy[i] = r;
+      if (dy_hi) {  // the consumer is a tcgen05 dgrad/wgrad: hand it the bf16 planes directly (no separate split pass)
+        const uint2 hh = pack_bf16x4(r.x, r.y, r.z, r.w);
+        dy_hi[i] = hh;
+        if (dy_lo) {
+          const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&hh.x), h1 = *reinterpret_cast<const __nv_bfloat162*>(&hh.y);
+          const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+          dy_lo[i] = pack_bf16x4(r.x - f0.x, r.y - f0.y, r.z - f1.x, r.w - f1.y);
+        }
       }
     }
   }
@@ -331,12 +438,11 @@ extern "C" int vspw_bn_act_fwd(const float* y, const float* scale, const float* 
   VSPW_REQUIRE(y && scale && (shift || mean) && (out || out_hi), "vspw_bn_act_fwd: null pointer");
   VSPW_REQUIRE(c > 0 && c % 4 == 0, "vspw_bn_act_fwd: channels must be a multiple of 4 (got %d)", c);
   VSPW_REQUIRE(pixels_per_image > 0, "vspw_bn_act_fwd: pixels_per_image must be positive");
-  size_t total4 = pixels * (size_t)(c / 4);
-  if (total4 == 0) return VSPW_OK;
-  bn_act_fwd_kernel<<<grid_for(total4, 256), 256, 0, as_stream(stream)>>>(
+  if (pixels == 0) return VSPW_OK;
+  bn_act_fwd_kernel<<<ew_grid(pixels, c / 4), kEwThreads, 0, as_stream(stream)>>>(
       (const float4*)y, (const float4*)scale, (const float4*)shift, (const float4*)mean, (const float4*)beta,
       (const float4*)residual, (const float4*)chan_scale,
-      relu, (float4*)out, (uint2*)out_hi, (uint2*)out_lo, total4, c / 4, pixels_per_image);
+      relu, (float4*)out, (uint2*)out_hi, (uint2*)out_lo, pixels, c / 4, pixels_per_image);
   return check_launch("vspw_bn_act_fwd");
 }
 
@@ -348,8 +454,9 @@ extern "C" int vspw_bn_bwd_reduce(const float* dout, const float* out, const uin
   VSPW_REQUIRE(!relu || out || out_hi, "vspw_bn_bwd_reduce: relu mask needs the forward output (fp32 or bf16 hi plane)");
   VSPW_REQUIRE(c > 0 && c % 4 == 0, "vspw_bn_bwd_reduce: channels must be a multiple of 4 (got %d)", c);
   if (pixels == 0) return VSPW_OK;
-  bn_bwd_reduce_kernel<<<stats_grid(pixels, c), kStatThreads, 2 * kStatThreads * sizeof(D4), as_stream(stream)>>>(
-      dout, out, out_hi, y, mean, invstd, chan_scale, relu, pixels, c, pixels_per_image, dbeta, dgamma);
+  bn_bwd_reduce_kernel<<<red_grid(pixels, c / 4), kEwThreads, 0, as_stream(stream)>>>(
+      (const float4*)dout, (const float4*)out, (const uint2*)out_hi, (const float4*)y, (const float4*)mean,
+      (const float4*)invstd, (const float4*)chan_scale, relu, pixels, c / 4, pixels_per_image, dbeta, dgamma);
   return check_launch("vspw_bn_bwd_reduce");
 }
 
@@ -364,12 +471,11 @@ extern "C" int vspw_bn_bwd_apply(const float* dout, const float* out, const uint
   VSPW_REQUIRE(count >= 1.0, "vspw_bn_bwd_apply: count must be >= 1");
   VSPW_REQUIRE(eval_mode || (y && mean && dbeta && dgamma), "vspw_bn_bwd_apply: train mode needs y/mean/sums");
   VSPW_REQUIRE(c > 0 && c % 4 == 0, "vspw_bn_bwd_apply: channels must be a multiple of 4 (got %d)", c);
-  size_t total4 = pixels * (size_t)(c / 4);
-  if (total4 == 0) return VSPW_OK;
-  bn_bwd_apply_kernel<<<grid_for(total4, 256), 256, 0, as_stream(stream)>>>(
+  if (pixels == 0) return VSPW_OK;
+  bn_bwd_apply_kernel<<<ew_grid(pixels, c / 4), kEwThreads, 0, as_stream(stream)>>>(
       (const float4*)dout, (const float4*)out, (const uint2*)out_hi, (const float4*)y, (const float4*)mean,
       (const float4*)invstd, (const float4*)gamma, (const float4*)chan_scale, relu, dbeta, dgamma, (float4*)dy,
-      (uint2*)dy_hi, (uint2*)dy_lo, (float4*)dres, total4, c / 4, pixels_per_image, 1.0 / count, eval_mode);
+      (uint2*)dy_hi, (uint2*)dy_lo, (float4*)dres, pixels, c / 4, pixels_per_image, 1.0 / count, eval_mode);
   int rc = check_launch("vspw_bn_bwd_apply");
   if (rc) return rc;
   if ((dgamma_f || dbeta_f) && dbeta && dgamma) {

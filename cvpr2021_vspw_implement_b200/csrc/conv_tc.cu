@@ -157,13 +157,15 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn_major, 
 struct ConvTcParams {
   float* out;          // [N][H][W][Nout] fp32
   const float* bias;   // [Nout] or null
-  int N, H, W, C;      // activation tensor (rows of the GEMM are its pixels; stride-1 conv keeps H x W)
+  int N, H, W, C;      // OUTPUT pixel grid N x H x W (rows of the GEMM); the A tensor is read at pixel*stride + tap offset
+  int stride;          // 1, or 2 (forward only: the TMA box then walks the input with elementStrides = 2)
   int Nout;
   int taps_h, taps_w;
   int off0, step;      // tap offset = off0 + tap*step (both axes)
   int bw, bh;          // pixel patch, bw*bh == 128
   int tiles_x, tiles_y, tiles_n;
   int x3;              // 1: hi/lo planes, 3 MMAs per k-step
+  int accumulate;      // 1: out += result (gradient fan-in: the residual branch already wrote its share)
   double* ch_sum;      // [Nout] per-channel sum of the outputs (train-mode BN statistics), or null
   double* ch_sqsum;    // [Nout] per-channel sum of squares
 };
@@ -248,7 +250,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = smem + stage * S::kStage;
             mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-            const int cx = x0 + p.off0 + s * p.step, cy = y0 + p.off0 + r * p.step;
+            const int cx = x0 * p.stride + p.off0 + s * p.step, cy = y0 * p.stride + p.off0 + r * p.step;
             const int kcol = ((r * p.taps_w + s) * kblocks_per_tap + kb) * BK;
             tma_load_4d(st, &map_a_hi, &full_bar[stage], kb * BK, cx, cy, img);
             tma_load_2d(st + 2 * S::kATile, &map_b_hi, &full_bar[stage], kcol, n0);
@@ -326,6 +328,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
               o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
             }
+            if (p.accumulate) {
+              const float4 e = *reinterpret_cast<const float4*>(dst + c0 + j);
+              o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+            }
             *reinterpret_cast<float4*>(dst + c0 + j) = o;
             v[j] = __float_as_uint(o.x); v[j + 1] = __float_as_uint(o.y);
             v[j + 2] = __float_as_uint(o.z); v[j + 3] = __float_as_uint(o.w);
@@ -390,13 +396,14 @@ EncodeTiledFn get_encode() {
 }
 
 // bf16 NHWC activation planes: dims (C, W, H, N), box (64, bw, bh, 1), 128-byte swizzle, zero OOB fill
-int make_act_map(CUtensorMap* m, const void* base, int n, int h, int w, int c, int bw, int bh, const char* who) {
+int make_act_map(CUtensorMap* m, const void* base, int n, int h, int w, int c, int bw, int bh, const char* who, int stride = 1) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("%s: cuTensorMapEncodeTiled entry point unavailable", who); return VSPW_ERR_CUDA; }
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
-  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  // stride 2: the box spans (b-1)*2+1 input pixels per axis and TMA keeps every second one -> bw x bh pixels land densely
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)((bw - 1) * stride + 1), (cuuint32_t)((bh - 1) * stride + 1), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -431,41 +438,46 @@ void pick_patch(int h, int w, int& bw, int& bh) {
 
 bool geometry_ok(const vspw_conv_desc* d) {
   if (!d) return false;
-  if (d->stride != 1) return false;
+  if (d->stride != 1 && d->stride != 2) return false;
   if (d->cin % 64 || d->cout % 64) return false;
-  if (d->ho != d->h || d->wo != d->w) return false;              // "same" convs only (pad == dil*(k-1)/2)
   if (d->kh != d->kw || (d->kh != 1 && d->kh != 3)) return false;
-  if ((long long)d->n * d->h * d->w < 256) return false;         // tiny maps (PPM s x s, <= 72 px) stay on the CUDA-core arm
+  if (d->pad != d->dil * (d->kh - 1) / 2) return false;          // "same" padding only
+  if (d->ho != (d->h - 1) / d->stride + 1 || d->wo != (d->w - 1) / d->stride + 1) return false;
+  if ((long long)d->n * d->ho * d->wo < 256) return false;         // tiny maps (PPM s x s, <= 72 px) stay on the CUDA-core arm
   return true;
 }
 
 constexpr int kBN = 128, kStages = 3;
 
-int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int taps, int off0, int step, const uint16_t* a_hi,
+int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int taps, int off0, int step, int stride,
+                   const uint16_t* a_hi,
                    const uint16_t* a_lo, const uint16_t* b_hi, const uint16_t* b_lo, const float* bias, float* out, int x3,
-                   double* ch_sum, double* ch_sqsum, cudaStream_t stream) {
+                   double* ch_sum, double* ch_sqsum, int accumulate, cudaStream_t stream) {
   VSPW_REQUIRE(a_hi && b_hi && out, "%s: null pointer", who);
   VSPW_REQUIRE(!x3 || (a_lo && b_lo), "%s: BF16X3 needs the lo planes", who);
-  if (taps == 1) {
+  int hin = h, win = w;                               // the A tensor's own grid
+  if (stride != 1) { h = (h - 1) / stride + 1; w = (w - 1) / stride + 1; }  // output grid = GEMM rows
+  if (taps == 1 && stride == 1) {
     // 1x1: no halo, so the N*H*W pixels are one flat row of a plain GEMM -> 128-pixel tiles with no patch padding
     // (a 60x107 map covered by 16x8 patches wastes 10.4 % of every tile; the flat view wastes < 0.1 %)
     const long long pix = (long long)n * h * w;
     VSPW_REQUIRE(pix < (1ll << 31), "%s: too many pixels", who);
     w = (int)pix; h = 1; n = 1;
+    hin = h; win = w;
   }
   ConvTcParams p;
-  p.out = out; p.bias = bias; p.N = n; p.H = h; p.W = w; p.C = c; p.Nout = nout;
+  p.out = out; p.bias = bias; p.N = n; p.H = h; p.W = w; p.C = c; p.Nout = nout; p.stride = stride;
   p.taps_h = taps; p.taps_w = taps; p.off0 = off0; p.step = step; p.x3 = x3;
   VSPW_REQUIRE((ch_sum == nullptr) == (ch_sqsum == nullptr), "%s: ch_sum and ch_sqsum go together", who);
-  p.ch_sum = ch_sum; p.ch_sqsum = ch_sqsum;
+  p.ch_sum = ch_sum; p.ch_sqsum = ch_sqsum; p.accumulate = accumulate;
   pick_patch(h, w, p.bw, p.bh);
   p.tiles_x = (w + p.bw - 1) / p.bw;
   p.tiles_y = (h + p.bh - 1) / p.bh;
   p.tiles_n = (nout + kBN - 1) / kBN;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
-  if ((rc = make_act_map(&ma_hi, a_hi, n, h, w, c, p.bw, p.bh, who))) return rc;
-  if ((rc = make_act_map(&ma_lo, x3 ? a_lo : a_hi, n, h, w, c, p.bw, p.bh, who))) return rc;
+  if ((rc = make_act_map(&ma_hi, a_hi, n, hin, win, c, p.bw, p.bh, who, stride))) return rc;
+  if ((rc = make_act_map(&ma_lo, x3 ? a_lo : a_hi, n, hin, win, c, p.bw, p.bh, who, stride))) return rc;
   const long long kdim = (long long)taps * taps * c;
   if ((rc = make_mat_map(&mb_hi, b_hi, nout, kdim, BK, kBN, who))) return rc;
   if ((rc = make_mat_map(&mb_lo, x3 ? b_lo : b_hi, nout, kdim, BK, kBN, who))) return rc;
@@ -498,7 +510,8 @@ constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
 struct WgradTcParams {
   float* dw;          // [Cout][taps][Cin] fp32, zero-initialised
   int N, H, W, Cin, Cout;
-  int taps_w, off0, step;   // x pixel = dy pixel + off0 + tap*step
+  int taps_w, off0, step;   // x pixel = dy pixel * stride + off0 + tap*step
+  int stride;
   int bw, bh;         // pixel patch, bw*bh == 64
   int tiles_x, tiles_y;
   int tiles_co, tiles_ci, splits, chunk;  // chunk = patches per split
@@ -565,13 +578,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy_hi, const __grid_cons
       // layout of a stage: [dy_hi c0][dy_hi c1][x_hi c0][x_hi c1][dy_lo c0][dy_lo c1][x_lo c0][x_lo c1]
       tma_load_4d(st + 0 * WG_BLK, &map_dy_hi, &full_bar[stage], tco * 128, x0, y0, img);
       tma_load_4d(st + 1 * WG_BLK, &map_dy_hi, &full_bar[stage], tco * 128 + 64, x0, y0, img);
-      tma_load_4d(st + 2 * WG_BLK, &map_x_hi, &full_bar[stage], tci * 128, x0 + dxo, y0 + dyo, img);
-      tma_load_4d(st + 3 * WG_BLK, &map_x_hi, &full_bar[stage], tci * 128 + 64, x0 + dxo, y0 + dyo, img);
+      const int xx = x0 * p.stride + dxo, xy = y0 * p.stride + dyo;
+      tma_load_4d(st + 2 * WG_BLK, &map_x_hi, &full_bar[stage], tci * 128, xx, xy, img);
+      tma_load_4d(st + 3 * WG_BLK, &map_x_hi, &full_bar[stage], tci * 128 + 64, xx, xy, img);
       if (p.x3) {
         tma_load_4d(st + 4 * WG_BLK, &map_dy_lo, &full_bar[stage], tco * 128, x0, y0, img);
         tma_load_4d(st + 5 * WG_BLK, &map_dy_lo, &full_bar[stage], tco * 128 + 64, x0, y0, img);
-        tma_load_4d(st + 6 * WG_BLK, &map_x_lo, &full_bar[stage], tci * 128, x0 + dxo, y0 + dyo, img);
-        tma_load_4d(st + 7 * WG_BLK, &map_x_lo, &full_bar[stage], tci * 128 + 64, x0 + dxo, y0 + dyo, img);
+        tma_load_4d(st + 6 * WG_BLK, &map_x_lo, &full_bar[stage], tci * 128, xx, xy, img);
+        tma_load_4d(st + 7 * WG_BLK, &map_x_lo, &full_bar[stage], tci * 128 + 64, xx, xy, img);
       }
       if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
     }
@@ -646,17 +660,18 @@ extern "C" int vspw_conv2d_fwd_tc(const vspw_conv_desc* d, const uint16_t* x_hi,
                                   void* stream) {
   VSPW_REQUIRE(geometry_ok(d), "vspw_conv2d_fwd_tc: geometry not supported by the tcgen05 path");
   VSPW_REQUIRE(d->precision == VSPW_PREC_BF16X3 || d->precision == VSPW_PREC_BF16, "vspw_conv2d_fwd_tc: precision must be BF16X3 or BF16");
-  return launch_conv_tc("vspw_conv2d_fwd_tc", d->n, d->h, d->w, d->cin, d->cout, d->kh, -d->pad, d->dil, x_hi, x_lo, w_hi, w_lo,
-                        bias, y, d->precision == VSPW_PREC_BF16X3, ch_sum, ch_sqsum, as_stream(stream));
+  return launch_conv_tc("vspw_conv2d_fwd_tc", d->n, d->h, d->w, d->cin, d->cout, d->kh, -d->pad, d->dil, d->stride, x_hi, x_lo, w_hi, w_lo,
+                        bias, y, d->precision == VSPW_PREC_BF16X3, ch_sum, ch_sqsum, 0, as_stream(stream));
 }
 
 extern "C" int vspw_conv2d_dgrad_tc(const vspw_conv_desc* d, const uint16_t* dy_hi, const uint16_t* dy_lo, const uint16_t* wt_hi,
-                                    const uint16_t* wt_lo, float* dx, void* stream) {
-  VSPW_REQUIRE(geometry_ok(d), "vspw_conv2d_dgrad_tc: geometry not supported by the tcgen05 path");
+                                    const uint16_t* wt_lo, float* dx, int32_t accumulate, void* stream) {
+  VSPW_REQUIRE(geometry_ok(d) && d->stride == 1, "vspw_conv2d_dgrad_tc: geometry not supported by the tcgen05 path "
+               "(a stride-2 dgrad is a stride-1 dgrad of the zero-inserted dy: vspw_zero_insert2_bf16)");
   VSPW_REQUIRE(d->precision == VSPW_PREC_BF16X3 || d->precision == VSPW_PREC_BF16, "vspw_conv2d_dgrad_tc: precision must be BF16X3 or BF16");
   // dx[p][ci] = sum_{tap,co} dy[p + pad - tap*dil][co] * Wt[ci][tap][co]
-  return launch_conv_tc("vspw_conv2d_dgrad_tc", d->n, d->h, d->w, d->cout, d->cin, d->kh, d->pad, -d->dil, dy_hi, dy_lo, wt_hi,
-                        wt_lo, nullptr, dx, d->precision == VSPW_PREC_BF16X3, nullptr, nullptr, as_stream(stream));
+  return launch_conv_tc("vspw_conv2d_dgrad_tc", d->n, d->h, d->w, d->cout, d->cin, d->kh, d->pad, -d->dil, 1, dy_hi, dy_lo, wt_hi,
+                        wt_lo, nullptr, dx, d->precision == VSPW_PREC_BF16X3, nullptr, nullptr, accumulate ? 1 : 0, as_stream(stream));
 }
 
 extern "C" int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* dy_hi,
@@ -668,10 +683,13 @@ extern "C" int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_h
   VSPW_REQUIRE(x_hi && dy_hi && dw_ohwi && (!x3 || (x_lo && dy_lo)), "%s: null pointer", who);
   cudaStream_t st = as_stream(stream);
   WgradTcParams p;
-  p.dw = dw_ohwi; p.N = d->n; p.H = d->h; p.W = d->w; p.Cin = d->cin; p.Cout = d->cout;
-  p.taps_w = d->kw; p.off0 = -d->pad; p.step = d->dil; p.x3 = x3;
-  if (d->kh == 1) {  // 1x1: flat pixel axis, no patch padding (see launch_conv_tc)
+  // p.N x p.H x p.W = the dy (output) pixel grid the K loop walks; x is read at pixel*stride + tap offset
+  p.dw = dw_ohwi; p.N = d->n; p.H = d->ho; p.W = d->wo; p.Cin = d->cin; p.Cout = d->cout;
+  p.taps_w = d->kw; p.off0 = -d->pad; p.step = d->dil; p.x3 = x3; p.stride = d->stride;
+  int xn = d->n, xh = d->h, xw = d->w;
+  if (d->kh == 1 && d->stride == 1) {  // 1x1: flat pixel axis, no patch padding (see launch_conv_tc)
     p.N = 1; p.H = 1; p.W = d->n * d->h * d->w;
+    xn = 1; xh = 1; xw = p.W;
   }
   pick_patch64(p.H, p.W, p.bw, p.bh);
   p.tiles_x = (p.W + p.bw - 1) / p.bw;
@@ -692,8 +710,8 @@ extern "C" int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_h
   int rc;
   if ((rc = make_act_map(&mdy_hi, dy_hi, p.N, p.H, p.W, d->cout, p.bw, p.bh, who))) return rc;
   if ((rc = make_act_map(&mdy_lo, x3 ? dy_lo : dy_hi, p.N, p.H, p.W, d->cout, p.bw, p.bh, who))) return rc;
-  if ((rc = make_act_map(&mx_hi, x_hi, p.N, p.H, p.W, d->cin, p.bw, p.bh, who))) return rc;
-  if ((rc = make_act_map(&mx_lo, x3 ? x_lo : x_hi, p.N, p.H, p.W, d->cin, p.bw, p.bh, who))) return rc;
+  if ((rc = make_act_map(&mx_hi, x_hi, xn, xh, xw, d->cin, p.bw, p.bh, who, d->stride))) return rc;
+  if ((rc = make_act_map(&mx_lo, x3 ? x_lo : x_hi, xn, xh, xw, d->cin, p.bw, p.bh, who, d->stride))) return rc;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] { attr_err = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM); });

@@ -205,3 +205,32 @@ extern "C" int vspw_cast_f64_f32(const double* x, float* y, size_t n, void* stre
   cast_f64_f32_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, y, n);
   return check_launch("vspw_cast_f64_f32");
 }
+
+// ---------------------------------------------------------------------------------------------
+// dst[n][h][w][c] = src[n][y/2][x/2][c] at even (y, x), zero elsewhere: the gradient of a stride-2 conv's output laid on
+// the input grid, so that its dgrad is the stride-1 tcgen05 dgrad of the same filter.  One thread = 8 bf16 channels.
+__global__ void zero_insert2_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n, int ho, int wo, int c8,
+                                    int h, int w) {
+  const size_t total = (size_t)n * h * w * c8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t t = i;
+    const int cc = (int)(t % c8); t /= c8;
+    const int x = (int)(t % w); t /= w;
+    const int y = (int)(t % h);
+    const int img = (int)(t / h);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (!(x & 1) && !(y & 1) && (y >> 1) < ho && (x >> 1) < wo)
+      v = __ldg(src + (((size_t)img * ho + (y >> 1)) * wo + (x >> 1)) * c8 + cc);
+    dst[i] = v;
+  }
+}
+extern "C" int vspw_zero_insert2_bf16(const uint16_t* src, uint16_t* dst, int32_t n, int32_t ho, int32_t wo, int32_t c,
+                                      int32_t h, int32_t w, void* stream) {
+  VSPW_REQUIRE(src && dst, "vspw_zero_insert2_bf16: null argument");
+  VSPW_REQUIRE(c > 0 && c % 8 == 0, "vspw_zero_insert2_bf16: channels must be a multiple of 8 (got %d)", c);
+  VSPW_REQUIRE(ho == (h - 1) / 2 + 1 && wo == (w - 1) / 2 + 1, "vspw_zero_insert2_bf16: %dx%d is not the stride-2 grid of %dx%d", ho, wo, h, w);
+  const size_t total = (size_t)n * h * w * (c / 8);
+  if (!total) return VSPW_OK;
+  zero_insert2_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const uint4*)src, (uint4*)dst, n, ho, wo, c / 8, h, w);
+  return check_launch("vspw_zero_insert2_bf16");
+}

@@ -372,16 +372,28 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1, want_stats=False)
             lib.call("vspw_bn_stats", _p(dy), n * ho * wo, co, _p(sums), None, st)
             bv.add_grad(_double_to_float(sums))
         if x.needs_grad:
-            dx = torch.empty((n, h, w, cin), device=dev, dtype=torch.float32)
+            # gradient fan-in: when another consumer of x already deposited its share, the tcgen05 epilogue adds into it
+            fan_in = use_tc and x.grad is not None and x.grad.is_contiguous() and tuple(x.grad.shape) == (n, h, w, cin)
+            dx = x.grad if fan_in else torch.empty((n, h, w, cin), device=dev, dtype=torch.float32)
             w_t = _weight_ihwo(tape, wv)
             if use_tc:
                 th, tl = _weight_planes(wv, "ihwo", w_t)
+                d1, g_hi, g_lo = desc, dyp[0], dyp[1]
+                if stride == 2:
+                    # dgrad of a stride-2 conv = stride-1 dgrad of dy laid on the input grid with zeros in between
+                    d1 = ConvDesc(n, h, w, cin, co, kh, kw, 1, pad, dil, h, w, prec)
+                    g_hi = torch.empty((n, h, w, co), device=dev, dtype=torch.bfloat16)
+                    lib.call("vspw_zero_insert2_bf16", _p(dyp[0]), _p(g_hi), n, ho, wo, co, h, w, st)
+                    if dyp[1] is not None:
+                        g_lo = torch.empty((n, h, w, co), device=dev, dtype=torch.bfloat16)
+                        lib.call("vspw_zero_insert2_bf16", _p(dyp[1]), _p(g_lo), n, ho, wo, co, h, w, st)
                 with _ConvTimer(flops, True):
-                    lib.call("vspw_conv2d_dgrad_tc", ctypes.byref(desc), _p(dyp[0]), _p(dyp[1]), _p(th), _p(tl), _p(dx), st)
+                    lib.call("vspw_conv2d_dgrad_tc", ctypes.byref(d1), _p(g_hi), _p(g_lo), _p(th), _p(tl), _p(dx), 1 if fan_in else 0, st)
             else:
                 with _ConvTimer(flops, False):
                     lib.call("vspw_conv2d_dgrad", ctypes.byref(desc), _p(dy), _p(w_t), _p(dx), st)
-            x.add_grad(dx)
+            if not fan_in:
+                x.add_grad(dx)
 
     tape.record(backward)
     return out

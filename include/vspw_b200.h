@@ -46,7 +46,7 @@ typedef struct vspw_conv_desc {
 
 const char* vspw_last_error(void);
 int vspw_version(void);
-/* 1 if the tcgen05 path can take this geometry (stride 1, cin%64==0, cout%64==0) */
+/* 1 if the tcgen05 path can take this geometry (stride 1 or 2, "same" padding, cin%64==0, cout%64==0, >= 256 pixels) */
 int vspw_conv2d_tc_supported(const vspw_conv_desc* d);
 /* 1 if vspw_conv2d_wgrad_tc can take this geometry (otherwise the fp32 wgrad kernel is used) */
 int vspw_conv2d_wgrad_tc_supported(const vspw_conv_desc* d);
@@ -61,6 +61,11 @@ int vspw_fill(float* dst, float value, size_t n, void* stream);
 int vspw_axpby(const float* x, float* y, float a, float b, size_t n, void* stream);
 /* fp32 -> (hi, lo) bf16 planes, hi = bf16(x), lo = bf16(x - hi): operands of the tcgen05 path */
 int vspw_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, size_t n, void* stream);
+/* dst[n][h][w][c] (bf16) = src[n][ho][wo][c] at the even positions, zero elsewhere, ho = (h-1)/2+1: lays the output
+ * gradient of a stride-2 conv (resnet.py:63 layer2.0.conv2, :130 downsample) on the input grid so that its dgrad is
+ * the stride-1 vspw_conv2d_dgrad_tc of the same filter */
+int vspw_zero_insert2_bf16(const uint16_t* src, uint16_t* dst, int32_t n, int32_t ho, int32_t wo, int32_t c,
+                           int32_t h, int32_t w, void* stream);
 /* copy a channel slice: dst[p][dst_off + c] = src[p][src_off + c], c < cc   (torch.cat(dim=1),
  * clip_psp.py:53, spatial_ocr_block.py:375; accumulate!=0 adds instead (backward of cat/split)) */
 /* double accumulators (BN sums, bias gradients) -> fp32 parameter-gradient vectors */
@@ -88,8 +93,11 @@ int vspw_conv2d_wgrad(const vspw_conv_desc* d, const float* x, const float* dy, 
 int vspw_conv2d_fwd_tc(const vspw_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo,
                        const uint16_t* w_hi, const uint16_t* w_lo, const float* bias, float* y,
                        double* ch_sum, double* ch_sqsum, void* stream);
+/* accumulate != 0: dx += dgrad (gradient fan-in at a residual junction, `out += residual` resnet.py:88-90, without
+ * a separate add pass) */
 int vspw_conv2d_dgrad_tc(const vspw_conv_desc* d, const uint16_t* dy_hi, const uint16_t* dy_lo,
-                         const uint16_t* wt_hi, const uint16_t* wt_lo, float* dx, void* stream);
+                         const uint16_t* wt_hi, const uint16_t* wt_lo, float* dx, int32_t accumulate,
+                         void* stream);
 int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo,
                          const uint16_t* dy_hi, const uint16_t* dy_lo, float* dw_ohwi, void* stream);
 

@@ -34,6 +34,9 @@ TC_GEOMS = [
     (2, 128, 33, 47, 192, 3, 1, 1, False),     # Cout = 1.5 tiles
     (1, 512, 60, 107, 512, 3, 4, 4, False),    # layer4 geometry at the real 480p map size
     (10, 256, 12, 20, 1024, 1, 0, 1, False),   # many images, 8 n-tiles
+    (2, 128, 31, 45, 128, 3, 1, 1, False, 2),  # layer2.0.conv2: 3x3 stride 2 (odd map: 31x45 -> 16x23), TMA elementStrides
+    (2, 256, 30, 44, 512, 1, 0, 1, False, 2),  # layer2.0.downsample: 1x1 stride 2 (even map)
+    (1, 64, 60, 107, 128, 3, 1, 1, True, 2),   # stride 2 with bias on the real 480p map width
 ]
 
 
@@ -41,15 +44,17 @@ TC_GEOMS = [
 @pytest.mark.parametrize("geom", TC_GEOMS)
 def test_conv_tc_fwd_dgrad(E, geom, prec, tol):
     from cvpr2021_vspw_implement_b200._lib import ConvDesc, lib, PREC_BF16X3
-    n, cin, h, w, cout, k, pad, dil, has_bias = geom
-    assert lib.tc_supported(ConvDesc(n, h, w, cin, cout, k, k, 1, pad, dil, h, w, PREC_BF16X3))
+    n, cin, h, w, cout, k, pad, dil, has_bias = geom[:9]
+    stride = geom[9] if len(geom) > 9 else 1
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    assert lib.tc_supported(ConvDesc(n, h, w, cin, cout, k, k, stride, pad, dil, ho, wo, PREC_BF16X3))
     g = torch.Generator().manual_seed(abs(hash(geom)) % 1000)
     x = torch.randn(n, cin, h, w, generator=g)
     wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
     b = torch.randn(cout, generator=g) if has_bias else None
     xr = x.clone().requires_grad_(True)
     wr = wt.clone().requires_grad_(True)
-    yr = F.conv2d(xr, wr, b, stride=1, padding=pad, dilation=dil)
+    yr = F.conv2d(xr, wr, b, stride=stride, padding=pad, dilation=dil)
     gy = torch.randn(yr.shape, generator=g)
     yr.backward(gy)
 
@@ -59,11 +64,14 @@ def test_conv_tc_fwd_dgrad(E, geom, prec, tol):
     xv = E.Var(nhwc(x).cuda(), needs_grad=True)
     with E.precision(prec):
         E.conv_profile_begin()
-        yv = E.conv2d(tape, xv, wp, bp, 1, pad, dil)
+        yv = E.conv2d(tape, xv, wp, bp, stride, pad, dil, want_stats=True)
         yv.grad = nhwc(gy).cuda()
         tape.backward()
         prof = E.conv_profile_end()
     assert prof["tc_launches"] >= 2, "the tcgen05 kernel must be the one that ran (fwd + dgrad)"
+    # the epilogue's fused BN statistics against the fp32 output it wrote
+    yd = yv.data.double().reshape(-1, cout)
+    assert C.rel_err(yv.stats[0].cpu(), yd.sum(0).cpu()) <= 1e-5 and C.rel_err(yv.stats[1].cpu(), (yd * yd).sum(0).cpu()) <= 1e-5
     e_fwd = C.rel_err(nchw(yv.data.cpu()), yr.detach())
     e_dx = C.rel_err(nchw(xv.grad.cpu()), xr.grad)
     e_dw = C.rel_err(tape.param(wp).grad.cpu(), wr.grad)

@@ -80,7 +80,7 @@ def main():
         calls = {
             "fwd": lambda: lib.call("vspw_conv2d_fwd_tc", ctypes.byref(d), P(xh), P(xl), P(wh), P(wl), None, P(y), None, None, st),
             "fwd+stats": lambda: lib.call("vspw_conv2d_fwd_tc", ctypes.byref(d), P(xh), P(xl), P(wh), P(wl), None, P(y), P(stats[0]), P(stats[1]), st),
-            "dgrad": lambda: lib.call("vspw_conv2d_dgrad_tc", ctypes.byref(d), P(gh), P(gl), P(th), P(tl), P(dx), st),
+            "dgrad": lambda: lib.call("vspw_conv2d_dgrad_tc", ctypes.byref(d), P(gh), P(gl), P(th), P(tl), P(dx), 0, st),
             "wgrad": lambda: lib.call("vspw_conv2d_wgrad_tc", ctypes.byref(d), P(xh), P(xl), P(gh), P(gl), P(dw), st),
         }
         for kind, fn in calls.items():
