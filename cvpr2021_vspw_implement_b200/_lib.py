@@ -51,7 +51,7 @@ _SIGNATURES = {
     "vspw_bn_bwd_apply": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_int, _c_d, _c_vp],
     "vspw_maxpool3x3s2_fwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp],
     "vspw_maxpool3x3s2_bwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp],
-    "vspw_tcb_pool_fwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_int, _c_vp],
+    "vspw_tcb_pool_fwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_int, _c_vp],
     "vspw_tcb_pool_bwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_int, _c_vp],
     "vspw_upsample_bilinear_fwd": [_c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp],
     "vspw_upsample_bilinear_bwd": [_c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp],
@@ -65,7 +65,7 @@ _SIGNATURES = {
     "vspw_confusion_add": [_c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_vp],
 }
 
-EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["vspw_last_error", "vspw_version"])
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["vspw_last_error", "vspw_version", "vspw_tcb_pool_workspace_floats"])
 
 
 class VspwError(RuntimeError):
@@ -94,6 +94,8 @@ class _Lib:
                     dll.vspw_last_error.argtypes = []
                     dll.vspw_version.restype = ctypes.c_int
                     dll.vspw_version.argtypes = []
+                    dll.vspw_tcb_pool_workspace_floats.restype = ctypes.c_size_t
+                    dll.vspw_tcb_pool_workspace_floats.argtypes = [_c_int, _c_int, _c_int, _c_int, _c_vp, _c_int]
                     self._dll = dll
         return self._dll
 

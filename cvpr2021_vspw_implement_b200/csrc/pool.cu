@@ -95,85 +95,117 @@ struct PoolGeom {
 __device__ __forceinline__ int bin_start(int i, int len, int s) { return (i * len) / s; }             // floor
 __device__ __forceinline__ int bin_end(int i, int len, int s) { return ((i + 1) * len + s - 1) / s; }  // ceil
 
-// One block = one (frame, row y, 1024-channel slab): the row is swept once, every pixel is added to
-// the column-bin accumulators of all scales (registers), then the row partials are scattered to the
-// <=2 row-bins per scale that contain y with the 1/(area*T) (x frame weight) factor applied.
-__global__ void __launch_bounds__(256) tcb_pool_fwd_kernel(const float4* __restrict__ feat,
-                                                            const float* __restrict__ frame_w, float* __restrict__ pooled,
-                                                            int t_frames, int n_clips, int h, int w, int c4, PoolGeom g) {
-  const int frame = blockIdx.z;  // t*n_clips + clip
-  const int y = blockIdx.y;
+// The x axis is cut at every bin boundary of every scale (<= 2*12 cuts -> <= kMaxSeg segments): each column bin is a run of
+// consecutive segments, so one sweep of a row with ONE accumulator live at a time yields all 12 column-bin sums, and the
+// backward value is constant inside a segment.  The cuts are computed on the host (no integer divisions per pixel).
+constexpr int kMaxSeg = 2 * kMaxBinsPerAxis + 1;
+struct XCuts {
+  int nseg;
+  int cut[kMaxSeg + 1];              // segment k = [cut[k], cut[k+1])
+  int seg_lo[kMaxBinsPerAxis];       // column bin (ax_base[si] + bx) = segments [seg_lo, seg_hi)
+  int seg_hi[kMaxBinsPerAxis];
+};
+
+// Stage 1: rowbins[frame][y][axbin][c] = sum over the columns of column-bin `axbin` of feat[frame][y][x][c].
+// One block = one (frame, row, 1024-channel slab); every pixel is loaded exactly once, 16 bytes per thread, coalesced.
+__global__ void __launch_bounds__(256) tcb_rowbins_kernel(const float4* __restrict__ feat, float4* __restrict__ rowbins, int h,
+                                                           int w, int c4, PoolGeom g, XCuts xc) {
+  const int frame = blockIdx.z, y = blockIdx.y;
   const int cg = blockIdx.x * blockDim.x + threadIdx.x;
   if (cg >= c4) return;
-  const int t = frame / n_clips, clip = frame - t * n_clips;
-  float4 acc[kMaxScales * 6];  // static slot si*6+b keeps the accumulators in registers
-#pragma unroll
-  for (int i = 0; i < kMaxScales * 6; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float4* row = feat + (((size_t)frame * h + y) * w) * c4 + cg;
-  for (int x = 0; x < w; ++x) {
-    float4 v = __ldg(row + (size_t)x * c4);
+  float4 seg[kMaxSeg];
 #pragma unroll
-    for (int si = 0; si < kMaxScales; ++si) {
-      const int s = g.scale[si];
-#pragma unroll
-      for (int b = 0; b < 6; ++b) {
-        if (si < g.n_scales && b < s && x >= bin_start(b, w, s) && x < bin_end(b, w, s)) {
-          float4& a = acc[si * 6 + b];
-          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-        }
+  for (int k = 0; k < kMaxSeg; ++k) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < xc.nseg) {
+      for (int x = xc.cut[k]; x < xc.cut[k + 1]; ++x) {
+        const float4 v = __ldcs(row + (size_t)x * c4);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
       }
     }
+    seg[k] = a;
   }
-  const float fw = (frame_w ? frame_w[frame] : 1.f) / (float)t_frames;
+  float4* dst = rowbins + (((size_t)frame * h + y) * g.total_ax) * c4 + cg;
 #pragma unroll
-  for (int si = 0; si < kMaxScales; ++si) {
-    if (si >= g.n_scales) continue;
-    const int s = g.scale[si];
-    for (int by = 0; by < s; ++by) {
-      int ys = bin_start(by, h, s), ye = bin_end(by, h, s);
-      if (y < ys || y >= ye) continue;
+  for (int b = 0; b < kMaxBinsPerAxis; ++b) {
+    if (b >= g.total_ax) break;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int bx = 0; bx < 6; ++bx) {
-        if (bx >= s) continue;
-        int xs = bin_start(bx, w, s), xe = bin_end(bx, w, s);
-        float k = fw / (float)((ye - ys) * (xe - xs));
-        float4 a = acc[si * 6 + bx];
-        float* dst = pooled + ((size_t)n_clips * g.bin_base[si] + (size_t)clip * s * s + by * s + bx) * (size_t)(c4 * 4) + cg * 4;
-        atomicAdd(dst + 0, a.x * k); atomicAdd(dst + 1, a.y * k);
-        atomicAdd(dst + 2, a.z * k); atomicAdd(dst + 3, a.w * k);
-      }
-    }
+    for (int k = 0; k < kMaxSeg; ++k)
+      if (k >= xc.seg_lo[b] && k < xc.seg_hi[b]) { a.x += seg[k].x; a.y += seg[k].y; a.z += seg[k].z; a.w += seg[k].w; }
+    dst[(size_t)b * c4] = a;
   }
 }
 
-// dfeat[frame][y][x][c] = sum over scales/bins containing (y,x) of dpooled[clip][bin][c] * fw/(T*area)
+// Stage 2: pooled[clip][bin][c] = sum over the T frames and the rows of the bin of rowbins * fw/(T*area).  No atomics:
+// the result is deterministic and `pooled` needs no zero fill.
+__global__ void __launch_bounds__(256) tcb_binreduce_kernel(const float4* __restrict__ rowbins, const float* __restrict__ frame_w,
+                                                             float4* __restrict__ pooled, int t_frames, int n_clips, int h,
+                                                             int w, int c4, PoolGeom g) {
+  const int cg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cg >= c4) return;
+  const int bin = blockIdx.y, clip = blockIdx.z;  // flat bin over all scales
+  int si = 0;
+  while (si + 1 < g.n_scales && bin >= g.bin_base[si + 1]) ++si;
+  const int s = g.scale[si], local = bin - g.bin_base[si];
+  const int by = local / s, bx = local - by * s;
+  const int ys = bin_start(by, h, s), ye = bin_end(by, h, s);
+  const int xs = bin_start(bx, w, s), xe = bin_end(bx, w, s);
+  const float inv = 1.f / ((float)t_frames * (float)((ye - ys) * (xe - xs)));
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < t_frames; ++t) {
+    const int frame = t * n_clips + clip;
+    const float k = (frame_w ? frame_w[frame] : 1.f) * inv;
+    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int y = ys; y < ye; ++y) {
+      const float4 v = __ldg(rowbins + (((size_t)frame * h + y) * g.total_ax + g.ax_base[si] + bx) * c4 + cg);
+      f.x += v.x; f.y += v.y; f.z += v.z; f.w += v.w;
+    }
+    a.x = fmaf(f.x, k, a.x); a.y = fmaf(f.y, k, a.y); a.z = fmaf(f.z, k, a.z); a.w = fmaf(f.w, k, a.w);
+  }
+  pooled[((size_t)n_clips * g.bin_base[si] + (size_t)clip * s * s + local) * c4 + cg] = a;
+}
+
+// dfeat[frame][y][x][c] = sum over scales/bins containing (y,x) of dpooled[clip][bin][c] * fw/(T*area): constant inside an
+// x segment, so a thread forms <= kMaxSeg values from <= 2 row bins x 12 column bins and then only streams stores.
 __global__ void __launch_bounds__(256) tcb_pool_bwd_kernel(const float4* __restrict__ dpooled,
                                                             const float* __restrict__ frame_w, float4* __restrict__ dfeat,
-                                                            int t_frames, int n_clips, int h, int w, int c4, PoolGeom g) {
+                                                            int t_frames, int n_clips, int h, int w, int c4, PoolGeom g,
+                                                            XCuts xc) {
   const int frame = blockIdx.z;
   const int y = blockIdx.y;
   const int cg = blockIdx.x * blockDim.x + threadIdx.x;
   if (cg >= c4) return;
   const int t = frame / n_clips, clip = frame - t * n_clips;
   const float fw = (frame_w ? frame_w[frame] : 1.f) / (float)t_frames;
-  float4* row = dfeat + (((size_t)frame * h + y) * w) * c4 + cg;
-  for (int x = 0; x < w; ++x) {
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int si = 0; si < g.n_scales; ++si) {
-      const int s = g.scale[si];
-      for (int by = 0; by < s; ++by) {
-        int ys = bin_start(by, h, s), ye = bin_end(by, h, s);
-        if (y < ys || y >= ye) continue;
-        for (int bx = 0; bx < s; ++bx) {
-          int xs = bin_start(bx, w, s), xe = bin_end(bx, w, s);
-          if (x < xs || x >= xe) continue;
-          float k = fw / (float)((ye - ys) * (xe - xs));
-          float4 d = __ldg(dpooled + ((size_t)n_clips * g.bin_base[si] + (size_t)clip * s * s + by * s + bx) * c4 + cg);
-          a.x = fmaf(d.x, k, a.x); a.y = fmaf(d.y, k, a.y); a.z = fmaf(d.z, k, a.z); a.w = fmaf(d.w, k, a.w);
-        }
+  float4 val[kMaxSeg];
+#pragma unroll
+  for (int k = 0; k < kMaxSeg; ++k) val[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int si = 0; si < g.n_scales; ++si) {
+    const int s = g.scale[si];
+    for (int by = 0; by < s; ++by) {
+      const int ys = bin_start(by, h, s), ye = bin_end(by, h, s);
+      if (y < ys || y >= ye) continue;
+      for (int bx = 0; bx < s; ++bx) {
+        const int ax = g.ax_base[si] + bx;
+        const int lo = xc.seg_lo[ax], hi = xc.seg_hi[ax];
+        const float k = fw / (float)((ye - ys) * (xc.cut[hi] - xc.cut[lo]));
+        const float4 d = __ldg(dpooled + ((size_t)n_clips * g.bin_base[si] + (size_t)clip * s * s + by * s + bx) * c4 + cg);
+#pragma unroll
+        for (int q = 0; q < kMaxSeg; ++q)
+          if (q >= lo && q < hi) {
+            val[q].x = fmaf(d.x, k, val[q].x); val[q].y = fmaf(d.y, k, val[q].y);
+            val[q].z = fmaf(d.z, k, val[q].z); val[q].w = fmaf(d.w, k, val[q].w);
+          }
       }
     }
-    row[(size_t)x * c4] = a;
+  }
+  float4* row = dfeat + (((size_t)frame * h + y) * w) * c4 + cg;
+#pragma unroll
+  for (int k = 0; k < kMaxSeg; ++k) {
+    if (k < xc.nseg)
+      for (int x = xc.cut[k]; x < xc.cut[k + 1]; ++x) __stcs(row + (size_t)x * c4, val[k]);
   }
 }
 
@@ -226,6 +258,37 @@ int make_geom(const int32_t* scales, int n_scales, PoolGeom& g, const char* who)
   }
   VSPW_REQUIRE(g.total_ax <= kMaxBinsPerAxis, "%s: sum of scales must be <= %d", who, kMaxBinsPerAxis);
   return VSPW_OK;
+}
+
+// host: cut the x axis at every bin boundary of every scale
+void make_xcuts(const PoolGeom& g, int w, XCuts& xc) {
+  int pts[2 * kMaxBinsPerAxis + 2];
+  int np = 0;
+  pts[np++] = 0;
+  pts[np++] = w;
+  for (int si = 0; si < g.n_scales; ++si)
+    for (int b = 0; b < g.scale[si]; ++b) {
+      pts[np++] = (b * w) / g.scale[si];
+      pts[np++] = ((b + 1) * w + g.scale[si] - 1) / g.scale[si];
+    }
+  for (int i = 1; i < np; ++i)  // insertion sort, then unique
+    for (int j = i; j > 0 && pts[j] < pts[j - 1]; --j) { int t = pts[j]; pts[j] = pts[j - 1]; pts[j - 1] = t; }
+  int nu = 0;
+  for (int i = 0; i < np; ++i)
+    if (nu == 0 || pts[i] != xc.cut[nu - 1]) xc.cut[nu++] = pts[i];
+  xc.nseg = nu - 1;
+  for (int i = nu; i <= kMaxSeg; ++i) xc.cut[i] = w;
+  for (int i = 0; i < kMaxBinsPerAxis; ++i) { xc.seg_lo[i] = 0; xc.seg_hi[i] = 0; }
+  for (int si = 0; si < g.n_scales; ++si)
+    for (int b = 0; b < g.scale[si]; ++b) {
+      const int xs = (b * w) / g.scale[si], xe = ((b + 1) * w + g.scale[si] - 1) / g.scale[si];
+      int lo = 0, hi = 0;
+      while (xc.cut[lo] < xs) ++lo;
+      hi = lo;
+      while (xc.cut[hi] < xe) ++hi;
+      xc.seg_lo[g.ax_base[si] + b] = lo;
+      xc.seg_hi[g.ax_base[si] + b] = hi;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -349,21 +412,34 @@ extern "C" int vspw_maxpool3x3s2_bwd(const float* dy, const uint8_t* idx, float*
   return check_launch("vspw_maxpool3x3s2_bwd");
 }
 
-extern "C" int vspw_tcb_pool_fwd(const float* feat, const float* frame_w, float* pooled, int32_t t_frames, int32_t n_clips,
-                                 int32_t h, int32_t w, int32_t c, const int32_t* scales_host, int32_t n_scales,
-                                 void* stream) {
-  VSPW_REQUIRE(feat && pooled, "vspw_tcb_pool_fwd: null pointer");
+extern "C" size_t vspw_tcb_pool_workspace_floats(int32_t t_frames, int32_t n_clips, int32_t h, int32_t c,
+                                                 const int32_t* scales_host, int32_t n_scales) {
+  size_t ax = 0;
+  for (int i = 0; scales_host && i < n_scales; ++i) ax += (size_t)scales_host[i];
+  return (size_t)t_frames * n_clips * h * ax * c;
+}
+
+extern "C" int vspw_tcb_pool_fwd(const float* feat, const float* frame_w, float* pooled, float* workspace, int32_t t_frames,
+                                 int32_t n_clips, int32_t h, int32_t w, int32_t c, const int32_t* scales_host,
+                                 int32_t n_scales, void* stream) {
+  VSPW_REQUIRE(feat && pooled && workspace, "vspw_tcb_pool_fwd: null pointer");
   VSPW_REQUIRE(t_frames > 0 && n_clips > 0 && h > 0 && w > 0 && c > 0 && c % 4 == 0, "vspw_tcb_pool_fwd: bad dims");
   PoolGeom g;
   int rc = make_geom(scales_host, n_scales, g, "vspw_tcb_pool_fwd");
   if (rc) return rc;
   VSPW_REQUIRE(h <= 65535 && t_frames * n_clips <= 65535, "vspw_tcb_pool_fwd: grid limit");
+  XCuts xc;
+  make_xcuts(g, w, xc);
   int c4 = c / 4;
   int threads = c4 < 256 ? ((c4 + 31) / 32 * 32) : 256;
   dim3 grid((c4 + threads - 1) / threads, h, t_frames * n_clips);
-  tcb_pool_fwd_kernel<<<grid, threads, 0, as_stream(stream)>>>((const float4*)feat, frame_w, pooled, t_frames, n_clips, h,
-                                                               w, c4, g);
-  return check_launch("vspw_tcb_pool_fwd");
+  tcb_rowbins_kernel<<<grid, threads, 0, as_stream(stream)>>>((const float4*)feat, (float4*)workspace, h, w, c4, g, xc);
+  rc = check_launch("vspw_tcb_pool_fwd(rowbins)");
+  if (rc) return rc;
+  dim3 grid2((c4 + threads - 1) / threads, g.total_bins, n_clips);
+  tcb_binreduce_kernel<<<grid2, threads, 0, as_stream(stream)>>>((const float4*)workspace, frame_w, (float4*)pooled, t_frames,
+                                                                 n_clips, h, w, c4, g);
+  return check_launch("vspw_tcb_pool_fwd(binreduce)");
 }
 
 extern "C" int vspw_tcb_pool_bwd(const float* dpooled, const float* frame_w, const float* feat, float* dfeat,
@@ -375,11 +451,13 @@ extern "C" int vspw_tcb_pool_bwd(const float* dpooled, const float* frame_w, con
   int rc = make_geom(scales_host, n_scales, g, "vspw_tcb_pool_bwd");
   if (rc) return rc;
   VSPW_REQUIRE(h <= 65535 && t_frames * n_clips <= 65535, "vspw_tcb_pool_bwd: grid limit");
+  XCuts xc;
+  make_xcuts(g, w, xc);
   int c4 = c / 4;
   int threads = c4 < 256 ? ((c4 + 31) / 32 * 32) : 256;
   dim3 grid((c4 + threads - 1) / threads, h, t_frames * n_clips);
   tcb_pool_bwd_kernel<<<grid, threads, 0, as_stream(stream)>>>((const float4*)dpooled, frame_w, (float4*)dfeat, t_frames,
-                                                               n_clips, h, w, c4, g);
+                                                               n_clips, h, w, c4, g, xc);
   rc = check_launch("vspw_tcb_pool_bwd");
   if (rc) return rc;
   if (dframe_w) {

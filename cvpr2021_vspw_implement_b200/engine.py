@@ -470,7 +470,9 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
     out = Var(o, needs_grad=needs)
     if want_planes:
         out.planes = (hi, lo)
-    mask_hi = hi if o is None else None  # ReLU mask source in the backward: fp32 output, else its bf16 hi plane
+    # ReLU mask source in the backward: the bf16 hi plane when there is one (2 bytes/element instead of 4), else fp32
+    mask_hi = hi
+    mask_o = o if hi is None else None
 
     def backward():
         dout = out.grad
@@ -489,13 +491,13 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
         dres = torch.empty_like(dout) if (residual is not None and residual.needs_grad) else None
         if training:
             dsum = torch.zeros((2, c), device=dev, dtype=torch.float64)
-            lib.call("vspw_bn_bwd_reduce", _p(dout), _p(o), _p(mask_hi), _p(y.data), _p(mean), _p(invstd), _p(chan_scale),
+            lib.call("vspw_bn_bwd_reduce", _p(dout), _p(mask_o), _p(mask_hi), _p(y.data), _p(mean), _p(invstd), _p(chan_scale),
                      1 if relu else 0, pixels, c, h * w, _p(dsum[0]), _p(dsum[1]), st)
             if world > 1:
                 _allreduce_sums(dsum)
             dgam = torch.empty(c, device=dev, dtype=torch.float32)
             dbet = torch.empty(c, device=dev, dtype=torch.float32)
-            lib.call("vspw_bn_bwd_apply", _p(dout), _p(o), _p(mask_hi), _p(y.data), _p(mean), _p(invstd), _p(gv.data),
+            lib.call("vspw_bn_bwd_apply", _p(dout), _p(mask_o), _p(mask_hi), _p(y.data), _p(mean), _p(invstd), _p(gv.data),
                      _p(chan_scale), 1 if relu else 0, _p(dsum[0]), _p(dsum[1]), _p(dy), _p(dy_hi), _p(dy_lo), _p(dres), _p(dgam),
                      _p(dbet), pixels, c, h * w, 0, float(pixels * world), st)
             if gv.needs_grad:
@@ -508,11 +510,11 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
             dsum = dgam = dbet = None
             if gv.needs_grad or bv.needs_grad:
                 dsum = torch.zeros((2, c), device=dev, dtype=torch.float64)
-                lib.call("vspw_bn_bwd_reduce", _p(dout), _p(o), _p(mask_hi), _p(y.data), _p(bn.running_mean), _p(invstd),
+                lib.call("vspw_bn_bwd_reduce", _p(dout), _p(mask_o), _p(mask_hi), _p(y.data), _p(bn.running_mean), _p(invstd),
                          _p(chan_scale), 1 if relu else 0, pixels, c, h * w, _p(dsum[0]), _p(dsum[1]), st)
                 dgam = torch.empty(c, device=dev, dtype=torch.float32)
                 dbet = torch.empty(c, device=dev, dtype=torch.float32)
-            lib.call("vspw_bn_bwd_apply", _p(dout), _p(o), _p(mask_hi), None, None, _p(scale), None, _p(chan_scale),
+            lib.call("vspw_bn_bwd_apply", _p(dout), _p(mask_o), _p(mask_hi), None, None, _p(scale), None, _p(chan_scale),
                      1 if relu else 0, _p(dsum[0]) if dsum is not None else None, _p(dsum[1]) if dsum is not None else None,
                      _p(dy), _p(dy_hi), _p(dy_lo), _p(dres), _p(dgam), _p(dbet), pixels, c, h * w, 1, float(pixels), st)
             if dsum is not None:
@@ -575,10 +577,11 @@ def tcb_pool(tape, feat, t_frames, n_clips, scales, frame_w=None):
     assert N == t_frames * n_clips
     dev = feat.data.device
     total_bins = sum(s * s for s in scales)
-    pooled = torch.zeros(n_clips * total_bins * c, device=dev, dtype=torch.float32)
+    pooled = torch.empty(n_clips * total_bins * c, device=dev, dtype=torch.float32)
     sc = (ctypes.c_int32 * len(scales))(*scales)
     fw = frame_w.data if frame_w is not None else None
-    lib.call("vspw_tcb_pool_fwd", _p(feat.data), _p(fw), _p(pooled), t_frames, n_clips, h, w, c, sc, len(scales), _stream())
+    ws = torch.empty(lib.dll().vspw_tcb_pool_workspace_floats(t_frames, n_clips, h, c, sc, len(scales)), device=dev, dtype=torch.float32)
+    lib.call("vspw_tcb_pool_fwd", _p(feat.data), _p(fw), _p(pooled), _p(ws), t_frames, n_clips, h, w, c, sc, len(scales), _stream())
     outs, off = [], 0
     needs = tape.grad_enabled and (feat.needs_grad or (frame_w is not None and frame_w.needs_grad))
     for s in scales:

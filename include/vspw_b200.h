@@ -154,10 +154,14 @@ int vspw_maxpool3x3s2_bwd(const float* dy, const uint8_t* idx, float* dx, int32_
  * block s is a dense NHWC map [n_clips][s][s][c] stored at float offset n_clips*c*(sum of earlier
  * s^2) (1,4,9,36 -> 50 bins per clip), averaged over the T frames; frame_w[t][i] (nullable)
  * are the psp_weight softmax weights already permuted to the reference's list order.
- * pooled must be zero-filled by the caller (fp32 atomics). */
-int vspw_tcb_pool_fwd(const float* feat, const float* frame_w, float* pooled, int32_t t_frames,
-                      int32_t n_clips, int32_t h, int32_t w, int32_t c, const int32_t* scales_host,
-                      int32_t n_scales, void* stream);
+ * Two launches, no atomics (deterministic): a single sweep of feat forms the column-bin sums of every row into
+ * `workspace` (vspw_tcb_pool_workspace_floats() floats = T*n*h*(sum of scales)*c), a small second kernel folds rows and
+ * frames into `pooled` (every element is written; no zero fill needed). */
+size_t vspw_tcb_pool_workspace_floats(int32_t t_frames, int32_t n_clips, int32_t h, int32_t c,
+                                      const int32_t* scales_host, int32_t n_scales);
+int vspw_tcb_pool_fwd(const float* feat, const float* frame_w, float* pooled, float* workspace,
+                      int32_t t_frames, int32_t n_clips, int32_t h, int32_t w, int32_t c,
+                      const int32_t* scales_host, int32_t n_scales, void* stream);
 /* dfeat (overwritten) from dpooled; dframe_w[t][i] (nullable, zeroed by the caller) */
 int vspw_tcb_pool_bwd(const float* dpooled, const float* frame_w, const float* feat, float* dfeat,
                       float* dframe_w, int32_t t_frames, int32_t n_clips, int32_t h, int32_t w,
