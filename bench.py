@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("VSPW_PRECISION", "fp32"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("VSPW_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--syncbn", action="store_true", help="all-reduce BN statistics across ranks (reference multi-GPU semantics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-run", action="store_true", help="for ncu captures only: honour --warmup below 3, skip e2e/cpu legs")

@@ -10,6 +10,7 @@ Layout: activations are fp32 NHWC ``(N, H, W, C)`` torch tensors (torch = alloca
 """
 import ctypes
 import math
+import os
 from contextlib import contextmanager
 
 import torch
@@ -17,7 +18,7 @@ import torch
 from ._lib import ConvDesc, PREC_BF16, PREC_BF16X3, PREC_FP32, VspwError, i4, lib
 
 _PRECISION = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
-_state = {"precision": "fp32", "syncbn_clamp": False, "syncbn": False}
+_state = {"precision": os.environ.get("VSPW_PRECISION", "bf16x3"), "syncbn_clamp": False, "syncbn": False}
 
 
 def set_precision(mode):
@@ -621,6 +622,51 @@ def tcb_pool(tape, feat, t_frames, n_clips, scales, frame_w=None):
 
     tape.record(backward)
     return outs
+
+
+def frame_weights(tape, score, t_frames, n_clips):
+    """The psp_weight branch of Clip_PSP after its 1x1 conv (clip_psp.py:147-152, 184-187): global average of the
+    (N, h, w, 1) score map per image (AdaptiveAvgPool2d((1,1))), softmax over the T frames of each clip, and the
+    reference's list-order quirk Q3: the weight taken from batch chunk j multiplies list position j, where position 0
+    is the CURRENT frame (batch chunk T-1) and position k >= 1 is batch chunk k-1.  Returns a (T, n) Var laid out for
+    vspw_tcb_pool: row t = the weight applied to batch chunk t = softmax row (t+1) % T."""
+    N, h, w, one = score.shape
+    assert one == 1 and N == t_frames * n_clips
+    dev = score.data.device
+    hw = h * w
+    st = _stream()
+    ones = torch.empty(hw, device=dev, dtype=torch.float32)
+    lib.call("vspw_fill", _p(ones), 1.0, hw, st)
+    raw = torch.empty(N, device=dev, dtype=torch.float32)
+    # raw[b] = (1/hw) sum_p score[b][p] * 1
+    lib.call("vspw_bgemm", _p(score.data), _p(ones), _p(raw), N, 1, 1, hw, hw, hw, 1, 0, 1, 1, 1, 1, 1, 1.0 / hw, 0.0, st)
+    sm = torch.empty_like(raw)  # [t][i]; softmax along t for every clip i
+    lib.call("vspw_softmax_strided_fwd", _p(raw), _p(sm), n_clips, t_frames, 1, n_clips, n_clips, 0, 1.0, st)
+    fw = torch.empty((t_frames, n_clips), device=dev, dtype=torch.float32)
+    for t in range(t_frames):
+        src = sm[((t + 1) % t_frames) * n_clips:((t + 1) % t_frames + 1) * n_clips]
+        lib.call("vspw_axpby", _p(src), _p(fw[t]), 1.0, 0.0, n_clips, st)
+    out = Var(fw, needs_grad=tape.grad_enabled and score.needs_grad)
+
+    def backward():
+        g = out.grad
+        out.grad = None
+        if g is None or not score.needs_grad:
+            return
+        st = _stream()
+        dsm = torch.empty_like(sm)
+        for t in range(t_frames):
+            j = (t + 1) % t_frames
+            lib.call("vspw_axpby", _p(g[t]), _p(dsm[j * n_clips:(j + 1) * n_clips]), 1.0, 0.0, n_clips, st)
+        draw = torch.empty_like(raw)
+        lib.call("vspw_softmax_strided_bwd", _p(sm), _p(dsm), _p(draw), n_clips, t_frames, 1, n_clips, n_clips, 0, 1.0, st)
+        dscore = torch.empty_like(score.data)
+        # dscore[b][p] = draw[b] / hw
+        lib.call("vspw_bgemm", _p(draw), _p(ones), _p(dscore), N, 1, hw, 1, 1, 1, 1, 0, 1, 1, hw, hw, 1, 1.0 / hw, 0.0, st)
+        score.add_grad(dscore)
+
+    tape.record(backward)
+    return out
 
 
 def ppm_concat(tape, base, pyramids):

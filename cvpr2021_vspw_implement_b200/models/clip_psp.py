@@ -96,7 +96,8 @@ class Clip_PSP(nn.Module):
     def _frame_weights(self, tape, feat, t_frames, n_clips):
         """psp_weight branch (reference :147-152,184-187): 1x1 conv 2048->1, global average, softmax over
         the T frames; returned as a (T, n) Var laid out for vspw_tcb_pool (frame t uses list slot (t+1)%T)."""
-        raise NotImplementedError("--psp_weight True is not wired into the CUDA graph yet (reference default is False)")
+        score = conv_op(tape, self.pspweight_conv[0], feat)  # 1x1 2048 -> 1, bias-free (reference :83)
+        return E.frame_weights(tape, score, t_frames, n_clips)
 
     def _logits(self, tape, frames, training):
         t_frames = len(frames)

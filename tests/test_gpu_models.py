@@ -18,7 +18,10 @@ TOL = 1e-3
 # eps flips about eps*N of the N ReLU masks of a layer and every flip moves the gradient by ~1/sqrt(N) of its norm,
 # so the gradient error is ~sqrt(eps) whatever N is: 3e-4 for fp32 (eps 2^-24; measured floor of the reference
 # itself 1.4e-4..4e-3, oracle/NOISE_FLOOR.md) and 3e-3 for bf16x3 (eps 2^-17), stacking over the layers below.
-GRAD_GATES = {"fp32": (10 * TOL, 2 * TOL, 30 * TOL), "bf16x3": (30 * TOL, 10 * TOL, 60 * TOL)}
+# The element-wise gate looks at the first 64 entries of each tensor relative to their largest one, so a single flipped
+# mask on a 7x9 map shows up at full size there (worst seen over the four fixtures: 1.3e-2 fp32, 9.8e-2 bf16x3) while the
+# norm of the same tensor moves by < 1e-2; tests/test_gpu_conv_tc.py pins the kernels themselves at 1e-4.
+GRAD_GATES = {"fp32": (10 * TOL, 2 * TOL, 30 * TOL), "bf16x3": (30 * TOL, 10 * TOL, 150 * TOL)}
 
 
 @pytest.fixture(scope="module")
@@ -47,7 +50,7 @@ def _train_step(E, name, prec):
     return m, loss, acc, cap
 
 
-@pytest.mark.parametrize("name", ["clip_psp", "clip_ocr", "segmodule_r18"])
+@pytest.mark.parametrize("name", ["clip_psp", "clip_psp_pspw", "clip_ocr", "segmodule_r18"])
 @pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
 def test_train_step_matches_reference(E, name, prec):
     g = C.golden(name)
@@ -90,7 +93,7 @@ def test_train_step_matches_reference(E, name, prec):
     print(f"{name}/{prec}: worst grad-norm rel err {worst:.2e}")
 
 
-@pytest.mark.parametrize("name", ["clip_psp", "clip_ocr", "segmodule_r18"])
+@pytest.mark.parametrize("name", ["clip_psp", "clip_psp_pspw", "clip_ocr", "segmodule_r18"])
 @pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
 def test_frozen_bn_step_gradients_match_reference(E, name, prec):
     """cfg.TRAIN.fix_bn path (module in eval mode, loss + backward): the whole dgrad/wgrad/BN/pool/loss backward
@@ -128,7 +131,7 @@ def test_frozen_bn_step_gradients_match_reference(E, name, prec):
     print(f"{name}/{prec} frozen-BN: worst grad-norm err {worst_n:.2e}, worst element err {worst_h:.2e}")
 
 
-@pytest.mark.parametrize("name", ["clip_psp", "clip_ocr", "segmodule_r18"])
+@pytest.mark.parametrize("name", ["clip_psp", "clip_psp_pspw", "clip_ocr", "segmodule_r18"])
 def test_eval_matches_reference(E, name):
     kind, arch, T, n, H, W, mseed, dseed = C.CASES[name]
     g = C.golden(name)
