@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-run", action="store_true", help="for ncu captures only: honour --warmup below 3, skip e2e/cpu legs")
     ap.add_argument("--cpu-sample", default="240x427", help="HxW of the bounded CPU sample")
+    ap.add_argument("--size", default="", help="HxW override, only with --profile-run (host-overhead probes); never a bench value")
     ap.add_argument("--kernel-profile", default="", help="write a per-entry-point CUDA-event breakdown of 2 extra steps to this file")
     return ap.parse_args()
 
@@ -132,22 +133,13 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def all_reduce_grads(params, world):
-    """DDP-style gradient averaging: one flat bucket, one NCCL all-reduce over NVLink."""
-    import torch.distributed as dist
-    grads = [p.grad for p in params if p.grad is not None]
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    flat.mul_(1.0 / world)
-    off = 0
-    for g in grads:
-        n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
-        off += n
-
-
 def run_ours(args):
+    global H, W
     import torch.distributed as dist
+    if args.size:
+        if not args.profile_run:
+            raise SystemExit("--size is a probe option: use it with --profile-run")
+        H, W = (int(x) for x in args.size.lower().split("x"))
     from cvpr2021_vspw_implement_b200 import engine as E
     from cvpr2021_vspw_implement_b200._lib import lib
     import tcb_oracle as O
@@ -164,8 +156,9 @@ def run_ours(args):
     if args.syncbn:
         E.set_syncbn(True)
 
+    from cvpr2021_vspw_implement_b200.parallel import GradBucket
     model = build_model(dev, seed=0)
-    params = [p for p in model.parameters()]
+    bucket = GradBucket(model.parameters())  # one flat bucket, one NCCL all-reduce over NVLink per step
     opt = make_optimizer(model)
     imgs_h, labs_h = O.synthetic_clip(T_FRAMES, N_CLIPS, H, W, NUM_CLASS, seed=304 + rank)
     imgs_h = [t.pin_memory() for t in imgs_h]
@@ -180,7 +173,7 @@ def run_ours(args):
         loss, acc = model(feed_from(imgs, labs))
         loss.backward()
         if world > 1:
-            all_reduce_grads(params, world)
+            bucket.all_reduce_mean()
         opt.step()
         return loss
 
@@ -285,7 +278,8 @@ def run_ours(args):
                       "frames_per_step_per_gpu": T_FRAMES * N_CLIPS, "parallelism": f"dp{world}", "precision_mode": args.precision,
                       "syncbn": bool(args.syncbn), "l2_flush": "256 MiB write between timed steps",
                       "optimizer": "torch.optim.SGD as the reference (train_clip2.py:215-236), outside the CUDA hot path",
-                      "loss": round(final_loss, 5), "wall_s_timed_region": round(wall, 3)},
+                      "loss": round(final_loss, 5), "wall_s_timed_region": round(wall, 3),
+                      "peak_hbm_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 2)},
            "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4, "steps": e2e_steps},
            "roofline": roof}

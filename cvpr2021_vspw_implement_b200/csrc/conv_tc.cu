@@ -170,30 +170,18 @@ struct ConvTcParams {
   double* ch_sqsum;    // [Nout] per-channel sum of squares
 };
 
+constexpr int kStgPitch = 36;  // floats per staged row: 32 + 4 pad -> 16-byte row writes and column reads are conflict-free
+
 template <int BN, int STAGES>
 struct ConvSmem {
   static constexpr int kATile = BM * BK * 2;  // 16 KB
   static constexpr int kBTile = BN * BK * 2;
   static constexpr int kStage = 2 * kATile + 2 * kBTile;  // hi+lo of A and B
   static constexpr int kStatBytes = 2 /*buffers*/ * 2 /*sum, sqsum*/ * BN * 4;
-  static constexpr int kBytes = STAGES * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/ + kStatBytes;
+  static constexpr int kStgBytes = 4 /*epilogue warps*/ * 32 * kStgPitch * 4;
+  static constexpr int kBytes = STAGES * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/ + kStatBytes + kStgBytes;
 };
 
-// Column sums over a warp's 32 rows: every lane enters with 32 column values v[0..31] of ITS row and leaves with the
-// sum over the 32 lanes of column `lane` in v[0] (recursive halving: 16+8+4+2+1 = 31 shuffles instead of 32*5).
-__device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float keep = upper ? v[i + off] : v[i];
-      const float send = upper ? v[i] : v[i + off];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0];
-}
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -209,6 +197,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   float* stat_s = reinterpret_cast<float*>(smem + STAGES * S::kStage + 256);  // [2 buffers][sum | sqsum][BN]
+  float* stg = stat_s + 4 * BN + (threadIdx.x >= 64 ? ((threadIdx.x >> 5) - 2) * 32 * kStgPitch : 0);  // per epilogue warp
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.N * p.tiles_y * p.tiles_x * p.tiles_n;
@@ -310,47 +299,68 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       int img = tm / p.tiles_y;
       const int px = tx * p.bw + row % p.bw, py = ty * p.bh + row / p.bw, n0 = tn * BN;
       const bool ok = px < p.W && py < p.H;
-      float* dst = p.out + (((size_t)img * p.H + py) * p.W + px) * p.Nout + n0;
+      const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
+      // element offset of this lane's output row; the rows the lane STORES (r = 4*i + lane/8, see below) come by shuffle
+      const unsigned long long my_off = (((unsigned long long)img * p.H + py) * p.W + px) * (unsigned long long)p.Nout + n0;
+      unsigned long long row_off[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) row_off[i] = __shfl_sync(0xffffffffu, my_off, 4 * i + (lane >> 3));
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= p.Nout) continue;  // warp-uniform
+        const int cq = (lane & 7) * 4;
+        float4 prev[8];
+        if (p.accumulate) {  // fan-in: fetch what is already there (coalesced, all 8 loads in flight) before touching TMEM
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            prev[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((okmask >> (4 * i + (lane >> 3))) & 1u)
+              prev[i] = __ldcs(reinterpret_cast<const float4*>(p.out + row_off[i] + c0 + cq));
+          }
+        }
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + c0, v);
         tmem_ld_wait();
-        if (ok && n0 + c0 < p.Nout) {
+        // TMEM gives one pixel row per lane; a row-per-lane global store would touch 32 different cache lines per
+        // instruction.  Transpose through this warp's private, padded staging block so that every store instruction
+        // writes 4 rows x 128 contiguous bytes, and the BN column sums become conflict-free column reads.
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                   __uint_as_float(v[j + 3]));
-            if (p.bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-            }
-            if (p.accumulate) {
-              const float4 e = *reinterpret_cast<const float4*>(dst + c0 + j);
-              o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
-            }
-            *reinterpret_cast<float4*>(dst + c0 + j) = o;
-            v[j] = __float_as_uint(o.x); v[j + 1] = __float_as_uint(o.y);
-            v[j + 2] = __float_as_uint(o.z); v[j + 3] = __float_as_uint(o.w);
+        for (int j = 0; j < 32; j += 4) {
+          float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                 __uint_as_float(v[j + 3]));
+          if (p.bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
           }
+          *reinterpret_cast<float4*>(stg + lane * kStgPitch + j) = o;
         }
-        if (p.ch_sum && n0 + c0 < p.Nout) {
-          // fused train-mode BN statistics (replaces a full re-read of the output by vspw_bn_stats): column sums of
-          // this warp's 32 rows by shuffles, the 4 epilogue warps meet in shared memory, one fp64 atomic per channel
-          float a[32], b[32];
+        __syncwarp();
+        if (p.ch_sum) {
+          // fused train-mode BN statistics (replaces a full re-read of the output by vspw_bn_stats): lane = column
+          float sa = 0.f, sb = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            a[j] = ok ? __uint_as_float(v[j]) : 0.f;
-            b[j] = a[j] * a[j];
+          for (int r = 0; r < 32; ++r) {
+            const float x = ((okmask >> r) & 1u) ? stg[r * kStgPitch + lane] : 0.f;
+            sa += x;
+            sb = fmaf(x, x, sb);
           }
-          const float sa = warp_column_sums(a, lane), sb = warp_column_sums(b, lane);
           float* buf = stat_s + acc * 2 * BN;
           atomicAdd(buf + c0 + lane, sa);
           atomicAdd(buf + BN + c0 + lane, sb);
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = 4 * i + (lane >> 3);
+          if ((okmask >> r) & 1u) {
+            float4 o = *reinterpret_cast<const float4*>(stg + r * kStgPitch + cq);
+            if (p.accumulate) { o.x += prev[i].x; o.y += prev[i].y; o.z += prev[i].z; o.w += prev[i].w; }
+            *reinterpret_cast<float4*>(p.out + row_off[i] + c0 + cq) = o;
+          }
+        }
+        __syncwarp();  // the staging block is rewritten by the next chunk
       }
       tcgen05_fence_before();
       __syncwarp();

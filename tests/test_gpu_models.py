@@ -36,6 +36,17 @@ def nchw(t):
     return t.permute(0, 3, 1, 2).contiguous()
 
 
+def head_err(grad, ref_head, ref_norm):
+    """Element-wise pin: largest deviation over the first 64 entries, relative to the larger of their own scale and the
+    tensor's RMS entry.  (Relative to the head alone the metric is ill-conditioned when those 64 entries happen to be a
+    cancelling row: `ppm_conv.ppm.0.0.weight` row 0 of the psp_weight fixture is 1000x below the tensor's RMS and moves
+    by 80 % under a 1e-5 operand perturbation while the tensor's norm moves by 8e-5.)"""
+    ours = grad.reshape(-1)[:64].double().cpu().numpy()
+    ref = np.asarray(ref_head, dtype=np.float64).reshape(-1)
+    scale = max(float(np.abs(ref).max()), ref_norm / float(grad.numel()) ** 0.5, 1e-30)
+    return float(np.abs(ours - ref).max() / scale)
+
+
 def _train_step(E, name, prec):
     kind, arch, T, n, H, W, mseed, dseed = C.CASES[name]
     m = C.no_dropout(C.build(kind, arch, mseed).cuda().train())
@@ -83,7 +94,7 @@ def test_train_step_matches_reference(E, name, prec):
         # (bf16x3 perturbs every operand by 2^-17 instead of 2^-24, i.e. 128x the fp32 rounding that already produces that
         # floor, so its element-wise pins on this chaotic fixture are only a sanity bound; the non-chaotic frozen-BN test
         # below and tests/test_gpu_conv_tc.py are where bf16x3 gradients are pinned tightly)
-        assert C.rel_err(p.grad.reshape(-1)[:64].cpu(), g["train/ghead/" + k]) <= (50 * TOL if prec == "fp32" else 0.3), k
+        assert head_err(p.grad, g["train/ghead/" + k], ref_norm) <= (50 * TOL if prec == "fp32" else 0.3), k
         checked += 1
     assert checked > 60
     sd = m.state_dict()
@@ -118,7 +129,7 @@ def test_frozen_bn_step_gradients_match_reference(E, name, prec):
             continue
         ref_norm = float(g[key])
         en = abs(float(p.grad.double().norm()) - ref_norm) / ref_norm
-        eh = C.rel_err(p.grad.reshape(-1)[:64].cpu(), g["fixbn/ghead/" + k])
+        eh = head_err(p.grad, g["fixbn/ghead/" + k], ref_norm)
         worst_n, worst_h = max(worst_n, en), max(worst_h, eh)
         assert en <= GRAD_GATES[prec][1], (k, en)
         # element-wise: one ReLU whose pre-activation is within fp32 rounding of zero flips between two fp32
