@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
 
 using namespace vspw;
 
@@ -63,6 +64,24 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// ---- thread-block-cluster helpers (cta_group::2 pair) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta_rank) {  // same offset in CTA `cta_rank`'s smem
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -183,6 +202,98 @@ struct ConvSmem {
 };
 
 
+// One output tile of the epilogue: wait for the accumulator, TMEM -> registers -> per-warp smem transpose -> coalesced NHWC
+// stores (+bias, +fan-in), fused BN statistics, release the accumulator.  Called by the 4 epilogue warps (warp 2..5).
+// empty_remote != 0: the accumulator-empty barrier lives in the peer (leader) CTA of a cta_group::2 pair.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, float* stg, float* stat_s, int acc, uint32_t acc_phase,
+                                              uint32_t tmem_base, uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar,
+                                              uint32_t empty_remote, int img, int ty, int tx, int n0, int warp, int lane) {
+  const int q = warp & 3;
+  const int row = q * 32 + lane;
+  const int px = tx * p.bw + row % p.bw, py = ty * p.bh + row / p.bw;
+  const bool ok = img < p.N && px < p.W && py < p.H;
+  const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
+  // element offset of this lane's output row; the rows the lane STORES (r = 4*i + lane/8, see below) come by shuffle
+  const unsigned long long my_off = (((unsigned long long)img * p.H + py) * p.W + px) * (unsigned long long)p.Nout + n0;
+  unsigned long long row_off[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) row_off[i] = __shfl_sync(0xffffffffu, my_off, 4 * i + (lane >> 3));
+  mbar_wait(tmem_full_bar, acc_phase);
+  tcgen05_fence_after();
+  const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    if (n0 + c0 >= p.Nout) continue;  // warp-uniform
+    const int cq = (lane & 7) * 4;
+    float4 prev[8];
+    if (p.accumulate) {  // fan-in: fetch what is already there (coalesced, all 8 loads in flight) before touching TMEM
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        prev[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((okmask >> (4 * i + (lane >> 3))) & 1u)
+          prev[i] = __ldcs(reinterpret_cast<const float4*>(p.out + row_off[i] + c0 + cq));
+      }
+    }
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(taddr + c0, v);
+    tmem_ld_wait();
+    // TMEM gives one pixel row per lane; a row-per-lane global store would touch 32 different cache lines per
+    // instruction.  Transpose through this warp's private, padded staging block so that every store instruction
+    // writes 4 rows x 128 contiguous bytes, and the BN column sums become conflict-free column reads.
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                             __uint_as_float(v[j + 3]));
+      if (p.bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
+        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+      }
+      *reinterpret_cast<float4*>(stg + lane * kStgPitch + j) = o;
+    }
+    __syncwarp();
+    if (p.ch_sum) {
+      // fused train-mode BN statistics (replaces a full re-read of the output by vspw_bn_stats): lane = column
+      float sa = 0.f, sb = 0.f;
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        const float x = ((okmask >> r) & 1u) ? stg[r * kStgPitch + lane] : 0.f;
+        sa += x;
+        sb = fmaf(x, x, sb);
+      }
+      float* buf = stat_s + acc * 2 * BN;
+      atomicAdd(buf + c0 + lane, sa);
+      atomicAdd(buf + BN + c0 + lane, sb);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = 4 * i + (lane >> 3);
+      if ((okmask >> r) & 1u) {
+        float4 o = *reinterpret_cast<const float4*>(stg + r * kStgPitch + cq);
+        if (p.accumulate) { o.x += prev[i].x; o.y += prev[i].y; o.z += prev[i].z; o.w += prev[i].w; }
+        *reinterpret_cast<float4*>(p.out + row_off[i] + c0 + cq) = o;
+      }
+    }
+    __syncwarp();  // the staging block is rewritten by the next chunk
+  }
+  tcgen05_fence_before();
+  __syncwarp();
+  if (lane == 0) { if (empty_remote) mbar_arrive_cluster(empty_remote); else mbar_arrive(tmem_empty_bar); }
+  if (p.ch_sum) {
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps have added their rows of this tile
+    float* buf = stat_s + acc * 2 * BN;
+#pragma unroll
+    for (int col = (warp - 2) * 32 + lane; col < BN; col += 128) {  // 128 threads sweep the BN columns
+      if (n0 + col < p.Nout) {
+        atomicAdd(p.ch_sum + n0 + col, (double)buf[col]);
+        atomicAdd(p.ch_sqsum + n0 + col, (double)buf[BN + col]);
+      }
+      buf[col] = 0.f; buf[BN + col] = 0.f;
+    }
+    // buffer `acc` is next written two tiles later, after the bar.sync of the tile in between
+  }
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -287,8 +398,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
   } else if (warp >= 2) {
     // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -297,85 +406,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       int tx = tm % p.tiles_x; tm /= p.tiles_x;
       int ty = tm % p.tiles_y;
       int img = tm / p.tiles_y;
-      const int px = tx * p.bw + row % p.bw, py = ty * p.bh + row / p.bw, n0 = tn * BN;
-      const bool ok = px < p.W && py < p.H;
-      const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
-      // element offset of this lane's output row; the rows the lane STORES (r = 4*i + lane/8, see below) come by shuffle
-      const unsigned long long my_off = (((unsigned long long)img * p.H + py) * p.W + px) * (unsigned long long)p.Nout + n0;
-      unsigned long long row_off[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) row_off[i] = __shfl_sync(0xffffffffu, my_off, 4 * i + (lane >> 3));
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (n0 + c0 >= p.Nout) continue;  // warp-uniform
-        const int cq = (lane & 7) * 4;
-        float4 prev[8];
-        if (p.accumulate) {  // fan-in: fetch what is already there (coalesced, all 8 loads in flight) before touching TMEM
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            prev[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if ((okmask >> (4 * i + (lane >> 3))) & 1u)
-              prev[i] = __ldcs(reinterpret_cast<const float4*>(p.out + row_off[i] + c0 + cq));
-          }
-        }
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + c0, v);
-        tmem_ld_wait();
-        // TMEM gives one pixel row per lane; a row-per-lane global store would touch 32 different cache lines per
-        // instruction.  Transpose through this warp's private, padded staging block so that every store instruction
-        // writes 4 rows x 128 contiguous bytes, and the BN column sums become conflict-free column reads.
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                 __uint_as_float(v[j + 3]));
-          if (p.bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-          }
-          *reinterpret_cast<float4*>(stg + lane * kStgPitch + j) = o;
-        }
-        __syncwarp();
-        if (p.ch_sum) {
-          // fused train-mode BN statistics (replaces a full re-read of the output by vspw_bn_stats): lane = column
-          float sa = 0.f, sb = 0.f;
-#pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            const float x = ((okmask >> r) & 1u) ? stg[r * kStgPitch + lane] : 0.f;
-            sa += x;
-            sb = fmaf(x, x, sb);
-          }
-          float* buf = stat_s + acc * 2 * BN;
-          atomicAdd(buf + c0 + lane, sa);
-          atomicAdd(buf + BN + c0 + lane, sb);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = 4 * i + (lane >> 3);
-          if ((okmask >> r) & 1u) {
-            float4 o = *reinterpret_cast<const float4*>(stg + r * kStgPitch + cq);
-            if (p.accumulate) { o.x += prev[i].x; o.y += prev[i].y; o.z += prev[i].z; o.w += prev[i].w; }
-            *reinterpret_cast<float4*>(p.out + row_off[i] + c0 + cq) = o;
-          }
-        }
-        __syncwarp();  // the staging block is rewritten by the next chunk
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (p.ch_sum) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps have added their rows of this tile
-        const int col = (warp - 2) * 32 + lane;         // 128 threads <-> BN = 128 columns
-        float* buf = stat_s + acc * 2 * BN;
-        if (col < BN && n0 + col < p.Nout) {
-          atomicAdd(p.ch_sum + n0 + col, (double)buf[col]);
-          atomicAdd(p.ch_sqsum + n0 + col, (double)buf[BN + col]);
-        }
-        if (col < BN) { buf[col] = 0.f; buf[BN + col] = 0.f; }
-        // buffer `acc` is next written two tiles later, after the bar.sync of the tile in between
-      }
+      const int n0 = tn * BN;
+      epilogue_tile<BN>(p, stg, stat_s, acc, acc_phase, tmem_base, &tmem_full[acc], &tmem_empty[acc], 0u, img, ty, tx, n0, warp, lane);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -384,6 +416,192 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   __syncthreads();
   tcgen05_fence_after();
   if (warp == 2) tmem_dealloc<2 * BN>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// cta_group::2 variant: a pair of CTAs (one thread-block cluster = the two SMs of a TPC) computes a 256-pixel x 256-channel
+// tile with UMMA 256x256x16.  Each CTA stages only ITS 128 pixels of A and ITS 128 rows of B per k-block, i.e. the same
+// bytes as the single-CTA kernel for twice the MMA work: L2->SM operand traffic per FLOP is halved (the single-CTA kernel
+// is bound by it: ~60 B/clk/SM, tensor pipe 70 % in bf16x3 and 50 % in bf16 on the large layers).
+//   * TMA: both CTAs issue their loads with .cta_group::2 and signal the LEADER's (rank 0) full barrier.
+//   * MMA: issued by the leader's thread only; tcgen05.commit multicasts to the empty / tmem_full barriers of BOTH CTAs.
+//   * accumulator: CTA r's TMEM holds rows [128 r, 128 r + 128) x 256 columns; each CTA's epilogue warps drain their half
+//     and arrive on the leader's tmem_empty barrier (count 8).
+constexpr int BN2 = 256;
+
+template <int STAGES>
+struct Conv2Smem {
+  static constexpr int kATile = BM * BK * 2;          // 16 KB: this CTA's 128 pixels
+  static constexpr int kBTile = (BN2 / 2) * BK * 2;   // 16 KB: this CTA's 128 of the 256 output channels
+  static constexpr int kStage = 2 * kATile + 2 * kBTile;
+  static constexpr int kStatBytes = 2 * 2 * BN2 * 4;
+  static constexpr int kStgBytes = 4 * 32 * kStgPitch * 4;
+  static constexpr int kBytes = STAGES * kStage + 1024 + 256 + kStatBytes + kStgBytes;
+};
+
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1,
+                                                int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint64_t desc_a, uint64_t desc_b, uint32_t tmem_d, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (count 1) on the barrier at this offset in BOTH CTAs of the pair once the issued MMAs have completed
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, ConvTcParams p) {
+  using S = Conv2Smem<STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStage);
+  uint64_t* full_bar = bars;                    // [STAGES]  used in the leader only
+  uint64_t* empty_bar = bars + STAGES;          // [STAGES]  one per CTA (multicast commit)
+  uint64_t* tmem_full = bars + 2 * STAGES;      // [2]       one per CTA (multicast commit)
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]       leader only, count 8 = 4 epilogue warps x 2 CTAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* stat_s = reinterpret_cast<float*>(smem + STAGES * S::kStage + 256);
+  float* stg = stat_s + 4 * BN2 + (threadIdx.x >= 64 ? ((threadIdx.x >> 5) - 2) * 32 * kStgPitch : 0);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int tiles_m = p.N * p.tiles_y * p.tiles_x;            // 128-pixel patches
+  const int pairs_m = (tiles_m + 1) >> 1;                     // a pair takes patches 2j and 2j+1
+  const int num_tiles = pairs_m * p.tiles_n;                  // tiles_n counts 256-channel tiles here
+  const int kblocks_per_tap = p.C / BK;
+  const int num_k = p.taps_h * p.taps_w * kblocks_per_tap;
+  const uint32_t stage_bytes = (uint32_t)(S::kATile + S::kBTile) * (p.x3 ? 2u : 1u);  // per CTA
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi);
+    tma_prefetch_desc(&map_b_hi);
+    if (p.x3) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_b_lo); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * BN2) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (p.ch_sum) for (int i = threadIdx.x; i < 4 * BN2; i += kThreads) stat_s[i] = 0.f;
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // barrier inits of both CTAs are visible before any remote arrive / peer-signalling TMA
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // m-patch of THIS CTA inside pair-tile `tile`; patches beyond the end are fetched as zeros (TMA OOB) and never stored
+  auto decode = [&](int tile, int& img, int& ty, int& tx, int& tn) {
+    tn = tile % p.tiles_n;
+    int tm = (tile / p.tiles_n) * 2 + (int)rank;
+    tx = tm % p.tiles_x; tm /= p.tiles_x;
+    ty = tm % p.tiles_y;
+    img = tm / p.tiles_y;  // == p.N for the padding patch of an odd patch count
+  };
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer (both CTAs; completion bytes go to the leader's barrier) =====
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      int img, ty, tx, tn;
+      decode(tile, img, ty, tx, tn);
+      const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * BN2 + (int)rank * (BN2 / 2);
+      for (int r = 0; r < p.taps_h; ++r)
+        for (int s = 0; s < p.taps_w; ++s)
+          for (int kb = 0; kb < kblocks_per_tap; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + stage * S::kStage;
+            const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
+            const int cx = x0 * p.stride + p.off0 + s * p.step, cy = y0 * p.stride + p.off0 + r * p.step;
+            const int kcol = ((r * p.taps_w + s) * kblocks_per_tap + kb) * BK;
+            tma_load_4d_2sm(st, &map_a_hi, fb, kb * BK, cx, cy, img);
+            tma_load_2d_2sm(st + 2 * S::kATile, &map_b_hi, fb, kcol, n0);
+            if (p.x3) {
+              tma_load_4d_2sm(st + S::kATile, &map_a_lo, fb, kb * BK, cx, cy, img);
+              tma_load_2d_2sm(st + 2 * S::kATile + S::kBTile, &map_b_lo, fb, kcol, n0);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+    }
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ===== MMA issuer (leader CTA only) =====
+    constexpr uint32_t idesc = make_idesc(2 * BM, BN2, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN2);
+      for (int k = 0; k < num_k; ++k) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        const uint32_t a_hi = smem_u32(smem + stage * S::kStage);
+        const uint32_t a_lo = a_hi + S::kATile;
+        const uint32_t b_hi = a_hi + 2 * S::kATile;
+        const uint32_t b_lo = b_hi + S::kBTile;
+#pragma unroll
+        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+          const uint32_t koff = kk * UMMA_K * 2;
+          const uint64_t da_hi = make_kmajor_sw128_desc(a_hi + koff), db_hi = make_kmajor_sw128_desc(b_hi + koff);
+          umma_bf16_2sm(da_hi, db_hi, tmem_d, idesc, (k | kk) != 0);
+          if (p.x3) {
+            const uint64_t da_lo = make_kmajor_sw128_desc(a_lo + koff), db_lo = make_kmajor_sw128_desc(b_lo + koff);
+            umma_bf16_2sm(da_hi, db_lo, tmem_d, idesc, 1);
+            umma_bf16_2sm(da_lo, db_hi, tmem_d, idesc, 1);
+          }
+        }
+        umma_commit_2sm(&empty_bar[stage]);  // frees this stage in both CTAs
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit_2sm(&tmem_full[acc]);      // both CTAs' epilogues may drain their half
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 2) {
+    // ===== epilogue (both CTAs): this CTA's 128 rows x 256 columns =====
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      int img, ty, tx, tn;
+      decode(tile, img, ty, tx, tn);
+      const uint32_t remote = rank == 0 ? 0u : mapa_shared(smem_u32(&tmem_empty[acc]), 0);
+      epilogue_tile<BN2>(p, stg, stat_s, acc, acc_phase, tmem_base, &tmem_full[acc], &tmem_empty[acc], remote, img, ty, tx,
+                         tn * BN2, warp, lane);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer may still be reading operands of / committing to this CTA
+  tcgen05_fence_after();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN2) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -459,6 +677,16 @@ bool geometry_ok(const vspw_conv_desc* d) {
 
 constexpr int kBN = 128, kStages = 3;
 
+// VSPW_CONV_PAIR=0 forces the single-CTA kernel everywhere (A/B comparisons, debugging)
+bool use_pair_kernel() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VSPW_CONV_PAIR");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int taps, int off0, int step, int stride,
                    const uint16_t* a_hi,
                    const uint16_t* a_lo, const uint16_t* b_hi, const uint16_t* b_lo, const float* bias, float* out, int x3,
@@ -491,6 +719,23 @@ int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int ta
   const long long kdim = (long long)taps * taps * c;
   if ((rc = make_mat_map(&mb_hi, b_hi, nout, kdim, BK, kBN, who))) return rc;
   if ((rc = make_mat_map(&mb_lo, x3 ? b_lo : b_hi, nout, kdim, BK, kBN, who))) return rc;
+  if (nout % BN2 == 0 && use_pair_kernel()) {
+    p.tiles_n = nout / BN2;
+    if ((rc = make_mat_map(&mb_hi, b_hi, nout, kdim, BK, BN2 / 2, who))) return rc;
+    if ((rc = make_mat_map(&mb_lo, x3 ? b_lo : b_hi, nout, kdim, BK, BN2 / 2, who))) return rc;
+    using S2 = Conv2Smem<kStages>;
+    static std::once_flag once2;
+    static cudaError_t attr_err2 = cudaSuccess;
+    std::call_once(once2, [] {
+      attr_err2 = cudaFuncSetAttribute(conv_tc2_kernel<kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2::kBytes);
+    });
+    if (attr_err2 != cudaSuccess) { set_error("%s: cudaFuncSetAttribute(pair): %s", who, cudaGetErrorString(attr_err2)); return VSPW_ERR_CUDA; }
+    const long long tiles_m = (long long)n * p.tiles_y * p.tiles_x;
+    const long long pair_tiles = ((tiles_m + 1) / 2) * p.tiles_n;
+    const int pairs = (int)(pair_tiles < kNumSMs / 2 ? pair_tiles : kNumSMs / 2);
+    conv_tc2_kernel<kStages><<<2 * pairs, kThreads, S2::kBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+    return check_launch(who);
+  }
   using S = ConvSmem<kBN, kStages>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
