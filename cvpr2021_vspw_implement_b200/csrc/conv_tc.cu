@@ -896,6 +896,142 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy_hi, const __grid_cons
   if (warp == 2) tmem_dealloc<128>(tmem_d);
 }
 
+// cta_group::2 variant of the wgrad kernel: a CTA pair accumulates a 256 (co) x 256 (ci) block of dW with UMMA 256x256x16.
+// Each CTA stages its own 128 co of dy and its own 128 ci of x per 64-pixel step (the same bytes as the single-CTA kernel
+// for twice the MMA work); CTA r ends up with rows co = 256*tco + 128*r + [0,128) x 256 ci columns in its TMEM.
+__device__ __forceinline__ void tma_load_4d_2sm_w(void* dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+wgrad_tc2_kernel(const __grid_constant__ CUtensorMap map_dy_hi, const __grid_constant__ CUtensorMap map_dy_lo,
+                 const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo, WgradTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+  uint64_t* full_bar = bars;               // leader only
+  uint64_t* empty_bar = bars + WG_STAGES;  // per CTA (multicast commit)
+  uint64_t* done_bar = bars + 2 * WG_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_STAGES + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  int t = blockIdx.x >> 1;  // pair index
+  const int split = t % p.splits; t /= p.splits;
+  const int tco = t % p.tiles_co; t /= p.tiles_co;   // 256-wide tiles here
+  const int tci = t % p.tiles_ci; t /= p.tiles_ci;
+  const int tap = t;
+  const int tr = tap / p.taps_w, ts = tap - tr * p.taps_w;
+  const int dxo = p.off0 + ts * p.step, dyo = p.off0 + tr * p.step;
+  const int total_patches = p.N * p.tiles_y * p.tiles_x;
+  const int pbeg = split * p.chunk;
+  const int pend = min(total_patches, pbeg + p.chunk);
+  const int num_k = pend - pbeg;
+  const uint32_t stage_bytes = (uint32_t)(4 * WG_BLK) * (p.x3 ? 2u : 1u);  // per CTA
+  const int co0 = tco * 256 + (int)rank * 128, ci0 = tci * 256 + (int)rank * 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_dy_hi);
+    tma_prefetch_desc(&map_x_hi);
+    if (p.x3) { tma_prefetch_desc(&map_dy_lo); tma_prefetch_desc(&map_x_lo); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int pi = pbeg; pi < pend; ++pi) {
+      int q = pi;
+      const int tx = q % p.tiles_x; q /= p.tiles_x;
+      const int ty = q % p.tiles_y;
+      const int img = q / p.tiles_y;
+      const int x0 = tx * p.bw, y0 = ty * p.bh;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* st = smem + stage * WG_STAGE_BYTES;
+      const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+      if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
+      tma_load_4d_2sm_w(st + 0 * WG_BLK, &map_dy_hi, fb, co0, x0, y0, img);
+      tma_load_4d_2sm_w(st + 1 * WG_BLK, &map_dy_hi, fb, co0 + 64, x0, y0, img);
+      const int xx = x0 * p.stride + dxo, xy = y0 * p.stride + dyo;
+      tma_load_4d_2sm_w(st + 2 * WG_BLK, &map_x_hi, fb, ci0, xx, xy, img);
+      tma_load_4d_2sm_w(st + 3 * WG_BLK, &map_x_hi, fb, ci0 + 64, xx, xy, img);
+      if (p.x3) {
+        tma_load_4d_2sm_w(st + 4 * WG_BLK, &map_dy_lo, fb, co0, x0, y0, img);
+        tma_load_4d_2sm_w(st + 5 * WG_BLK, &map_dy_lo, fb, co0 + 64, x0, y0, img);
+        tma_load_4d_2sm_w(st + 6 * WG_BLK, &map_x_lo, fb, ci0, xx, xy, img);
+        tma_load_4d_2sm_w(st + 7 * WG_BLK, &map_x_lo, fb, ci0 + 64, xx, xy, img);
+      }
+      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    constexpr uint32_t idesc = make_idesc(256, 256, 1, 1);  // both operands MN-major
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int k = 0; k < num_k; ++k) {
+      mbar_wait(&full_bar[stage], phase);
+      tcgen05_fence_after();
+      const uint32_t base = smem_u32(smem + stage * WG_STAGE_BYTES);
+#pragma unroll
+      for (int kk = 0; kk < WG_PIX / UMMA_K; ++kk) {
+        const uint32_t koff = kk * UMMA_K * 128;
+        const uint64_t a_hi = make_mnmajor_sw128_desc(base + 0 * WG_BLK + koff, WG_BLK);
+        const uint64_t b_hi = make_mnmajor_sw128_desc(base + 2 * WG_BLK + koff, WG_BLK);
+        umma_bf16_2sm(a_hi, b_hi, tmem_d, idesc, (k | kk) != 0);
+        if (p.x3) {
+          const uint64_t a_lo = make_mnmajor_sw128_desc(base + 4 * WG_BLK + koff, WG_BLK);
+          const uint64_t b_lo = make_mnmajor_sw128_desc(base + 6 * WG_BLK + koff, WG_BLK);
+          umma_bf16_2sm(a_hi, b_lo, tmem_d, idesc, 1);
+          umma_bf16_2sm(a_lo, b_hi, tmem_d, idesc, 1);
+        }
+      }
+      umma_commit_2sm(&empty_bar[stage]);
+      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+    }
+    umma_commit_2sm(done_bar);
+  } else if (warp >= 2) {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tcgen05_fence_after();
+    const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
+    const int taps = p.taps_w * p.taps_w;
+    float* dst = p.dw + ((size_t)co * taps + tap) * p.Cin + tci * 256;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 256; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(taddr + c0, v);
+      tmem_ld_wait();
+      if (co < p.Cout && tci * 256 + c0 < p.Cin) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          red_add_v4(dst + c0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                     __uint_as_float(v[j + 3]));
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(256) : "memory");
+}
+
 void pick_patch64(int h, int w, int& bw, int& bh) {
   const int cand[7][2] = {{16, 4}, {8, 8}, {32, 2}, {4, 16}, {64, 1}, {2, 32}, {1, 64}};
   long long best = -1;
@@ -952,9 +1088,11 @@ extern "C" int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_h
   p.tiles_co = (d->cout + 127) / 128;
   p.tiles_ci = (d->cin + 127) / 128;
   const int taps = d->kh * d->kw;
+  const bool pair = d->cout % 256 == 0 && d->cin % 256 == 0 && use_pair_kernel();
+  if (pair) { p.tiles_co = d->cout / 256; p.tiles_ci = d->cin / 256; }
   const long long tiles = (long long)p.tiles_co * p.tiles_ci * taps;
   const int total_patches = p.N * p.tiles_y * p.tiles_x;
-  int splits = (int)((2 * kNumSMs) / tiles);  // ~2 CTAs per SM's worth of work items; one resident at a time
+  int splits = (int)(((pair ? 1 : 2) * kNumSMs) / tiles);  // ~2 CTAs per SM's worth of work items; one resident at a time
   if (splits < 1) splits = 1;
   if (splits > total_patches) splits = total_patches;
   p.chunk = (total_patches + splits - 1) / splits;
@@ -972,7 +1110,15 @@ extern "C" int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_h
   std::call_once(once, [] { attr_err = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM); });
   if (attr_err != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(attr_err)); return VSPW_ERR_CUDA; }
   const long long grid = tiles * p.splits;
-  VSPW_REQUIRE(grid < (1ll << 31), "%s: grid too large", who);
+  VSPW_REQUIRE(grid < (1ll << 30), "%s: grid too large", who);
+  if (pair) {
+    static std::once_flag once2;
+    static cudaError_t attr_err2 = cudaSuccess;
+    std::call_once(once2, [] { attr_err2 = cudaFuncSetAttribute(wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM); });
+    if (attr_err2 != cudaSuccess) { set_error("%s: cudaFuncSetAttribute(pair): %s", who, cudaGetErrorString(attr_err2)); return VSPW_ERR_CUDA; }
+    wgrad_tc2_kernel<<<(unsigned)(2 * grid), kThreads, WG_SMEM, st>>>(mdy_hi, mdy_lo, mx_hi, mx_lo, p);
+    return check_launch(who);
+  }
   wgrad_tc_kernel<<<(unsigned)grid, kThreads, WG_SMEM, st>>>(mdy_hi, mdy_lo, mx_hi, mx_lo, p);
   return check_launch(who);
 }
