@@ -219,25 +219,30 @@ def run_ours(args):
     final_loss = float(loss.item())
 
     # ---- timed: end to end from pinned host buffers ---------------------------------------------------------------
+    # Every step's images+labels are copied from pinned host memory (H2D) and every step's loss is read back (D2H), all
+    # inside one CUDA-event pair around the whole region.  The feed is the repo's DevicePrefetcher (clip i+1 copies on a
+    # side stream while clip i computes) and the loss of step i is read after step i+1 has been queued, as the training
+    # entry point does; nothing is cached across steps.
+    from cvpr2021_vspw_implement_b200.data import DevicePrefetcher
     e2e_steps = 0 if args.profile_run else max(2, min(args.steps, 5))
-    barrier()
-    evs = []
-    for _ in range(e2e_steps):
+    e2e_value = 0.0
+    if e2e_steps:
+        barrier()
+        loss_host = torch.empty(e2e_steps, dtype=torch.float32).pin_memory()
         flush.fill_(0.0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        imgs = [t.to(dev, non_blocking=True) for t in imgs_h]
-        labs = [t.to(dev, non_blocking=True) for t in labs_h]
-        loss = step(imgs, labs)
-        _ = loss.item()  # D2H read of the step's result
+        feed = DevicePrefetcher(((imgs_h, labs_h) for _ in range(e2e_steps)), dev)
+        for i, (imgs, labs) in enumerate(feed):
+            loss = step(imgs, labs)
+            loss_host[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)  # D2H read of the step's result
         e1.record()
-        evs.append((e0, e1))
-    barrier()
-    e2e_ms = sum(a.elapsed_time(b) for a, b in evs)
-    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = frames_per_step / (float(t.item()) / e2e_steps / 1e3) if e2e_steps else 0.0
+        barrier()
+        assert all(v == v for v in loss_host.tolist())
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_value = frames_per_step / (float(t.item()) / e2e_steps / 1e3)
 
     if args.kernel_profile and rank == 0:
         lib.profile_begin()

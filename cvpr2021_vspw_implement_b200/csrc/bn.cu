@@ -169,7 +169,7 @@ inline dim3 ew_grid(size_t pixels, int c4) {
   const int PL = kEwThreads / G;
   const unsigned gy = (unsigned)((c4 + G - 1) / G);
   size_t bx = (pixels + (size_t)PL * kUnroll - 1) / ((size_t)PL * kUnroll);
-  size_t cap = (size_t)kNumSMs * 8 / gy;
+  size_t cap = (size_t)kNumSMs * 12 / gy;
   if (cap < 1) cap = 1;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
@@ -241,15 +241,14 @@ __device__ __forceinline__ float4 apply_mask(float4 g, bool has_o, float4 o, boo
   return g;
 }
 
-// backward pass 1: per-channel dbeta = sum g, dgamma = sum g * xhat.  fp32 partials over <= kRedPix pixels per
+// backward pass 1: per-channel dbeta = sum g, dgamma = sum g * xhat.  fp32 partials over `red_pix` pixels per
 // thread (kUnroll independent streams), lanes meet in shared memory, one fp64 atomic per channel per block.
-constexpr int kRedPix = 64;
-
+// red_pix is chosen on the host so that the grid is ~6 blocks per SM whatever the channel count.
 __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(
     const float4* __restrict__ dout, const float4* __restrict__ out, const uint2* __restrict__ out_hi,
     const float4* __restrict__ y, const float4* __restrict__ mean, const float4* __restrict__ invstd,
     const float4* __restrict__ chan_scale, int relu, size_t pixels, int c4, size_t pix_per_img, double* dbeta,
-    double* dgamma) {
+    double* dgamma, int red_pix) {
   __shared__ float4 sh[2][kEwThreads];
   const int G = c4 < kEwThreads ? c4 : kEwThreads;
   const int PL = kEwThreads / G;
@@ -260,8 +259,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(
   if (active) {
     const float4 mu = __ldg(mean + cg), is = __ldg(invstd + cg);
     const bool has_o = relu && out, has_h = relu && !out;
-    const size_t pbeg = (size_t)blockIdx.x * PL * kRedPix + pl;
-    const size_t pend = min(pixels, (size_t)(blockIdx.x + 1) * PL * kRedPix);
+    const size_t pbeg = (size_t)blockIdx.x * PL * red_pix + pl;
+    const size_t pend = min(pixels, (size_t)(blockIdx.x + 1) * PL * red_pix);
     for (size_t p = pbeg; p < pend; p += (size_t)PL * kUnroll) {
       float4 d[kUnroll], yv[kUnroll], o[kUnroll];
       uint2 h[kUnroll];
@@ -308,11 +307,20 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(
     atomicAdd(dgamma + cg * 4 + 2, v2); atomicAdd(dgamma + cg * 4 + 3, v3);
   }
 }
-inline dim3 red_grid(size_t pixels, int c4) {
+inline dim3 red_grid(size_t pixels, int c4, int& red_pix) {
   const int G = c4 < kEwThreads ? c4 : kEwThreads;
   const int PL = kEwThreads / G;
-  const size_t per_block = (size_t)PL * kRedPix;
-  return dim3((unsigned)((pixels + per_block - 1) / per_block), (unsigned)((c4 + G - 1) / G), 1);
+  const unsigned gy = (unsigned)((c4 + G - 1) / G);
+  // pixels per thread: a multiple of kUnroll, sized for ~6 blocks per SM (more blocks = more fp64 atomics, fewer = idle SMs)
+  size_t want_blocks = (size_t)kNumSMs * 6 / gy;
+  if (want_blocks < 1) want_blocks = 1;
+  size_t rp = (pixels + want_blocks * PL - 1) / (want_blocks * PL);
+  rp = (rp + kUnroll - 1) / kUnroll * kUnroll;
+  if (rp < (size_t)kUnroll) rp = kUnroll;
+  if (rp > 256) rp = 256;
+  red_pix = (int)rp;
+  const size_t per_block = (size_t)PL * rp;
+  return dim3((unsigned)((pixels + per_block - 1) / per_block), gy, 1);
 }
 
 // backward pass 2: dy = gamma*invstd*(g - dbeta/P - xhat*dgamma/P)  (eval_mode: dy = g*scale), dres = g
@@ -321,9 +329,17 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(
     const float4* __restrict__ y, const float4* __restrict__ mean, const float4* __restrict__ invstd,
     const float4* __restrict__ gamma, const float4* __restrict__ chan_scale, int relu, const double* __restrict__ dbeta,
     const double* __restrict__ dgamma, float4* __restrict__ dy, uint2* __restrict__ dy_hi, uint2* __restrict__ dy_lo,
-    float4* __restrict__ dres, size_t pixels, int c4, size_t pix_per_img, double inv_count, int eval_mode) {
+    float4* __restrict__ dres, float4* __restrict__ dgamma_f, float4* __restrict__ dbeta_f, size_t pixels, int c4,
+    size_t pix_per_img, double inv_count, int eval_mode) {
   const EwMap m = ew_map(c4);
   if (m.cg < 0) return;
+  if (blockIdx.x == 0 && threadIdx.x < (c4 < kEwThreads ? c4 : kEwThreads) && dbeta && dgamma) {
+    // the fp64 sums become the fp32 parameter gradients here (one thread per channel group; no extra launch)
+    const double* db = dbeta + (size_t)m.cg * 4;
+    const double* dg = dgamma + (size_t)m.cg * 4;
+    if (dgamma_f) dgamma_f[m.cg] = make_float4((float)dg[0], (float)dg[1], (float)dg[2], (float)dg[3]);
+    if (dbeta_f) dbeta_f[m.cg] = make_float4((float)db[0], (float)db[1], (float)db[2], (float)db[3]);
+  }
   // dy = ka*g - kb - kc*(y - mean)
   const float4 is = __ldg(invstd + m.cg);
   const float4 gm = gamma ? __ldg(gamma + m.cg) : make_float4(1.f, 1.f, 1.f, 1.f);
@@ -388,12 +404,6 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(
   }
 }
 
-__global__ void d2f_kernel(const double* a, float* fa, const double* b, float* fb, int c) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c) return;
-  if (fa) fa[i] = (float)a[i];
-  if (fb) fb[i] = (float)b[i];
-}
 
 }  // namespace
 
@@ -454,9 +464,11 @@ extern "C" int vspw_bn_bwd_reduce(const float* dout, const float* out, const uin
   VSPW_REQUIRE(!relu || out || out_hi, "vspw_bn_bwd_reduce: relu mask needs the forward output (fp32 or bf16 hi plane)");
   VSPW_REQUIRE(c > 0 && c % 4 == 0, "vspw_bn_bwd_reduce: channels must be a multiple of 4 (got %d)", c);
   if (pixels == 0) return VSPW_OK;
-  bn_bwd_reduce_kernel<<<red_grid(pixels, c / 4), kEwThreads, 0, as_stream(stream)>>>(
+  int red_pix = kUnroll;
+  const dim3 rg = red_grid(pixels, c / 4, red_pix);
+  bn_bwd_reduce_kernel<<<rg, kEwThreads, 0, as_stream(stream)>>>(
       (const float4*)dout, (const float4*)out, (const uint2*)out_hi, (const float4*)y, (const float4*)mean,
-      (const float4*)invstd, (const float4*)chan_scale, relu, pixels, c / 4, pixels_per_image, dbeta, dgamma);
+      (const float4*)invstd, (const float4*)chan_scale, relu, pixels, c / 4, pixels_per_image, dbeta, dgamma, red_pix);
   return check_launch("vspw_bn_bwd_reduce");
 }
 
@@ -475,12 +487,8 @@ extern "C" int vspw_bn_bwd_apply(const float* dout, const float* out, const uint
   bn_bwd_apply_kernel<<<ew_grid(pixels, c / 4), kEwThreads, 0, as_stream(stream)>>>(
       (const float4*)dout, (const float4*)out, (const uint2*)out_hi, (const float4*)y, (const float4*)mean,
       (const float4*)invstd, (const float4*)gamma, (const float4*)chan_scale, relu, dbeta, dgamma, (float4*)dy,
-      (uint2*)dy_hi, (uint2*)dy_lo, (float4*)dres, pixels, c / 4, pixels_per_image, 1.0 / count, eval_mode);
+      (uint2*)dy_hi, (uint2*)dy_lo, (float4*)dres, (float4*)dgamma_f, (float4*)dbeta_f, pixels, c / 4, pixels_per_image,
+      1.0 / count, eval_mode);
   int rc = check_launch("vspw_bn_bwd_apply");
-  if (rc) return rc;
-  if ((dgamma_f || dbeta_f) && dbeta && dgamma) {
-    d2f_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(dgamma, dgamma_f, dbeta, dbeta_f, c);
-    rc = check_launch("vspw_bn_bwd_apply(d2f)");
-  }
   return rc;
 }

@@ -62,3 +62,42 @@ class SyntheticClipTest(Dataset):
         img, gt = self.frames[i]
         nb = [self.frames[max(0, i - o)] for o in self.offsets]  # earlier frames, clamped at the start of the video
         return img, gt, [f[0] for f in nb], [f[1] for f in nb], f"{i:08d}.png"
+
+
+class DevicePrefetcher:
+    """Double-buffered host -> device feed for the train loop: the H2D copy of clip i+1 runs on a side stream while clip i
+    computes (the reference copies synchronously with `.cuda()` before every step, train_clip2.py:45-47).  `source` yields
+    (clip_imgs, clip_gts) lists of pinned host tensors; iteration yields the same lists on `device`, valid until the next
+    item is requested."""
+
+    def __init__(self, source, device):
+        self.it = iter(source)
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self.next = None
+        self._preload()
+
+    def _preload(self):
+        try:
+            imgs, gts = next(self.it)
+        except StopIteration:
+            self.next = None
+            return
+        with torch.cuda.stream(self.stream):
+            d_imgs = [t.to(self.device, non_blocking=True) for t in imgs]
+            d_gts = [t.to(self.device, non_blocking=True) for t in gts]
+        self.next = (d_imgs, d_gts)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.next is None:
+            raise StopIteration
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(self.stream)          # this clip's copies have landed
+        imgs, gts = self.next
+        for t in imgs + gts:
+            t.record_stream(cur)              # the caching allocator must not recycle them while the step still reads them
+        self._preload()                       # start copying the next clip behind the step about to be launched
+        return imgs, gts

@@ -11,6 +11,7 @@ Layout: activations are fp32 NHWC ``(N, H, W, C)`` torch tensors (torch = alloca
 import ctypes
 import math
 import os
+import weakref
 from contextlib import contextmanager
 
 import torch
@@ -193,11 +194,43 @@ class PVar:
             lib.call("vspw_axpby", _p(g), _p(self.grad), 1.0, 1.0, g.numel(), _stream())
 
 
+_ARENA_BYTES = 8 << 20
+_arenas = {}  # device -> [fp64 buffer, owning tape or None]: per-step pool of zeroed accumulators
+
+
 class Tape:
     def __init__(self, grad_enabled):
         self.grad_enabled = grad_enabled
         self._nodes = []
         self._params = {}
+        self._arena = None
+        self._arena_off = 0
+        self._done = False  # set once backward has run (or the tape was released): its arena slices are dead
+
+    def zeros_f64(self, shape, device):
+        """Zero-initialised fp64 accumulator (BN sums, bias gradients).  One memset per step instead of one fill launch
+        per BN layer: slices of a per-device arena that this tape zeroes once, the first time it asks."""
+        n = 1
+        for d in shape:
+            n *= int(d)
+        n_al = (n + 15) // 16 * 16
+        if self._arena is None:
+            slot = _arenas.get(device)
+            if slot is None:
+                slot = _arenas[device] = [torch.empty(_ARENA_BYTES // 8, device=device, dtype=torch.float64), None]
+            owner = slot[1]() if slot[1] is not None else None
+            if owner is None or owner._done:
+                slot[1] = weakref.ref(self)
+                self._arena = slot[0]
+                # fp64 zeros are zero words: one fill of the whole arena per step
+                lib.call("vspw_fill", _p(self._arena), 0.0, self._arena.numel() * 2, _stream())
+            else:
+                self._arena = False  # another tape is still between its forward and backward on this device
+        if self._arena is False or self._arena_off + n_al > self._arena.numel():
+            return torch.zeros(shape, device=device, dtype=torch.float64)
+        out = self._arena[self._arena_off:self._arena_off + n].view(shape)
+        self._arena_off += n_al
+        return out
 
     def param(self, p):
         if p is None:
@@ -215,9 +248,11 @@ class Tape:
         for fn in reversed(self._nodes):
             fn()
         self._nodes = []
+        self._done = True
 
     def release(self):
         self._nodes = []
+        self._done = True
 
 
 # ------------------------------------------------------------------------------------------------
@@ -330,7 +365,7 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1, want_stats=False)
         xh, xl = _var_planes(x)
         wh, wl = _weight_planes(wv, "ohwi", w_ohwi)
         if want_stats:
-            stats = torch.zeros((2, co), device=y.device, dtype=torch.float64)
+            stats = tape.zeros_f64((2, co), y.device)
         with _ConvTimer(flops, True):
             lib.call("vspw_conv2d_fwd_tc", ctypes.byref(desc), _p(xh), _p(xl), _p(wh), _p(wl), _p(bv.data if bv else None), _p(y),
                      _p(stats[0]) if stats is not None else None, _p(stats[1]) if stats is not None else None, _stream())
@@ -369,7 +404,7 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1, want_stats=False)
                 permute4d(dw, dw_oihw, (co, kh, kw, ci), (0, 3, 1, 2))
                 wv.add_grad(dw_oihw)
         if bv is not None and bv.needs_grad:
-            sums = torch.zeros(co, device=dev, dtype=torch.float64)
+            sums = tape.zeros_f64((co,), dev)
             lib.call("vspw_bn_stats", _p(dy), n * ho * wo, co, _p(sums), None, st)
             bv.add_grad(_double_to_float(sums))
         if x.needs_grad:
@@ -442,7 +477,7 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
             raise ValueError(f"Expected more than 1 value per channel when training, got input size {[n, c, h, w]}")
         sums = y.stats
         if sums is None:
-            sums = torch.zeros((2, c), device=dev, dtype=torch.float64)
+            sums = tape.zeros_f64((2, c), dev)
             lib.call("vspw_bn_stats", _p(y.data), pixels, c, _p(sums[0]), _p(sums[1]), st)
         world = _syncbn_world()
         if world > 1:
@@ -491,7 +526,7 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
             dy = torch.empty_like(dout)
         dres = torch.empty_like(dout) if (residual is not None and residual.needs_grad) else None
         if training:
-            dsum = torch.zeros((2, c), device=dev, dtype=torch.float64)
+            dsum = tape.zeros_f64((2, c), dev)
             lib.call("vspw_bn_bwd_reduce", _p(dout), _p(mask_o), _p(mask_hi), _p(y.data), _p(mean), _p(invstd), _p(chan_scale),
                      1 if relu else 0, pixels, c, h * w, _p(dsum[0]), _p(dsum[1]), st)
             if world > 1:
@@ -510,7 +545,7 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
             # dbeta = sum g, dgamma = sum g * (y - running_mean) * invstd
             dsum = dgam = dbet = None
             if gv.needs_grad or bv.needs_grad:
-                dsum = torch.zeros((2, c), device=dev, dtype=torch.float64)
+                dsum = tape.zeros_f64((2, c), dev)
                 lib.call("vspw_bn_bwd_reduce", _p(dout), _p(mask_o), _p(mask_hi), _p(y.data), _p(bn.running_mean), _p(invstd),
                          _p(chan_scale), 1 if relu else 0, pixels, c, h * w, _p(dsum[0]), _p(dsum[1]), st)
                 dgam = torch.empty(c, device=dev, dtype=torch.float32)
@@ -946,6 +981,8 @@ class _GraphFunction(torch.autograd.Function):
     def forward(ctx, runner, params, grad_on, *param_tensors):
         tape = Tape(grad_enabled=grad_on)
         outs, seed = runner(tape)
+        if not grad_on:
+            tape.release()  # no backward will come: the per-step accumulator arena is free again
         ctx.tape = tape
         ctx.seed = seed
         ctx.params = params

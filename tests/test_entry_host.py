@@ -17,6 +17,19 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def _entry(name):
+    """Import this repo's entry point by path (another test puts the reference tree, which has files of the same
+    name, in front of sys.path)."""
+    import importlib.util
+    if name in sys.modules and getattr(sys.modules[name], "__file__", "").startswith(ROOT):
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def test_cfg_defaults_merge_and_overrides(tmp_path):
     from cvpr2021_vspw_implement_b200.config import get_defaults
     c = get_defaults()
@@ -97,8 +110,8 @@ def _ref_flags(path):
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted (GPU box)")
 def test_cli_flags_cover_the_reference():
-    import train_clip2
-    import test_clip2
+    train_clip2 = _entry("train_clip2")
+    test_clip2 = _entry("test_clip2")
     for mod, ref in ((train_clip2, "train_clip2.py"), (test_clip2, "test_clip2.py")):
         mine = {s for a in mod.make_parser()._actions for s in a.option_strings}
         missing = _ref_flags(os.path.join(REF, ref)) - mine
@@ -111,7 +124,7 @@ def test_cli_flags_cover_the_reference():
 
 def test_other_methods_raise_not_implemented():
     import argparse
-    import train_clip2
+    train_clip2 = _entry("train_clip2")
     from cvpr2021_vspw_implement_b200.config import get_defaults
     c = get_defaults()
     c.MODEL.arch_encoder = "resnet18dilated"
@@ -121,7 +134,7 @@ def test_other_methods_raise_not_implemented():
 
 def test_poly_lr_schedule_and_groups():
     import argparse
-    import train_clip2
+    train_clip2 = _entry("train_clip2")
     from cvpr2021_vspw_implement_b200.config import get_defaults
     import cases as C
     c = get_defaults()

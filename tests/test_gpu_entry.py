@@ -13,6 +13,19 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def _entry(name):
+    """Import this repo's entry point by path (another test puts the reference tree, which has files of the same
+    name, in front of sys.path)."""
+    import importlib.util
+    if name in sys.modules and getattr(sys.modules[name], "__file__", "").startswith(ROOT):
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
 @pytest.fixture(scope="module")
 def need_gpu():
     if not torch.cuda.is_available():
@@ -21,8 +34,8 @@ def need_gpu():
 
 @pytest.mark.parametrize("method", ["clip_psp", "clip_ocr"])
 def test_train_then_test_entry_points(need_gpu, method, tmp_path, monkeypatch):
-    import train_clip2
-    import test_clip2
+    train_clip2 = _entry("train_clip2")
+    test_clip2 = _entry("test_clip2")
     from cvpr2021_vspw_implement_b200.config import cfg, get_defaults
     monkeypatch.chdir(tmp_path)
     cfg.clear()

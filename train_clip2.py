@@ -22,7 +22,7 @@ import torch.nn as nn
 from cvpr2021_vspw_implement_b200 import engine as E
 from cvpr2021_vspw_implement_b200 import parallel as P
 from cvpr2021_vspw_implement_b200.config import cfg
-from cvpr2021_vspw_implement_b200.data import SyntheticClipTrain
+from cvpr2021_vspw_implement_b200.data import DevicePrefetcher, SyntheticClipTrain
 from cvpr2021_vspw_implement_b200.models import Clip_PSP, ClipOCRNet, ModelBuilder
 from cvpr2021_vspw_implement_b200.utils import AverageMeter, parse_devices, setup_logger
 
@@ -42,9 +42,8 @@ def train(segmentation_module, data_loader, optimizer, bucket, history, epoch, c
     epoch_iters = len(data_loader)
     max_iters = epoch_iters * cfg.TRAIN.num_epoch
     tic = time.time()
-    for i, (clip_imgs, clip_gts) in enumerate(data_loader):
-        clip_imgs = [t.to(device, non_blocking=True) for t in clip_imgs]
-        clip_gts = [t.to(device, non_blocking=True) for t in clip_gts]
+    # pinned batches are copied to the device one step ahead on a side stream (the reference does a blocking .cuda())
+    for i, (clip_imgs, clip_gts) in enumerate(DevicePrefetcher(data_loader, device)):
         batch_data = build_batch(clip_imgs, clip_gts, i + 1)
         data_time.update(time.time() - tic)
         segmentation_module.zero_grad()
