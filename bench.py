@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-run", action="store_true", help="for ncu captures only: honour --warmup below 3, skip e2e/cpu legs")
     ap.add_argument("--cpu-sample", default="240x427", help="HxW of the bounded CPU sample")
+    ap.add_argument("--model", default="psp", choices=["psp", "ocr"], help="psp = TCB-PSP (the headline metric, BASELINE configs[1]); ocr = TCB-OCR (configs[2], reported under its own metric name)")
     ap.add_argument("--size", default="", help="HxW override, only with --profile-run (host-overhead probes); never a bench value")
     ap.add_argument("--kernel-profile", default="", help="write a per-entry-point CUDA-event breakdown of 2 extra steps to this file")
     return ap.parse_args()
@@ -57,12 +58,13 @@ def peaks():
 
 
 # --------------------------------------------------------------------------------------------------
-def build_model(device, seed=0):
+def build_model(device, seed=0, kind="psp"):
     from cvpr2021_vspw_implement_b200 import models as M
     torch.manual_seed(seed)
     ns = argparse.Namespace(num_class=NUM_CLASS, psp_weight=False, use_memory=False, memory_num=8, clipocr_all=False)
     enc = M.ModelBuilder.build_encoder("resnet101dilated")
-    m = M.Clip_PSP(enc, torch.nn.NLLLoss(ignore_index=255), ns, deep_sup_scale=0.4)
+    cls = M.Clip_PSP if kind == "psp" else M.ClipOCRNet
+    m = cls(enc, torch.nn.NLLLoss(ignore_index=255), ns, deep_sup_scale=0.4)
     return m.to(device).train()
 
 
@@ -157,7 +159,7 @@ def run_ours(args):
         E.set_syncbn(True)
 
     from cvpr2021_vspw_implement_b200.parallel import GradBucket
-    model = build_model(dev, seed=0)
+    model = build_model(dev, seed=0, kind=args.model)
     bucket = GradBucket(model.parameters())  # one flat bucket, one NCCL all-reduce over NVLink per step
     opt = make_optimizer(model)
     imgs_h, labs_h = O.synthetic_clip(T_FRAMES, N_CLIPS, H, W, NUM_CLASS, seed=304 + rank)
@@ -181,6 +183,12 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # Python's cyclic GC is paused inside the timed regions (a gen-2 sweep over a step's few thousand tape closures
+    # stalls the launching thread for tens of ms; the train entry point does the same per epoch)
+    import gc
+    gc.collect()
+    gc.disable()
 
     # ---- warm-up ------------------------------------------------------------------------------------------------
     n_warm = args.warmup if args.profile_run else max(args.warmup, 3)
@@ -261,7 +269,11 @@ def run_ours(args):
                 f.write(f"| `{name}` | {n // 2} | {ms / 2:.2f} | {100 * ms / 2 / tot:.1f}% |\n")
                 acc += ms / 2
             f.write(f"| (outside the C ABI: optimizer, allocator fills, gaps) | | {tot - acc:.2f} | {100 * (tot - acc) / tot:.1f}% |\n")
+            f.write("\nslowest single calls (index in call order, entry point, ms):\n")
+            for i, name, ms in sorted(lib.last_profile_calls, key=lambda r: -r[2])[:12]:
+                f.write(f"- #{i} `{name}` {ms:.3f}\n")
 
+    gc.enable()
     pk = peaks()
     roof = None
     if conv_prof["launches"]:
@@ -275,11 +287,15 @@ def run_ours(args):
                          "bf16x3": "each algorithmic FLOP costs 3 tensor FLOPs (hi/lo split): algorithmic ceiling = peak/3",
                          "bf16": "single-pass bf16 operands"}[args.precision]}
 
-    out = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
+    metric = METRIC if args.model == "psp" else METRIC.replace("TCB-PSP", "TCB-OCR")
+    step_tflop = STEP_TFLOP if args.model == "psp" else 22.907
+    if roof is not None and args.model != "psp":
+        roof["note"] += "; TCB-OCR: %.3f algorithmic TFLOP/step" % step_tflop
+    out = {"metric": metric, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
            "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (bf16 hi+lo operands, f32 accumulate)", "bf16": "bf16"}[args.precision],
            "data": "synthetic", "impl": "ours",
-           "config": {"workload": "TCB-PSP ResNet101-dilated train fwd+bwd+SGD, T=5, n=2 clips/GPU, 480x854, K=124 (BASELINE configs[1])",
+           "config": {"workload": ("TCB-PSP" if args.model == "psp" else "TCB-OCR") + " ResNet101-dilated train fwd+bwd+SGD, T=5, n=2 clips/GPU, 480x854, K=124 (BASELINE configs[%d])" % (1 if args.model == "psp" else 2),
                       "frames_per_step_per_gpu": T_FRAMES * N_CLIPS, "parallelism": f"dp{world}", "precision_mode": args.precision,
                       "syncbn": bool(args.syncbn), "l2_flush": "256 MiB write between timed steps",
                       "optimizer": "torch.optim.SGD as the reference (train_clip2.py:215-236), outside the CUDA hot path",

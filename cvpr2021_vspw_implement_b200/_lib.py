@@ -109,9 +109,12 @@ class _Lib:
         rec, self._prof = self._prof or [], None
         torch.cuda.synchronize()
         out = {}
-        for name, e0, e1 in rec:
-            n, ms = out.get(name, (0, 0.0))
-            out[name] = (n + 1, ms + e0.elapsed_time(e1))
+        self.last_profile_calls = []  # (index in call order, entry point, ms) of every call, for outlier hunting
+        for i, (name, e0, e1) in enumerate(rec):
+            ms = e0.elapsed_time(e1)
+            n, tot = out.get(name, (0, 0.0))
+            out[name] = (n + 1, tot + ms)
+            self.last_profile_calls.append((i, name, ms))
         return out
 
     def call(self, name, *args):

@@ -12,6 +12,7 @@ Differences that are the point of this repo:
   * ``--precision {bf16x3,bf16,fp32}`` selects the convolution arithmetic (default bf16x3 = parity mode).
 """
 import argparse
+import gc
 import os
 import time
 from collections import OrderedDict
@@ -42,6 +43,10 @@ def train(segmentation_module, data_loader, optimizer, bucket, history, epoch, c
     epoch_iters = len(data_loader)
     max_iters = epoch_iters * cfg.TRAIN.num_epoch
     tic = time.time()
+    # The cyclic GC is paused inside the step loop (a gen-2 sweep over a step's tape closures stalls the launching thread
+    # for tens of ms and idles the GPU); everything a step allocates is freed by reference counting after backward.
+    gc.collect()
+    gc.disable()
     # pinned batches are copied to the device one step ahead on a side stream (the reference does a blocking .cuda())
     for i, (clip_imgs, clip_gts) in enumerate(DevicePrefetcher(data_loader, device)):
         batch_data = build_batch(clip_imgs, clip_gts, i + 1)
@@ -66,8 +71,11 @@ def train(segmentation_module, data_loader, optimizer, bucket, history, epoch, c
         history['train']['epoch'].append(epoch - 1 + 1. * i / epoch_iters)
         history['train']['loss'].append(loss_v)
         history['train']['acc'].append(acc_v)
+        if (i + 1) % 500 == 0:
+            gc.collect()
         if args.max_iters_per_epoch and i + 1 >= args.max_iters_per_epoch:
             break
+    gc.enable()
 
 
 def checkpoint(opt, nets, history, args, epoch):
