@@ -61,24 +61,22 @@ class GradBucket:
         ref = next(p for p in self.params if p.grad is not None)
         if self.flat is None or self.flat.device != ref.grad.device:
             self.flat = torch.zeros(self.numel, device=ref.grad.device, dtype=torch.float32)
-        off = 0
-        views = []
-        for p in self.params:
-            n = p.numel()
-            v = self.flat[off:off + n]
+            self.views, off = [], 0
+            for p in self.params:
+                self.views.append(self.flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+        have = [(v, p.grad) for v, p in zip(self.views, self.params) if p.grad is not None]
+        for v, p in zip(self.views, self.params):
             if p.grad is None:
                 v.zero_()  # a rank whose shard did not touch this parameter contributes zero
-            else:
-                v.copy_(p.grad.reshape(-1))
-            views.append(v)
-            off += n
+        # pack / unpack as two multi-tensor launches instead of one tiny copy kernel per parameter
+        torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
         self.flat.mul_(1.0 / world)
-        for p, v in zip(self.params, views):
+        torch._foreach_copy_([g for _, g in have], [v for v, _ in have])
+        for v, p in zip(self.views, self.params):
             if p.grad is None:
-                p.grad = v.view_as(p).clone()
-            else:
-                p.grad.copy_(v.view_as(p))
+                p.grad = v.clone()
 
 
 def mean_scalar(t):
