@@ -35,6 +35,7 @@ _SIGNATURES = {
     "vspw_axpby": [_c_vp, _c_vp, _c_f, _c_f, _c_sz, _c_vp],
     "vspw_split_bf16": [_c_vp, _c_vp, _c_vp, _c_sz, _c_vp],
     "vspw_zero_insert2_bf16": [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp],
+    "vspw_conv_weight_prep": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp],
     "vspw_cast_f64_f32": [_c_vp, _c_vp, _c_sz, _c_vp],
     "vspw_copy_channels": [_c_vp, _c_int, _c_int, _c_vp, _c_int, _c_int, _c_int, _c_sz, _c_int, _c_vp],
     "vspw_conv2d_fwd": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],

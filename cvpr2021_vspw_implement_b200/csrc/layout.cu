@@ -234,3 +234,86 @@ extern "C" int vspw_zero_insert2_bf16(const uint16_t* src, uint16_t* dst, int32_
   zero_insert2_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const uint4*)src, (uint4*)dst, n, ho, wo, c / 8, h, w);
   return check_launch("vspw_zero_insert2_bf16");
 }
+
+// ---------------------------------------------------------------------------------------------
+// One pass over a conv weight in the reference's OIHW fp32 layout produces every operand the tcgen05 convs read:
+// OHWI planes (forward B operand, K = taps*Cin contiguous) and IHWO planes (dgrad B operand, K = taps*Cout contiguous),
+// each as bf16 hi (+ lo).  Replaces 2 permutes + 2 splits per conv per step.  One block = a 32 (co) x 32 (ci) tile, all taps.
+template <int TILE>  // TILE x TILE (co x ci) per block; TILE = 64 for 1x1 (2 channels per lane, 4-byte stores), 32 for 3x3
+__global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ ohwi_hi,
+                                                           __nv_bfloat16* __restrict__ ohwi_lo, __nv_bfloat16* __restrict__ ihwo_hi,
+                                                           __nv_bfloat16* __restrict__ ihwo_lo, int co_n, int ci_n, int taps) {
+  constexpr int MAXT = TILE == 64 ? 1 : 9;
+  constexpr int V = TILE / 32;  // channels per lane
+  __shared__ float tile[TILE][TILE * MAXT + 1];  // [co][ci*taps + tap], odd pitch: both transposed reads are conflict-free
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co0 = blockIdx.y * TILE, ci0 = blockIdx.x * TILE;
+  const int run = TILE * taps;  // contiguous floats of one co row inside this tile
+  // all of a warp's loads are issued before the first shared-memory store (a load -> store -> load chain costs one DRAM
+  // latency per element row: 20 us for a 3x3 tile)
+  constexpr int ROWS = TILE / 8;                       // rows per warp
+  constexpr int PER_ROW = (TILE * MAXT + 31) / 32;     // 32-float chunks per row
+  float buf[ROWS][PER_ROW];
+#pragma unroll
+  for (int i = 0; i < ROWS; ++i) {
+    const int r = warp + 8 * i;
+    const float* src = w + ((size_t)(co0 + r) * ci_n + ci0) * taps;
+#pragma unroll
+    for (int k = 0; k < PER_ROW; ++k) {
+      const int e = lane + 32 * k;
+      buf[i][k] = (e < run && co0 + r < co_n && ci0 + e / taps < ci_n) ? __ldg(src + e) : 0.f;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < ROWS; ++i)
+#pragma unroll
+    for (int k = 0; k < PER_ROW; ++k) {
+      const int e = lane + 32 * k;
+      if (e < run) tile[warp + 8 * i][e] = buf[i][k];
+    }
+  __syncthreads();
+  for (int idx = warp; idx < run; idx += 8) {
+    const int r = idx / taps, t = idx - r * taps;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      // pass 0: OHWI, r = co, lane -> ci;  pass 1: IHWO, r = ci, lane -> co
+      const int fix = pass == 0 ? co0 + r : ci0 + r, fix_n = pass == 0 ? co_n : ci_n;
+      const int var0 = (pass == 0 ? ci0 : co0) + lane * V, var_n = pass == 0 ? ci_n : co_n;
+      if (fix >= fix_n || var0 >= var_n) continue;
+      float v[V];
+#pragma unroll
+      for (int u = 0; u < V; ++u) v[u] = pass == 0 ? tile[r][(lane * V + u) * taps + t] : tile[lane * V + u][r * taps + t];
+      const size_t o = ((size_t)fix * taps + t) * var_n + var0;
+      __nv_bfloat16* hi = pass == 0 ? ohwi_hi : ihwo_hi;
+      __nv_bfloat16* lo = pass == 0 ? ohwi_lo : ihwo_lo;
+      if (V == 2) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[0], v[V - 1]);
+        *reinterpret_cast<__nv_bfloat162*>(hi + o) = h;
+        if (lo) {
+          const float2 f = __bfloat1622float2(h);
+          *reinterpret_cast<__nv_bfloat162*>(lo + o) = __floats2bfloat162_rn(v[0] - f.x, v[V - 1] - f.y);
+        }
+      } else {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v[0]);
+        hi[o] = h;
+        if (lo) lo[o] = __float2bfloat16_rn(v[0] - __bfloat162float(h));
+      }
+    }
+  }
+}
+extern "C" int vspw_conv_weight_prep(const float* w_oihw, uint16_t* ohwi_hi, uint16_t* ohwi_lo, uint16_t* ihwo_hi,
+                                     uint16_t* ihwo_lo, int32_t cout, int32_t cin, int32_t kh, int32_t kw, void* stream) {
+  VSPW_REQUIRE(w_oihw && ohwi_hi && ihwo_hi, "vspw_conv_weight_prep: null argument");
+  VSPW_REQUIRE((ohwi_lo == nullptr) == (ihwo_lo == nullptr), "vspw_conv_weight_prep: lo planes go together");
+  VSPW_REQUIRE(cout > 0 && cin > 0 && kh * kw >= 1 && kh * kw <= 9, "vspw_conv_weight_prep: unsupported shape %dx%dx%dx%d", cout, cin, kh, kw);
+  if (kh * kw == 1 && cin % 2 == 0 && cout % 2 == 0) {
+    dim3 grid((cin + 63) / 64, (cout + 63) / 64);
+    weight_prep_kernel<64><<<grid, 256, 0, as_stream(stream)>>>(w_oihw, (__nv_bfloat16*)ohwi_hi, (__nv_bfloat16*)ohwi_lo,
+                                                               (__nv_bfloat16*)ihwo_hi, (__nv_bfloat16*)ihwo_lo, cout, cin, 1);
+  } else {
+    dim3 grid((cin + 31) / 32, (cout + 31) / 32);
+    weight_prep_kernel<32><<<grid, 256, 0, as_stream(stream)>>>(w_oihw, (__nv_bfloat16*)ohwi_hi, (__nv_bfloat16*)ohwi_lo,
+                                                               (__nv_bfloat16*)ihwo_hi, (__nv_bfloat16*)ihwo_lo, cout, cin, kh * kw);
+  }
+  return check_launch("vspw_conv_weight_prep");
+}

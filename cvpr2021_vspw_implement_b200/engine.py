@@ -350,11 +350,21 @@ def _var_planes(v):
     return v.planes
 
 
-def _weight_planes(wv, key, t):
-    pk = key + "_planes_" + _state["precision"]
+def _tc_weight_planes(wv):
+    """{'ohwi': (hi, lo), 'ihwo': (hi, lo)} bf16 operand planes of a conv weight, produced from the OIHW parameter by one
+    kernel and cached on the tape's PVar (i.e. once per step)."""
+    pk = "tc_planes_" + _state["precision"]
     pl = wv.cache.get(pk)
     if pl is None:
-        pl = wv.cache[pk] = _planes_of(t)
+        w = wv.data
+        co, ci, kh, kw = w.shape
+        x3 = _state["precision"] == "bf16x3"
+        mk = lambda shape: torch.empty(shape, device=w.device, dtype=torch.bfloat16)
+        oh, ih = mk((co, kh, kw, ci)), mk((ci, kh, kw, co))
+        ol, il = (mk((co, kh, kw, ci)), mk((ci, kh, kw, co))) if x3 else (None, None)
+        lib.call("vspw_conv_weight_prep", _p(w if w.is_contiguous() else w.contiguous()), _p(oh), _p(ol), _p(ih), _p(il), co, ci, kh, kw,
+                 _stream())
+        pl = wv.cache[pk] = {"ohwi": (oh, ol), "ihwo": (ih, il)}
     return pl
 
 
@@ -379,18 +389,18 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1, want_stats=False)
     if not use_tc and x.data is None:
         raise VspwError("conv2d: the input was materialised as bf16 planes only but this geometry runs on the fp32 arm")
     y = torch.empty((n, ho, wo, co), device=dev, dtype=torch.float32)
-    w_ohwi = _weight_ohwi(tape, wv)
     flops = 2.0 * n * ho * wo * co * kh * kw * ci
     stats = None
     if use_tc:
         xh, xl = _var_planes(x)
-        wh, wl = _weight_planes(wv, "ohwi", w_ohwi)
+        wh, wl = _tc_weight_planes(wv)["ohwi"]
         if want_stats:
             stats = tape.zeros_f64((2, co), y.device)
         with _ConvTimer(flops, True):
             lib.call("vspw_conv2d_fwd_tc", ctypes.byref(desc), _p(xh), _p(xl), _p(wh), _p(wl), _p(bv.data if bv else None), _p(y),
                      _p(stats[0]) if stats is not None else None, _p(stats[1]) if stats is not None else None, _stream())
     else:
+        w_ohwi = _weight_ohwi(tape, wv)
         with _ConvTimer(flops, False):
             lib.call("vspw_conv2d_fwd", ctypes.byref(desc), _p(x.data), _p(w_ohwi), _p(bv.data if bv else None), _p(y), _stream())
     out = Var(y, needs_grad=tape.grad_enabled and (x.needs_grad or wv.needs_grad))
@@ -440,9 +450,8 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1, want_stats=False)
             # gradient fan-in: when another consumer of x already deposited its share, the tcgen05 epilogue adds into it
             fan_in = use_tc and x.grad is not None and x.grad.is_contiguous() and tuple(x.grad.shape) == (n, h, w, cin)
             dx = x.grad if fan_in else torch.empty((n, h, w, cin), device=dev, dtype=torch.float32)
-            w_t = _weight_ihwo(tape, wv)
             if use_tc:
-                th, tl = _weight_planes(wv, "ihwo", w_t)
+                th, tl = _tc_weight_planes(wv)["ihwo"]
                 d1, g_hi, g_lo = desc, dyp[0], dyp[1]
                 if stride == 2:
                     # dgrad of a stride-2 conv = stride-1 dgrad of dy laid on the input grid with zeros in between
@@ -455,6 +464,7 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1, want_stats=False)
                 with _ConvTimer(flops, True):
                     lib.call("vspw_conv2d_dgrad_tc", ctypes.byref(d1), _p(g_hi), _p(g_lo), _p(th), _p(tl), _p(dx), 1 if fan_in else 0, st)
             else:
+                w_t = _weight_ihwo(tape, wv)
                 with _ConvTimer(flops, False):
                     lib.call("vspw_conv2d_dgrad", ctypes.byref(desc), _p(dy), _p(w_t), _p(dx), st)
             if not fan_in:

@@ -66,6 +66,10 @@ int vspw_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, size_t n, void* 
  * the stride-1 vspw_conv2d_dgrad_tc of the same filter */
 int vspw_zero_insert2_bf16(const uint16_t* src, uint16_t* dst, int32_t n, int32_t ho, int32_t wo, int32_t c,
                            int32_t h, int32_t w, void* stream);
+/* OIHW fp32 conv weight (the reference's nn.Conv2d.weight) -> the four bf16 operand planes of the tcgen05 convs in one
+ * pass: OHWI hi/lo (forward, wgrad layout) and IHWO hi/lo (dgrad); lo planes null in VSPW_PREC_BF16 mode */
+int vspw_conv_weight_prep(const float* w_oihw, uint16_t* ohwi_hi, uint16_t* ohwi_lo, uint16_t* ihwo_hi,
+                          uint16_t* ihwo_lo, int32_t cout, int32_t cin, int32_t kh, int32_t kw, void* stream);
 /* copy a channel slice: dst[p][dst_off + c] = src[p][src_off + c], c < cc   (torch.cat(dim=1),
  * clip_psp.py:53, spatial_ocr_block.py:375; accumulate!=0 adds instead (backward of cat/split)) */
 /* double accumulators (BN sums, bias gradients) -> fp32 parameter-gradient vectors */

@@ -169,10 +169,10 @@ def test_train_step_gradient_matches_finite_difference(E, kind):
     params = [p for n_, p in m.named_parameters() if n_.startswith(("ppm_conv.conv_last_", "deepsup", "head.", "dsn_head"))]
     loss, _ = m(_feed(imgs, labs))
     loss.backward()
-    g = torch.Generator().manual_seed(9)
-    dirs = [torch.randn(p.shape, generator=g).cuda() * p.detach().abs().mean() for p in params]
+    # direction = the gradient itself, rescaled per tensor to the size of the weights: the steepest, best-conditioned probe
+    dirs = [p.grad.detach() * (p.detach().abs().mean() / p.grad.detach().abs().mean().clamp_min(1e-30)) for p in params]
     slope = sum(float((p.grad.double() * d.double()).sum()) for p, d in zip(params, dirs))
-    eps = 2e-3
+    eps = 0.01 / abs(slope)  # a step that moves the loss by ~0.01 along the steepest direction
     vals = []
     with torch.no_grad():
         for sgn in (+1.0, -1.0):

@@ -305,3 +305,37 @@ def test_confusion_matrix_matches_evaluator(E):
     ev = O.Evaluator(124)
     ev.add_batch(labs[0].squeeze(1).numpy(), pred.numpy())
     assert np.array_equal(conf.cpu().numpy(), ev.confusion_matrix.astype(np.int64))
+
+
+@pytest.mark.parametrize("shape", [(128, 64, 1, 1), (192, 320, 1, 1), (64, 128, 3, 3), (96, 160, 3, 3), (124, 512, 1, 1)])
+@pytest.mark.parametrize("x3", [True, False])
+def test_conv_weight_prep_and_zero_insert(E, shape, x3):
+    """vspw_conv_weight_prep: OIHW fp32 -> OHWI / IHWO bf16 hi(/lo) planes, bit-exact against torch's permute + bf16
+    rounding; vspw_zero_insert2_bf16: the stride-2 gradient laid on the input grid."""
+    import ctypes
+    from cvpr2021_vspw_implement_b200._lib import lib
+    co, ci, kh, kw = shape
+    g = torch.Generator().manual_seed(co + ci)
+    w = torch.randn(co, ci, kh, kw, generator=g).cuda()
+    P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    mk = lambda *s: torch.full(s, float("nan"), device="cuda", dtype=torch.bfloat16)
+    oh, ih = mk(co, kh, kw, ci), mk(ci, kh, kw, co)
+    ol, il = (mk(co, kh, kw, ci), mk(ci, kh, kw, co)) if x3 else (None, None)
+    lib.call("vspw_conv_weight_prep", P(w), P(oh), P(ol), P(ih), P(il), co, ci, kh, kw, st)
+    ref_o = w.permute(0, 2, 3, 1).contiguous()
+    ref_i = w.permute(1, 2, 3, 0).contiguous()
+    for got_hi, got_lo, ref in ((oh, ol, ref_o), (ih, il, ref_i)):
+        hi = ref.to(torch.bfloat16)
+        assert torch.equal(got_hi, hi)
+        if x3:
+            assert torch.equal(got_lo, (ref - hi.float()).to(torch.bfloat16))
+    # zero insertion
+    n, h, wd, c = 2, 7, 9, 16
+    ho, wo = (h - 1) // 2 + 1, (wd - 1) // 2 + 1
+    src = torch.randn(n, ho, wo, c, generator=g).to(torch.bfloat16).cuda()
+    dst = mk(n, h, wd, c)
+    lib.call("vspw_zero_insert2_bf16", P(src), P(dst), n, ho, wo, c, h, wd, st)
+    ref = torch.zeros(n, h, wd, c, dtype=torch.bfloat16, device="cuda")
+    ref[:, ::2, ::2] = src
+    assert torch.equal(dst, ref)
