@@ -26,23 +26,51 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
+def _deps():
+    return sorted([os.path.join(CSRC, s) for s in SOURCES] + [
+        os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))
+    ] + [os.path.join(HERE, "..", "include", "vspw_b200.h")])
+
+
+def _source_hash():
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in _deps():
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+STAMP = os.path.join(CSRC, "libvspw_b200.stamp")
+
+
 def _stale():
+    """Content-based (a snapshot copy to the GPU box does not preserve mtimes reliably): the library is current when the
+    hash of its sources and flags equals the stamp written next to it at build time."""
     if not os.path.exists(LIB):
         return True
+    if os.path.exists(STAMP):
+        return open(STAMP).read().strip() != _source_hash()
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [
-        os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))
-    ] + [os.path.join(HERE, "..", "include", "vspw_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in _deps())
 
 
 def build_library(force=False, verbose=False):
     """Compile every .cu into objects (in parallel) and link libvspw_b200.so."""
     if not force and not _stale():
         return LIB
-    nvcc = _nvcc()
+    import fcntl
     objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
+    with open(os.path.join(objdir, ".lock"), "w") as lock:  # ranks of one job must not rebuild the same file concurrently
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not _stale():
+            return LIB
+        return _build_locked(objdir, verbose)
+
+
+def _build_locked(objdir, verbose):
+    nvcc = _nvcc()
     procs = []
     for s in SOURCES:
         obj = os.path.join(objdir, s.replace(".cu", ".o"))
@@ -58,10 +86,14 @@ def build_library(force=False, verbose=False):
         objs.append(obj)
     with open(os.path.join(objdir, "ptxas.log"), "w") as f:
         f.write("\n".join(log))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    tmp = LIB + f".tmp{os.getpid()}"
+    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    os.replace(tmp, LIB)  # atomic: a process that already mapped the old file keeps it
+    with open(STAMP, "w") as f:
+        f.write(_source_hash())
     if verbose:
         print("\n".join(log))
     return LIB
