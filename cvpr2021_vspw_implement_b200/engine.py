@@ -196,7 +196,9 @@ class PVar:
 
     @property
     def data(self):
-        return self.param.data
+        d = self.param.data
+        # nn.Conv3d(kernel_size=1) weights (NLBlockND, non_local.py:51-72) are 1x1 convs over the (t, h, w) positions
+        return d.view(d.shape[0], d.shape[1], 1, 1) if d.dim() == 5 and tuple(d.shape[2:]) == (1, 1, 1) else d
 
     @property
     def needs_grad(self):
@@ -861,6 +863,129 @@ def loss_combine(tape, main, aux, aux_scale):
 
     tape.record(backward)
     return loss, pixacc, gslot
+
+
+def loss_mean_of_terms(tape, terms):
+    """loss = mean_t NLL_t, acc = mean_t acc_t over per-frame terms (Non_local3d.forward, non_local_models.py:49-61:
+    every frame is supervised and the per-frame MEANS are averaged).  Returns (loss, acc, gslot)."""
+    dev = terms[0].logits.data.device
+    st = _stream()
+    loss = torch.empty((), device=dev, dtype=torch.float32)
+    pixacc = torch.empty((), device=dev, dtype=torch.float32)
+    inv = 1.0 / len(terms)
+    for i, term in enumerate(terms):
+        li = torch.empty((), device=dev, dtype=torch.float32)
+        ai = torch.empty((), device=dev, dtype=torch.float32)
+        lib.call("vspw_loss_finalize", _p(term.acc), None, 0.0, _p(li), _p(ai), st)
+        lib.call("vspw_axpby", _p(li), _p(loss), inv, 0.0 if i == 0 else 1.0, 1, st)
+        lib.call("vspw_axpby", _p(ai), _p(pixacc), inv, 0.0 if i == 0 else 1.0, 1, st)
+    gslot = {"g": None}
+
+    def backward():
+        g = gslot["g"]
+        st = _stream()
+        for term in terms:
+            if not term.logits.needs_grad:
+                continue
+            n, h, w, k = term.logits.shape
+            H, W = term.labels.shape[2], term.labels.shape[3]
+            dl = torch.empty_like(term.logits.data)
+            scratch = torch.empty_like(term.logits.data)
+            lib.call("vspw_logsoftmax_up_nll_bwd", _p(term.logp), _p(term.labels), _p(term.acc), _p(g), float(inv), _p(dl),
+                     _p(scratch), n, h, w, k, H, W, term.ignore_index, st)
+            term.logits.add_grad(dl)
+
+    tape.record(backward)
+    return loss, pixacc, gslot
+
+
+def nl_dot_affinity(tape, theta, phi, g, t_frames, n_clips):
+    """NLBlockND(mode='dot', dimension=3) core (non_local.py:106-136): for every clip, over its P = T*h*w positions,
+    y = (theta . phi^T / P) . g.  Without a softmax the P x P affinity never has to exist: by associativity
+    y = theta . M with M = phi^T . g / P, a C x C matrix per clip (C = 128) — 2*P*C^2 instead of 2*P^2*C multiply-adds
+    (2.1 GFLOP instead of 0.53 TFLOP per clip at 480p T=5), the same function up to fp32 rounding.
+    theta, phi, g: (T*n, h, w, C) Vars with image index t*n + clip.  Returns y with the same layout."""
+    N, h, w, c = theta.shape
+    assert N == t_frames * n_clips
+    hw = h * w
+    P = t_frames * hw
+    dev = theta.data.device
+    st = _stream()
+    M = torch.empty((n_clips, c, c), device=dev, dtype=torch.float32)  # [clip][c_phi][c_g]
+    for t in range(t_frames):
+        ph, gg = phi.data[t * n_clips:(t + 1) * n_clips], g.data[t * n_clips:(t + 1) * n_clips]
+        # M[b][i][j] (+)= (1/P) sum_p phi[b][p][i] * g[b][p][j]
+        lib.call("vspw_bgemm", _p(ph), _p(gg), _p(M), n_clips, c, c, hw, hw * c, 1, c, hw * c, c, 1, c * c, c, 1, 1.0 / P,
+                 0.0 if t == 0 else 1.0, st)
+    y = torch.empty_like(theta.data)
+    for t in range(t_frames):
+        th = theta.data[t * n_clips:(t + 1) * n_clips]
+        # y[b][p][j] = sum_i theta[b][p][i] * M[b][i][j]
+        lib.call("vspw_bgemm", _p(th), _p(M), _p(y[t * n_clips:(t + 1) * n_clips]), n_clips, hw, c, c, hw * c, c, 1, c * c, c, 1,
+                 hw * c, c, 1, 1.0, 0.0, st)
+    out = Var(y, needs_grad=tape.grad_enabled and (theta.needs_grad or phi.needs_grad or g.needs_grad))
+
+    def backward():
+        dy = out.grad
+        out.grad = None
+        if dy is None:
+            return
+        st = _stream()
+        dM = torch.empty_like(M)
+        for t in range(t_frames):
+            sl = slice(t * n_clips, (t + 1) * n_clips)
+            # dM[b][i][j] (+)= sum_p theta[b][p][i] * dy[b][p][j]
+            lib.call("vspw_bgemm", _p(theta.data[sl]), _p(dy[sl]), _p(dM), n_clips, c, c, hw, hw * c, 1, c, hw * c, c, 1, c * c, c, 1,
+                     1.0, 0.0 if t == 0 else 1.0, st)
+        if theta.needs_grad:
+            dth = torch.empty_like(theta.data)
+            for t in range(t_frames):
+                sl = slice(t * n_clips, (t + 1) * n_clips)
+                # dtheta[b][p][i] = sum_j dy[b][p][j] * M[b][i][j]
+                lib.call("vspw_bgemm", _p(dy[sl]), _p(M), _p(dth[sl]), n_clips, hw, c, c, hw * c, c, 1, c * c, 1, c, hw * c, c, 1,
+                         1.0, 0.0, st)
+            theta.add_grad(dth)
+        if phi.needs_grad:
+            dph = torch.empty_like(phi.data)
+            for t in range(t_frames):
+                sl = slice(t * n_clips, (t + 1) * n_clips)
+                # dphi[b][p][i] = (1/P) sum_j g[b][p][j] * dM[b][i][j]
+                lib.call("vspw_bgemm", _p(g.data[sl]), _p(dM), _p(dph[sl]), n_clips, hw, c, c, hw * c, c, 1, c * c, 1, c, hw * c, c, 1,
+                         1.0 / P, 0.0, st)
+            phi.add_grad(dph)
+        if g.needs_grad:
+            dg = torch.empty_like(g.data)
+            for t in range(t_frames):
+                sl = slice(t * n_clips, (t + 1) * n_clips)
+                # dg[b][p][j] = (1/P) sum_i phi[b][p][i] * dM[b][i][j]
+                lib.call("vspw_bgemm", _p(phi.data[sl]), _p(dM), _p(dg[sl]), n_clips, hw, c, c, hw * c, c, 1, c * c, c, 1, hw * c, c, 1,
+                         1.0 / P, 0.0, st)
+            g.add_grad(dg)
+
+    tape.record(backward)
+    return out
+
+
+def add_vars(tape, a, b):
+    """a + b (the residual `z = W_y + x` of NLBlockND, non_local.py:150)."""
+    o = torch.empty_like(a.data)
+    lib.call("vspw_axpby", _p(a.data), _p(o), 1.0, 0.0, o.numel(), _stream())
+    lib.call("vspw_axpby", _p(b.data), _p(o), 1.0, 1.0, o.numel(), _stream())
+    out = Var(o, needs_grad=tape.grad_enabled and (a.needs_grad or b.needs_grad))
+
+    def backward():
+        gr = out.grad
+        out.grad = None
+        if gr is None:
+            return
+        for v in (a, b):
+            if v.needs_grad:
+                d = torch.empty_like(gr)
+                lib.call("vspw_axpby", _p(gr), _p(d), 1.0, 0.0, gr.numel(), _stream())
+                v.add_grad(d)
+
+    tape.record(backward)
+    return out
 
 
 def up_softmax(logits, H, W, want_pred=False):

@@ -3,3 +3,4 @@
 from .models import ModelBuilder, SegmentationModule, Resnet, ResnetDilated, PPMDeepsup
 from .clip_psp import Clip_PSP, PPM_conv
 from .clip_ocr import ClipOCRNet
+from .non_local import NLBlockND, Non_local3d

@@ -34,6 +34,7 @@ CASES = {
     "clip_psp_pspw": ("Clip_PSP_pspw", "resnet50dilated", 3, 2, 49, 65, 12, 305),
     "clip_ocr": ("ClipOCRNet", "resnet50dilated", 3, 2, 49, 65, 13, 306),
     "segmodule_r18": ("SegmentationModule", "resnet18dilated", 1, 2, 49, 65, 14, 307),
+    "non_local3d": ("Non_local3d", "resnet50dilated", 3, 2, 49, 65, 15, 308),
 }
 NUM_CLASS = 124
 
@@ -54,11 +55,14 @@ def build(ref, kind, arch, seed, **kw):
         m = ref.Clip_PSP(enc, crit, ns(psp_weight=True, **kw), deep_sup_scale=0.4)
     elif kind == "ClipOCRNet":
         m = ref.ClipOCRNet(enc, crit, ns(**kw), deep_sup_scale=0.4)
+    elif kind == "Non_local3d":
+        m = ref.Non_local3d(ns(**kw), enc, crit)
     else:
         dec = ref.ModelBuilder.build_decoder("ppm_deepsup", fc_dim=512, num_class=NUM_CLASS)
         m = ref.SegmentationModule(enc, dec, crit, deep_sup_scale=0.4)
     sd = m.state_dict()
     O.condition_weights(sd)
+    O.condition_nonlocal(sd)
     m.load_state_dict(sd)
     return m
 
@@ -90,8 +94,42 @@ def feed(imgs, labs, train):
     return d
 
 
+def run_nonlocal_case(ref, name, spec):
+    """Non_local3d: every frame is supervised, inference returns one probability map per frame."""
+    kind, arch, T, n, H, W, mseed, dseed = spec
+    imgs, labs = O.synthetic_clip(T, n, H, W, NUM_CLASS, seed=dseed, block=16)
+    rec = {"meta": np.array([T, n, H, W, mseed, dseed])}
+    for mode in ("train", "fixbn"):
+        m = build(ref, kind, arch, mseed)
+        m.train(mode == "train")
+        captured = {}
+        h = m.last_layer.register_forward_hook(lambda mod, i, o: captured.__setitem__("logits", o.detach()))
+        loss, acc = m({"clipimgs_data": list(imgs), "cliplabels_data": list(labs)})
+        loss.backward()
+        h.remove()
+        rec[mode + "/loss"] = np.float64(loss.item())
+        rec[mode + "/acc"] = np.float64(acc.item())
+        rec[mode + "/logits"] = captured["logits"].numpy().copy()
+        rec.update({mode + "/" + k: v for k, v in grad_summary(m).items()})
+        if mode == "train":
+            sd = m.state_dict()
+            for k in ("nonlocalblock.W_z.1.running_mean", "nonlocalblock.W_z.1.running_var"):
+                rec["train/after/" + k] = sd[k].numpy().copy()
+    m = build(ref, kind, arch, mseed)
+    m.eval()
+    with torch.no_grad():
+        probs = m({"clipimgs_data": list(imgs), "cliplabels_data": list(labs)}, segSize=(H, W))
+    rec["eval/probs_sub"] = torch.stack([p[:, :, ::4, ::4] for p in probs]).numpy().copy()
+    rec["eval/pred"] = torch.stack([p.argmax(1) for p in probs]).numpy().astype(np.uint8)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **rec)
+    print(f"{name}: loss={rec['train/loss']:.6f} acc={rec['train/acc']:.6f} -> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def run_case(ref, name, spec):
     kind, arch, T, n, H, W, mseed, dseed = spec
+    if kind == "Non_local3d":
+        return run_nonlocal_case(ref, name, spec)
     imgs, labs = O.synthetic_clip(T, n, H, W, NUM_CLASS, seed=dseed, block=16)
     rec = {"meta": np.array([T, n, H, W, mseed, dseed])}
     # ---- train step -------------------------------------------------------------------------------

@@ -187,6 +187,39 @@ def clip_psp_forward(sd, frames, labels=None, args_psp_weight=False, deep_sup_sc
 
 
 # --------------------------------------------------------------------------------------------------
+def non_local3d_forward(sd, frames, labels=None, train=True, seg_size=None, ignore_index=255):
+    """Non_local3d.forward (non_local_models.py:19-71) with NLBlockND(mode='dot', dimension=3) (non_local.py:82-151),
+    written with the reference's explicit (T h w) x (T h w) affinity: f = theta^T phi, f / P, y = f g.
+    `frames` / `labels`: lists of T tensors, every frame supervised.  Returns dict(loss, acc, logits) or dict(probs list)."""
+    T, n = len(frames), frames[0].shape[0]
+    x = resnet_forward(sd, "encoder.", torch.cat(frames, dim=0), train)[-1]
+    emb = conv2d(x, sd["emb.weight"], sd["emb.bias"])
+    v = torch.cat([e.unsqueeze(2) for e in torch.split(emb, n, dim=0)], 2)  # (n, 256, T, h, w)
+    q = "nonlocalblock."
+    c = sd[q + "g.weight"].shape[0]
+    g_x = F.conv3d(v, sd[q + "g.weight"], sd[q + "g.bias"]).view(n, c, -1).permute(0, 2, 1)
+    theta_x = F.conv3d(v, sd[q + "theta.weight"], sd[q + "theta.bias"]).view(n, c, -1).permute(0, 2, 1)
+    phi_x = F.conv3d(v, sd[q + "phi.weight"], sd[q + "phi.bias"]).view(n, c, -1)
+    f = torch.matmul(theta_x, phi_x)
+    y = torch.matmul(f / f.size(-1), g_x).permute(0, 2, 1).contiguous().view(n, c, *v.shape[2:])
+    w_y = F.conv3d(y, sd[q + "W_z.0.weight"], sd[q + "W_z.0.bias"])
+    w_y = F.batch_norm(w_y, sd[q + "W_z.1.running_mean"], sd[q + "W_z.1.running_var"], sd[q + "W_z.1.weight"],
+                       sd[q + "W_z.1.bias"], train, BN_MOMENTUM, BN_EPS)
+    z = w_y + v
+    z = torch.cat([t.squeeze(2) for t in torch.split(z, 1, dim=2)], dim=0)
+    logits = conv2d(torch.cat((emb, z), dim=1), sd["last_layer.weight"], sd["last_layer.bias"])
+    per_frame = torch.split(logits, n, dim=0)
+    if seg_size is not None:
+        return {"logits": logits, "probs": [F.softmax(bilinear(p, seg_size), dim=1) for p in per_frame]}
+    losses, accs = [], []
+    for p, lab in zip(per_frame, labels):
+        l, lp, lb = nll_up(p, lab, ignore_index)
+        losses.append(l)
+        accs.append(pixel_acc(lp, lb))
+    return {"logits": logits, "loss": sum(losses) / len(losses), "acc": sum(accs) / len(accs)}
+
+
+# --------------------------------------------------------------------------------------------------
 def region_gather(feats, probs, T):
     """SpatialTemporalGather_Module.forward without memory (spatial_ocr_block.py:95-109)."""
     n = feats.shape[0] // T
@@ -338,6 +371,18 @@ def synthetic_clip(T, n, H, W, num_class=124, seed=304, block=32, ignore_frac=0.
         lab = tiles.repeat_interleave(block, dim=2).repeat_interleave(block, dim=3)[:, :, :H, :W].contiguous()
         labs.append(lab)
     return imgs, labs
+
+
+def condition_nonlocal(sd, seed=8):
+    """NLBlockND's output BN is initialised to weight = bias = 0 (the block is the identity at init, non_local.py:62-63),
+    which would hide the whole affinity path from a parity fixture: give it live values.  In place; returns sd."""
+    g = torch.Generator().manual_seed(seed)
+    for k, v in sd.items():
+        if k.endswith("W_z.1.weight"):
+            v.copy_(torch.rand(v.shape, generator=g) + 0.5)
+        elif k.endswith("W_z.1.bias"):
+            v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+    return sd
 
 
 def condition_weights(sd, bn3_gamma=0.25, seed=7):

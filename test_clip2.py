@@ -70,6 +70,10 @@ def build_module(cfg, args, num_class):
         return Clip_PSP(net_encoder, crit, args)
     if args.method == 'clip_ocr':
         return ClipOCRNet(net_encoder, crit, args)
+    if args.method == 'nonlocal3d':
+        # inference of Non_local3d goes through the reference's separate whole-clip loop (test_all, test_clip2.py:90-195);
+        # the module's eval path (list of per-frame probability maps) is implemented and parity-tested, the loop is not
+        raise NotImplementedError("--method nonlocal3d: use Non_local3d(...)(feed, segSize) directly; test_all is not ported")
     raise NotImplementedError(f"--method {args.method!r}: only clip_psp / clip_ocr run on the B200 engine")
 
 
@@ -142,7 +146,7 @@ def make_parser():
                                ("use_memory", str2bool, False), ("memory_num", int, 8), ("vc_clip_num", int, 8),
                                ("psp_weight", str2bool, False)):
         parser.add_argument("--" + name, type=typ, default=default)
-    parser.add_argument("--method", type=str, default='', choices=['clip_psp', 'clip_ocr'] + OTHER_METHODS)
+    parser.add_argument("--method", type=str, default='', choices=['clip_psp', 'clip_ocr', 'nonlocal3d'] + OTHER_METHODS)
     parser.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32"])
     parser.add_argument("--synthetic", type=str2bool, default=False)
     parser.add_argument("--synthetic_size", type=str, default="480x854")

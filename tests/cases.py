@@ -15,7 +15,11 @@ CASES = {
     "clip_psp_pspw": ("Clip_PSP_pspw", "resnet50dilated", 3, 2, 49, 65, 12, 305),
     "clip_ocr": ("ClipOCRNet", "resnet50dilated", 3, 2, 49, 65, 13, 306),
     "segmodule_r18": ("SegmentationModule", "resnet18dilated", 1, 2, 49, 65, 14, 307),
+    "non_local3d": ("Non_local3d", "resnet50dilated", 3, 2, 49, 65, 15, 308),
 }
+
+# cases driven through the img_data / clipimgs_data feed (Non_local3d has its own: every frame is supervised)
+CLIP_CASES = [k for k in CASES if k != "non_local3d"]
 
 
 def ns(**kw):
@@ -35,12 +39,15 @@ def build(kind, arch, seed, conditioned=True, **kw):
         m = M.Clip_PSP(enc, crit, ns(psp_weight=True, **kw), deep_sup_scale=0.4)
     elif kind == "ClipOCRNet":
         m = M.ClipOCRNet(enc, crit, ns(**kw), deep_sup_scale=0.4)
+    elif kind == "Non_local3d":
+        m = M.Non_local3d(ns(**kw), enc, crit)
     else:
         dec = M.ModelBuilder.build_decoder("ppm_deepsup", fc_dim=512, num_class=NUM_CLASS)
         m = M.SegmentationModule(enc, dec, crit, deep_sup_scale=0.4)
     if conditioned:
         sd = m.state_dict()
         O.condition_weights(sd)
+        O.condition_nonlocal(sd)
         m.load_state_dict(sd)
     return m
 

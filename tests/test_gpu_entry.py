@@ -66,3 +66,20 @@ def test_train_then_test_entry_points(need_gpu, method, tmp_path, monkeypatch):
     res = test_clip2.main(cfg, 0, targs)
     assert 0.0 <= res["mIoU"] <= 1.0 and 0.0 <= res["Acc"] <= 1.0 and res["VC"] == res["VC"]
     assert len(os.listdir(tmp_path / "pred" / "synthetic_000")) == 6
+
+
+def test_train_entry_point_nonlocal3d(need_gpu, tmp_path, monkeypatch):
+    """--method nonlocal3d through the training entry point: the whole clip is fed and supervised."""
+    train_clip2 = _entry("train_clip2")
+    from cvpr2021_vspw_implement_b200.config import cfg, get_defaults
+    monkeypatch.chdir(tmp_path)
+    cfg.clear()
+    cfg.update(get_defaults())
+    yaml = os.path.join(ROOT, "config", "vsp-resnet101dilated-ppm_deepsup_clip.yaml")
+    argv = ["--cfg", yaml, "--method", "nonlocal3d", "--clip_num", "3", "--dilation2", "3,6", "--batchsize", "2", "--gpu_num", "1",
+            "--lr", "0.01", "--totalepoch", "4", "--synthetic", "True", "--synthetic_size", "64x96", "--synthetic_clips", "2",
+            "MODEL.arch_encoder", "resnet50dilated", "TRAIN.seed", "5"]
+    args = train_clip2.make_parser().parse_args(argv)
+    train_clip2.configure(args)
+    losses = train_clip2.main(cfg, args)["train"]["loss"]
+    assert len(losses) == 4 and all(l == l for l in losses) and losses[-1] < losses[0]

@@ -219,3 +219,50 @@ def test_encoder_api_returns_nchw_maps(E):
         assert C.rel_err(a.cpu(), b) <= TOL
     with torch.no_grad():
         assert len(enc(x.cuda())) == 1
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+def test_non_local3d_matches_reference(E, prec):
+    """SURVEY 8f row f1 — Non_local3d / NLBlockND(mode='dot'): the engine evaluates theta (phi^T g / P) instead of the
+    reference's explicit (T h w) x (T h w) affinity; logits, loss, acc, running statistics within 1e-3 and frozen-BN
+    gradients within the gradient gates, against the golden outputs of the reference module."""
+    name = "non_local3d"
+    kind, arch, T, n, H, W, mseed, dseed = C.CASES[name]
+    g = C.golden(name)
+    imgs, labs = C.clip_inputs(name)
+    feed = lambda: {"clipimgs_data": [i.cuda() for i in imgs], "cliplabels_data": [l.cuda() for l in labs]}
+    for mode in ("train", "fixbn"):
+        m = C.build(kind, arch, mseed).cuda()
+        m.train(mode == "train")
+        with E.precision(prec), E.capturing() as cap:
+            loss, acc = m(feed())
+            loss.backward()
+        torch.cuda.synchronize()
+        assert abs(loss.item() - float(g[mode + "/loss"])) <= TOL * abs(float(g[mode + "/loss"]))
+        assert abs(acc.item() - float(g[mode + "/acc"])) <= TOL
+        assert C.rel_err(nchw(cap["logits"].cpu()), g[mode + "/logits"]) <= TOL
+        if mode == "train":
+            sd = m.state_dict()
+            for k in ("nonlocalblock.W_z.1.running_mean", "nonlocalblock.W_z.1.running_var"):
+                assert C.rel_err(sd[k].cpu(), g["train/after/" + k]) <= TOL, k
+        else:
+            checked = 0
+            for k, p in m.named_parameters():
+                key = "fixbn/gnorm/" + k
+                if key not in g or float(g[key]) < 1e-9:
+                    continue
+                ref_norm = float(g[key])
+                assert p.grad is not None, k
+                en = abs(float(p.grad.double().norm()) - ref_norm) / ref_norm
+                assert en <= GRAD_GATES[prec][1], (k, en)
+                assert head_err(p.grad, g["fixbn/ghead/" + k], ref_norm) <= GRAD_GATES[prec][2], k
+                checked += 1
+            assert checked > 60
+    m = C.build(kind, arch, mseed).cuda().eval()
+    with torch.no_grad(), E.precision(prec):
+        probs = m(feed(), segSize=(H, W))
+    assert len(probs) == T and tuple(probs[0].shape) == (n, C.NUM_CLASS, H, W)
+    sub = torch.stack([p[:, :, ::4, ::4].cpu() for p in probs])
+    assert C.rel_err(sub, g["eval/probs_sub"]) <= TOL
+    pred = torch.stack([p.argmax(1).cpu() for p in probs]).numpy()
+    assert (pred == g["eval/pred"]).mean() >= 0.999

@@ -27,7 +27,7 @@ def _oracle_train(name):
     return out, sd, params
 
 
-@pytest.mark.parametrize("name", list(C.CASES))
+@pytest.mark.parametrize("name", C.CLIP_CASES)
 def test_oracle_train_matches_reference(name):
     g = C.golden(name)
     out, sd, params = _oracle_train(name)
@@ -56,7 +56,7 @@ def test_oracle_train_matches_reference(name):
         assert C.rel_err(sd[k].detach(), g["train/after/" + k]) <= 1e-5, k
 
 
-@pytest.mark.parametrize("name", list(C.CASES))
+@pytest.mark.parametrize("name", C.CLIP_CASES)
 def test_oracle_frozen_bn_step_matches_reference(name):
     """loss + gradients with BN in eval mode (cfg.TRAIN.fix_bn): non-chaotic, so gradients pin at 1e-4."""
     kind, arch, T, n, H, W, mseed, dseed = C.CASES[name]
@@ -87,7 +87,7 @@ def test_oracle_frozen_bn_step_matches_reference(name):
     assert checked > 60
 
 
-@pytest.mark.parametrize("name", list(C.CASES))
+@pytest.mark.parametrize("name", C.CLIP_CASES)
 def test_oracle_eval_matches_reference(name):
     kind, arch, T, n, H, W, mseed, dseed = C.CASES[name]
     g = C.golden(name)
@@ -139,3 +139,34 @@ def test_bn_formula_pin():
     assert torch.allclose(y, torch.from_numpy(g["y"]), atol=1e-6)
     assert torch.allclose(sd["bn.running_mean"], torch.from_numpy(g["running_mean"]), atol=1e-6)
     assert torch.allclose(sd["bn.running_var"], torch.from_numpy(g["running_var"]), atol=1e-6)
+
+
+def test_oracle_non_local3d_matches_reference():
+    """Non_local3d: train step, frozen-BN step and inference of the restatement against the golden
+    outputs of the reference module."""
+    name = "non_local3d"
+    kind, arch, T, n, H, W, mseed, dseed = C.CASES[name]
+    g = C.golden(name)
+    imgs, labs = C.clip_inputs(name)
+    for mode in ("train", "fixbn"):
+        m = C.build(kind, arch, mseed)
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        params = [k for k, _ in m.named_parameters()]
+        for k in params:
+            sd[k].requires_grad_(True)
+        out = O.non_local3d_forward(sd, list(imgs), list(labs), train=(mode == "train"))
+        out["loss"].backward()
+        assert abs(out["loss"].item() - float(g[mode + "/loss"])) <= 1e-5 * abs(float(g[mode + "/loss"]))
+        assert abs(out["acc"].item() - float(g[mode + "/acc"])) <= 1e-6
+        assert C.rel_err(out["logits"].detach(), g[mode + "/logits"]) <= 1e-4
+        if mode == "fixbn":
+            for k in params:
+                key = "fixbn/gnorm/" + k
+                if key in g and float(g[key]) > 1e-10:
+                    assert abs(float(sd[k].grad.double().norm()) - float(g[key])) <= 1e-3 * float(g[key]), k
+    m = C.build(kind, arch, mseed)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        out = O.non_local3d_forward(sd, list(imgs), None, train=False, seg_size=(H, W))
+    probs = torch.stack([p[:, :, ::4, ::4] for p in out["probs"]])
+    assert C.rel_err(probs, g["eval/probs_sub"]) <= 1e-4

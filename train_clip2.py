@@ -24,14 +24,17 @@ from cvpr2021_vspw_implement_b200 import engine as E
 from cvpr2021_vspw_implement_b200 import parallel as P
 from cvpr2021_vspw_implement_b200.config import cfg
 from cvpr2021_vspw_implement_b200.data import DevicePrefetcher, SyntheticClipTrain
-from cvpr2021_vspw_implement_b200.models import Clip_PSP, ClipOCRNet, ModelBuilder
+from cvpr2021_vspw_implement_b200.models import Clip_PSP, ClipOCRNet, ModelBuilder, Non_local3d
 from cvpr2021_vspw_implement_b200.utils import AverageMeter, parse_devices, setup_logger
 
-OTHER_METHODS = ["netwarp", "ETC", "nonlocal3d", "tdnet", "our_warp", "propnet", "our_warp_merge", "netwarp_ocr", "etc_ocr"]
+OTHER_METHODS = ["netwarp", "ETC", "tdnet", "our_warp", "propnet", "our_warp_merge", "netwarp_ocr", "etc_ocr"]
 
 
-def build_batch(clip_imgs, clip_gts, it_):
-    """train_clip2.py:75-83: frame 0 of the sampled clip is the current frame."""
+def build_batch(clip_imgs, clip_gts, it_, method="clip_psp"):
+    """train_clip2.py:54-83: clip_psp / clip_ocr take frame 0 of the sampled clip as the current frame; nonlocal3d gets the
+    whole clip and supervises every frame."""
+    if method == "nonlocal3d":
+        return {"clipimgs_data": list(clip_imgs), "cliplabels_data": list(clip_gts), "step": it_}
     return {"img_data": clip_imgs[0], "seg_label": clip_gts[0], "clipimgs_data": list(clip_imgs[1:]),
             "cliplabels_data": list(clip_gts[1:]), "step": it_}
 
@@ -49,7 +52,7 @@ def train(segmentation_module, data_loader, optimizer, bucket, history, epoch, c
     gc.disable()
     # pinned batches are copied to the device one step ahead on a side stream (the reference does a blocking .cuda())
     for i, (clip_imgs, clip_gts) in enumerate(DevicePrefetcher(data_loader, device)):
-        batch_data = build_batch(clip_imgs, clip_gts, i + 1)
+        batch_data = build_batch(clip_imgs, clip_gts, i + 1, args.method)
         data_time.update(time.time() - tic)
         segmentation_module.zero_grad()
         adjust_learning_rate(optimizer, i + (epoch - 1) * epoch_iters, cfg, max_iters, args)
@@ -132,8 +135,10 @@ def build_module(cfg, args):
         return Clip_PSP(net_encoder, crit, args, deep_sup_scale=0.4)
     if args.method == 'clip_ocr':
         return ClipOCRNet(net_encoder, crit, args, deep_sup_scale=0.4)
+    if args.method == 'nonlocal3d':
+        return Non_local3d(args, net_encoder, crit)
     # the other methods of the reference are outside the TCB hot path this engine implements
-    raise NotImplementedError(f"--method {args.method!r}: only clip_psp / clip_ocr run on the B200 engine")
+    raise NotImplementedError(f"--method {args.method!r}: only clip_psp / clip_ocr / nonlocal3d run on the B200 engine")
 
 
 def make_loader(args, world, rank):
@@ -224,7 +229,7 @@ def make_parser():
                                ("clipocr_all", str2bool, False), ("use_memory", str2bool, False), ("memory_num", int, 8),
                                ("st_weight", float, 0.1), ("psp_weight", str2bool, False)):
         parser.add_argument("--" + name, type=typ, default=default)
-    parser.add_argument("--method", type=str, default='', choices=['clip_psp', 'clip_ocr'] + OTHER_METHODS)
+    parser.add_argument("--method", type=str, default='', choices=['clip_psp', 'clip_ocr', 'nonlocal3d'] + OTHER_METHODS)
     # ---- flags of this engine (not in the reference) ----
     parser.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32"])
     parser.add_argument("--syncbn", type=str2bool, default=True, help="all-reduce BN statistics over ranks (reference multi-GPU semantics)")
