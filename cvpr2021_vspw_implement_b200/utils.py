@@ -67,6 +67,28 @@ class Evaluator(object):
         assert gt_image.shape == pre_image.shape
         self.confusion_matrix += self._generate_matrix(gt_image, pre_image)
 
+    def add_batch_device(self, gt, pred):
+        """Same as add_batch for CUDA tensors: `gt` (n,1,H,W) or (n,H,W) float labels, `pred` (n,H,W) integer argmax.
+        The 124x124 histogram is accumulated on the device by vspw_confusion_add; only the matrix
+        crosses to the host, when a metric is read (`sync_device`)."""
+        import ctypes
+        import torch
+        from ._lib import lib
+        gt = gt.reshape(pred.shape).contiguous().float()
+        pred = pred.contiguous().to(torch.int32)
+        assert gt.is_cuda and pred.is_cuda and gt.shape == pred.shape
+        if getattr(self, "_dev_conf", None) is None or self._dev_conf.device != gt.device:
+            self._dev_conf = torch.zeros((self.num_class, self.num_class), device=gt.device, dtype=torch.int64)
+        lib.call("vspw_confusion_add", ctypes.c_void_p(pred.data_ptr()), ctypes.c_void_p(gt.data_ptr()),
+                 ctypes.c_void_p(self._dev_conf.data_ptr()), gt.numel(), self.num_class,
+                 ctypes.c_void_p(torch.cuda.current_stream(gt.device).cuda_stream))
+
+    def sync_device(self):
+        """Fold the on-device histogram into confusion_matrix (call before reading metrics)."""
+        if getattr(self, "_dev_conf", None) is not None:
+            self.confusion_matrix += self._dev_conf.cpu().numpy()
+            self._dev_conf.zero_()
+
     def add_confusion(self, conf):
         """Accumulate a (num_class, num_class) histogram computed on the device (vspw_confusion_add)."""
         conf = np.asarray(conf)
@@ -75,6 +97,8 @@ class Evaluator(object):
 
     def reset(self):
         self.confusion_matrix = np.zeros((self.num_class,) * 2)
+        if getattr(self, "_dev_conf", None) is not None:
+            self._dev_conf.zero_()
 
 
 class AverageMeter(object):

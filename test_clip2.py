@@ -46,10 +46,12 @@ def test(segmentation_module, loader, gpu, args, evaluator, eval_video, video):
             batch_data['is_clean_memory'] = (i == 0)
         with torch.no_grad():
             scores = segmentation_module(batch_data, segSize=(imgs.size(2), imgs.size(3)))
-            pred = torch.argmax(scores, dim=1).cpu().numpy()
+            pred_d = torch.argmax(scores, dim=1)
+        # confusion matrices on the device (vspw_confusion_add); the host copies below feed the VC metric / PNG dump only
+        evaluator.add_batch_device(gts, pred_d)
+        eval_video.add_batch_device(gts, pred_d)
+        pred = pred_d.cpu().numpy()
         target = gts.squeeze(1).cpu().numpy()
-        evaluator.add_batch(target, pred)
-        eval_video.add_batch(target, pred)
         for jj in range(pred.shape[0]):
             predlist_.append(pred[jj])
             gtlist_.append(target[jj])
@@ -117,12 +119,14 @@ def main(cfg, gpu, args):
         if accs:
             print(sum(accs) / len(accs))
         total_VC_acc.extend(accs)
+        eval_video.sync_device()
         v_mIOU = eval_video.Mean_Intersection_over_Union()
         total_vmIOU += v_mIOU
         total_vfwIOU += eval_video.Frequency_Weighted_Intersection_over_Union()
         print(video, v_mIOU)
     total_vmIOU /= len(videolists)
     total_vfwIOU /= len(videolists)
+    evaluator.sync_device()
     Acc, Acc_class = evaluator.Pixel_Accuracy(), evaluator.Pixel_Accuracy_Class()
     mIoU, FWIoU = evaluator.Mean_Intersection_over_Union(), evaluator.Frequency_Weighted_Intersection_over_Union()
     print("Acc:{}, Acc_class:{}, mIoU:{}, fwIoU: {}, video mIOU: {}, video fwIOU: {}".format(Acc, Acc_class, mIoU, FWIoU, total_vmIOU, total_vfwIOU))

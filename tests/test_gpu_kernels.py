@@ -339,3 +339,23 @@ def test_conv_weight_prep_and_zero_insert(E, shape, x3):
     ref = torch.zeros(n, h, wd, c, dtype=torch.bfloat16, device="cuda")
     ref[:, ::2, ::2] = src
     assert torch.equal(dst, ref)
+
+
+def test_evaluator_device_path_matches_host_path(E):
+    """utils.Evaluator.add_batch_device (vspw_confusion_add on the device) == add_batch (reference
+    utils.py:86-99 on NumPy), including ignore labels 255."""
+    from cvpr2021_vspw_implement_b200.utils import Evaluator
+    g = torch.Generator().manual_seed(3)
+    gt = torch.randint(0, 124, (3, 1, 37, 53), generator=g).float()
+    gt[torch.rand(gt.shape, generator=g) < 0.1] = 255.0
+    pred = torch.randint(0, 124, (3, 37, 53), generator=g)
+    a, b = Evaluator(124), Evaluator(124)
+    a.add_batch(gt.squeeze(1).numpy(), pred.numpy())
+    for _ in range(2):
+        b.add_batch_device(gt.cuda(), pred.cuda())
+    b.sync_device()
+    assert np.array_equal(2 * a.confusion_matrix, b.confusion_matrix)
+    b.reset()
+    b.add_batch_device(gt.cuda(), pred.cuda())
+    b.sync_device()
+    assert abs(a.Mean_Intersection_over_Union() - b.Mean_Intersection_over_Union()) < 1e-12
