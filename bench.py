@@ -235,8 +235,10 @@ def run_ours(args):
     e2e_steps = 0 if args.profile_run else max(2, min(args.steps, 5))
     e2e_value = 0.0
     if e2e_steps:
-        barrier()
         loss_host = torch.empty(e2e_steps, dtype=torch.float32).pin_memory()
+        for imgs, labs in DevicePrefetcher(((imgs_h, labs_h) for _ in range(2)), dev):  # untimed: lets the caching allocator
+            step(imgs, labs)                                                            # size its pools for this feed path
+        barrier()
         flush.fill_(0.0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
