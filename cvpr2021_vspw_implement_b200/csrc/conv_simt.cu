@@ -426,6 +426,64 @@ extern "C" int vspw_conv2d_dgrad(const vspw_conv_desc* d, const float* dy, const
   return check_launch("vspw_conv2d_dgrad");
 }
 
+// Weight gradient of a conv with a tiny im2col width (the Cin = 3 stem conv: NW = 27 columns, Cout = 64).  The tiled
+// kernel above fills 10 % of its 128 x 128 tile on this shape; here a block walks its share of the output pixels in groups of
+// 32, stages dy[32][Cout] and the im2col patch[32][NW] in shared memory, and thread (co, lane-group) keeps <= kSmallCols
+// accumulators in registers; one fp32 atomic per (co, column) per block at the end.
+constexpr int kSmallPix = 32;
+constexpr int kSmallNW = 36;
+constexpr int kSmallCols = 9;
+
+__global__ void __launch_bounds__(256) wgrad_small_kernel(WGradParams p) {
+  __shared__ float dys[kSmallPix][256 + 1];
+  __shared__ float pat[kSmallPix][kSmallNW + 1];
+  const int tid = threadIdx.x;
+  const int G = 256 / p.Cout;             // column groups (Cout divides 256)
+  const int co = tid % p.Cout, grp = tid / p.Cout;
+  const int HoWo = p.Ho * p.Wo;
+  float acc[kSmallCols];
+#pragma unroll
+  for (int j = 0; j < kSmallCols; ++j) acc[j] = 0.f;
+  const int groups = (p.M + kSmallPix - 1) / kSmallPix;
+  for (int gi = blockIdx.x; gi < groups; gi += gridDim.x) {
+    const int m0 = gi * kSmallPix;
+    for (int e = tid; e < kSmallPix * p.Cout; e += 256) {
+      const int pp = e / p.Cout, c = e - pp * p.Cout;
+      dys[pp][c] = (m0 + pp < p.M) ? __ldg(p.DY + (size_t)(m0 + pp) * p.Cout + c) : 0.f;
+    }
+    for (int e = tid; e < kSmallPix * p.NW; e += 256) {
+      const int pp = e / p.NW, col = e - pp * p.NW;
+      float v = 0.f;
+      const int m = m0 + pp;
+      if (m < p.M) {
+        const int tap = col / p.Cin, ci = col - tap * p.Cin;
+        const int r = tap / p.KW, sx = tap - r * p.KW;
+        const int n = m / HoWo, rem = m - n * HoWo;
+        const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
+        const int ih = oh * p.stride - p.pad + r * p.dil, iw = ow * p.stride - p.pad + sx * p.dil;
+        if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) v = __ldg(p.X + (((size_t)n * p.H + ih) * p.W + iw) * p.Cin + ci);
+      }
+      pat[pp][col] = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int pp = 0; pp < kSmallPix; ++pp) {
+      const float d = dys[pp][co];
+#pragma unroll
+      for (int j = 0; j < kSmallCols; ++j) {
+        const int col = grp + j * G;
+        if (col < p.NW) acc[j] = fmaf(d, pat[pp][col], acc[j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < kSmallCols; ++j) {
+    const int col = grp + j * G;
+    if (col < p.NW) atomicAdd(p.DW + (size_t)co * p.NW + col, acc[j]);
+  }
+}
+
 extern "C" int vspw_conv2d_wgrad(const vspw_conv_desc* d, const float* x, const float* dy, float* dw_ohwi, void* stream) {
   int rc = validate_desc(d, "vspw_conv2d_wgrad");
   if (rc) return rc;
@@ -449,6 +507,11 @@ extern "C" int vspw_conv2d_wgrad(const vspw_conv_desc* d, const float* x, const 
   if (e != cudaSuccess) {
     set_error("vspw_conv2d_wgrad: memset: %s", cudaGetErrorString(e));
     return VSPW_ERR_CUDA;
+  }
+  if (p.NW <= kSmallNW && p.Cout <= 256 && 256 % p.Cout == 0 && (p.NW + 256 / p.Cout - 1) / (256 / p.Cout) <= kSmallCols &&
+      p.M >= 4096) {
+    wgrad_small_kernel<<<kNumSMs * 4, 256, 0, as_stream(stream)>>>(p);
+    return check_launch("vspw_conv2d_wgrad(small)");
   }
   dim3 grid((p.Cout + BM - 1) / BM, (p.NW + BN - 1) / BN, split);
   bool vec = (d->cin % 4 == 0) && (d->cout % 4 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)dy % 16 == 0);

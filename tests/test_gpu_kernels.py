@@ -29,6 +29,7 @@ def nchw(t):
 CONV_GEOMS = [
     # n, cin, h, w, cout, k, stride, pad, dil, bias
     (2, 3, 33, 45, 64, 3, 2, 1, 1, False),      # stem conv1 (scalar path)
+    (4, 3, 95, 129, 64, 3, 2, 1, 1, False),     # stem conv1, > 4096 output pixels: the small-NW weight-gradient kernel
     (2, 64, 17, 23, 64, 3, 1, 1, 1, False),
     (2, 128, 13, 19, 128, 3, 2, 1, 1, False),   # layer2 strided 3x3
     (2, 256, 13, 19, 512, 1, 2, 0, 1, False),   # strided 1x1 downsample

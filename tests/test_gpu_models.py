@@ -266,3 +266,14 @@ def test_non_local3d_matches_reference(E, prec):
     assert C.rel_err(sub, g["eval/probs_sub"]) <= TOL
     pred = torch.stack([p.argmax(1).cpu() for p in probs]).numpy()
     assert (pred == g["eval/pred"]).mean() >= 0.999
+
+
+@pytest.mark.parametrize("name", ["clip_psp", "clip_ocr"])
+def test_fast_mode_bf16_is_sane(E, name):
+    """Single-pass bf16 operands (the reported fast mode) cannot meet the 1e-3 gate (1e-2..1e-1 on this
+    network); this only pins that the mode runs the same graph and stays in that error class."""
+    g = C.golden(name)
+    m, loss, acc, cap = _train_step(E, name, "bf16")
+    assert abs(loss.item() - float(g["train/loss"])) <= 2e-2 * abs(float(g["train/loss"]))
+    assert C.rel_l2(nchw(cap["logits"].cpu()), g["train/logits"]) <= 0.3
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
