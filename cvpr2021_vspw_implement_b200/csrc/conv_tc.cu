@@ -254,16 +254,25 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, float* stg,
     __syncwarp();
     if (p.ch_sum) {
       // fused train-mode BN statistics (replaces a full re-read of the output by vspw_bn_stats): lane = column
-      float sa = 0.f, sb = 0.f;
+      float sa = 0.f, sb = 0.f, sa2 = 0.f, sb2 = 0.f;  // two independent chains
+      if (okmask == 0xffffffffu) {
 #pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        const float x = ((okmask >> r) & 1u) ? stg[r * kStgPitch + lane] : 0.f;
-        sa += x;
-        sb = fmaf(x, x, sb);
+        for (int r = 0; r < 32; r += 2) {
+          const float x = stg[r * kStgPitch + lane], x2 = stg[(r + 1) * kStgPitch + lane];
+          sa += x; sb = fmaf(x, x, sb);
+          sa2 += x2; sb2 = fmaf(x2, x2, sb2);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          const float x = ((okmask >> r) & 1u) ? stg[r * kStgPitch + lane] : 0.f;
+          sa += x;
+          sb = fmaf(x, x, sb);
+        }
       }
       float* buf = stat_s + acc * 2 * BN;
-      atomicAdd(buf + c0 + lane, sa);
-      atomicAdd(buf + BN + c0 + lane, sb);
+      atomicAdd(buf + c0 + lane, sa + sa2);
+      atomicAdd(buf + BN + c0 + lane, sb + sb2);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
