@@ -16,7 +16,7 @@ SOURCES = ["layout.cu", "conv_simt.cu", "conv_tc.cu", "bn.cu", "pool.cu", "loss.
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
-]
+] + os.environ.get("VSPW_NVCC_EXTRA", "").split()  # e.g. -DVSPW_BN_UNROLL=8 for tuning experiments
 
 
 def _nvcc():

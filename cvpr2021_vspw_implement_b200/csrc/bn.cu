@@ -147,7 +147,10 @@ __device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d)
 // coefficients live in registers for the whole kernel) and walks over pixels, kUnroll independent 16-byte loads in
 // flight per stream.  G = min(C/4, 256) channel groups side by side, 256/G pixel lanes, grid.y = channel slabs.
 constexpr int kEwThreads = 256;
-constexpr int kUnroll = 4;
+#ifndef VSPW_BN_UNROLL
+#define VSPW_BN_UNROLL 4
+#endif
+constexpr int kUnroll = VSPW_BN_UNROLL;
 
 struct EwMap {
   int cg;          // channel group of this thread (float4 index inside a pixel), -1 = idle thread
