@@ -60,7 +60,9 @@ class SyntheticClipTest(Dataset):
 
     def __getitem__(self, i):
         img, gt = self.frames[i]
-        nb = [self.frames[max(0, i - o)] for o in self.offsets]  # earlier frames, clamped at the start of the video
+        # neighbour frames as TestDataset_longclip picks them (dataset2.py:467-472): +offsets, or -offsets near the end
+        back = i + self.offsets[-1] >= len(self.frames) if self.offsets else False
+        nb = [self.frames[max(0, i - o) if back else i + o] for o in self.offsets]
         return img, gt, [f[0] for f in nb], [f[1] for f in nb], f"{i:08d}.png"
 
 

@@ -3,8 +3,9 @@
 :349-405; per-video loop :280-321; metrics :323-331) for ``--method clip_psp`` and ``--method clip_ocr``.
 
 Per batch: ``scores = module(batch_data, segSize=(H, W))`` -> argmax -> Evaluator (global + per video) -> VC metric,
-exactly the reference's sequence (test_clip2.py:28-89).  ``--synthetic True`` evaluates seeded synthetic videos
-(the VSPW loader is outside the hot path); ``--load`` may be empty with ``--synthetic`` (random weights).
+exactly the reference's sequence (test_clip2.py:28-89).  ``--dataroot`` reads the videos of ``--split`` with
+``vspw_data.VSPWClipTest`` (= the reference's ``TestDataset_longclip``); ``--synthetic True`` evaluates seeded synthetic
+videos instead, and then ``--load`` may be empty (random weights).
 Replicas only: videos are independent and the OCR memory bank is per-video state, so multi-GPU inference is one
 process per GPU over disjoint video lists.
 """
@@ -107,12 +108,8 @@ def main(cfg, gpu, args):
             h, w = (int(x) for x in args.synthetic_size.lower().split("x"))
             test_dataset = SyntheticClipTest(args, video, frames=args.synthetic_frames, height=h, width=w, seed=cfg.TRAIN.seed)
         else:
-            try:
-                from dataset2 import TestDataset_longclip  # the caller's VSPW loader (reference dataset2.py:344-490)
-            except ImportError as e:
-                raise RuntimeError("the VSPW JPEG/PNG loader is outside this engine's scope: put the reference's dataset2.py "
-                                   "on PYTHONPATH, or run with --synthetic True") from e
-            test_dataset = TestDataset_longclip(args.dataroot, video, args, is_train=False)
+            from cvpr2021_vspw_implement_b200.vspw_data import VSPWClipTest  # = dataset2.TestDataset_longclip (:344-490)
+            test_dataset = VSPWClipTest(args.dataroot, video, args, is_train=False)
         loader_test = torch.utils.data.DataLoader(test_dataset, batch_size=args.batchsize, shuffle=False, num_workers=0, drop_last=False)
         gtlist_, predlist_, h, w = test(segmentation_module, loader_test, gpu, args, evaluator, eval_video, video)
         accs = get_common(gtlist_, predlist_, args.vc_clip_num, h, w)

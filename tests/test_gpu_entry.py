@@ -83,3 +83,44 @@ def test_train_entry_point_nonlocal3d(need_gpu, tmp_path, monkeypatch):
     train_clip2.configure(args)
     losses = train_clip2.main(cfg, args)["train"]["loss"]
     assert len(losses) == 4 and all(l == l for l in losses) and losses[-1] < losses[0]
+
+
+def test_entry_points_on_a_vspw_directory(need_gpu, tmp_path, monkeypatch):
+    """train_clip2.py --dataroot / test_clip2.py --dataroot end to end on a generated VSPW-layout directory (JPEG frames,
+    PNG masks, split lists): the f3 data path feeding the hot path through the reference's CLI."""
+    import numpy as np
+    from PIL import Image
+    train_clip2 = _entry("train_clip2")
+    test_clip2 = _entry("test_clip2")
+    from cvpr2021_vspw_implement_b200.config import cfg, get_defaults
+    root = tmp_path / "vspw"
+    rng = np.random.RandomState(1)
+    for v in ("v0", "v1"):
+        os.makedirs(root / "data" / v / "origin")
+        os.makedirs(root / "data" / v / "mask")
+        for i in range(8):
+            Image.fromarray(rng.randint(0, 256, (72, 104, 3), dtype=np.uint8)).save(root / "data" / v / "origin" / f"{i:08d}.jpg")
+            Image.fromarray(np.repeat(np.repeat(rng.randint(0, 125, (9, 13), dtype=np.uint8), 8, 0), 8, 1)).save(
+                root / "data" / v / "mask" / f"{i:08d}.png")
+    for split in ("train", "val"):
+        (root / f"{split}.txt").write_text("v0\nv1\n")
+    monkeypatch.chdir(tmp_path)
+    cfg.clear()
+    cfg.update(get_defaults())
+    yaml = os.path.join(ROOT, "config", "vsp-resnet101dilated-ppm_deepsup_clip.yaml")
+    save = str(tmp_path / "ckpt")
+    argv = ["--cfg", yaml, "--method", "clip_psp", "--clip_num", "3", "--dilation2", "1,3", "--batchsize", "2", "--gpu_num", "1",
+            "--lr", "0.01", "--totalepoch", "2", "--dataroot", str(root), "--cropsize", "64", "--multi_scale", "True",
+            "--saveroot", save, "--checkpoint_every", "2", "MODEL.arch_encoder", "resnet50dilated"]
+    args = train_clip2.make_parser().parse_args(argv)
+    train_clip2.configure(args)
+    losses = train_clip2.main(cfg, args)["train"]["loss"]
+    assert len(losses) == 2 and all(l == l and l < 20 for l in losses)
+    targv = ["--cfg", yaml, "--method", "clip_psp", "--clip_num", "3", "--dilation2", "1,3", "--batchsize", "2",
+             "--load", os.path.join(save, "model_epoch_2.pth"), "--dataroot", str(root), "--split", "val", "--vc_clip_num", "2",
+             "--saveroot", str(tmp_path / "pred"), "MODEL.arch_encoder", "resnet50dilated"]
+    targs = test_clip2.make_parser().parse_args(targv)
+    targs.max_distances = [10]
+    cfg.merge_from_list(targs.opts)
+    res = test_clip2.main(cfg, 0, targs)
+    assert 0.0 <= res["mIoU"] <= 1.0 and 0.0 < res["Acc"] <= 1.0

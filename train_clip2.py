@@ -7,8 +7,8 @@ Differences that are the point of this repo:
   * multi-GPU is one process per GPU under torchrun (`python -m torch.distributed.run --nproc-per-node N
     train_clip2.py ...`), clips sharded over ranks, one NCCL gradient all-reduce per step (+ SyncBN statistics with
     ``--syncbn True``) instead of nn.DataParallel; ``--gpu_num`` is checked against WORLD_SIZE;
-  * ``--synthetic True`` feeds seeded synthetic clips with the dataset contract (the VSPW JPEG/PNG loader is outside
-    the hot path); with ``--dataroot`` the caller's own ``dataset2.BaseDataset_longclip`` is imported if present;
+  * ``--dataroot`` reads VSPW clips with ``vspw_data.VSPWClipTrain`` (bit-identical to the reference's
+    ``dataset2.BaseDataset_longclip`` under the same RNG seeds); ``--synthetic True`` feeds seeded synthetic clips instead;
   * ``--precision {bf16x3,bf16,fp32}`` selects the convolution arithmetic (default bf16x3 = parity mode).
 """
 import argparse
@@ -149,12 +149,8 @@ def make_loader(args, world, rank):
         h, w = (int(x) for x in args.synthetic_size.lower().split("x"))
         ds = SyntheticClipTrain(args, length=args.synthetic_clips, height=h, width=w, seed=cfg.TRAIN.seed)
     else:
-        try:
-            from dataset2 import BaseDataset_longclip  # the caller's VSPW loader (reference dataset2.py:852-1048)
-        except ImportError as e:
-            raise RuntimeError("the VSPW JPEG/PNG loader is outside this engine's scope: put the reference's dataset2.py on "
-                               "PYTHONPATH, or run with --synthetic True") from e
-        ds = BaseDataset_longclip(args, 'train')
+        from cvpr2021_vspw_implement_b200.vspw_data import VSPWClipTrain  # = dataset2.BaseDataset_longclip (:852-1048)
+        ds = VSPWClipTrain(args, 'train')
     sampler = None
     if world > 1:
         sampler = torch.utils.data.distributed.DistributedSampler(ds, num_replicas=world, rank=rank, shuffle=True, drop_last=True)
