@@ -48,6 +48,8 @@ _SIGNATURES = {
     "vspw_bn_finalize_train": [_c_vp, _c_vp, _c_d, _c_vp, _c_vp, _c_f, _c_f, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_vp],
     "vspw_bn_fold_eval": [_c_vp, _c_vp, _c_vp, _c_vp, _c_f, _c_vp, _c_vp, _c_vp, _c_int, _c_vp],
     "vspw_bn_act_fwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_vp],
+    "vspw_bn_train_fwd": [_c_vp, _c_vp, _c_vp, _c_d, _c_vp, _c_vp, _c_f, _c_f, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_int,
+                          _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_vp],
     "vspw_bn_bwd_reduce": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_sz, _c_vp, _c_vp, _c_vp],
     "vspw_bn_bwd_apply": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_int, _c_d, _c_vp],
     "vspw_maxpool3x3s2_fwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp],

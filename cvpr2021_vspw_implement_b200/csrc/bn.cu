@@ -182,17 +182,63 @@ inline dim3 ew_grid(size_t pixels, int c4) {
 __device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
 __device__ __forceinline__ uint2 ld_stream(const uint2* p) { return __ldcs(p); }
 
+struct BnTrainStats {  // non-null `sum` = train mode with the finalize step fused into the element-wise kernel
+  const double* sum;
+  const double* sqsum;
+  double count;
+  const float* gamma;
+  const float* beta;
+  float eps, momentum;
+  float* running_mean;
+  float* running_var;
+  float* mean_out;
+  float* invstd_out;
+  int clamp_mode;
+};
+
 __global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(
     const float4* __restrict__ y, const float4* __restrict__ scale, const float4* __restrict__ shift,
     const float4* __restrict__ mean, const float4* __restrict__ beta, const float4* __restrict__ residual,
     const float4* __restrict__ chan_scale, int relu, float4* __restrict__ out, uint2* __restrict__ out_hi,
-    uint2* __restrict__ out_lo, size_t pixels, int c4, size_t pix_per_img) {
+    uint2* __restrict__ out_lo, size_t pixels, int c4, size_t pix_per_img, BnTrainStats ts) {
   const EwMap m = ew_map(c4);
   if (m.cg < 0) return;
-  const float4 sc = __ldg(scale + m.cg);
-  // centred form (x-mean)*scale+beta (no cancellation when |mean| >> std) or folded x*scale+shift
-  const float4 mu = mean ? __ldg(mean + m.cg) : make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 add = mean ? (beta ? __ldg(beta + m.cg) : make_float4(0.f, 0.f, 0.f, 0.f)) : __ldg(shift + m.cg);
+  float4 sc, mu, add;
+  if (ts.sum) {
+    // train mode, finalize fused in: every thread derives its 4 channels' mean / invstd / scale from the fp64 sums with the
+    // arithmetic of bn_finalize_train_kernel; the threads of block column 0 also publish them and update the running stats
+    float mf[4], isf[4], scf[4], bt[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ch = m.cg * 4 + j;
+      const double mm = ts.sum[ch] / ts.count;
+      double var = ts.sqsum[ch] / ts.count - mm * mm;
+      if (var < 0) var = 0;
+      const double is = ts.clamp_mode ? 1.0 / sqrt(var < (double)ts.eps ? (double)ts.eps : var) : 1.0 / sqrt(var + (double)ts.eps);
+      mf[j] = (float)mm;
+      isf[j] = (float)is;
+      const float gm = ts.gamma ? ts.gamma[ch] : 1.f;
+      bt[j] = ts.beta ? ts.beta[ch] : 0.f;
+      scf[j] = gm * isf[j];
+      if (blockIdx.x == 0 && threadIdx.x < (c4 < kEwThreads ? c4 : kEwThreads)) {
+        ts.mean_out[ch] = mf[j];
+        ts.invstd_out[ch] = isf[j];
+        if (ts.running_mean) ts.running_mean[ch] = (1.f - ts.momentum) * ts.running_mean[ch] + ts.momentum * mf[j];
+        if (ts.running_var) {
+          const double unbiased = ts.count > 1 ? var * ts.count / (ts.count - 1.0) : var;
+          ts.running_var[ch] = (1.f - ts.momentum) * ts.running_var[ch] + ts.momentum * (float)unbiased;
+        }
+      }
+    }
+    sc = make_float4(scf[0], scf[1], scf[2], scf[3]);
+    mu = make_float4(mf[0], mf[1], mf[2], mf[3]);
+    add = make_float4(bt[0], bt[1], bt[2], bt[3]);
+  } else {
+    sc = __ldg(scale + m.cg);
+    // centred form (x-mean)*scale+beta (no cancellation when |mean| >> std) or folded x*scale+shift
+    mu = mean ? __ldg(mean + m.cg) : make_float4(0.f, 0.f, 0.f, 0.f);
+    add = mean ? (beta ? __ldg(beta + m.cg) : make_float4(0.f, 0.f, 0.f, 0.f)) : __ldg(shift + m.cg);
+  }
   for (size_t p = m.p0; p < pixels; p += m.dp * kUnroll) {
     float4 v[kUnroll], r[kUnroll];
 #pragma unroll
@@ -455,8 +501,25 @@ extern "C" int vspw_bn_act_fwd(const float* y, const float* scale, const float* 
   bn_act_fwd_kernel<<<ew_grid(pixels, c / 4), kEwThreads, 0, as_stream(stream)>>>(
       (const float4*)y, (const float4*)scale, (const float4*)shift, (const float4*)mean, (const float4*)beta,
       (const float4*)residual, (const float4*)chan_scale,
-      relu, (float4*)out, (uint2*)out_hi, (uint2*)out_lo, pixels, c / 4, pixels_per_image);
+      relu, (float4*)out, (uint2*)out_hi, (uint2*)out_lo, pixels, c / 4, pixels_per_image, BnTrainStats{});
   return check_launch("vspw_bn_act_fwd");
+}
+
+extern "C" int vspw_bn_train_fwd(const float* y, const double* sum, const double* sqsum, double count, const float* gamma,
+                                 const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                                 float* mean, float* invstd, int32_t clamp_mode, const float* residual, const float* chan_scale,
+                                 int32_t relu, float* out, uint16_t* out_hi, uint16_t* out_lo, size_t pixels, int32_t c,
+                                 size_t pixels_per_image, void* stream) {
+  VSPW_REQUIRE(y && sum && sqsum && mean && invstd && (out || out_hi), "vspw_bn_train_fwd: null pointer");
+  VSPW_REQUIRE(count >= 1, "vspw_bn_train_fwd: empty batch");
+  VSPW_REQUIRE(c > 0 && c % 4 == 0, "vspw_bn_train_fwd: channels must be a multiple of 4 (got %d)", c);
+  VSPW_REQUIRE(pixels_per_image > 0, "vspw_bn_train_fwd: pixels_per_image must be positive");
+  if (pixels == 0) return VSPW_OK;
+  BnTrainStats ts{sum, sqsum, count, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, clamp_mode};
+  bn_act_fwd_kernel<<<ew_grid(pixels, c / 4), kEwThreads, 0, as_stream(stream)>>>(
+      (const float4*)y, nullptr, nullptr, nullptr, nullptr, (const float4*)residual, (const float4*)chan_scale, relu,
+      (float4*)out, (uint2*)out_hi, (uint2*)out_lo, pixels, c / 4, pixels_per_image, ts);
+  return check_launch("vspw_bn_train_fwd");
 }
 
 extern "C" int vspw_bn_bwd_reduce(const float* dout, const float* out, const uint16_t* out_hi, const float* y,

@@ -526,9 +526,6 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
         count = float(pixels * world)
         mean = torch.empty(c, device=dev, dtype=torch.float32)
         invstd = torch.empty(c, device=dev, dtype=torch.float32)
-        lib.call("vspw_bn_finalize_train", _p(sums[0]), _p(sums[1]), count, _p(gv.data), _p(bv.data), float(bn.eps),
-                 float(bn.momentum), _p(bn.running_mean), _p(bn.running_var), _p(mean), _p(invstd), _p(scale), _p(shift), c,
-                 1 if _state["syncbn_clamp"] else 0, st)
     else:
         invstd = torch.empty(c, device=dev, dtype=torch.float32)
         lib.call("vspw_bn_fold_eval", _p(gv.data), _p(bv.data), _p(bn.running_mean), _p(bn.running_var), float(bn.eps),
@@ -539,10 +536,16 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
         hi = torch.empty(y.shape, device=dev, dtype=torch.bfloat16)
         lo = torch.empty(y.shape, device=dev, dtype=torch.bfloat16) if _state["precision"] == "bf16x3" else None
     o = torch.empty_like(y.data) if (fp32_out or not want_planes) else None
-    center = mean if training else bn.running_mean
-    lib.call("vspw_bn_act_fwd", _p(y.data), _p(scale), _p(shift), _p(center), _p(bv.data),
-             _p(residual.data if residual is not None else None),
-             _p(chan_scale), 1 if relu else 0, _p(o), _p(hi), _p(lo), pixels, c, h * w, st)
+    if training:
+        # finalize (mean / invstd / running statistics from the fp64 sums) + normalise + residual + ReLU + planes: one launch
+        lib.call("vspw_bn_train_fwd", _p(y.data), _p(sums[0]), _p(sums[1]), count, _p(gv.data), _p(bv.data), float(bn.eps),
+                 float(bn.momentum), _p(bn.running_mean), _p(bn.running_var), _p(mean), _p(invstd),
+                 1 if _state["syncbn_clamp"] else 0, _p(residual.data if residual is not None else None), _p(chan_scale),
+                 1 if relu else 0, _p(o), _p(hi), _p(lo), pixels, c, h * w, st)
+    else:
+        lib.call("vspw_bn_act_fwd", _p(y.data), _p(scale), _p(shift), _p(bn.running_mean), _p(bv.data),
+                 _p(residual.data if residual is not None else None),
+                 _p(chan_scale), 1 if relu else 0, _p(o), _p(hi), _p(lo), pixels, c, h * w, st)
     needs = tape.grad_enabled and (y.needs_grad or gv.needs_grad or (residual is not None and residual.needs_grad))
     out = Var(o, needs_grad=needs)
     if want_planes:

@@ -130,6 +130,14 @@ int vspw_bn_act_fwd(const float* y, const float* scale, const float* shift, cons
                     const float* chan_scale, int32_t relu, float* out, uint16_t* out_hi,
                     uint16_t* out_lo, size_t pixels, int32_t c, size_t pixels_per_image,
                     void* stream);
+/* train mode in ONE launch: vspw_bn_finalize_train (same arithmetic, same outputs mean/invstd, same running-statistics
+ * update) fused into vspw_bn_act_fwd's centred form; `sum`/`sqsum` come from vspw_bn_stats or from the conv epilogue */
+int vspw_bn_train_fwd(const float* y, const double* sum, const double* sqsum, double count,
+                      const float* gamma, const float* beta, float eps, float momentum,
+                      float* running_mean, float* running_var, float* mean, float* invstd,
+                      int32_t clamp_mode, const float* residual, const float* chan_scale, int32_t relu,
+                      float* out, uint16_t* out_hi, uint16_t* out_lo, size_t pixels, int32_t c,
+                      size_t pixels_per_image, void* stream);
 /* backward pass 1: g = dout * chan_scale * [out>0]; dbeta = sum g; dgamma = sum g*xhat.  The ReLU mask is read from
  * the fp32 output `out` or, when that is null, from its bf16 hi plane `out_hi` */
 int vspw_bn_bwd_reduce(const float* dout, const float* out, const uint16_t* out_hi, const float* y,
