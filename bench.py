@@ -286,6 +286,11 @@ def run_ours(args):
                 # executed tensor FLOPs (3 MMAs per algorithmic product in bf16x3) against the same peak: what the tensor pipe sees
                 "tensor_tflops_executed": round(ach * (3 if args.precision == "bf16x3" else 1), 2),
                 "tensor_frac_executed": round(ach * (3 if args.precision == "bf16x3" else 1) / peak, 4) if args.precision != "fp32" else 0.0,
+                # `traffic` (DRAM bytes per launch) is per kernel and this line aggregates 341 launches of 60 geometries, so it stays
+                # null; the ncu --set full capture of the most frequent heavy launch is quoted instead (profiles/r1_ncu_full_final.md)
+                "traffic_example": {"launch": "conv_tc2_kernel, layer3 3x3 d2 256->256 fwd, bf16x3 (23 per step)",
+                                    "dram_bytes": 93.0e6, "algorithmic_bytes": 134.0e6,
+                                    "note": "operand planes 65.7 MB + weights 2.4 MB read, 65.7 MB fp32 written; a third of the output is still in L2 when the kernel ends: no re-reads"},
                 "launches_per_step": conv_prof["launches"] // args.steps, "ms_per_step": round(conv_prof["ms"] / args.steps, 3),
                 "algorithmic_tflop_per_step": round(conv_prof["tflop"] / args.steps, 3),
                 "note": {"fp32": "CUDA-core FFMA arm: tensor pipe idle, frac is vs the tensor roofline the tcgen05 arm is judged on",
