@@ -184,3 +184,26 @@ def test_train_step_gradient_matches_finite_difference(E, kind):
     fd = (vals[0] - vals[1]) / (2 * eps)
     assert abs(slope) > 1e-5
     assert abs(fd - slope) <= 5e-2 * abs(slope), (fd, slope)
+
+
+def test_config5_shape_720p_T9_ocr_inference(E):
+    """BASELINE configs[4] geometry (TCB-OCR, T=9, 720x1280 frames, 90x160 stride-8 maps, n=2) through the inference path:
+    exercises the tile maps on a map size none of the 480p tests see (160 = 10 full 16-pixel patches, 90 = 11.25 patch rows).
+    Properties only — there is no CPU oracle at this size: a distribution per pixel, run-to-run agreement, clip independence."""
+    global T, H, W
+    old = (T, H, W)
+    T, H, W = 9, 720, 1280
+    try:
+        m = _model("ocr").eval()
+        imgs, _ = _clip(11)
+        other, _ = _clip(12)
+        mixed = [torch.stack([a[0], b[1]]) for a, b in zip(imgs, other)]
+        with torch.no_grad():
+            p = m(_feed(imgs), segSize=(H, W))
+            q = m(_feed(mixed), segSize=(H, W))
+        assert tuple(p.shape) == (N_CLIPS, K, H, W)
+        assert torch.isfinite(p).all() and float((p.sum(1) - 1.0).abs().max()) <= 1e-5
+        assert float((p[0] - q[0]).abs().max()) <= 1e-5 and float((p[1] - q[1]).abs().max()) > 1e-3
+        assert p.argmax(1).unique().numel() > 1
+    finally:
+        T, H, W = old
