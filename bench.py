@@ -236,8 +236,11 @@ def run_ours(args):
     e2e_value = 0.0
     if e2e_steps:
         loss_host = torch.empty(e2e_steps, dtype=torch.float32).pin_memory()
-        for imgs, labs in DevicePrefetcher(((imgs_h, labs_h) for _ in range(2)), dev):  # untimed: lets the caching allocator
-            step(imgs, labs)                                                            # size its pools for this feed path
+        # untimed rehearsal of the same loop: the host runs several steps ahead of the device here, so the feed path needs as
+        # many in-flight input buffers as steps; the caching allocator gets them now (a cudaMalloc inside the timed region
+        # costs tens of ms next to 40 GB of live allocations) and the timed region below only recycles them
+        for imgs, labs in DevicePrefetcher(((imgs_h, labs_h) for _ in range(e2e_steps)), dev):
+            step(imgs, labs)
         barrier()
         flush.fill_(0.0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
