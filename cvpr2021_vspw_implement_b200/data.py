@@ -66,6 +66,9 @@ class SyntheticClipTest(Dataset):
         return img, gt, [f[0] for f in nb], [f[1] for f in nb], f"{i:08d}.png"
 
 
+_copy_streams = {}
+
+
 class DevicePrefetcher:
     """Double-buffered host -> device feed for the train loop: the H2D copy of clip i+1 runs on a side stream while clip i
     computes (the reference copies synchronously with `.cuda()` before every step, train_clip2.py:45-47).  `source` yields
@@ -75,7 +78,12 @@ class DevicePrefetcher:
     def __init__(self, source, device):
         self.it = iter(source)
         self.device = device
-        self.stream = torch.cuda.Stream(device=device)
+        # one copy stream per device for the life of the process: the caching allocator keeps a pool per stream, so a fresh
+        # stream per prefetcher would cudaMalloc its input buffers again every epoch
+        key = torch.device(device)
+        if key not in _copy_streams:
+            _copy_streams[key] = torch.cuda.Stream(device=key)
+        self.stream = _copy_streams[key]
         self.next = None
         self._preload()
 
