@@ -10,8 +10,11 @@
  * Conventions
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it says "host";
  *   - activations are fp32, NHWC ("channels last"): x[n][h][w][c];
- *   - weights cross the boundary in the reference's OIHW layout and are re-laid out by
- *     vspw_permute4d into OHWI (forward / wgrad) or IHWO-flattened "HWOI" (dgrad);
+ *   - weights cross the boundary in the reference's OIHW layout; vspw_conv_weight_prep turns one into the
+ *     bf16 OHWI / IHWO operand planes of the tensor-core convs, vspw_permute4d into the fp32 OHWI / IHWO
+ *     layouts of the CUDA-core arm;
+ *   - tensor-core convs read bf16 planes hi = bf16(x), lo = bf16(x - hi) of NHWC activations (written by
+ *     vspw_bn_act_fwd / vspw_bn_train_fwd / vspw_bn_bwd_apply / vspw_split_bf16) and write fp32;
  *   - `stream` is a cudaStream_t passed as void* (the caller's current stream);
  *   - every function returns 0 on success, <0 on error; vspw_last_error() gives the message
  *     (thread local).  No function synchronises the device or allocates device memory.
