@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--profile-run", action="store_true", help="for ncu captures only: honour --warmup below 3, skip e2e/cpu legs")
     ap.add_argument("--cpu-sample", default="240x427", help="HxW of the bounded CPU sample")
     ap.add_argument("--model", default="psp", choices=["psp", "ocr"], help="psp = TCB-PSP (the headline metric, BASELINE configs[1]); ocr = TCB-OCR (configs[2], reported under its own metric name)")
+    ap.add_argument("--torch-sgd", action="store_true", help="use torch.optim.SGD instead of the fused vspw_sgd_momentum_step (same update rule)")
     ap.add_argument("--size", default="", help="HxW override, only with --profile-run (host-overhead probes); never a bench value")
     ap.add_argument("--kernel-profile", default="", help="write a per-entry-point CUDA-event breakdown of 2 extra steps to this file")
     return ap.parse_args()
@@ -68,7 +69,7 @@ def build_model(device, seed=0, kind="psp"):
     return m.to(device).train()
 
 
-def make_optimizer(m, lr=0.002):
+def make_optimizer(m, lr=0.002, fused=True):
     """create_optimizers of the reference (train_clip2.py:215-236): SGD momentum .9, 4 param groups.  The duplicate
     yields of the generators (quirk Q10) are de-duplicated here because torch >= 2 rejects duplicate parameters."""
     def uniq(gen, seen):
@@ -85,6 +86,9 @@ def make_optimizer(m, lr=0.002):
         {"params": uniq(m.get_1x_lr_params_bias(), seen), "lr": lr * 0.1, "weight_decay": 0.0},
         {"params": uniq(m.get_10x_lr_params_bias(), seen), "lr": lr, "weight_decay": 0.0},
     ]
+    if fused:
+        from cvpr2021_vspw_implement_b200.optim import FusedSGD
+        return FusedSGD([g for g in groups if g["params"]], lr=lr, momentum=0.9)
     return torch.optim.SGD([g for g in groups if g["params"]], lr=lr, momentum=0.9)
 
 
@@ -161,7 +165,7 @@ def run_ours(args):
     from cvpr2021_vspw_implement_b200.parallel import GradBucket
     model = build_model(dev, seed=0, kind=args.model)
     bucket = GradBucket(model.parameters())  # one flat bucket, one NCCL all-reduce over NVLink per step
-    opt = make_optimizer(model)
+    opt = make_optimizer(model, fused=not args.torch_sgd)
     imgs_h, labs_h = O.synthetic_clip(T_FRAMES, N_CLIPS, H, W, NUM_CLASS, seed=304 + rank)
     imgs_h = [t.pin_memory() for t in imgs_h]
     labs_h = [t.pin_memory() for t in labs_h]
@@ -315,7 +319,7 @@ def run_ours(args):
            "config": {"workload": ("TCB-PSP" if args.model == "psp" else "TCB-OCR") + " ResNet101-dilated train fwd+bwd+SGD, T=5, n=2 clips/GPU, 480x854, K=124 (BASELINE configs[%d])" % (1 if args.model == "psp" else 2),
                       "frames_per_step_per_gpu": T_FRAMES * N_CLIPS, "parallelism": f"dp{world}", "precision_mode": args.precision,
                       "syncbn": bool(args.syncbn), "l2_flush": "256 MiB write between timed steps",
-                      "optimizer": "torch.optim.SGD as the reference (train_clip2.py:215-236), outside the CUDA hot path",
+                      "optimizer": ("torch.optim.SGD" if args.torch_sgd else "FusedSGD (vspw_sgd_momentum_step)") + ": the reference's update rule and 4 param groups (train_clip2.py:215-236), inside the timed step",
                       "loss": round(final_loss, 5), "wall_s_timed_region": round(wall, 3),
                       "peak_hbm_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 2)},
            "clocks": clocks, "gpu_launches": int(launches),

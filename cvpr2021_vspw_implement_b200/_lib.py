@@ -65,10 +65,11 @@ _SIGNATURES = {
     "vspw_softmax_strided_fwd": [_c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_sz, _c_int, _c_sz, _c_f, _c_vp],
     "vspw_softmax_strided_bwd": [_c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_sz, _c_int, _c_sz, _c_f, _c_vp],
     "vspw_bgemm": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int] + [_c_i64] * 9 + [_c_f, _c_f, _c_vp],
+    "vspw_sgd_momentum_step": [_c_vp, _c_vp, _c_vp, _c_int, _c_f, _c_vp],
     "vspw_confusion_add": [_c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_vp],
 }
 
-EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["vspw_last_error", "vspw_version", "vspw_tcb_pool_workspace_floats"])
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["vspw_last_error", "vspw_version", "vspw_tcb_pool_workspace_floats", "vspw_sgd_chunk_elems"])
 
 
 class VspwError(RuntimeError):
@@ -97,6 +98,8 @@ class _Lib:
                     dll.vspw_last_error.argtypes = []
                     dll.vspw_version.restype = ctypes.c_int
                     dll.vspw_version.argtypes = []
+                    dll.vspw_sgd_chunk_elems.restype = ctypes.c_int32
+                    dll.vspw_sgd_chunk_elems.argtypes = []
                     dll.vspw_tcb_pool_workspace_floats.restype = ctypes.c_size_t
                     dll.vspw_tcb_pool_workspace_floats.argtypes = [_c_int, _c_int, _c_int, _c_int, _c_vp, _c_int]
                     self._dll = dll

@@ -230,6 +230,20 @@ int vspw_bgemm(const float* a, const float* b, float* c, int32_t batch, int32_t 
                int64_t b_cs, int64_t c_bs, int64_t c_rs, int64_t c_cs, float alpha, float beta,
                void* stream);
 
+/* ---- optimizer step (train_clip2.py:215-252: torch.optim.SGD, momentum 0.9, per-group lr / weight decay) ----
+ * One launch over a DEVICE table of tensors: d = g + wd*p; buf = momentum*buf + d; p -= lr*buf (dampening 0, no Nesterov).
+ * block b works on elements [block_chunk[b]*vspw_sgd_chunk_elems(), +vspw_sgd_chunk_elems()) of tensor block_tensor[b]. */
+typedef struct vspw_sgd_tensor {
+  float* p;          /* parameter (updated in place)            */
+  const float* g;    /* gradient                                */
+  float* buf;        /* momentum buffer (updated in place)      */
+  uint64_t n;        /* elements                                */
+  float lr, wd;      /* this tensor's learning rate and weight decay */
+} vspw_sgd_tensor;
+int32_t vspw_sgd_chunk_elems(void);
+int vspw_sgd_momentum_step(const vspw_sgd_tensor* table_dev, const uint32_t* block_tensor_dev,
+                           const uint32_t* block_chunk_dev, int32_t n_blocks, float momentum, void* stream);
+
 /* ---- evaluation (utils.py:55-107 Evaluator._generate_matrix): conf[gt][pred] += 1 ---------- */
 int vspw_confusion_add(const int32_t* pred, const float* labels, int64_t* conf, size_t pixels,
                        int32_t num_class, void* stream);

@@ -360,3 +360,37 @@ def test_evaluator_device_path_matches_host_path(E):
     b.add_batch_device(gt.cuda(), pred.cuda())
     b.sync_device()
     assert abs(a.Mean_Intersection_over_Union() - b.Mean_Intersection_over_Union()) < 1e-12
+
+
+def test_fused_sgd_matches_torch_sgd(E):
+    """optim.FusedSGD (one vspw_sgd_momentum_step launch) against torch.optim.SGD — the reference's optimizer — over several
+    steps: per-group lr / weight decay, momentum buffers, odd sizes, a parameter without gradient, state_dict exchange."""
+    from cvpr2021_vspw_implement_b200.optim import FusedSGD
+    g = torch.Generator().manual_seed(0)
+    shapes = [(64, 3, 3, 3), (5000,), (17,), (128, 64, 1, 1), (3, 4097), (1,)]
+    pa = [torch.nn.Parameter(torch.randn(s, generator=g).cuda()) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    mk = lambda ps: [{"params": ps[:3], "lr": 0.02, "weight_decay": 1e-4}, {"params": ps[3:], "lr": 0.002, "weight_decay": 0.0}]
+    oa, ob = torch.optim.SGD(mk(pa), lr=0.02, momentum=0.9, weight_decay=1e-4), FusedSGD(mk(pb), lr=0.02, momentum=0.9, weight_decay=1e-4)
+    for step in range(4):
+        for i, (a, b) in enumerate(zip(pa, pb)):
+            if i == 2 and step == 1:
+                a.grad = b.grad = None       # a parameter the step did not touch
+                continue
+            gr = torch.randn(a.shape, generator=g).cuda()
+            a.grad, b.grad = gr.clone(), gr.clone()
+        for o in (oa, ob):
+            o.param_groups[0]["lr"] = 0.02 * (1 - step / 10) ** 0.9   # poly schedule edits the groups in place
+        oa.step()
+        ob.step()
+    torch.cuda.synchronize()
+    for a, b in zip(pa, pb):
+        assert C.rel_err(b.detach().cpu(), a.detach().cpu()) <= 2e-6
+        assert C.rel_err(ob.state[b]["momentum_buffer"].cpu(), oa.state[a]["momentum_buffer"].cpu()) <= 2e-6
+    # checkpoints travel both ways (opt_epoch_E.pth, train_clip2.py:186-188)
+    oc = FusedSGD(mk(pb), lr=0.02, momentum=0.9, weight_decay=1e-4)
+    oc.load_state_dict(oa.state_dict())
+    od = torch.optim.SGD(mk(pa), lr=0.02, momentum=0.9, weight_decay=1e-4)
+    od.load_state_dict(ob.state_dict())
+    with pytest.raises(NotImplementedError):
+        FusedSGD(pb, lr=0.1, momentum=0.9, nesterov=True)

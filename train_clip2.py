@@ -114,6 +114,9 @@ def create_optimizers(model, cfg, args):
                   {'params': _params(model.get_10x_lr_params(), seen, kd), 'lr': args.lr, 'weight_decay': wd},
                   {'params': _params(model.get_1x_lr_params_bias(), seen, kd), 'lr': args.lr * 0.1, 'weight_decay': 0},
                   {'params': _params(model.get_10x_lr_params_bias(), seen, kd), 'lr': args.lr, 'weight_decay': 0}]
+    if args.fused_sgd and not kd:
+        from cvpr2021_vspw_implement_b200.optim import FusedSGD  # same update rule and state_dict, one launch per step
+        return FusedSGD(groups, lr=args.lr, momentum=cfg.TRAIN.beta1, weight_decay=wd)
     return torch.optim.SGD(groups, lr=args.lr, momentum=cfg.TRAIN.beta1, weight_decay=wd)
 
 
@@ -236,6 +239,7 @@ def make_parser():
     parser.add_argument("--max_iters_per_epoch", type=int, default=0)
     parser.add_argument("--checkpoint_every", type=int, default=20)
     parser.add_argument("--keep_duplicate_params", type=str2bool, default=False)
+    parser.add_argument("--fused_sgd", type=str2bool, default=True, help="vspw_sgd_momentum_step instead of torch.optim.SGD (same update rule)")
     parser.add_argument("opts", help="Modify config options using the command-line", default=None, nargs=argparse.REMAINDER)
     return parser
 
