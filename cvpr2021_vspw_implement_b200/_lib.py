@@ -36,6 +36,7 @@ _SIGNATURES = {
     "vspw_split_bf16": [_c_vp, _c_vp, _c_vp, _c_sz, _c_vp],
     "vspw_zero_insert2_bf16": [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp],
     "vspw_conv_weight_prep": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp],
+    "vspw_conv_weight_prep_multi": [_c_vp, _c_int, _c_int, _c_int, _c_vp],
     "vspw_cast_f64_f32": [_c_vp, _c_vp, _c_sz, _c_vp],
     "vspw_copy_channels": [_c_vp, _c_int, _c_int, _c_vp, _c_int, _c_int, _c_int, _c_sz, _c_int, _c_vp],
     "vspw_conv2d_fwd": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
@@ -69,7 +70,8 @@ _SIGNATURES = {
     "vspw_confusion_add": [_c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_vp],
 }
 
-EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["vspw_last_error", "vspw_version", "vspw_tcb_pool_workspace_floats", "vspw_sgd_chunk_elems"])
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["vspw_last_error", "vspw_version", "vspw_tcb_pool_workspace_floats", "vspw_sgd_chunk_elems",
+                                                   "vspw_conv_weight_prep_tile"])
 
 
 class VspwError(RuntimeError):
@@ -100,6 +102,8 @@ class _Lib:
                     dll.vspw_version.argtypes = []
                     dll.vspw_sgd_chunk_elems.restype = ctypes.c_int32
                     dll.vspw_sgd_chunk_elems.argtypes = []
+                    dll.vspw_conv_weight_prep_tile.restype = ctypes.c_int32
+                    dll.vspw_conv_weight_prep_tile.argtypes = [_c_int] * 4
                     dll.vspw_tcb_pool_workspace_floats.restype = ctypes.c_size_t
                     dll.vspw_tcb_pool_workspace_floats.argtypes = [_c_int, _c_int, _c_int, _c_int, _c_vp, _c_int]
                     self._dll = dll

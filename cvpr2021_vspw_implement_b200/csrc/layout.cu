@@ -240,14 +240,13 @@ extern "C" int vspw_zero_insert2_bf16(const uint16_t* src, uint16_t* dst, int32_
 // OHWI planes (forward B operand, K = taps*Cin contiguous) and IHWO planes (dgrad B operand, K = taps*Cout contiguous),
 // each as bf16 hi (+ lo).  Replaces 2 permutes + 2 splits per conv per step.  One block = a 32 (co) x 32 (ci) tile, all taps.
 template <int TILE>  // TILE x TILE (co x ci) per block; TILE = 64 for 1x1 (2 channels per lane, 4-byte stores), 32 for 3x3
-__global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ ohwi_hi,
-                                                           __nv_bfloat16* __restrict__ ohwi_lo, __nv_bfloat16* __restrict__ ihwo_hi,
-                                                           __nv_bfloat16* __restrict__ ihwo_lo, int co_n, int ci_n, int taps) {
+__device__ __forceinline__ void weight_prep_tile(const float* __restrict__ w, __nv_bfloat16* __restrict__ ohwi_hi,
+                                                 __nv_bfloat16* __restrict__ ohwi_lo, __nv_bfloat16* __restrict__ ihwo_hi,
+                                                 __nv_bfloat16* __restrict__ ihwo_lo, int co_n, int ci_n, int taps, int co0, int ci0) {
   constexpr int MAXT = TILE == 64 ? 1 : 9;
   constexpr int V = TILE / 32;  // channels per lane
   __shared__ float tile[TILE][TILE * MAXT + 1];  // [co][ci*taps + tap], odd pitch: both transposed reads are conflict-free
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int co0 = blockIdx.y * TILE, ci0 = blockIdx.x * TILE;
   const int run = TILE * taps;  // contiguous floats of one co row inside this tile
   // all of a warp's loads are issued before the first shared-memory store (a load -> store -> load chain costs one DRAM
   // latency per element row: 20 us for a 3x3 tile)
@@ -301,12 +300,47 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restric
     }
   }
 }
+template <int TILE>
+__global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ ohwi_hi,
+                                                           __nv_bfloat16* __restrict__ ohwi_lo, __nv_bfloat16* __restrict__ ihwo_hi,
+                                                           __nv_bfloat16* __restrict__ ihwo_lo, int co_n, int ci_n, int taps) {
+  weight_prep_tile<TILE>(w, ohwi_hi, ohwi_lo, ihwo_hi, ihwo_lo, co_n, ci_n, taps, blockIdx.y * TILE, blockIdx.x * TILE);
+}
+// Every conv weight of the model in one launch per tile kind: a block finds its tensor by bisecting the table's block prefix
+// (block0 ascending) and then does exactly what the single-tensor kernel does.  ~110 launches of 9-15 us -> 2 per step.
+template <int TILE>
+__global__ void __launch_bounds__(256) weight_prep_multi_kernel(const vspw_wprep_tensor* __restrict__ table, int n_tensors) {
+  int lo = 0, hi = n_tensors - 1;
+  while (lo < hi) {  // last entry with block0 <= blockIdx.x
+    const int mid = (lo + hi + 1) >> 1;
+    if ((uint32_t)__ldg(&table[mid].block0) <= blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const vspw_wprep_tensor t = table[lo];
+  const int b = (int)blockIdx.x - t.block0;
+  const int by = b / t.blocks_x, bx = b - by * t.blocks_x;
+  weight_prep_tile<TILE>(t.w_oihw, (__nv_bfloat16*)t.ohwi_hi, (__nv_bfloat16*)t.ohwi_lo, (__nv_bfloat16*)t.ihwo_hi,
+                         (__nv_bfloat16*)t.ihwo_lo, t.cout, t.cin, t.taps, by * TILE, bx * TILE);
+}
+extern "C" int32_t vspw_conv_weight_prep_tile(int32_t cout, int32_t cin, int32_t kh, int32_t kw) {
+  if (cout <= 0 || cin <= 0 || kh * kw < 1 || kh * kw > 9) return 0;
+  return (kh * kw == 1 && cin % 2 == 0 && cout % 2 == 0) ? 64 : 32;
+}
+extern "C" int vspw_conv_weight_prep_multi(const vspw_wprep_tensor* table_dev, int32_t n_tensors, int32_t n_blocks, int32_t tile,
+                                           void* stream) {
+  VSPW_REQUIRE(table_dev || n_tensors == 0, "vspw_conv_weight_prep_multi: null table");
+  VSPW_REQUIRE(tile == 64 || tile == 32, "vspw_conv_weight_prep_multi: tile must be 64 or 32 (got %d)", tile);
+  VSPW_REQUIRE(n_tensors >= 0 && n_blocks >= 0, "vspw_conv_weight_prep_multi: negative count");
+  if (n_tensors == 0 || n_blocks == 0) return VSPW_OK;
+  if (tile == 64) weight_prep_multi_kernel<64><<<(unsigned)n_blocks, 256, 0, as_stream(stream)>>>(table_dev, n_tensors);
+  else weight_prep_multi_kernel<32><<<(unsigned)n_blocks, 256, 0, as_stream(stream)>>>(table_dev, n_tensors);
+  return check_launch("vspw_conv_weight_prep_multi");
+}
 extern "C" int vspw_conv_weight_prep(const float* w_oihw, uint16_t* ohwi_hi, uint16_t* ohwi_lo, uint16_t* ihwo_hi,
                                      uint16_t* ihwo_lo, int32_t cout, int32_t cin, int32_t kh, int32_t kw, void* stream) {
   VSPW_REQUIRE(w_oihw && ohwi_hi && ihwo_hi, "vspw_conv_weight_prep: null argument");
   VSPW_REQUIRE((ohwi_lo == nullptr) == (ihwo_lo == nullptr), "vspw_conv_weight_prep: lo planes go together");
   VSPW_REQUIRE(cout > 0 && cin > 0 && kh * kw >= 1 && kh * kw <= 9, "vspw_conv_weight_prep: unsupported shape %dx%dx%dx%d", cout, cin, kh, kw);
-  if (kh * kw == 1 && cin % 2 == 0 && cout % 2 == 0) {
+  if (vspw_conv_weight_prep_tile(cout, cin, kh, kw) == 64) {
     dim3 grid((cin + 63) / 64, (cout + 63) / 64);
     weight_prep_kernel<64><<<grid, 256, 0, as_stream(stream)>>>(w_oihw, (__nv_bfloat16*)ohwi_hi, (__nv_bfloat16*)ohwi_lo,
                                                                (__nv_bfloat16*)ihwo_hi, (__nv_bfloat16*)ihwo_lo, cout, cin, 1);

@@ -15,6 +15,7 @@ import os
 import weakref
 from contextlib import contextmanager
 
+import numpy as np
 import torch
 
 from ._lib import ConvDesc, PREC_BF16, PREC_BF16X3, PREC_FP32, VspwError, i4, lib
@@ -25,7 +26,10 @@ _state = {"precision": os.environ.get("VSPW_PRECISION", "bf16x3"), "syncbn_clamp
           # the backward chain reads them) so that the tensor-bound wgrad kernels overlap the HBM-bound BN backward kernels.
           # Measured gain on B200: 1.2 % of the step (the persistent conv CTAs already fill every SM), and per-kernel event
           # times stop being meaningful under overlap, so it is off by default.
-          "wgrad_stream": os.environ.get("VSPW_WGRAD_STREAM", "0") == "1"}
+          "wgrad_stream": os.environ.get("VSPW_WGRAD_STREAM", "0") == "1",
+          # VSPW_WPREP_MULTI=0: rebuild the conv weights' bf16 operand planes with one launch per weight instead of the
+          # per-step batched launch (_WeightPrepPlan); for A/B timing only.
+          "wprep_multi": os.environ.get("VSPW_WPREP_MULTI", "1") != "0"}
 _side_streams = {}
 
 
@@ -225,6 +229,7 @@ class Tape:
         self._done = False  # set once backward has run (or the tape was released): its arena slices are dead
         self._side = None     # side stream used by this tape's backward (joined at the end of backward)
         self._keepalive = []  # tensors read by side-stream kernels: not returned to the allocator before the join
+        self._wprep_done = set()  # weight-prep plans this tape has already refreshed
 
     def zeros_f64(self, shape, device):
         """Zero-initialised fp64 accumulator (BN sums, bias gradients).  One memset per step instead of one fill launch
@@ -352,21 +357,110 @@ def _var_planes(v):
     return v.planes
 
 
-def _tc_weight_planes(wv):
-    """{'ohwi': (hi, lo), 'ihwo': (hi, lo)} bf16 operand planes of a conv weight, produced from the OIHW parameter by one
-    kernel and cached on the tape's PVar (i.e. once per step)."""
-    pk = "tc_planes_" + _state["precision"]
+def _tc_weight_planes_once(w, x3):
+    """The four operand planes of one OIHW weight by the single-tensor kernel."""
+    co, ci, kh, kw = w.shape
+    mk = lambda shape: torch.empty(shape, device=w.device, dtype=torch.bfloat16)
+    oh, ih = mk((co, kh, kw, ci)), mk((ci, kh, kw, co))
+    ol, il = (mk((co, kh, kw, ci)), mk((ci, kh, kw, co))) if x3 else (None, None)
+    lib.call("vspw_conv_weight_prep", _p(w), _p(oh), _p(ol), _p(ih), _p(il), co, ci, kh, kw, _stream())
+    return {"ohwi": (oh, ol), "ihwo": (ih, il)}
+
+
+_WPREP_ENTRY = np.dtype([("w", "<u8"), ("oh", "<u8"), ("ol", "<u8"), ("ih", "<u8"), ("il", "<u8"), ("cout", "<i4"), ("cin", "<i4"),
+                         ("taps", "<i4"), ("block0", "<i4"), ("blocks_x", "<i4"), ("reserved", "<i4")])  # == struct vspw_wprep_tensor
+assert _WPREP_ENTRY.itemsize == 64
+
+
+class _WeightPrepPlan:
+    """The conv weights the tcgen05 path has used on one device in one precision, their (persistent) bf16 operand planes and
+    the device table that rebuilds ALL of them with one launch per tile kind when a new tape first asks for a weight: the
+    weights change every optimizer step, and ~110 single-tensor launches of 9-15 us are latency, not bytes.
+
+    The first tape that meets a weight registers it (single-tensor launch, as before); a parameter whose storage moved or
+    that died is dropped and re-registered on its next use.  Planes are shared between tapes: a tape that is still waiting
+    for its backward sees the planes of the CURRENT weights, which is only wrong for a program that updates weights between
+    a forward and its backward -- torch.autograd rejects that program too (in-place version check)."""
+
+    def __init__(self, device, x3):
+        self.device, self.x3 = device, x3
+        self.entries = {}   # id(param) -> [weakref(param), data_ptr, shape, planes, tile]
+        self.tables = None  # [(tile, device table, n_tensors, n_blocks)]; None = rebuild before the next batched launch
+
+    def refresh(self):
+        """Rebuild the planes of every registered weight from its current values."""
+        for k in [k for k, e in self.entries.items() if not self._current(e)]:
+            del self.entries[k]
+            self.tables = None
+        if not self.entries:
+            return
+        if self.tables is None:
+            self._build_tables()
+        for tile, tab, n_t, n_b in self.tables:
+            lib.call("vspw_conv_weight_prep_multi", _p(tab), n_t, n_b, tile, _stream())
+
+    @staticmethod
+    def _view(param):
+        d = param.data
+        return d.view(d.shape[0], d.shape[1], 1, 1) if d.dim() == 5 and tuple(d.shape[2:]) == (1, 1, 1) else d
+
+    def _current(self, e):
+        p = e[0]()
+        if p is None:
+            return False
+        d = self._view(p)
+        return d.data_ptr() == e[1] and tuple(d.shape) == e[2] and d.is_contiguous() and d.device == self.device
+
+    def _build_tables(self):
+        self.tables = []
+        for tile in (64, 32):
+            ents = [e for e in self.entries.values() if e[4] == tile]
+            if not ents:
+                continue
+            table = np.zeros(len(ents), dtype=_WPREP_ENTRY)
+            block0 = 0
+            for i, e in enumerate(ents):
+                co, ci, kh, kw = e[2]
+                (oh, ol), (ih, il) = e[3]["ohwi"], e[3]["ihwo"]
+                bx, by = (ci + tile - 1) // tile, (co + tile - 1) // tile
+                table[i] = (e[1], oh.data_ptr(), ol.data_ptr() if ol is not None else 0, ih.data_ptr(),
+                            il.data_ptr() if il is not None else 0, co, ci, kh * kw, block0, bx, 0)
+                block0 += bx * by
+            dev = torch.from_numpy(table.view(np.uint8).copy()).to(self.device)  # pageable copy: synchronous, only on a rebuild
+            self.tables.append((tile, dev, len(ents), block0))
+
+    def planes(self, tape, wv):
+        if id(self) not in tape._wprep_done:  # this tape's first weight: bring every known weight up to date at once
+            tape._wprep_done.add(id(self))
+            self.refresh()
+        e = self.entries.get(id(wv.param))
+        if e is None or e[0]() is not wv.param or not self._current(e):
+            w = wv.data
+            tile = int(lib.dll().vspw_conv_weight_prep_tile(*[int(d) for d in w.shape]))
+            e = self.entries[id(wv.param)] = [weakref.ref(wv.param), w.data_ptr(), tuple(w.shape), _tc_weight_planes_once(w, self.x3), tile]
+            self.tables = None
+        return e[3]
+
+
+_wprep_plans = {}  # (device, precision) -> _WeightPrepPlan
+
+
+def _tc_weight_planes(tape, wv):
+    """{'ohwi': (hi, lo), 'ihwo': (hi, lo)} bf16 operand planes of a conv weight, rebuilt from the OIHW parameter once per
+    step: by the plan's batched launch (contiguous parameters), else by one single-tensor launch cached on the tape's PVar."""
+    prec = _state["precision"]
+    pk = "tc_planes_" + prec
     pl = wv.cache.get(pk)
     if pl is None:
         w = wv.data
-        co, ci, kh, kw = w.shape
-        x3 = _state["precision"] == "bf16x3"
-        mk = lambda shape: torch.empty(shape, device=w.device, dtype=torch.bfloat16)
-        oh, ih = mk((co, kh, kw, ci)), mk((ci, kh, kw, co))
-        ol, il = (mk((co, kh, kw, ci)), mk((ci, kh, kw, co))) if x3 else (None, None)
-        lib.call("vspw_conv_weight_prep", _p(w if w.is_contiguous() else w.contiguous()), _p(oh), _p(ol), _p(ih), _p(il), co, ci, kh, kw,
-                 _stream())
-        pl = wv.cache[pk] = {"ohwi": (oh, ol), "ihwo": (ih, il)}
+        if w.is_contiguous() and _state["wprep_multi"]:
+            plan = _wprep_plans.get((w.device, prec))
+            if plan is None:
+                plan = _wprep_plans[(w.device, prec)] = _WeightPrepPlan(w.device, prec == "bf16x3")
+            pl = plan.planes(tape, wv)
+        else:
+            pl = _tc_weight_planes_once(w if w.is_contiguous() else w.contiguous(), prec == "bf16x3")
+        wv.cache[pk] = pl
     return pl
 
 
@@ -395,7 +489,7 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1, want_stats=False)
     stats = None
     if use_tc:
         xh, xl = _var_planes(x)
-        wh, wl = _tc_weight_planes(wv)["ohwi"]
+        wh, wl = _tc_weight_planes(tape, wv)["ohwi"]
         if want_stats:
             stats = tape.zeros_f64((2, co), y.device)
         with _ConvTimer(flops, True):
@@ -453,7 +547,7 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1, want_stats=False)
             fan_in = use_tc and x.grad is not None and x.grad.is_contiguous() and tuple(x.grad.shape) == (n, h, w, cin)
             dx = x.grad if fan_in else torch.empty((n, h, w, cin), device=dev, dtype=torch.float32)
             if use_tc:
-                th, tl = _tc_weight_planes(wv)["ihwo"]
+                th, tl = _tc_weight_planes(tape, wv)["ihwo"]
                 d1, g_hi, g_lo = desc, dyp[0], dyp[1]
                 if stride == 2:
                     # dgrad of a stride-2 conv = stride-1 dgrad of dy laid on the input grid with zeros in between

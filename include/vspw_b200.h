@@ -73,6 +73,24 @@ int vspw_zero_insert2_bf16(const uint16_t* src, uint16_t* dst, int32_t n, int32_
  * pass: OHWI hi/lo (forward, wgrad layout) and IHWO hi/lo (dgrad); lo planes null in VSPW_PREC_BF16 mode */
 int vspw_conv_weight_prep(const float* w_oihw, uint16_t* ohwi_hi, uint16_t* ohwi_lo, uint16_t* ihwo_hi,
                           uint16_t* ihwo_lo, int32_t cout, int32_t cin, int32_t kh, int32_t kw, void* stream);
+/* The same for every conv weight of a model in ONE launch per tile kind (the weights change every optimizer step, so the
+ * planes are rebuilt every step: ~110 small launches otherwise).  `table_dev` is a device array of n_tensors entries that
+ * all share one tile kind (vspw_conv_weight_prep_tile of their shape), in ascending block0; entry i owns blocks
+ * [block0, block0 + blocks_x * ceil(cout/tile)), blocks_x = ceil(cin/tile); n_blocks is the total. */
+typedef struct vspw_wprep_tensor {
+  const float* w_oihw;
+  uint16_t* ohwi_hi;
+  uint16_t* ohwi_lo; /* null in VSPW_PREC_BF16 mode (together with ihwo_lo) */
+  uint16_t* ihwo_hi;
+  uint16_t* ihwo_lo;
+  int32_t cout, cin, taps; /* taps = kh*kw */
+  int32_t block0, blocks_x;
+  int32_t reserved;
+} vspw_wprep_tensor;
+/* 64 or 32: the tile kind the library uses for this weight shape (0 = unsupported shape) */
+int32_t vspw_conv_weight_prep_tile(int32_t cout, int32_t cin, int32_t kh, int32_t kw);
+int vspw_conv_weight_prep_multi(const vspw_wprep_tensor* table_dev, int32_t n_tensors, int32_t n_blocks, int32_t tile,
+                                void* stream);
 /* copy a channel slice: dst[p][dst_off + c] = src[p][src_off + c], c < cc   (torch.cat(dim=1),
  * clip_psp.py:53, spatial_ocr_block.py:375; accumulate!=0 adds instead (backward of cat/split)) */
 /* double accumulators (BN sums, bias gradients) -> fp32 parameter-gradient vectors */

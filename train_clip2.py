@@ -114,7 +114,7 @@ def create_optimizers(model, cfg, args):
                   {'params': _params(model.get_10x_lr_params(), seen, kd), 'lr': args.lr, 'weight_decay': wd},
                   {'params': _params(model.get_1x_lr_params_bias(), seen, kd), 'lr': args.lr * 0.1, 'weight_decay': 0},
                   {'params': _params(model.get_10x_lr_params_bias(), seen, kd), 'lr': args.lr, 'weight_decay': 0}]
-    if args.fused_sgd and not kd:
+    if getattr(args, "fused_sgd", False) and not kd:
         from cvpr2021_vspw_implement_b200.optim import FusedSGD  # same update rule and state_dict, one launch per step
         return FusedSGD(groups, lr=args.lr, momentum=cfg.TRAIN.beta1, weight_decay=wd)
     return torch.optim.SGD(groups, lr=args.lr, momentum=cfg.TRAIN.beta1, weight_decay=wd)
