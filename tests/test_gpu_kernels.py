@@ -342,6 +342,56 @@ def test_conv_weight_prep_and_zero_insert(E, shape, x3):
     assert torch.equal(dst, ref)
 
 
+@pytest.mark.parametrize("x3", [True, False])
+def test_weight_prep_plan_batched_launch_tracks_parameter_updates(E, x3):
+    """engine._WeightPrepPlan: the second tape's first weight request rebuilds the planes of EVERY registered weight with
+    vspw_conv_weight_prep_multi (one launch per tile kind) and they are bit-identical to torch's permute + bf16 rounding
+    of the CURRENT values (i.e. after an in-place optimizer update), for mixed 1x1 / 3x3 / ragged shapes and a 5-D
+    Conv3d 1x1x1 weight; a parameter whose storage moved is re-registered."""
+    from cvpr2021_vspw_implement_b200._lib import lib
+    g = torch.Generator().manual_seed(11)
+    shapes = [(128, 64, 1, 1), (64, 128, 3, 3), (192, 320, 1, 1), (96, 160, 3, 3), (124, 512, 1, 1), (256, 256, 1, 1, 1), (33, 65, 1, 1)]
+    params = [torch.nn.Parameter(torch.randn(*s, generator=g).cuda()) for s in shapes]
+    plan = E._WeightPrepPlan(torch.device("cuda", torch.cuda.current_device()), x3)
+
+    def check(pl, p):
+        w = p.data.view(p.shape[0], p.shape[1], *(p.shape[2:4] if p.dim() == 4 else (1, 1)))
+        for key, perm in (("ohwi", (0, 2, 3, 1)), ("ihwo", (1, 2, 3, 0))):
+            ref = w.permute(*perm).contiguous()
+            hi = ref.to(torch.bfloat16)
+            assert torch.equal(pl[key][0], hi)
+            if x3:
+                assert torch.equal(pl[key][1], (ref - hi.float()).to(torch.bfloat16))
+            else:
+                assert pl[key][1] is None
+
+    t1 = E.Tape(False)
+    for p in params:
+        check(plan.planes(t1, t1.param(p)), p)
+    assert len(plan.entries) == len(params) and plan.tables is None
+    with torch.no_grad():  # an optimizer step: same storage, new values
+        for p in params:
+            p.add_(torch.randn(p.shape, generator=g).cuda())
+    n0 = lib.launches
+    t2 = E.Tape(False)
+    first = plan.planes(t2, t2.param(params[0]))
+    assert lib.launches - n0 == 2  # one batched launch per tile kind, nothing per weight
+    assert {t[0] for t in plan.tables} == {64, 32}
+    for p in params:
+        pl = plan.planes(t2, t2.param(p))
+        check(pl, p)
+    assert lib.launches - n0 == 2 and first is plan.planes(t2, t2.param(params[0]))
+    # storage moved: the entry is dropped at the next refresh and the weight registers again on use
+    params[1].data = params[1].data.clone() * 2
+    t3 = E.Tape(False)
+    for p in params:
+        check(plan.planes(t3, t3.param(p)), p)
+    assert plan.tables is None and len(plan.entries) == len(params)
+    t4 = E.Tape(False)
+    for p in params:
+        check(plan.planes(t4, t4.param(p)), p)
+
+
 def test_evaluator_device_path_matches_host_path(E):
     """utils.Evaluator.add_batch_device (vspw_confusion_add on the device) == add_batch (reference
     utils.py:86-99 on NumPy), including ignore labels 255."""
