@@ -285,6 +285,12 @@ def run_ours(args):
             f.write("\nslowest single calls (index in call order, entry point, ms):\n")
             for i, name, ms in sorted(lib.last_profile_calls, key=lambda r: -r[2])[:12]:
                 f.write(f"- #{i} `{name}` {ms:.3f}\n")
+            E.conv_profile_begin()
+            step(imgs_d, labs_d)
+            arm = E.conv_profile_end()["fp32_arm"]
+            f.write(f"\nconvs left on the CUDA-core arm ({len(arm)} launches, {sum(m for _, m in arm):.2f} ms/step):\n")
+            for tag, ms in sorted(arm, key=lambda r: -r[1]):
+                f.write(f"- {tag}: {ms:.3f} ms\n")
 
     gc.enable()
     pk = peaks()

@@ -389,6 +389,66 @@ int validate_desc(const vspw_conv_desc* d, const char* who) {
   return VSPW_OK;
 }
 
+// 1x1 conv over a handful of pixels (the PPM branches: 2048 -> 512 on the s x s pooled maps, M = n*s*s <= 72 rows): the tiled
+// kernel above would run K = 2048 serially in M/128 x Nout/128 = 4 CTAs.  Here a block owns kSkN output channels, its 256
+// threads split K, and the M rows go through in groups of kSkM with a block reduction per group: Nout/4 CTAs stream the
+// weight matrix once (it is the only HBM traffic; A stays in L2).  Fixed summation order: deterministic.
+constexpr int kSkN = 4, kSkM = 8, kSkinnyMaxM = 128;
+
+__global__ void __launch_bounds__(256) skinny_gemm_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                           const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K) {
+  __shared__ float red[8][kSkN * kSkM];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * kSkN;
+  for (int m0 = 0; m0 < M; m0 += kSkM) {
+    float acc[kSkN][kSkM];
+#pragma unroll
+    for (int j = 0; j < kSkN; ++j)
+#pragma unroll
+      for (int i = 0; i < kSkM; ++i) acc[j][i] = 0.f;
+    for (int k = threadIdx.x * 4; k < K; k += 256 * 4) {
+      float4 b[kSkN], a[kSkM];
+#pragma unroll
+      for (int j = 0; j < kSkN; ++j)
+        b[j] = n0 + j < N ? __ldg(reinterpret_cast<const float4*>(B + (size_t)(n0 + j) * K + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < kSkM; ++i)
+        a[i] = m0 + i < M ? __ldg(reinterpret_cast<const float4*>(A + (size_t)(m0 + i) * K + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < kSkN; ++j)
+#pragma unroll
+        for (int i = 0; i < kSkM; ++i)
+          acc[j][i] = fmaf(a[i].x, b[j].x, fmaf(a[i].y, b[j].y, fmaf(a[i].z, b[j].z, fmaf(a[i].w, b[j].w, acc[j][i]))));
+    }
+#pragma unroll
+    for (int j = 0; j < kSkN; ++j)
+#pragma unroll
+      for (int i = 0; i < kSkM; ++i) {
+        float v = acc[j][i];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][j * kSkM + i] = v;
+      }
+    __syncthreads();
+    if (threadIdx.x < kSkN * kSkM) {
+      const int j = threadIdx.x / kSkM, i = threadIdx.x % kSkM;
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+      if (n0 + j < N && m0 + i < M) C[(size_t)(m0 + i) * N + n0 + j] = v + (bias ? bias[n0 + j] : 0.f);
+    }
+    __syncthreads();
+  }
+}
+
+// true when the conv is a plain [M][K] x [N][K]^T product with few rows; launches the skinny kernel
+bool try_skinny(const vspw_conv_desc* d, const float* A, const float* B, const float* bias, float* C, int M, int N, int K, void* stream) {
+  if (d->kh != 1 || d->kw != 1 || d->stride != 1 || d->pad != 0 || M > kSkinnyMaxM || K % 4 != 0) return false;
+  if (((uintptr_t)A | (uintptr_t)B) % 16 != 0) return false;
+  skinny_gemm_kernel<<<(N + kSkN - 1) / kSkN, 256, 0, as_stream(stream)>>>(A, B, bias, C, M, N, K);
+  return true;
+}
+
 }  // namespace
 
 extern "C" int vspw_conv2d_fwd(const vspw_conv_desc* d, const float* x, const float* w_ohwi, const float* bias, float* y,
@@ -396,6 +456,7 @@ extern "C" int vspw_conv2d_fwd(const vspw_conv_desc* d, const float* x, const fl
   int rc = validate_desc(d, "vspw_conv2d_fwd");
   if (rc) return rc;
   VSPW_REQUIRE(x && w_ohwi && y, "vspw_conv2d_fwd: null pointer");
+  if (try_skinny(d, x, w_ohwi, bias, y, d->n * d->ho * d->wo, d->cout, d->cin, stream)) return check_launch("vspw_conv2d_fwd (skinny)");
   IGemmParams p;
   p.A = x; p.B = w_ohwi; p.bias = bias; p.Cmat = y;
   p.N = d->n; p.H = d->h; p.W = d->w; p.C = d->cin;
@@ -413,6 +474,7 @@ extern "C" int vspw_conv2d_dgrad(const vspw_conv_desc* d, const float* dy, const
   int rc = validate_desc(d, "vspw_conv2d_dgrad");
   if (rc) return rc;
   VSPW_REQUIRE(dy && w_t_ihwo && dx, "vspw_conv2d_dgrad: null pointer");
+  if (try_skinny(d, dy, w_t_ihwo, nullptr, dx, d->n * d->h * d->w, d->cin, d->cout, stream)) return check_launch("vspw_conv2d_dgrad (skinny)");
   IGemmParams p;
   p.A = dy; p.B = w_t_ihwo; p.bias = nullptr; p.Cmat = dx;
   p.N = d->n; p.H = d->ho; p.W = d->wo; p.C = d->cout;

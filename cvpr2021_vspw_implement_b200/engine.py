@@ -77,17 +77,19 @@ def conv_profile_end():
     global _prof
     rec, _prof = _prof or [], None
     torch.cuda.synchronize()
-    ms = sum(a.elapsed_time(b) for a, b, _, _ in rec)
+    ms = sum(r[0].elapsed_time(r[1]) for r in rec)
     tc = sum(1 for r in rec if r[3])
     kern = "conv_tc_kernel (tcgen05 implicit GEMM)" if tc * 2 > len(rec) else "igemm_kernel/wgrad_kernel (fp32 FFMA implicit GEMM)"
-    return {"launches": len(rec), "ms": ms, "tflop": sum(r[2] for r in rec) / 1e12, "kernel": kern, "tc_launches": tc}
+    return {"launches": len(rec), "ms": ms, "tflop": sum(r[2] for r in rec) / 1e12, "kernel": kern, "tc_launches": tc,
+            # the launches that stayed on the CUDA-core arm, with their geometry: what is left to move
+            "fp32_arm": [(r[4], r[0].elapsed_time(r[1])) for r in rec if not r[3]]}
 
 
 class _ConvTimer:
-    __slots__ = ("e0", "flops", "tc")
+    __slots__ = ("e0", "flops", "tc", "tag")
 
-    def __init__(self, flops, tc):
-        self.flops, self.tc = flops, tc
+    def __init__(self, flops, tc, tag=None):
+        self.flops, self.tc, self.tag = flops, tc, tag
         self.e0 = None
 
     def __enter__(self):
@@ -100,7 +102,7 @@ class _ConvTimer:
         if self.e0 is not None and _prof is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            _prof.append((self.e0, e1, self.flops, self.tc))
+            _prof.append((self.e0, e1, self.flops, self.tc, self.tag))
         return False
 
 
@@ -486,6 +488,7 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1, want_stats=False)
         raise VspwError("conv2d: the input was materialised as bf16 planes only but this geometry runs on the fp32 arm")
     y = torch.empty((n, ho, wo, co), device=dev, dtype=torch.float32)
     flops = 2.0 * n * ho * wo * co * kh * kw * ci
+    geom = f"{n}x{h}x{w} {kh}x{kw} {ci}->{co} s{stride} d{dil}"
     stats = None
     if use_tc:
         xh, xl = _var_planes(x)
@@ -497,7 +500,7 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1, want_stats=False)
                      _p(stats[0]) if stats is not None else None, _p(stats[1]) if stats is not None else None, _stream())
     else:
         w_ohwi = _weight_ohwi(tape, wv)
-        with _ConvTimer(flops, False):
+        with _ConvTimer(flops, False, "fwd " + geom):
             lib.call("vspw_conv2d_fwd", ctypes.byref(desc), _p(x.data), _p(w_ohwi), _p(bv.data if bv else None), _p(y), _stream())
     out = Var(y, needs_grad=tape.grad_enabled and (x.needs_grad or wv.needs_grad))
     out.stats = stats
@@ -530,7 +533,7 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1, want_stats=False)
                     with _ConvTimer(flops, True):
                         lib.call("vspw_conv2d_wgrad_tc", ctypes.byref(desc), _p(xh), _p(xl), _p(dyp[0]), _p(dyp[1]), _p(dw), sw)
                 else:
-                    with _ConvTimer(flops, False):
+                    with _ConvTimer(flops, False, "wgrad " + geom):
                         lib.call("vspw_conv2d_wgrad", ctypes.byref(desc), _p(x.data), _p(dy), _p(dw), sw)
                 if kh == 1 and kw == 1:
                     wv.add_grad(dw.view(co, ci, 1, 1))
@@ -561,7 +564,7 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1, want_stats=False)
                     lib.call("vspw_conv2d_dgrad_tc", ctypes.byref(d1), _p(g_hi), _p(g_lo), _p(th), _p(tl), _p(dx), 1 if fan_in else 0, st)
             else:
                 w_t = _weight_ihwo(tape, wv)
-                with _ConvTimer(flops, False):
+                with _ConvTimer(flops, False, "dgrad " + geom):
                     lib.call("vspw_conv2d_dgrad", ctypes.byref(desc), _p(dy), _p(w_t), _p(dx), st)
             if not fan_in:
                 x.add_grad(dx)

@@ -39,7 +39,10 @@ CONV_GEOMS = [
     (2, 512, 7, 9, 124, 1, 1, 0, 1, True),      # classifier with bias, Cout not multiple of 128
     (2, 2048, 6, 6, 1, 1, 1, 0, 1, False),      # pspweight conv, Cout=1
     (2, 96, 5, 7, 40, 3, 1, 1, 1, True),        # odd channel counts
-    (2, 2048, 1, 1, 512, 1, 1, 0, 1, False),    # PPM scale-1 map
+    (2, 2048, 1, 1, 512, 1, 1, 0, 1, False),    # PPM scale-1 map (skinny-M kernel, M = 2)
+    (2, 2048, 3, 3, 512, 1, 1, 0, 1, False),    # PPM scale-3 map (skinny-M kernel, M = 18: partial row group)
+    (3, 20, 3, 3, 7, 1, 1, 0, 1, True),         # skinny-M kernel with ragged Cout and bias; dgrad K = 7 stays on the tiled kernel
+    (1, 64, 11, 12, 36, 1, 1, 0, 1, True),      # M = 132: just above the skinny-M limit
 ]
 
 
