@@ -39,6 +39,13 @@ constexpr uint32_t kSpinLimit = 1u << 27;
 // PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// 1024-byte alignment (SWIZZLE_128B atoms) by OFFSET on the __shared__ array: rounding the pointer up through uintptr_t makes
+// the compiler forget the address space, and every staging access of the epilogue becomes a generic LD.E/ST.E that cannot be
+// reordered across the global stores (ncu source page, r1c: LD.E -> STG.E chains, generic ATOM with a run-time space check).
+__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* smem_raw) {
+  return smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -196,7 +203,7 @@ struct ConvSmem {
   static constexpr int kATile = BM * BK * 2;  // 16 KB
   static constexpr int kBTile = BN * BK * 2;
   static constexpr int kStage = 2 * kATile + 2 * kBTile;  // hi+lo of A and B
-  static constexpr int kStatBytes = 2 /*buffers*/ * 2 /*sum, sqsum*/ * BN * 4;
+  static constexpr int kStatBytes = 4 /*epilogue warps*/ * 2 /*sum, sqsum*/ * BN * 4;
   static constexpr int kStgBytes = 4 /*epilogue warps*/ * 32 * kStgPitch * 4;
   static constexpr int kBytes = STAGES * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/ + kStatBytes + kStgBytes;
 };
@@ -222,9 +229,11 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, float* stg,
   mbar_wait(tmem_full_bar, acc_phase);
   tcgen05_fence_after();
   const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+  const int c_end = p.Nout - n0 < BN ? p.Nout - n0 : BN;  // Nout % 64 == 0: whole 32-column chunks
+  uint32_t v[32];
+  tmem_ld_32x32b_x32(taddr, v);
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 32) {
-    if (n0 + c0 >= p.Nout) continue;  // warp-uniform
+  for (int c0 = 0; c0 < c_end; c0 += 32) {
     const int cq = (lane & 7) * 4;
     float4 prev[8];
     if (p.accumulate) {  // fan-in: fetch what is already there (coalesced, all 8 loads in flight) before touching TMEM
@@ -235,9 +244,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, float* stg,
           prev[i] = __ldcs(reinterpret_cast<const float4*>(p.out + row_off[i] + c0 + cq));
       }
     }
-    uint32_t v[32];
-    tmem_ld_32x32b_x32(taddr + c0, v);
-    tmem_ld_wait();
+    tmem_ld_wait();  // v = accumulator columns [c0, c0 + 32) of this lane's pixel
     // TMEM gives one pixel row per lane; a row-per-lane global store would touch 32 different cache lines per
     // instruction.  Transpose through this warp's private, padded staging block so that every store instruction
     // writes 4 rows x 128 contiguous bytes, and the BN column sums become conflict-free column reads.
@@ -251,6 +258,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, float* stg,
       }
       *reinterpret_cast<float4*>(stg + lane * kStgPitch + j) = o;
     }
+    // the next chunk's columns travel out of TMEM while this one is reduced and stored
+    if (c0 + 32 < c_end) tmem_ld_32x32b_x32(taddr + c0 + 32, v);
     __syncwarp();
     if (p.ch_sum) {
       // fused train-mode BN statistics (replaces a full re-read of the output by vspw_bn_stats): lane = column
@@ -270,9 +279,10 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, float* stg,
           sb = fmaf(x, x, sb);
         }
       }
-      float* buf = stat_s + acc * 2 * BN;
-      atomicAdd(buf + c0 + lane, sa + sa2);
-      atomicAdd(buf + BN + c0 + lane, sb + sb2);
+      // this warp's own row of partial sums: plain stores (shared-memory fp32 atomics are CAS loops)
+      float* buf = stat_s + (warp - 2) * 2 * BN;
+      buf[c0 + lane] = sa + sa2;
+      buf[BN + c0 + lane] = sb + sb2;
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -289,17 +299,18 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, float* stg,
   __syncwarp();
   if (lane == 0) { if (empty_remote) mbar_arrive_cluster(empty_remote); else mbar_arrive(tmem_empty_bar); }
   if (p.ch_sum) {
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps have added their rows of this tile
-    float* buf = stat_s + acc * 2 * BN;
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps have written their partial sums of this tile
 #pragma unroll
     for (int col = (warp - 2) * 32 + lane; col < BN; col += 128) {  // 128 threads sweep the BN columns
       if (n0 + col < p.Nout) {
-        atomicAdd(p.ch_sum + n0 + col, (double)buf[col]);
-        atomicAdd(p.ch_sqsum + n0 + col, (double)buf[BN + col]);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { s1 += stat_s[w * 2 * BN + col]; s2 += stat_s[(w * 2 + 1) * BN + col]; }
+        atomicAdd(p.ch_sum + n0 + col, (double)s1);
+        atomicAdd(p.ch_sqsum + n0 + col, (double)s2);
       }
-      buf[col] = 0.f; buf[BN + col] = 0.f;
     }
-    // buffer `acc` is next written two tiles later, after the bar.sync of the tile in between
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // the rows are rewritten by the next tile
   }
 }
 
@@ -309,15 +320,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, ConvTcParams p) {
   using S = ConvSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStage);
   uint64_t* full_bar = bars;                    // [STAGES]
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* stat_s = reinterpret_cast<float*>(smem + STAGES * S::kStage + 256);  // [2 buffers][sum | sqsum][BN]
-  float* stg = stat_s + 4 * BN + (threadIdx.x >= 64 ? ((threadIdx.x >> 5) - 2) * 32 * kStgPitch : 0);  // per epilogue warp
+  float* stat_s = reinterpret_cast<float*>(smem + STAGES * S::kStage + 256);  // [4 epilogue warps][sum | sqsum][BN]
+  float* stg = stat_s + 8 * BN + (threadIdx.x >= 64 ? ((threadIdx.x >> 5) - 2) * 32 * kStgPitch : 0);  // per epilogue warp
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.N * p.tiles_y * p.tiles_x * p.tiles_n;
@@ -336,7 +347,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
-  if (p.ch_sum) for (int i = threadIdx.x; i < 4 * BN; i += kThreads) stat_s[i] = 0.f;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -443,7 +453,7 @@ struct Conv2Smem {
   static constexpr int kATile = BM * BK * 2;          // 16 KB: this CTA's 128 pixels
   static constexpr int kBTile = (BN2 / 2) * BK * 2;   // 16 KB: this CTA's 128 of the 256 output channels
   static constexpr int kStage = 2 * kATile + 2 * kBTile;
-  static constexpr int kStatBytes = 2 * 2 * BN2 * 4;
+  static constexpr int kStatBytes = 4 * 2 * BN2 * 4;
   static constexpr int kStgBytes = 4 * 32 * kStgPitch * 4;
   static constexpr int kBytes = STAGES * kStage + 1024 + 256 + kStatBytes + kStgBytes;
 };
@@ -481,7 +491,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, ConvTcParams p) {
   using S = Conv2Smem<STAGES>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStage);
   uint64_t* full_bar = bars;                    // [STAGES]  used in the leader only
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]  one per CTA (multicast commit)
@@ -489,7 +499,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]       leader only, count 8 = 4 epilogue warps x 2 CTAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   float* stat_s = reinterpret_cast<float*>(smem + STAGES * S::kStage + 256);
-  float* stg = stat_s + 4 * BN2 + (threadIdx.x >= 64 ? ((threadIdx.x >> 5) - 2) * 32 * kStgPitch : 0);
+  float* stg = stat_s + 8 * BN2 + (threadIdx.x >= 64 ? ((threadIdx.x >> 5) - 2) * 32 * kStgPitch : 0);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -515,7 +525,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * BN2) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
-  if (p.ch_sum) for (int i = threadIdx.x; i < 4 * BN2; i += kThreads) stat_s[i] = 0.f;
   tcgen05_fence_before();
   __syncthreads();
   cluster_sync_all();  // barrier inits of both CTAs are visible before any remote arrive / peer-signalling TMA
@@ -790,7 +799,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy_hi, const __grid_constant__ CUtensorMap map_dy_lo,
                 const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo, WgradTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + WG_STAGES;
@@ -919,7 +928,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 wgrad_tc2_kernel(const __grid_constant__ CUtensorMap map_dy_hi, const __grid_constant__ CUtensorMap map_dy_lo,
                  const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo, WgradTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
   uint64_t* full_bar = bars;               // leader only
   uint64_t* empty_bar = bars + WG_STAGES;  // per CTA (multicast commit)
