@@ -90,7 +90,8 @@ class _Lib:
             with self._lock:
                 if self._dll is None:
                     # (re)build when the sources are newer than the .so; raises if nvcc fails: no silent fallback
-                    path = _build.build_library()
+                    # VSPW_LIB_PATH: load this prebuilt variant instead (A/B timing of compile-time options only)
+                    path = os.environ.get("VSPW_LIB_PATH") or _build.build_library()
                     dll = ctypes.CDLL(path)
                     for name, argtypes in _SIGNATURES.items():
                         fn = getattr(dll, name)

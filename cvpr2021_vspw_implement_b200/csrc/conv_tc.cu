@@ -196,60 +196,97 @@ struct ConvTcParams {
   double* ch_sqsum;    // [Nout] per-channel sum of squares
 };
 
-constexpr int kStgPitch = 36;  // floats per staged row: 32 + 4 pad -> 16-byte row writes and column reads are conflict-free
+// Epilogue geometry of the conv kernels.  The accumulator drain (TMEM -> registers -> smem transpose -> global) is a chain
+// of dependent latencies per warp, and on the wide-N / small-K 1x1 convs (256 -> 1024: 4 k-blocks of MMA per 128 x 256 fp32
+// outputs per CTA) it, not the tensor pipe, sets the tile time (ncu r1d: 63 % tensor busy with 4 warps).
+// -DVSPW_EPI_WARPS=8 builds the variant with 8 epilogue warps: warps w and w + 4 share a TMEM lane quadrant (w % 4) and
+// split the accumulator columns; the staging blocks then have to shrink to 16 columns per step to fit next to the
+// 3 x 64 KB operand stages.  Measured on B200 (tools/bench_conv.py, both builds in one session): 8 warps are SLOWER on
+// exactly those shapes (256 -> 1024 fwd 0.090 -> 0.097 ms, fwd + statistics 0.101 -> 0.114 ms) -- 64-byte row segments per
+// store instead of 128 -- and equal within noise elsewhere, so 4 warps with 32-column steps stay the default.
+#ifndef VSPW_EPI_WARPS
+#define VSPW_EPI_WARPS 4
+#endif
+constexpr int kEpiWarps = VSPW_EPI_WARPS;
+static_assert(kEpiWarps == 4 || kEpiWarps == 8, "4 or 8 epilogue warps");
+constexpr int kConvThreads = 64 + 32 * kEpiWarps;  // TMA warp, MMA warp, epilogue warps
+constexpr int kChunk = kEpiWarps == 8 ? 16 : 32;   // accumulator columns per epilogue step
+constexpr int kStgPitch = kChunk + 4;  // floats per staged row (36 / 20): 16-byte row writes, column reads and the 16-byte
+                                       // reads of the store phase are all bank-conflict-free (row pairs r, r + 4 for pitch 20)
+constexpr int kStoreIters = kChunk / 4;  // float4 stores per lane per step: 32 rows x kChunk columns / (32 lanes x 4)
 
 template <int BN, int STAGES>
 struct ConvSmem {
   static constexpr int kATile = BM * BK * 2;  // 16 KB
   static constexpr int kBTile = BN * BK * 2;
   static constexpr int kStage = 2 * kATile + 2 * kBTile;  // hi+lo of A and B
-  static constexpr int kStatBytes = 4 /*epilogue warps*/ * 2 /*sum, sqsum*/ * BN * 4;
-  static constexpr int kStgBytes = 4 /*epilogue warps*/ * 32 * kStgPitch * 4;
+  static constexpr int kStatBytes = 4 /*lane quadrants*/ * 2 /*sum, sqsum*/ * BN * 4;
+  static constexpr int kStgBytes = kEpiWarps * 32 * kStgPitch * 4;
   static constexpr int kBytes = STAGES * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/ + kStatBytes + kStgBytes;
 };
 
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld_32x32b_x32(taddr, v); }
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// staged row that lane `lane` stores in store iteration i (and whose global offset it needs)
+__device__ __forceinline__ int store_row(int i, int lane) {
+  if constexpr (kChunk == 32) return 4 * i + (lane >> 3);                               // 4 rows x 128 B per instruction
+  else return 8 * i + ((lane >> 3) & 3) + 4 * ((lane >> 2) & 1);                        // 8 rows x 64 B per instruction
+}
 
 // One output tile of the epilogue: wait for the accumulator, TMEM -> registers -> per-warp smem transpose -> coalesced NHWC
-// stores (+bias, +fan-in), fused BN statistics, release the accumulator.  Called by the 4 epilogue warps (warp 2..5).
+// stores (+bias, +fan-in), fused BN statistics, release the accumulator.  Called by the epilogue warps (warp 2 ..).
 // empty_remote != 0: the accumulator-empty barrier lives in the peer (leader) CTA of a cta_group::2 pair.
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, float* stg, float* stat_s, int acc, uint32_t acc_phase,
                                               uint32_t tmem_base, uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar,
                                               uint32_t empty_remote, int img, int ty, int tx, int n0, int warp, int lane) {
+  constexpr int kColsPerWarp = BN / (kEpiWarps / 4);  // warps w and w + 4 split the columns
   const int q = warp & 3;
   const int row = q * 32 + lane;
   const int px = tx * p.bw + row % p.bw, py = ty * p.bh + row / p.bw;
   const bool ok = img < p.N && px < p.W && py < p.H;
   const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
-  // element offset of this lane's output row; the rows the lane STORES (r = 4*i + lane/8, see below) come by shuffle
+  // element offset of this lane's output row; the rows the lane STORES (store_row) come by shuffle
   const unsigned long long my_off = (((unsigned long long)img * p.H + py) * p.W + px) * (unsigned long long)p.Nout + n0;
-  unsigned long long row_off[8];
+  unsigned long long row_off[kStoreIters];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) row_off[i] = __shfl_sync(0xffffffffu, my_off, 4 * i + (lane >> 3));
+  for (int i = 0; i < kStoreIters; ++i) row_off[i] = __shfl_sync(0xffffffffu, my_off, store_row(i, lane));
+  const int cq = (kChunk == 32 ? (lane & 7) : (lane & 3)) * 4;
   mbar_wait(tmem_full_bar, acc_phase);
   tcgen05_fence_after();
   const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-  const int c_end = p.Nout - n0 < BN ? p.Nout - n0 : BN;  // Nout % 64 == 0: whole 32-column chunks
-  uint32_t v[32];
-  tmem_ld_32x32b_x32(taddr, v);
+  const int c_begin = ((warp - 2) >> 2) * kColsPerWarp;
+  int c_end = c_begin + kColsPerWarp;
+  if (c_end > p.Nout - n0) c_end = p.Nout - n0;  // Nout % 64 == 0: whole chunks; may leave this warp without columns
+  float* stat_row = stat_s + q * 2 * BN;  // this quadrant's [sum | sqsum][BN]; the two warps of a quadrant own disjoint columns
+  uint32_t v[kChunk];
+  if (c_begin < c_end) tmem_ld_chunk(taddr + c_begin, v);
 #pragma unroll 1
-  for (int c0 = 0; c0 < c_end; c0 += 32) {
-    const int cq = (lane & 7) * 4;
-    float4 prev[8];
-    if (p.accumulate) {  // fan-in: fetch what is already there (coalesced, all 8 loads in flight) before touching TMEM
+  for (int c0 = c_begin; c0 < c_end; c0 += kChunk) {
+    float4 prev[kStoreIters];
+    if (p.accumulate) {  // fan-in: fetch what is already there (coalesced, all loads in flight) before touching TMEM
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < kStoreIters; ++i) {
         prev[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if ((okmask >> (4 * i + (lane >> 3))) & 1u)
+        if ((okmask >> store_row(i, lane)) & 1u)
           prev[i] = __ldcs(reinterpret_cast<const float4*>(p.out + row_off[i] + c0 + cq));
       }
     }
-    tmem_ld_wait();  // v = accumulator columns [c0, c0 + 32) of this lane's pixel
+    tmem_ld_wait();  // v = accumulator columns [c0, c0 + kChunk) of this lane's pixel
     // TMEM gives one pixel row per lane; a row-per-lane global store would touch 32 different cache lines per
     // instruction.  Transpose through this warp's private, padded staging block so that every store instruction
-    // writes 4 rows x 128 contiguous bytes, and the BN column sums become conflict-free column reads.
+    // writes whole 64/128-byte row segments, and the BN column sums become conflict-free column reads.
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
+    for (int j = 0; j < kChunk; j += 4) {
       float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
                              __uint_as_float(v[j + 3]));
       if (p.bias) {
@@ -259,34 +296,65 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, float* stg,
       *reinterpret_cast<float4*>(stg + lane * kStgPitch + j) = o;
     }
     // the next chunk's columns travel out of TMEM while this one is reduced and stored
-    if (c0 + 32 < c_end) tmem_ld_32x32b_x32(taddr + c0 + 32, v);
+    if (c0 + kChunk < c_end) tmem_ld_chunk(taddr + c0 + kChunk, v);
     __syncwarp();
     if (p.ch_sum) {
-      // fused train-mode BN statistics (replaces a full re-read of the output by vspw_bn_stats): lane = column
+      // fused train-mode BN statistics (replaces a full re-read of the output by vspw_bn_stats)
       float sa = 0.f, sb = 0.f, sa2 = 0.f, sb2 = 0.f;  // two independent chains
-      if (okmask == 0xffffffffu) {
+      if constexpr (kChunk == 32) {  // lane = column, all 32 rows
+        if (okmask == 0xffffffffu) {
 #pragma unroll
-        for (int r = 0; r < 32; r += 2) {
-          const float x = stg[r * kStgPitch + lane], x2 = stg[(r + 1) * kStgPitch + lane];
-          sa += x; sb = fmaf(x, x, sb);
-          sa2 += x2; sb2 = fmaf(x2, x2, sb2);
+          for (int r = 0; r < 32; r += 2) {
+            const float x = stg[r * kStgPitch + lane], x2 = stg[(r + 1) * kStgPitch + lane];
+            sa += x; sb = fmaf(x, x, sb);
+            sa2 += x2; sb2 = fmaf(x2, x2, sb2);
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            const float x = ((okmask >> r) & 1u) ? stg[r * kStgPitch + lane] : 0.f;
+            sa += x;
+            sb = fmaf(x, x, sb);
+          }
         }
-      } else {
+        stat_row[c0 + lane] = sa + sa2;
+        stat_row[BN + c0 + lane] = sb + sb2;
+      } else {  // lane & 15 = column; lanes 16.. take the rows 4 further down (the other 16 banks), halves meet by shuffle
+        const int col = lane & 15, hb = (lane >> 4) * 4;
+        if (okmask == 0xffffffffu) {
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          const float x = ((okmask >> r) & 1u) ? stg[r * kStgPitch + lane] : 0.f;
-          sa += x;
-          sb = fmaf(x, x, sb);
+          for (int rb = 0; rb < 32; rb += 8) {
+#pragma unroll
+            for (int rr = 0; rr < 4; rr += 2) {
+              const float x = stg[(rb + rr + hb) * kStgPitch + col], x2 = stg[(rb + rr + 1 + hb) * kStgPitch + col];
+              sa += x; sb = fmaf(x, x, sb);
+              sa2 += x2; sb2 = fmaf(x2, x2, sb2);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int rb = 0; rb < 32; rb += 8) {
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+              const int r = rb + rr + hb;
+              const float x = ((okmask >> r) & 1u) ? stg[r * kStgPitch + col] : 0.f;
+              sa += x;
+              sb = fmaf(x, x, sb);
+            }
+          }
+        }
+        sa += sa2; sb += sb2;
+        sa += __shfl_xor_sync(0xffffffffu, sa, 16);
+        sb += __shfl_xor_sync(0xffffffffu, sb, 16);
+        if (lane < 16) {  // plain stores into the quadrant's row (shared-memory fp32 atomics are CAS loops)
+          stat_row[c0 + col] = sa;
+          stat_row[BN + c0 + col] = sb;
         }
       }
-      // this warp's own row of partial sums: plain stores (shared-memory fp32 atomics are CAS loops)
-      float* buf = stat_s + (warp - 2) * 2 * BN;
-      buf[c0 + lane] = sa + sa2;
-      buf[BN + c0 + lane] = sb + sb2;
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = 4 * i + (lane >> 3);
+    for (int i = 0; i < kStoreIters; ++i) {
+      const int r = store_row(i, lane);
       if ((okmask >> r) & 1u) {
         float4 o = *reinterpret_cast<const float4*>(stg + r * kStgPitch + cq);
         if (p.accumulate) { o.x += prev[i].x; o.y += prev[i].y; o.z += prev[i].z; o.w += prev[i].w; }
@@ -299,9 +367,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, float* stg,
   __syncwarp();
   if (lane == 0) { if (empty_remote) mbar_arrive_cluster(empty_remote); else mbar_arrive(tmem_empty_bar); }
   if (p.ch_sum) {
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps have written their partial sums of this tile
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");  // every epilogue warp has written its partial sums
 #pragma unroll
-    for (int col = (warp - 2) * 32 + lane; col < BN; col += 128) {  // 128 threads sweep the BN columns
+    for (int col = (warp - 2) * 32 + lane; col < BN; col += 32 * kEpiWarps) {
       if (n0 + col < p.Nout) {
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -310,12 +378,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, float* stg,
         atomicAdd(p.ch_sqsum + n0 + col, (double)s2);
       }
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // the rows are rewritten by the next tile
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");  // the rows are rewritten by the next tile
   }
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, ConvTcParams p) {
   using S = ConvSmem<BN, STAGES>;
@@ -343,7 +411,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
@@ -445,7 +513,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 //   * TMA: both CTAs issue their loads with .cta_group::2 and signal the LEADER's (rank 0) full barrier.
 //   * MMA: issued by the leader's thread only; tcgen05.commit multicasts to the empty / tmem_full barriers of BOTH CTAs.
 //   * accumulator: CTA r's TMEM holds rows [128 r, 128 r + 128) x 256 columns; each CTA's epilogue warps drain their half
-//     and arrive on the leader's tmem_empty barrier (count 8).
+//     and arrive on the leader's tmem_empty barrier (count 2 x kEpiWarps).
 constexpr int BN2 = 256;
 
 template <int STAGES>
@@ -454,7 +522,7 @@ struct Conv2Smem {
   static constexpr int kBTile = (BN2 / 2) * BK * 2;   // 16 KB: this CTA's 128 of the 256 output channels
   static constexpr int kStage = 2 * kATile + 2 * kBTile;
   static constexpr int kStatBytes = 4 * 2 * BN2 * 4;
-  static constexpr int kStgBytes = 4 * 32 * kStgPitch * 4;
+  static constexpr int kStgBytes = kEpiWarps * 32 * kStgPitch * 4;
   static constexpr int kBytes = STAGES * kStage + 1024 + 256 + kStatBytes + kStgBytes;
 };
 
@@ -486,7 +554,7 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 }
 
 template <int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, ConvTcParams p) {
   using S = Conv2Smem<STAGES>;
@@ -496,7 +564,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   uint64_t* full_bar = bars;                    // [STAGES]  used in the leader only
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]  one per CTA (multicast commit)
   uint64_t* tmem_full = bars + 2 * STAGES;      // [2]       one per CTA (multicast commit)
-  uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]       leader only, count 8 = 4 epilogue warps x 2 CTAs
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]       leader only, count = epilogue warps x 2 CTAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   float* stat_s = reinterpret_cast<float*>(smem + STAGES * S::kStage + 256);
   float* stg = stat_s + 8 * BN2 + (threadIdx.x >= 64 ? ((threadIdx.x >> 5) - 2) * 32 * kStgPitch : 0);
@@ -518,7 +586,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -751,7 +819,7 @@ int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int ta
     const long long tiles_m = (long long)n * p.tiles_y * p.tiles_x;
     const long long pair_tiles = ((tiles_m + 1) / 2) * p.tiles_n;
     const int pairs = (int)(pair_tiles < kNumSMs / 2 ? pair_tiles : kNumSMs / 2);
-    conv_tc2_kernel<kStages><<<2 * pairs, kThreads, S2::kBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+    conv_tc2_kernel<kStages><<<2 * pairs, kConvThreads, S2::kBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
     return check_launch(who);
   }
   using S = ConvSmem<kBN, kStages>;
@@ -763,7 +831,7 @@ int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int ta
   if (attr_err != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(attr_err)); return VSPW_ERR_CUDA; }
   long long tiles = (long long)n * p.tiles_y * p.tiles_x * p.tiles_n;
   int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  conv_tc_kernel<kBN, kStages><<<grid, kThreads, S::kBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  conv_tc_kernel<kBN, kStages><<<grid, kConvThreads, S::kBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   return check_launch(who);
 }
 
