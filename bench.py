@@ -34,7 +34,7 @@ STEP_TFLOP = 20.631
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("VSPW_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
@@ -97,23 +97,33 @@ def feed_from(imgs, labs):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms (B200_PROFILING.md).  The process is started before the
+    warm-up (its start-up takes longer than a short timed region) and only the samples whose timestamp falls between
+    mark() and stop(), i.e. inside the timed region, are reported."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.proc = None
+        self.t0 = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
+    def mark(self):
+        """The timed region starts now."""
+        import datetime
+        self.t0 = datetime.datetime.now()
+
     def stop(self):
+        import datetime
+        t1 = datetime.datetime.now()
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -129,6 +139,9 @@ class ClockSampler:
             if len(f) < 9:
                 continue
             try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                if self.t0 is not None and not (self.t0 <= ts <= t1):
+                    continue
                 sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
@@ -195,14 +208,15 @@ def run_ours(args):
     gc.disable()
 
     # ---- warm-up ------------------------------------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
     n_warm = args.warmup if args.profile_run else max(args.warmup, 3)
     for _ in range(n_warm):
         step(imgs_d, labs_d)
     barrier()
 
     # ---- timed: device-resident inputs ------------------------------------------------------------------------------
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark()
     E.conv_profile_begin()
     l0 = lib.launches
     evs = []
