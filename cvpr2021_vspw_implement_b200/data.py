@@ -66,6 +66,40 @@ class SyntheticClipTest(Dataset):
         return img, gt, [f[0] for f in nb], [f[1] for f in nb], f"{i:08d}.png"
 
 
+class SyntheticWindowTest(SyntheticClipTest):
+    """The synthetic video served as `TestDataset_clip` serves a real one (vspw_data.VSPWWindowTest): the clip_num window
+    around frame i inside its dilation sub-list, including frame i and with the window's frame names for nonlocal3d."""
+
+    def __init__(self, args, video="synthetic_000", frames=12, height=480, width=854, seed=304):
+        t, args_t = int(args.clip_num), args
+        super().__init__(_WithOffsets(args_t, t), video, frames, height, width, seed)
+        self.whole_clip = args.method == "nonlocal3d"
+        self.step = int(args.dilation_num) + 1
+
+    def __getitem__(self, i):
+        from .vspw_data import clip_window
+        img, gt = self.frames[i]
+        sub = list(range(i % self.step, len(self.frames), self.step))
+        pos = sub.index(i)
+        start, end = clip_window(len(sub), pos, self.t)
+        name = f"{i:08d}.png"
+        if end - start < 2:
+            return img, gt, [img], [gt], ([] if self.whole_clip else name)
+        ks = [sub[k] for k in range(start, end) if self.whole_clip or k != pos]
+        names = [f"{k:08d}.png" for k in ks] if self.whole_clip else name
+        return img, gt, [self.frames[k][0] for k in ks], [self.frames[k][1] for k in ks], names
+
+
+class _WithOffsets:
+    """args view whose dilation2 always has clip_num - 1 entries (the window datasets do not use the offsets)."""
+
+    def __init__(self, args, t):
+        self._args, self.dilation2 = args, ",".join(str(k + 1) for k in range(t - 1))
+
+    def __getattr__(self, k):
+        return getattr(self._args, k)
+
+
 _copy_streams = {}
 
 

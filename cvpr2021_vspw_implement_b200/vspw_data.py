@@ -1,7 +1,7 @@
 """VSPW clip datasets for the entry points: the loaders on either side of the hot path.
 
-Reference: dataset2.py — `BaseDataset_longclip` (:852-1048, training clips) and `TestDataset_longclip` (:344-490,
-per-video inference).  Directory layout: `<dataroot>/<split>.txt` lists the videos; `<dataroot>/data/<video>/origin/*.jpg`
+Reference: dataset2.py — `BaseDataset_longclip` (:852-1048, training clips), `TestDataset_longclip` (:344-490,
+per-video inference of the TCB models) and `TestDataset_clip` (:154-337, sliding-window clips for `test_all`).  Directory layout: `<dataroot>/<split>.txt` lists the videos; `<dataroot>/data/<video>/origin/*.jpg`
 are the frames and `<dataroot>/data/<video>/mask/*.png` the label maps (`mask_42label/` with `--lesslabel`).
 
 The sampling consumes NumPy's and Python's global RNGs in the reference's order (direction flip, start frame, mirror
@@ -146,3 +146,69 @@ class VSPWClipTest(torch.utils.data.Dataset):
             clip_i.append(ci)
             clip_l.append(cl)
         return img, lab, clip_i, clip_l, name
+
+
+def dilation_sublists(names, num):
+    """dataset2.py:143-151: the frame list split into num + 1 interleaved sub-lists (every (num+1)-th frame)."""
+    return [[n for k, n in enumerate(names) if k % (num + 1) == a] for a in range(num + 1)]
+
+
+def clip_window(length, index, clip_num):
+    """[start, end) of the clip_num-frame window around position `index` of a `length`-frame list, clamped at both ends
+    (dataset2.py:276-300): clip_num // 2 frames to the left, one fewer to the right when clip_num is even."""
+    left = clip_num // 2
+    right = left - 1 if clip_num % 2 == 0 else left
+    if index - left < 0:
+        start, end = 0, min(clip_num, length)
+    elif index + right >= length:
+        end = length
+        start = max(end - clip_num, 0)
+    else:
+        start = index - left
+        end = start + clip_num
+    return start, end
+
+
+class VSPWWindowTest(torch.utils.data.Dataset):
+    """`TestDataset_clip` (dataset2.py:154-337): item i = (frame i, its labels, the frames of the clip_num window around it in
+    its dilation sub-list, their labels, names).  With ``args.method == 'nonlocal3d'`` the window includes frame i itself and
+    `names` is the list of the window's file names (what `test_all` averages over); otherwise frame i is left out of the
+    window and `names` is its own file name.  A sub-list shorter than 2 frames yields the frame alone -- and, as in the
+    reference, an EMPTY name list in nonlocal3d mode, so `test_all` never scores such a frame."""
+
+    def __init__(self, dataroot, video, args, is_train=False):
+        self.dataroot, self.video, self.args = dataroot, video, args
+        self.clip_num = int(args.clip_num)
+        self.names = sorted(os.listdir(os.path.join(dataroot, "data", video, "origin")))
+        self.sublists = dilation_sublists(self.names, int(args.dilation_num))
+        self.is_train = is_train
+        self.subset = [n for k, n in enumerate(self.names) if k % 15 == 0] if is_train else []
+        self.mask_dir = "mask_42label" if getattr(args, "lesslabel", False) else "mask"
+        self.whole_clip = args.method == "nonlocal3d"
+
+    def __len__(self):
+        return len(self.subset) if self.is_train else len(self.names)
+
+    _load = VSPWClipTest._load
+
+    def __getitem__(self, index):
+        name = (self.subset if self.is_train else self.names)[index]
+        img, lab = self._load(name)
+        sub = next(l for l in reversed(self.sublists) if name in l)  # the reference keeps the LAST sub-list that matches
+        pos = sub.index(name)
+        start, end = clip_window(len(sub), pos, self.clip_num)
+        names = [] if self.whole_clip else name
+        clip_i, clip_l = [], []
+        if end - start < 2:
+            clip_i.append(img)
+            clip_l.append(lab)
+        else:
+            for k in range(start, end):
+                if k == pos and not self.whole_clip:
+                    continue
+                if self.whole_clip:
+                    names.append(sub[k])
+                ci, cl = self._load(sub[k])
+                clip_i.append(ci)
+                clip_l.append(cl)
+        return img, lab, clip_i, clip_l, names

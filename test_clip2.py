@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Video inference / evaluation entry point on the B200 engine — same CLI as the reference's test_clip2.py (flags
-:349-405; per-video loop :280-321; metrics :323-331) for ``--method clip_psp`` and ``--method clip_ocr``.
+:349-405; per-video loop :280-321; metrics :323-331) for ``--method clip_psp`` and ``--method clip_ocr`` (per-frame loop
+``test``, :28-89) and ``--method nonlocal3d`` (sliding-window loop ``test_all``, :90-195).
 
 Per batch: ``scores = module(batch_data, segSize=(H, W))`` -> argmax -> Evaluator (global + per video) -> VC metric,
 exactly the reference's sequence (test_clip2.py:28-89).  ``--dataroot`` reads the videos of ``--split`` with
@@ -19,8 +20,8 @@ import torch.nn as nn
 
 from cvpr2021_vspw_implement_b200 import engine as E
 from cvpr2021_vspw_implement_b200.config import cfg
-from cvpr2021_vspw_implement_b200.data import SyntheticClipTest
-from cvpr2021_vspw_implement_b200.models import Clip_PSP, ClipOCRNet, ModelBuilder
+from cvpr2021_vspw_implement_b200.data import SyntheticClipTest, SyntheticWindowTest
+from cvpr2021_vspw_implement_b200.models import Clip_PSP, ClipOCRNet, ModelBuilder, Non_local3d
 from cvpr2021_vspw_implement_b200.utils import Evaluator, get_common, setup_logger
 from train_clip2 import OTHER_METHODS, str2bool
 
@@ -57,12 +58,62 @@ def test(segmentation_module, loader, gpu, args, evaluator, eval_video, video):
             predlist_.append(pred[jj])
             gtlist_.append(target[jj])
         if args.is_save:
-            from PIL import Image
-            os.makedirs(os.path.join(args.saveroot, video), exist_ok=True)
             for j in range(pred.shape[0]):
-                im = Image.fromarray(pred[j].astype('uint8')).convert('P')
-                im.putpalette(vspw_palette())
-                im.save(os.path.join(args.saveroot, video, gtnames[j].split('.')[0] + '.png'))
+                _save_pred(args, video, gtnames[j], pred[j])
+    return gtlist_, predlist_, h, w
+
+
+def _save_pred(args, video, name, pred_hw):
+    from PIL import Image
+    os.makedirs(os.path.join(args.saveroot, video), exist_ok=True)
+    im = Image.fromarray(pred_hw.astype('uint8')).convert('P')
+    im.putpalette(vspw_palette())
+    im.save(os.path.join(args.saveroot, video, name.split('.')[0] + '.png'))
+
+
+def test_all(segmentation_module, loader, gpu, args, evaluator, eval_video, video):
+    """The reference's whole-clip loop (test_clip2.py:90-195) for models that score EVERY frame of a clip (Non_local3d): the
+    loader slides a clip_num window over the video, each frame therefore receives up to clip_num probability maps, and a
+    frame is decided -- mean of its maps, argmax -- as soon as clip_num maps have arrived; frames near the ends that never
+    collect clip_num maps are decided after the last clip from what they have.  Frames enter the metric lists in the order
+    they are decided, as in the reference."""
+    segmentation_module.eval()
+    dev = torch.device("cuda", args.start_gpu)
+    gtlist_, predlist_ = [], []
+    target_dic, pred_dic, done = {}, {}, set()
+    h = w = 0
+
+    def decide(name, maps):
+        prob = torch.cat(maps, dim=0).mean(dim=0, keepdim=True)
+        pred_d = torch.argmax(prob, dim=1)
+        gts = target_dic.pop(name).to(dev).unsqueeze(0)  # (1, 1, H, W)
+        evaluator.add_batch_device(gts, pred_d)
+        eval_video.add_batch_device(gts, pred_d)
+        pred, target = pred_d.cpu().numpy(), gts.squeeze(1).cpu().numpy()
+        for jj in range(pred.shape[0]):
+            predlist_.append(pred[jj])
+            gtlist_.append(target[jj])
+            if args.is_save:
+                _save_pred(args, video, name, pred[jj])
+
+    for data in loader:
+        imgs, _, clip_imgs, clip_targets, gtnames = data
+        _, _, h, w = imgs.size()
+        batch_data = {'clipimgs_data': [c.to(dev) for c in clip_imgs], 'cliplabels_data': clip_targets}
+        with torch.no_grad():
+            scores = segmentation_module(batch_data, segSize=(imgs.size(2), imgs.size(3)))
+        for score, clip_target, gtname in zip(scores, clip_targets, gtnames):
+            for ii in range(score.size(0)):
+                nn_ = gtname[ii]
+                if nn_ in done:
+                    continue
+                target_dic.setdefault(nn_, clip_target[ii])
+                pred_dic.setdefault(nn_, []).append(score[ii].unsqueeze(0))
+                if len(pred_dic[nn_]) > args.clip_num - 1:
+                    decide(nn_, pred_dic.pop(nn_))
+                    done.add(nn_)
+    for name, maps in pred_dic.items():
+        decide(name, maps)
     return gtlist_, predlist_, h, w
 
 
@@ -74,10 +125,8 @@ def build_module(cfg, args, num_class):
     if args.method == 'clip_ocr':
         return ClipOCRNet(net_encoder, crit, args)
     if args.method == 'nonlocal3d':
-        # inference of Non_local3d goes through the reference's separate whole-clip loop (test_all, test_clip2.py:90-195);
-        # the module's eval path (list of per-frame probability maps) is implemented and parity-tested, the loop is not
-        raise NotImplementedError("--method nonlocal3d: use Non_local3d(...)(feed, segSize) directly; test_all is not ported")
-    raise NotImplementedError(f"--method {args.method!r}: only clip_psp / clip_ocr run on the B200 engine")
+        return Non_local3d(args, net_encoder, crit)
+    raise NotImplementedError(f"--method {args.method!r}: only clip_psp / clip_ocr / nonlocal3d run on the B200 engine")
 
 
 def main(cfg, gpu, args):
@@ -104,14 +153,18 @@ def main(cfg, gpu, args):
     total_VC_acc = []
     for video in videolists:
         eval_video.reset()
+        whole_clip = args.method == 'nonlocal3d'  # test_clip2.py:300-308: TestDataset_clip + test_all
         if args.synthetic:
             h, w = (int(x) for x in args.synthetic_size.lower().split("x"))
-            test_dataset = SyntheticClipTest(args, video, frames=args.synthetic_frames, height=h, width=w, seed=cfg.TRAIN.seed)
+            cls = SyntheticWindowTest if whole_clip else SyntheticClipTest
+            test_dataset = cls(args, video, frames=args.synthetic_frames, height=h, width=w, seed=cfg.TRAIN.seed)
         else:
-            from cvpr2021_vspw_implement_b200.vspw_data import VSPWClipTest  # = dataset2.TestDataset_longclip (:344-490)
-            test_dataset = VSPWClipTest(args.dataroot, video, args, is_train=False)
+            # = dataset2.TestDataset_clip (:154-337) / TestDataset_longclip (:344-490)
+            from cvpr2021_vspw_implement_b200.vspw_data import VSPWClipTest, VSPWWindowTest
+            test_dataset = (VSPWWindowTest if whole_clip else VSPWClipTest)(args.dataroot, video, args, is_train=False)
         loader_test = torch.utils.data.DataLoader(test_dataset, batch_size=args.batchsize, shuffle=False, num_workers=0, drop_last=False)
-        gtlist_, predlist_, h, w = test(segmentation_module, loader_test, gpu, args, evaluator, eval_video, video)
+        run = test_all if whole_clip else test
+        gtlist_, predlist_, h, w = run(segmentation_module, loader_test, gpu, args, evaluator, eval_video, video)
         accs = get_common(gtlist_, predlist_, args.vc_clip_num, h, w)
         if accs:
             print(sum(accs) / len(accs))

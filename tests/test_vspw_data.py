@@ -87,6 +87,28 @@ def test_test_items_are_bit_identical_to_the_reference(fake_vspw, lesslabel):
                 assert torch.equal(p, q)
 
 
+@pytest.mark.parametrize("method", ["nonlocal3d", "netwarp"])
+@pytest.mark.parametrize("clip_num,dilation_num", [(5, 0), (4, 0), (4, 1), (5, 2), (2, 0)])
+def test_window_items_are_bit_identical_to_the_reference(fake_vspw, method, clip_num, dilation_num):
+    """VSPWWindowTest == dataset2.TestDataset_clip (:154-337): window placement and clamping at both ends, dilation
+    sub-lists, the frame itself inside (nonlocal3d) or left out of (other methods) its window, the names `test_all` keys
+    on, and the sub-list-shorter-than-2 corner (vid_short with dilation_num 2: one frame per sub-list)."""
+    from cvpr2021_vspw_implement_b200.vspw_data import VSPWWindowTest
+    R = _ref_dataset2()
+    args = _args(fake_vspw, clip_num=clip_num, dilation_num=dilation_num, method=method)
+    for video, is_train in (("vid_a", False), ("vid_b", False), ("vid_short", False), ("vid_a", True)):
+        a = R.TestDataset_clip(fake_vspw, video, args, is_train=is_train)
+        b = VSPWWindowTest(fake_vspw, video, args, is_train=is_train)
+        assert len(a) == len(b)
+        for i in range(len(a)):
+            xa, xb = a[i], b[i]
+            assert xa[4] == xb[4] and type(xa[4]) is type(xb[4])
+            assert torch.equal(xa[0], xb[0]) and torch.equal(xa[1], xb[1])
+            assert len(xa[2]) == len(xb[2]) and len(xa[3]) == len(xb[3])
+            for p, q in zip(xa[2] + xa[3], xb[2] + xb[3]):
+                assert torch.equal(p, q)
+
+
 def test_loader_contract_feeds_the_entry_point_batches(fake_vspw):
     from cvpr2021_vspw_implement_b200.vspw_data import VSPWClipTrain
     ds = VSPWClipTrain(_args(fake_vspw), "train")
