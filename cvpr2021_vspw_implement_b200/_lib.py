@@ -66,6 +66,7 @@ _SIGNATURES = {
     "vspw_softmax_strided_fwd": [_c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_sz, _c_int, _c_sz, _c_f, _c_vp],
     "vspw_softmax_strided_bwd": [_c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_sz, _c_int, _c_sz, _c_f, _c_vp],
     "vspw_bgemm": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int] + [_c_i64] * 9 + [_c_f, _c_f, _c_vp],
+    "vspw_vc_counts": [_c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_vp, _c_vp],
     "vspw_sgd_momentum_step": [_c_vp, _c_vp, _c_vp, _c_int, _c_f, _c_vp],
     "vspw_confusion_add": [_c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_vp],
 }

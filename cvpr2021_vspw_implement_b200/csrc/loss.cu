@@ -254,7 +254,49 @@ __global__ void confusion_kernel(const int* __restrict__ pred, const float* __re
   }
 }
 
+// Video-consistency counts (utils.py:37-53 get_common): window i = frames [i, i + clip_num).  counts[i][1] = pixels whose
+// label is the same in every frame of the window, counts[i][0] = those whose prediction is constant over the window too.
+// grid = (pixel blocks, windows); integer counts, so the ratio the host forms is the reference's bit for bit.
+__global__ void vc_counts_kernel(const float* __restrict__ labels, const int* __restrict__ pred, size_t pixels, int clip_num,
+                                 unsigned long long* __restrict__ counts) {
+  const size_t base = (size_t)blockIdx.y * pixels;
+  unsigned both = 0, gt_const = 0;
+  for (size_t px = blockIdx.x * (size_t)blockDim.x + threadIdx.x; px < pixels; px += (size_t)gridDim.x * blockDim.x) {
+    const float g0 = labels[base + px];
+    const int p0 = pred[base + px];
+    bool gc = true, pc = true;
+    for (int j = 1; j < clip_num; ++j) {
+      gc = gc && labels[base + (size_t)j * pixels + px] == g0;
+      pc = pc && pred[base + (size_t)j * pixels + px] == p0;
+    }
+    gt_const += gc;
+    both += gc && pc;
+  }
+  both = __reduce_add_sync(0xffffffffu, both);
+  gt_const = __reduce_add_sync(0xffffffffu, gt_const);
+  if ((threadIdx.x & 31) == 0) {
+    if (both) atomicAdd(counts + 2 * (size_t)blockIdx.y, (unsigned long long)both);
+    if (gt_const) atomicAdd(counts + 2 * (size_t)blockIdx.y + 1, (unsigned long long)gt_const);
+  }
+}
+
 }  // namespace
+
+extern "C" int vspw_vc_counts(const float* labels, const int32_t* pred, int32_t frames, size_t pixels, int32_t clip_num,
+                              int64_t* counts, void* stream) {
+  VSPW_REQUIRE(labels && pred && counts, "vspw_vc_counts: null pointer");
+  VSPW_REQUIRE(frames >= 0 && clip_num >= 1, "vspw_vc_counts: frames >= 0 and clip_num >= 1 (got %d, %d)", frames, clip_num);
+  const int windows = frames - clip_num;  // the reference's range(len - clip_num): the last full window is not scored
+  if (windows <= 0 || !pixels) return VSPW_OK;
+  VSPW_REQUIRE(windows <= 65535, "vspw_vc_counts: at most 65535 windows per call (got %d)", windows);
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)windows * 2 * sizeof(int64_t), st);
+  if (e != cudaSuccess) { set_error("vspw_vc_counts: memset: %s", cudaGetErrorString(e)); return VSPW_ERR_CUDA; }
+  unsigned gx = (unsigned)((pixels + 1023) / 1024);
+  if (gx > 148 * 4) gx = 148 * 4;
+  vc_counts_kernel<<<dim3(gx, (unsigned)windows), 256, 0, st>>>(labels, pred, pixels, clip_num, (unsigned long long*)counts);
+  return check_launch("vspw_vc_counts");
+}
 
 extern "C" int vspw_logsoftmax_up_nll_fwd(const float* logits, const float* labels, float* logp, double* acc, int32_t n,
                                           int32_t h, int32_t w, int32_t k, int32_t H, int32_t W, int32_t ignore_index,

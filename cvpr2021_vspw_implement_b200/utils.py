@@ -26,6 +26,29 @@ def get_common(list_, predlist, clip_num, h, w):
     return accs
 
 
+def get_common_device(labels, pred, clip_num):
+    """get_common for one video resident on the device: `labels` float and `pred` integer CUDA tensors of
+    shape (frames, H, W).  One launch of vspw_vc_counts; only the 2 integers per window cross to the host, and the ratios
+    formed from them are the reference's bit for bit (nan where no pixel has a constant label, like NumPy's 0/0)."""
+    import ctypes
+    import torch
+    from ._lib import lib
+    assert labels.is_cuda and pred.is_cuda and labels.shape == pred.shape and labels.dim() == 3
+    frames = int(labels.shape[0])
+    windows = frames - int(clip_num)
+    if windows <= 0:
+        return []
+    labels = labels.contiguous().float()
+    pred = pred.contiguous().to(torch.int32)
+    counts = torch.empty((windows, 2), device=labels.device, dtype=torch.int64)
+    lib.call("vspw_vc_counts", ctypes.c_void_p(labels.data_ptr()), ctypes.c_void_p(pred.data_ptr()), frames,
+             labels[0].numel(), int(clip_num), ctypes.c_void_p(counts.data_ptr()),
+             ctypes.c_void_p(torch.cuda.current_stream(labels.device).cuda_stream))
+    c = counts.cpu().numpy().astype(np.float64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return list(c[:, 0] / c[:, 1])
+
+
 class Evaluator(object):
     def __init__(self, num_class):
         self.num_class = num_class

@@ -265,6 +265,12 @@ int vspw_sgd_momentum_step(const vspw_sgd_tensor* table_dev, const uint32_t* blo
 /* ---- evaluation (utils.py:55-107 Evaluator._generate_matrix): conf[gt][pred] += 1 ---------- */
 int vspw_confusion_add(const int32_t* pred, const float* labels, int64_t* conf, size_t pixels,
                        int32_t num_class, void* stream);
+/* Video-consistency metric VC_n (utils.py:37-53 get_common) for one video held on the device: labels [frames][pixels]
+ * float, pred [frames][pixels] argmax.  For every window i < frames - clip_num (the reference's range): counts[i][1] = pixels
+ * whose label is constant over frames [i, i + clip_num), counts[i][0] = those whose prediction is constant too.  counts
+ * ([frames - clip_num][2]) is zeroed by the call; VC of window i = counts[i][0] / counts[i][1]. */
+int vspw_vc_counts(const float* labels, const int32_t* pred, int32_t frames, size_t pixels, int32_t clip_num,
+                   int64_t* counts, void* stream);
 
 #ifdef __cplusplus
 }

@@ -22,7 +22,7 @@ from cvpr2021_vspw_implement_b200 import engine as E
 from cvpr2021_vspw_implement_b200.config import cfg
 from cvpr2021_vspw_implement_b200.data import SyntheticClipTest, SyntheticWindowTest
 from cvpr2021_vspw_implement_b200.models import Clip_PSP, ClipOCRNet, ModelBuilder, Non_local3d
-from cvpr2021_vspw_implement_b200.utils import Evaluator, get_common, setup_logger
+from cvpr2021_vspw_implement_b200.utils import Evaluator, get_common_device, setup_logger
 from train_clip2 import OTHER_METHODS, str2bool
 
 
@@ -35,6 +35,9 @@ def vspw_palette():
 
 
 def test(segmentation_module, loader, gpu, args, evaluator, eval_video, video):
+    """Per-frame loop (test_clip2.py:28-89).  Labels and argmax predictions stay on the device: the confusion matrices are
+    accumulated there (vspw_confusion_add) and the returned lists hold CUDA tensors for the on-device VC metric
+    (utils.get_common_device); a prediction only crosses to the host when --is_save asks for its PNG."""
     segmentation_module.eval()
     gtlist_, predlist_ = [], []
     h = w = 0
@@ -48,16 +51,13 @@ def test(segmentation_module, loader, gpu, args, evaluator, eval_video, video):
             batch_data['is_clean_memory'] = (i == 0)
         with torch.no_grad():
             scores = segmentation_module(batch_data, segSize=(imgs.size(2), imgs.size(3)))
-            pred_d = torch.argmax(scores, dim=1)
-        # confusion matrices on the device (vspw_confusion_add); the host copies below feed the VC metric / PNG dump only
+            pred_d = torch.argmax(scores, dim=1).to(torch.int32)
         evaluator.add_batch_device(gts, pred_d)
         eval_video.add_batch_device(gts, pred_d)
-        pred = pred_d.cpu().numpy()
-        target = gts.squeeze(1).cpu().numpy()
-        for jj in range(pred.shape[0]):
-            predlist_.append(pred[jj])
-            gtlist_.append(target[jj])
+        predlist_.append(pred_d)
+        gtlist_.append(gts.squeeze(1))
         if args.is_save:
+            pred = pred_d.cpu().numpy()
             for j in range(pred.shape[0]):
                 _save_pred(args, video, gtnames[j], pred[j])
     return gtlist_, predlist_, h, w
@@ -89,12 +89,10 @@ def test_all(segmentation_module, loader, gpu, args, evaluator, eval_video, vide
         gts = target_dic.pop(name).to(dev).unsqueeze(0)  # (1, 1, H, W)
         evaluator.add_batch_device(gts, pred_d)
         eval_video.add_batch_device(gts, pred_d)
-        pred, target = pred_d.cpu().numpy(), gts.squeeze(1).cpu().numpy()
-        for jj in range(pred.shape[0]):
-            predlist_.append(pred[jj])
-            gtlist_.append(target[jj])
-            if args.is_save:
-                _save_pred(args, video, name, pred[jj])
+        predlist_.append(pred_d.to(torch.int32))
+        gtlist_.append(gts.squeeze(1))
+        if args.is_save:
+            _save_pred(args, video, name, pred_d[0].cpu().numpy())
 
     for data in loader:
         imgs, _, clip_imgs, clip_targets, gtnames = data
@@ -165,7 +163,8 @@ def main(cfg, gpu, args):
         loader_test = torch.utils.data.DataLoader(test_dataset, batch_size=args.batchsize, shuffle=False, num_workers=0, drop_last=False)
         run = test_all if whole_clip else test
         gtlist_, predlist_, h, w = run(segmentation_module, loader_test, gpu, args, evaluator, eval_video, video)
-        accs = get_common(gtlist_, predlist_, args.vc_clip_num, h, w)
+        # VC_n on the device: one launch per video, 2 integers per window come back
+        accs = get_common_device(torch.cat(gtlist_, dim=0), torch.cat(predlist_, dim=0), args.vc_clip_num) if gtlist_ else []
         if accs:
             print(sum(accs) / len(accs))
         total_VC_acc.extend(accs)

@@ -133,9 +133,9 @@ def test_test_all_sliding_window_average(need_gpu):
     ev2 = Evaluator(K)
     for k, n in enumerate(order):
         want = torch.argmax(torch.cat(maps[n], 0).mean(0, keepdim=True), 1)[0].cpu().numpy()
-        assert np.array_equal(preds[k], want), n
+        assert np.array_equal(preds[k][0].cpu().numpy(), want), n
         frame_gt = ds.frames[int(n.split(".")[0])][1].squeeze(0).numpy()
-        assert np.array_equal(gts[k], frame_gt)
+        assert np.array_equal(gts[k][0].cpu().numpy(), frame_gt)
         ev2.add_batch(frame_gt[None], want[None])
     ev.sync_device()
     assert np.array_equal(ev.confusion_matrix, ev2.confusion_matrix)

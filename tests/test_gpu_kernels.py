@@ -395,6 +395,32 @@ def test_weight_prep_plan_batched_launch_tracks_parameter_updates(E, x3):
         check(plan.planes(t4, t4.param(p)), p)
 
 
+@pytest.mark.parametrize("frames,clip_num", [(12, 8), (9, 2), (5, 5), (3, 8), (20, 3)])
+def test_vc_counts_device_matches_get_common(E, frames, clip_num):
+    """utils.get_common_device (vspw_vc_counts) == utils.get_common (reference utils.py:37-53) bit for bit:
+    same windows (the reference's range(len - clip_num)), same ratios, nan where no pixel keeps its label."""
+    import numpy as np
+    from cvpr2021_vspw_implement_b200.utils import get_common, get_common_device
+    g = torch.Generator().manual_seed(frames * 10 + clip_num)
+    h, w = 37, 53
+    # slowly changing labels / predictions so that constant runs of every length occur
+    gt = torch.randint(0, 5, (1, h, w), generator=g).float().repeat(frames, 1, 1)
+    pr = torch.randint(0, 5, (1, h, w), generator=g).repeat(frames, 1, 1)
+    for f in range(1, frames):
+        flip = torch.rand(h, w, generator=g) < 0.08
+        gt[f:][:, flip] = torch.randint(0, 5, (int(flip.sum()),), generator=g).float()
+        flip = torch.rand(h, w, generator=g) < 0.1
+        pr[f:][:, flip] = torch.randint(0, 5, (int(flip.sum()),), generator=g)
+    gt[gt == 4] = 255.0
+    if frames == 9:  # a window in which no pixel keeps its label: 0/0 -> nan on both sides
+        gt[3] = gt[2] + 1.0
+    want = get_common([x.numpy() for x in gt], [x.numpy() for x in pr], clip_num, h, w)
+    got = get_common_device(gt.cuda(), pr.cuda(), clip_num)
+    assert len(got) == len(want) == max(frames - clip_num, 0)
+    for a, b in zip(got, want):
+        assert (a == b) or (a != a and b != b)
+
+
 def test_evaluator_device_path_matches_host_path(E):
     """utils.Evaluator.add_batch_device (vspw_confusion_add on the device) == add_batch (reference
     utils.py:86-99 on NumPy), including ignore labels 255."""
