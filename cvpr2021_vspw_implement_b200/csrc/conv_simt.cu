@@ -441,6 +441,106 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(const float* __restric
   }
 }
 
+// The deep-stem conv1 (resnet.py:100: 3x3, stride 2, pad 1, Cin = 3 -> Cout = 64; 1 M output pixels per step at 480p T=5 n=2):
+// im2col width 27, so the tiled kernels fill a fifth of their tiles.  Here a lane owns TWO output channels and keeps their
+// 2 x 27 weights (forward) or weight-gradient accumulators (wgrad) in registers; a warp walks output pixels, reads the
+// pixel's 3 x 9 input floats as shared-memory broadcasts from three staged input-row segments (NHWC with C = 3: a tap row
+// is 9 contiguous floats) and does 54 FMAs per lane per pixel; the output pixel (64 floats = 256 B) is one coalesced
+// warp store / load.  HBM: x once (49 MB) + y or dy once (262 MB).
+constexpr int kStemTile = 64;                          // output pixels of one output row per tile
+constexpr int kStemRow = (2 * kStemTile + 1) * 3;      // staged floats per input row: 129 pixels x 3 channels
+
+struct StemParams {
+  const float* X;   // [N][H][W][3]
+  const float* Wt;  // [64][27] OHWI (forward)
+  float* Y;         // [N][Ho][Wo][64] (forward)
+  const float* DY;  // (wgrad)
+  float* DW;        // [64][27], zeroed by the caller (wgrad)
+  int N, H, W, Ho, Wo, tiles_x;
+};
+
+template <bool WGRAD>
+__global__ void __launch_bounds__(256) stem_conv_kernel(StemParams p) {
+  __shared__ float rows[3][kStemRow + 1];
+  __shared__ float sum_s[WGRAD ? 64 * 27 : 1];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float w[2][27];
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int k = 0; k < 27; ++k) w[c][k] = WGRAD ? 0.f : __ldg(p.Wt + (2 * lane + c) * 27 + k);
+  const int total = p.N * p.Ho * p.tiles_x;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int tx = tile % p.tiles_x;
+    const int oy = (tile / p.tiles_x) % p.Ho;
+    const int img = tile / (p.tiles_x * p.Ho);
+    const int ox0 = tx * kStemTile;
+    __syncthreads();  // the previous tile's patch reads are done
+    for (int e = tid; e < 3 * kStemRow; e += 256) {
+      const int r = e / kStemRow, c = e - r * kStemRow;
+      const int ih = 2 * oy - 1 + r;
+      const int col = (2 * ox0 - 1) * 3 + c;  // float index inside the input row
+      float v = 0.f;
+      if (ih >= 0 && ih < p.H && col >= 0 && col < p.W * 3) v = __ldg(p.X + ((size_t)img * p.H + ih) * p.W * 3 + col);
+      rows[r][c] = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int k = 0; k < kStemTile / 8; ++k) {
+      const int pxl = warp * (kStemTile / 8) + k;
+      const int ox = ox0 + pxl;
+      if (ox >= p.Wo) break;  // warp-uniform
+      float pt[27];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int j = 0; j < 9; ++j) pt[r * 9 + j] = rows[r][6 * pxl + j];
+      const size_t m = ((size_t)img * p.Ho + oy) * p.Wo + ox;
+      if (WGRAD) {
+        const float2 d = __ldcs(reinterpret_cast<const float2*>(p.DY + m * 64 + 2 * lane));
+#pragma unroll
+        for (int c = 0; c < 27; ++c) { w[0][c] = fmaf(d.x, pt[c], w[0][c]); w[1][c] = fmaf(d.y, pt[c], w[1][c]); }
+      } else {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 27; ++c) { a0 = fmaf(w[0][c], pt[c], a0); a1 = fmaf(w[1][c], pt[c], a1); }
+        *reinterpret_cast<float2*>(p.Y + m * 64 + 2 * lane) = make_float2(a0, a1);
+      }
+    }
+  }
+  if (WGRAD) {
+    for (int e = tid; e < 64 * 27; e += 256) sum_s[e] = 0.f;
+    __syncthreads();
+    for (int wi = 0; wi < 8; ++wi) {  // the 8 warps fold their accumulators in turn: no shared-memory atomics
+      if (warp == wi) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int k = 0; k < 27; ++k) sum_s[(2 * lane + c) * 27 + k] += w[c][k];
+      }
+      __syncthreads();
+    }
+    for (int e = tid; e < 64 * 27; e += 256) atomicAdd(p.DW + e, sum_s[e]);
+  }
+}
+
+bool is_stem_conv(const vspw_conv_desc* d) {
+  return d->cin == 3 && d->cout == 64 && d->kh == 3 && d->kw == 3 && d->stride == 2 && d->pad == 1 && d->dil == 1;
+}
+
+StemParams stem_params(const vspw_conv_desc* d) {
+  StemParams p{};
+  p.N = d->n; p.H = d->h; p.W = d->w; p.Ho = d->ho; p.Wo = d->wo;
+  p.tiles_x = (d->wo + kStemTile - 1) / kStemTile;
+  return p;
+}
+
+unsigned stem_grid(const StemParams& p) {
+  const long long tiles = (long long)p.N * p.Ho * p.tiles_x;
+  const long long cap = kNumSMs * 3;  // 80 registers x 256 threads: 3 resident blocks per SM
+  return (unsigned)(tiles < cap ? tiles : cap);
+}
+
 // true when the conv is a plain [M][K] x [N][K]^T product with few rows; launches the skinny kernel
 bool try_skinny(const vspw_conv_desc* d, const float* A, const float* B, const float* bias, float* C, int M, int N, int K, void* stream) {
   if (d->kh != 1 || d->kw != 1 || d->stride != 1 || d->pad != 0 || M > kSkinnyMaxM || K % 4 != 0) return false;
@@ -457,6 +557,12 @@ extern "C" int vspw_conv2d_fwd(const vspw_conv_desc* d, const float* x, const fl
   if (rc) return rc;
   VSPW_REQUIRE(x && w_ohwi && y, "vspw_conv2d_fwd: null pointer");
   if (try_skinny(d, x, w_ohwi, bias, y, d->n * d->ho * d->wo, d->cout, d->cin, stream)) return check_launch("vspw_conv2d_fwd (skinny)");
+  if (is_stem_conv(d) && !bias && (uintptr_t)y % 8 == 0) {
+    StemParams sp = stem_params(d);
+    sp.X = x; sp.Wt = w_ohwi; sp.Y = y;
+    stem_conv_kernel<false><<<stem_grid(sp), 256, 0, as_stream(stream)>>>(sp);
+    return check_launch("vspw_conv2d_fwd (stem)");
+  }
   IGemmParams p;
   p.A = x; p.B = w_ohwi; p.bias = bias; p.Cmat = y;
   p.N = d->n; p.H = d->h; p.W = d->w; p.C = d->cin;
@@ -569,6 +675,12 @@ extern "C" int vspw_conv2d_wgrad(const vspw_conv_desc* d, const float* x, const 
   if (e != cudaSuccess) {
     set_error("vspw_conv2d_wgrad: memset: %s", cudaGetErrorString(e));
     return VSPW_ERR_CUDA;
+  }
+  if (is_stem_conv(d) && (uintptr_t)dy % 8 == 0) {
+    StemParams sp = stem_params(d);
+    sp.X = x; sp.DY = dy; sp.DW = dw_ohwi;
+    stem_conv_kernel<true><<<stem_grid(sp), 256, 0, as_stream(stream)>>>(sp);
+    return check_launch("vspw_conv2d_wgrad (stem)");
   }
   if (p.NW <= kSmallNW && p.Cout <= 256 && 256 % p.Cout == 0 && (p.NW + 256 / p.Cout - 1) / (256 / p.Cout) <= kSmallCols &&
       p.M >= 4096) {
