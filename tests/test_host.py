@@ -99,3 +99,43 @@ def test_state_dict_and_init_identical_to_reference():
     b = ref.SegmentationModule(ref.ModelBuilder.build_encoder("resnet18dilated"), ref.ModelBuilder.build_decoder("ppm_deepsup", fc_dim=512, num_class=124), crit, 0.4)
     sa, sb = a.state_dict(), b.state_dict()
     assert list(sa) == list(sb) and all(torch.equal(sa[k], sb[k]) for k in sa)
+
+
+def test_clip_window_and_sublists_follow_the_reference_rule():
+    """vspw_data.clip_window / dilation_sublists (dataset2.py:143-151, 276-300) against a literal restatement of the
+    reference's branches for every (length, index, clip_num); the synthetic window dataset serves the same windows."""
+    import argparse
+    from cvpr2021_vspw_implement_b200.data import SyntheticWindowTest
+    from cvpr2021_vspw_implement_b200.vspw_data import clip_window, dilation_sublists
+
+    def ref(length, imgindex, clip_num):
+        add = int(clip_num / 2) if clip_num % 2 == 0 else int((clip_num - 1) / 2)
+        addleft, addright = add, (add - 1 if clip_num % 2 == 0 else add)
+        if imgindex - addleft < 0:
+            start, end = 0, clip_num
+            if end >= length:
+                end = length
+        elif imgindex + addright >= length:
+            end = length
+            start = max(end - clip_num, 0)
+        else:
+            start = imgindex - addleft
+            end = start + clip_num
+        return start, end
+
+    for length in range(1, 15):
+        for clip_num in range(1, 9):
+            for i in range(length):
+                assert clip_window(length, i, clip_num) == ref(length, i, clip_num)
+    names = [f"{i:03d}" for i in range(11)]
+    subs = dilation_sublists(names, 2)
+    assert subs == [names[0::3], names[1::3], names[2::3]] and sorted(sum(subs, [])) == names
+    args = argparse.Namespace(clip_num=4, num_class=5, dilation2="1,2,3", dilation_num=1, method="nonlocal3d")
+    ds = SyntheticWindowTest(args, "v", frames=9, height=8, width=8, seed=1)
+    for i in range(9):
+        sub = list(range(i % 2, 9, 2))
+        s, e = ref(len(sub), sub.index(i), 4)
+        assert ds[i][4] == [f"{k:08d}.png" for k in sub[s:e]] and len(ds[i][2]) == e - s
+    args.method = "clip_psp"
+    ds = SyntheticWindowTest(args, "v", frames=9, height=8, width=8, seed=1)
+    assert ds[4][4] == "00000004.png" and len(ds[4][2]) == 3
