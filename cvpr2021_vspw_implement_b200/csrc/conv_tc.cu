@@ -773,6 +773,16 @@ bool use_pair_kernel() {
   return v == 1;
 }
 
+// VSPW_CONV_NARROW=0 sends 64-channel outputs through the 128-wide kernel (A/B comparisons)
+bool use_narrow_kernel() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VSPW_CONV_NARROW");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int taps, int off0, int step, int stride,
                    const uint16_t* a_hi,
                    const uint16_t* a_lo, const uint16_t* b_hi, const uint16_t* b_lo, const float* bias, float* out, int x3,
@@ -820,6 +830,25 @@ int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int ta
     const long long pair_tiles = ((tiles_m + 1) / 2) * p.tiles_n;
     const int pairs = (int)(pair_tiles < kNumSMs / 2 ? pair_tiles : kNumSMs / 2);
     conv_tc2_kernel<kStages><<<2 * pairs, kConvThreads, S2::kBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+    return check_launch(who);
+  }
+  if (nout == 64 && use_narrow_kernel()) {
+    // 64 output channels (stem conv2, layer1 interiors, the dgrads into 64-channel maps; 1 M / 257 k pixels): a 128-wide
+    // tile would zero-fill half of every B box and spend half of every MMA on it, and these layers are bound by L2->SM
+    // operand traffic (64 KB per k-block for 12 MMAs).  UMMA 128x64x16 with 48 KB stages, 4 of them in flight.
+    using S6 = ConvSmem<64, 4>;
+    p.tiles_n = 1;
+    if ((rc = make_mat_map(&mb_hi, b_hi, nout, kdim, BK, 64, who))) return rc;
+    if ((rc = make_mat_map(&mb_lo, x3 ? b_lo : b_hi, nout, kdim, BK, 64, who))) return rc;
+    static std::once_flag once6;
+    static cudaError_t attr_err6 = cudaSuccess;
+    std::call_once(once6, [] {
+      attr_err6 = cudaFuncSetAttribute(conv_tc_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, S6::kBytes);
+    });
+    if (attr_err6 != cudaSuccess) { set_error("%s: cudaFuncSetAttribute(narrow): %s", who, cudaGetErrorString(attr_err6)); return VSPW_ERR_CUDA; }
+    const long long tiles6 = (long long)n * p.tiles_y * p.tiles_x;
+    const int grid6 = (int)(tiles6 < kNumSMs ? tiles6 : kNumSMs);
+    conv_tc_kernel<64, 4><<<grid6, kConvThreads, S6::kBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
     return check_launch(who);
   }
   using S = ConvSmem<kBN, kStages>;

@@ -37,6 +37,8 @@ TC_GEOMS = [
     (2, 128, 31, 45, 128, 3, 1, 1, False, 2),  # layer2.0.conv2: 3x3 stride 2 (odd map: 31x45 -> 16x23), TMA elementStrides
     (2, 256, 30, 44, 512, 1, 0, 1, False, 2),  # layer2.0.downsample: 1x1 stride 2 (even map)
     (1, 64, 60, 107, 128, 3, 1, 1, True, 2),   # stride 2 with bias on the real 480p map width
+    (2, 64, 33, 47, 64, 3, 1, 1, False),       # layer1 3x3 64->64: the 64-wide (UMMA 128x64x16, 4-stage) kernel, fwd and dgrad
+    (2, 256, 24, 40, 64, 1, 0, 1, True),       # layer1 1x1 256->64 with bias: narrow forward, pair-kernel dgrad
 ]
 
 
