@@ -886,6 +886,7 @@ struct WgradTcParams {
   int tiles_x, tiles_y;
   int tiles_co, tiles_ci, splits, chunk;  // chunk = patches per split
   int x3;
+  int n64;            // Cin == 64: the GEMM's N is one 64-channel block (UMMA 128x64x16), the second x box is not fetched
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -915,7 +916,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy_hi, const __grid_cons
   const int pbeg = split * p.chunk;
   const int pend = min(total_patches, pbeg + p.chunk);
   const int num_k = pend - pbeg;  // host guarantees >= 1
-  const uint32_t stage_bytes = (uint32_t)(4 * WG_BLK) * (p.x3 ? 2u : 1u);
+  const uint32_t stage_bytes = (uint32_t)((p.n64 ? 3 : 4) * WG_BLK) * (p.x3 ? 2u : 1u);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_dy_hi);
@@ -950,17 +951,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy_hi, const __grid_cons
       tma_load_4d(st + 1 * WG_BLK, &map_dy_hi, &full_bar[stage], tco * 128 + 64, x0, y0, img);
       const int xx = x0 * p.stride + dxo, xy = y0 * p.stride + dyo;
       tma_load_4d(st + 2 * WG_BLK, &map_x_hi, &full_bar[stage], tci * 128, xx, xy, img);
-      tma_load_4d(st + 3 * WG_BLK, &map_x_hi, &full_bar[stage], tci * 128 + 64, xx, xy, img);
+      if (!p.n64) tma_load_4d(st + 3 * WG_BLK, &map_x_hi, &full_bar[stage], tci * 128 + 64, xx, xy, img);
       if (p.x3) {
         tma_load_4d(st + 4 * WG_BLK, &map_dy_lo, &full_bar[stage], tco * 128, x0, y0, img);
         tma_load_4d(st + 5 * WG_BLK, &map_dy_lo, &full_bar[stage], tco * 128 + 64, x0, y0, img);
         tma_load_4d(st + 6 * WG_BLK, &map_x_lo, &full_bar[stage], tci * 128, xx, xy, img);
-        tma_load_4d(st + 7 * WG_BLK, &map_x_lo, &full_bar[stage], tci * 128 + 64, xx, xy, img);
+        if (!p.n64) tma_load_4d(st + 7 * WG_BLK, &map_x_lo, &full_bar[stage], tci * 128 + 64, xx, xy, img);
       }
       if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1 && lane == 0) {
-    constexpr uint32_t idesc = make_idesc(128, 128, 1, 1);  // both operands MN-major
+    const uint32_t idesc = p.n64 ? make_idesc(128, 64, 1, 1) : make_idesc(128, 128, 1, 1);  // both operands MN-major
     int stage = 0;
     uint32_t phase = 0;
     for (int k = 0; k < num_k; ++k) {
@@ -993,7 +994,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy_hi, const __grid_cons
     const int taps = p.taps_w * p.taps_w;
     float* dst = p.dw + ((size_t)co * taps + tap) * p.Cin + tci * 128;
 #pragma unroll 1
-    for (int c0 = 0; c0 < 128; c0 += 32) {
+    for (int c0 = 0; c0 < (p.n64 ? 64 : 128); c0 += 32) {
       uint32_t v[32];
       tmem_ld_32x32b_x32(taddr + c0, v);
       tmem_ld_wait();
@@ -1192,6 +1193,7 @@ extern "C" int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_h
   // p.N x p.H x p.W = the dy (output) pixel grid the K loop walks; x is read at pixel*stride + tap offset
   p.dw = dw_ohwi; p.N = d->n; p.H = d->ho; p.W = d->wo; p.Cin = d->cin; p.Cout = d->cout;
   p.taps_w = d->kw; p.off0 = -d->pad; p.step = d->dil; p.x3 = x3; p.stride = d->stride;
+  p.n64 = (d->cin == 64 && use_narrow_kernel()) ? 1 : 0;  // stem conv2/conv3, layer1: half of a 128-wide N tile would be zero fill
   int xn = d->n, xh = d->h, xw = d->w;
   if (d->kh == 1 && d->stride == 1) {  // 1x1: flat pixel axis, no patch padding (see launch_conv_tc)
     p.N = 1; p.H = 1; p.W = d->n * d->h * d->w;
