@@ -18,9 +18,18 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (ROOT, os.path.join(ROOT, "oracle")):
-    if _p not in sys.path:
-        sys.path.insert(0, _p)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def _oracle():
+    """The CPU oracle (test infrastructure) — imported ONLY by the cpu_baseline / --impl reference / gpu_library_baseline
+    legs, never by the product arm's timed path."""
+    od = os.path.join(ROOT, "oracle")
+    if od not in sys.path:
+        sys.path.insert(0, od)
+    import tcb_oracle
+    return tcb_oracle
 
 import torch  # noqa: E402
 
@@ -38,8 +47,12 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("VSPW_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
-    ap.add_argument("--syncbn", action="store_true", help="all-reduce BN statistics across ranks (reference multi-GPU semantics)")
+    ap.add_argument("--syncbn", default="auto", choices=["auto", "on", "off"],
+                    help="cross-rank BN statistics (the reference's multi-GPU semantics and train_clip2.py's default); auto = on when N > 1")
+    ap.add_argument("--syncbn-exchange", default="peer", choices=["peer", "nccl"],
+                    help="peer = one-shot exchange over NVLink peer memory per BN layer (csrc/peer.cu); nccl = a library all-reduce per layer")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-library-baseline", action="store_true", help="skip the stated-context leg: the oracle port on this GPU through cuDNN")
     ap.add_argument("--profile-run", action="store_true", help="for ncu captures only: honour --warmup below 3, skip e2e/cpu legs")
     ap.add_argument("--cpu-sample", default="240x427", help="HxW of the bounded CPU sample")
     ap.add_argument("--model", default="psp", choices=["psp", "ocr"], help="psp = TCB-PSP (the headline metric, BASELINE configs[1]); ocr = TCB-OCR (configs[2], reported under its own metric name)")
@@ -160,8 +173,9 @@ def run_ours(args):
             raise SystemExit("--size is a probe option: use it with --profile-run")
         H, W = (int(x) for x in args.size.lower().split("x"))
     from cvpr2021_vspw_implement_b200 import engine as E
+    from cvpr2021_vspw_implement_b200 import parallel as P
     from cvpr2021_vspw_implement_b200._lib import lib
-    import tcb_oracle as O
+    from cvpr2021_vspw_implement_b200.data import synthetic_clip
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -172,14 +186,15 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     E.set_precision(args.precision)
-    if args.syncbn:
-        E.set_syncbn(True)
+    syncbn = world > 1 and args.syncbn != "off"
+    sync_group = P.make_syncbn_group(args.syncbn_exchange) if syncbn else None
+    E.set_syncbn(syncbn, group=sync_group)
 
-    from cvpr2021_vspw_implement_b200.parallel import GradBucket
     model = build_model(dev, seed=0, kind=args.model)
-    bucket = GradBucket(model.parameters())  # one flat bucket, one NCCL all-reduce over NVLink per step
+    # every p.grad is a slice of ONE flat buffer the backward kernels write into; one NCCL all-reduce per step
+    bucket = P.GradBucket(model.parameters())
     opt = make_optimizer(model, fused=not args.torch_sgd)
-    imgs_h, labs_h = O.synthetic_clip(T_FRAMES, N_CLIPS, H, W, NUM_CLASS, seed=304 + rank)
+    imgs_h, labs_h = synthetic_clip(T_FRAMES, N_CLIPS, H, W, NUM_CLASS, seed=304 + rank)
     imgs_h = [t.pin_memory() for t in imgs_h]
     labs_h = [t.pin_memory() for t in labs_h]
     imgs_d = [t.to(dev) for t in imgs_h]
@@ -188,11 +203,10 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
 
     def step(imgs, labs):
-        opt.zero_grad(set_to_none=True)
+        bucket.zero_grad()
         loss, acc = model(feed_from(imgs, labs))
         loss.backward()
-        if world > 1:
-            bucket.all_reduce_mean()
+        bucket.all_reduce_mean()
         opt.step()
         return loss
 
@@ -279,6 +293,26 @@ def run_ours(args):
             region_ms.append(float(t.item()))
         e2e_value = frames_per_step / (min(region_ms) / e2e_steps / 1e3)
 
+    # ---- N > 1: the same step with LOCAL BN statistics (no statistics exchange), reported next to the headline ----------
+    local_bn = None
+    if syncbn and not args.profile_run:
+        E.set_syncbn(False)
+        for _ in range(2):
+            step(imgs_d, labs_d)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        k_loc = max(3, min(args.steps, 5))
+        for _ in range(k_loc):
+            step(imgs_d, labs_d)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        local_bn = {"value": round(frames_per_step / (float(t.item()) / k_loc / 1e3), 3), "unit": UNIT, "ms_per_step": round(float(t.item()) / k_loc, 3),
+                    "steps": k_loc, "note": "same step with per-rank BN statistics (syncbn off), no L2 flush between steps"}
+        E.set_syncbn(True, group=sync_group)
+
     if args.kernel_profile and rank == 0:
         lib.profile_begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -317,17 +351,20 @@ def run_ours(args):
                 # executed tensor FLOPs (3 MMAs per algorithmic product in bf16x3) against the same peak: what the tensor pipe sees
                 "tensor_tflops_executed": round(ach * (3 if args.precision == "bf16x3" else 1), 2),
                 "tensor_frac_executed": round(ach * (3 if args.precision == "bf16x3" else 1) / peak, 4) if args.precision != "fp32" else 0.0,
-                # `traffic` (DRAM bytes per launch) is per kernel and this line aggregates 341 launches of 60 geometries, so it stays
-                # null; the ncu --set full capture of the most frequent heavy launch is quoted instead (profiles/r1_ncu_full_final.md)
-                "traffic_example": {"launch": "conv_tc2_kernel, layer3 3x3 d2 256->256 fwd, bf16x3 (23 per step)",
-                                    "dram_bytes": 93.0e6, "algorithmic_bytes": 134.0e6,
-                                    "note": "operand planes 65.7 MB + weights 2.4 MB read, 65.7 MB fp32 written; a third of the output is still in L2 when the kernel ends: no re-reads"},
                 "launches_per_step": conv_prof["launches"] // args.steps, "ms_per_step": round(conv_prof["ms"] / args.steps, 3),
                 "algorithmic_tflop_per_step": round(conv_prof["tflop"] / args.steps, 3),
                 "note": {"fp32": "CUDA-core FFMA arm: tensor pipe idle, frac is vs the tensor roofline the tcgen05 arm is judged on",
                          "bf16x3": "each algorithmic FLOP costs 3 tensor FLOPs (hi/lo split): algorithmic ceiling = peak/3",
                          "bf16": "single-pass bf16 operands"}[args.precision]}
 
+    if roof is not None:
+        # `traffic`: dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel's most frequent geometry, parsed
+        # from the committed ncu --set full capture (tools/ncu_traffic.py writes this file from the .ncu-rep's raw CSV page)
+        tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            roof["traffic"] = tj.get("dram_bytes_per_launch")
+            roof["traffic_detail"] = {k: tj[k] for k in ("kernel", "launch", "algorithmic_bytes_per_launch", "source") if k in tj}
     metric = METRIC if args.model == "psp" else METRIC.replace("TCB-PSP", "TCB-OCR")
     step_tflop = STEP_TFLOP if args.model == "psp" else 22.907
     if roof is not None and args.model != "psp":
@@ -338,41 +375,100 @@ def run_ours(args):
            "data": "synthetic", "impl": "ours",
            "config": {"workload": ("TCB-PSP" if args.model == "psp" else "TCB-OCR") + " ResNet101-dilated train fwd+bwd+SGD, T=5, n=2 clips/GPU, 480x854, K=124 (BASELINE configs[%d])" % (1 if args.model == "psp" else 2),
                       "frames_per_step_per_gpu": T_FRAMES * N_CLIPS, "parallelism": f"dp{world}", "precision_mode": args.precision,
-                      "syncbn": bool(args.syncbn), "l2_flush": "256 MiB write between timed steps",
+                      "syncbn": bool(syncbn), "syncbn_exchange": (args.syncbn_exchange if syncbn else None), "l2_flush": "256 MiB write between timed steps",
                       "optimizer": ("torch.optim.SGD" if args.torch_sgd else "FusedSGD (vspw_sgd_momentum_step)") + ": the reference's update rule and 4 param groups (train_clip2.py:215-236), inside the timed step",
                       "loss": round(final_loss, 5), "wall_s_timed_region": round(wall, 3),
                       "peak_hbm_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 2)},
            "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4, "steps": e2e_steps,
-                   "regions_ms": [round(x, 1) for x in region_ms] if e2e_steps else []},
+                   "regions_ms": [round(x, 1) for x in region_ms] if e2e_steps else [],
+                   "region_values": [round(frames_per_step / (x / e2e_steps / 1e3), 3) for x in region_ms] if e2e_steps else [],
+                   "note": "value = the faster of the two timed regions (both listed); every region copies every step's inputs H2D and reads its loss D2H"},
            "roofline": roof}
+    if local_bn is not None:
+        out["local_bn"] = local_bn
+    if rank == 0 and not args.profile_run and world == 1 and not args.no_gpu_library_baseline:
+        del model, opt, bucket
+        out["gpu_library_baseline"] = gpu_library_baseline(dev, imgs_d, labs_d, args)
     if rank == 0 and not args.no_cpu_baseline and not args.profile_run and world == 1:
         out["cpu_baseline"] = cpu_baseline(args)
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
+        if sync_group is not None and hasattr(sync_group, "close"):
+            sync_group.close()
         dist.destroy_process_group()
 
 
+def gpu_library_baseline(dev, imgs_d, labs_d, args):
+    """Stated context, never the target: the oracle port — the reference's ATen call sequence — on THIS
+    GPU through cuDNN/cuBLAS, fp32 with TF32 disabled (the numerical truth the parity tests use) and with torch's default
+    TF32 convolutions; train fwd+bwd of the same clip, CUDA events, 1 warm-up + 2 timed steps each."""
+    res = {"unit": UNIT, "what": "oracle/tcb_oracle.py (reference ATen calls) on cuda through cuDNN, train fwd+bwd only (no optimizer), T=5 n=2 480x854"}
+    try:
+        O = _oracle()
+        torch.cuda.empty_cache()
+        sd, _, _ = _cpu_setup(8, 8, kind=args.model)
+        sd = {k: v.detach().to(dev) for k, v in sd.items()}
+        for k, v in sd.items():
+            if v.is_floating_point() and not k.endswith(("running_mean", "running_var")):
+                v.requires_grad_(True)
+        fwd = O.clip_psp_forward if args.model == "psp" else O.clip_ocr_forward
+        fr, lb = list(imgs_d[1:]) + [imgs_d[0]], list(labs_d[1:]) + [labs_d[0]]
+        for name, tf32 in (("fp32_tf32_off", False), ("tf32_on_torch_default", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            ms = []
+            for i in range(3):
+                for v in sd.values():
+                    v.grad = None
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = fwd(sd, fr, lb, train=True)
+                out["loss"].backward()
+                e1.record()
+                torch.cuda.synchronize()
+                if i:
+                    ms.append(e0.elapsed_time(e1))
+                del out
+            res[name] = {"value": round(T_FRAMES * N_CLIPS / (min(ms) / 1e3), 2), "ms_per_step": round(min(ms), 2)}
+        torch.backends.cudnn.allow_tf32 = True
+    except Exception as e:  # noqa: BLE001 — context only: never fail the bench line over it
+        res["error"] = f"{type(e).__name__}: {e}"[:300]
+    return res
+
+
 # --------------------------------------------------------------------------------------------------
-def _cpu_step(sd, imgs, labs):
-    import tcb_oracle as O
+def _cpu_threads():
+    """All the host threads the box offers, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1)."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0)) or n
+    except AttributeError:
+        pass
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def _cpu_step(sd, imgs, labs, kind="psp"):
+    O = _oracle()
     for v in sd.values():
         if v.grad is not None:
             v.grad = None
     fr, lb = list(imgs[1:]) + [imgs[0]], list(labs[1:]) + [labs[0]]
-    out = O.clip_psp_forward(sd, fr, lb, train=True)
+    out = (O.clip_psp_forward if kind == "psp" else O.clip_ocr_forward)(sd, fr, lb, train=True)
     out["loss"].backward()
     return float(out["loss"].item())
 
 
-def _cpu_setup(hs, ws):
-    import tcb_oracle as O
+def _cpu_setup(hs, ws, kind="psp"):
+    O = _oracle()
     from cvpr2021_vspw_implement_b200 import models as M  # parameter containers only (CPU), no kernels involved
     torch.manual_seed(0)
     ns = argparse.Namespace(num_class=NUM_CLASS, psp_weight=False, use_memory=False, memory_num=8, clipocr_all=False)
-    m = M.Clip_PSP(M.ModelBuilder.build_encoder("resnet101dilated"), torch.nn.NLLLoss(ignore_index=255), ns, deep_sup_scale=0.4)
+    cls = M.Clip_PSP if kind == "psp" else M.ClipOCRNet
+    m = cls(M.ModelBuilder.build_encoder("resnet101dilated"), torch.nn.NLLLoss(ignore_index=255), ns, deep_sup_scale=0.4)
     sd = {k: v.clone() for k, v in m.state_dict().items()}
     for k, _ in m.named_parameters():
         sd[k].requires_grad_(True)
@@ -380,46 +476,86 @@ def _cpu_setup(hs, ws):
     return sd, imgs, labs
 
 
+def _host_desc():
+    model = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    model = line.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    return f"{model or 'unknown CPU'}, {os.cpu_count()} logical CPUs"
+
+
+def _avail_ram_gb():
+    try:
+        import psutil
+        return psutil.virtual_memory().available / 2 ** 30
+    except Exception:  # noqa: BLE001
+        return 0.0
+
+
 def cpu_baseline(args):
     """The CPU oracle (reference path restated in PyTorch-CPU fp32) on a bounded sample: the same T=5, n=2 train step at
-    `--cpu-sample` resolution, throughput scaled by the pixel ratio to the 480x854 workload (conv cost is linear in pixels)."""
+    `--cpu-sample` resolution (1 warm-up + 1 timed step), throughput scaled by the pixel ratio to the 480x854 workload (conv cost
+    is linear in pixels).  `--impl reference` runs the full-size arm."""
     hs, ws = (int(x) for x in args.cpu_sample.lower().split("x"))
-    sd, imgs, labs = _cpu_setup(hs, ws)
+    threads = _cpu_threads()
+    sd, imgs, labs = _cpu_setup(hs, ws, args.model)
+    _cpu_step(sd, imgs, labs, args.model)
     t0 = time.perf_counter()
-    _cpu_step(sd, imgs, labs)
+    _cpu_step(sd, imgs, labs, args.model)
     dt = time.perf_counter() - t0
     raw = T_FRAMES * N_CLIPS / dt
     scaled = raw * (hs * ws) / (H * W)
-    return {"value": round(scaled, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"one TCB-PSP R101 train fwd+bwd step, T=5 n=2 at {hs}x{ws} ({dt:.1f} s, {raw:.3f} clip-frames/s at that size), "
-                      f"scaled by the pixel ratio {hs * ws}/{H * W} to 480x854; host has {os.cpu_count()} logical CPUs"}
+    return {"value": round(scaled, 4), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"one warmed TCB-{args.model.upper()} R101 train fwd+bwd step, T=5 n=2 at {hs}x{ws} ({dt:.1f} s, {raw:.3f} clip-frames/s at that "
+                      f"size), scaled by the pixel ratio {hs * ws}/{H * W} to 480x854; PyTorch-CPU fp32 (oneDNN), {threads} threads; {_host_desc()}"}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port) on the host cores."""
+    """--impl reference: the reference's CPU implementation of the path (the oracle port: the same ATen call sequence, PyTorch
+    CPU fp32) on the host cores, ALL of them.  Exactly --warmup W + --steps K steps are run; each step is one T=5, n=2 train
+    fwd+bwd on a bounded sample of the workload: the full 480x854 clip when K+W such steps fit ~5 minutes on this host (probed
+    with one quarter-size step) and there is RAM for the fp32 autograd graph, else the 240x427 clip (a quarter of the pixels;
+    conv cost is linear in pixels) with the throughput scaled by the pixel ratio.  `ms_per_step` is always what was measured."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    hs, ws = (int(x) for x in args.cpu_sample.lower().split("x"))
-    sd, imgs, labs = _cpu_setup(hs, ws)
-    steps = max(1, min(args.steps, 2))
-    warm = 1 if args.warmup > 0 else 0
+    threads = _cpu_threads()
+    qs = tuple(int(x) for x in args.cpu_sample.lower().split("x"))
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    sd, imgs, labs = _cpu_setup(*qs, args.model)
+    _cpu_step(sd, imgs, labs, args.model)  # untimed: oneDNN primitive creation
+    t0 = time.perf_counter()
+    _cpu_step(sd, imgs, labs, args.model)
+    t_q = time.perf_counter() - t0
+    ratio = (H * W) / (qs[0] * qs[1])
+    full = (steps + warm) * t_q * ratio <= 300.0 and _avail_ram_gb() >= 64.0  # (the full-size fp32 autograd graph peaks at ~45 GB)
+    hs, ws = (H, W) if full else qs
+    if full:
+        sd, imgs, labs = _cpu_setup(hs, ws, args.model)
     for _ in range(warm):
-        _cpu_step(sd, imgs, labs)
+        _cpu_step(sd, imgs, labs, args.model)
     t0 = time.perf_counter()
     for _ in range(steps):
-        _cpu_step(sd, imgs, labs)
+        _cpu_step(sd, imgs, labs, args.model)
     dt = (time.perf_counter() - t0) / steps
     raw = T_FRAMES * N_CLIPS / dt
     scaled = raw * (hs * ws) / (H * W)
-    sample = (f"{steps} TCB-PSP R101 train fwd+bwd step(s) after {warm} warm-up, T=5 n=2 at {hs}x{ws} ({dt:.1f} s/step, {raw:.3f} clip-frames/s "
-              f"at that size) scaled by the pixel ratio {hs * ws}/{H * W} to 480x854; PyTorch-CPU fp32 (oneDNN), {torch.get_num_threads()} threads of "
-              f"{os.cpu_count()} logical CPUs")
-    out = {"metric": METRIC, "value": round(scaled, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-           "ms_per_step": round(dt * 1e3 * (H * W) / (hs * ws), 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+    sample = (f"{steps} timed TCB-{args.model.upper()} R101 train fwd+bwd steps after {warm} warm-up, T=5 n=2 at {hs}x{ws} ({dt:.2f} s/step"
+              + ("" if full else f", {raw:.3f} clip-frames/s at that size, scaled by the pixel ratio {hs * ws}/{H * W} to 480x854")
+              + f"); quarter-size probe step {t_q:.2f} s; PyTorch-CPU fp32 (oneDNN), {threads} threads; {_host_desc()}")
+    metric = METRIC if args.model == "psp" else METRIC.replace("TCB-PSP", "TCB-OCR")
+    out = {"metric": metric, "value": round(scaled, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+           "ms_per_step": round(dt * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic", "impl": "reference",
-           "config": {"workload": "TCB-PSP ResNet101-dilated train fwd+bwd, T=5, n=2 clips, 480x854, K=124 (BASELINE configs[1])", "sample": sample},
-           "cpu_baseline": {"value": round(scaled, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+           "config": {"workload": f"TCB-{args.model.upper()} ResNet101-dilated train fwd+bwd, T=5, n=2 clips, 480x854, K=124 (BASELINE configs[{1 if args.model == 'psp' else 2}])",
+                      "sample": sample, "sample_hw": [hs, ws], "full_size": bool(full),
+                      "quarter_size_clip_frames_per_s_scaled": round(T_FRAMES * N_CLIPS / t_q / ratio, 4)},
+           "cpu_baseline": {"value": round(scaled, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
            "e2e": {"value": round(scaled, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 

@@ -52,7 +52,7 @@ _SIGNATURES = {
     "vspw_bn_train_fwd": [_c_vp, _c_vp, _c_vp, _c_d, _c_vp, _c_vp, _c_f, _c_f, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_int,
                           _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_vp],
     "vspw_bn_bwd_reduce": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_sz, _c_vp, _c_vp, _c_vp],
-    "vspw_bn_bwd_apply": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_int, _c_d, _c_vp],
+    "vspw_bn_bwd_apply": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_int, _c_d, _c_d, _c_vp],
     "vspw_maxpool3x3s2_fwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp],
     "vspw_maxpool3x3s2_bwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp],
     "vspw_tcb_pool_fwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_int, _c_vp],
@@ -69,10 +69,15 @@ _SIGNATURES = {
     "vspw_vc_counts": [_c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_vp, _c_vp],
     "vspw_sgd_momentum_step": [_c_vp, _c_vp, _c_vp, _c_int, _c_f, _c_vp],
     "vspw_confusion_add": [_c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_vp],
+    "vspw_peer_alloc": [_c_sz, ctypes.POINTER(_c_vp), _c_vp],
+    "vspw_peer_open": [_c_vp, ctypes.POINTER(_c_vp)],
+    "vspw_peer_close": [_c_vp],
+    "vspw_peer_free": [_c_vp],
+    "vspw_peer_allreduce_f64": [_c_vp, _c_int, _c_vp, _c_int, _c_int, ctypes.c_uint64, _c_int, _c_int, _c_vp],
 }
 
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["vspw_last_error", "vspw_version", "vspw_tcb_pool_workspace_floats", "vspw_sgd_chunk_elems",
-                                                   "vspw_conv_weight_prep_tile"])
+                                                   "vspw_conv_weight_prep_tile", "vspw_peer_inbox_bytes"])
 
 
 class VspwError(RuntimeError):
@@ -106,6 +111,8 @@ class _Lib:
                     dll.vspw_sgd_chunk_elems.argtypes = []
                     dll.vspw_conv_weight_prep_tile.restype = ctypes.c_int32
                     dll.vspw_conv_weight_prep_tile.argtypes = [_c_int] * 4
+                    dll.vspw_peer_inbox_bytes.restype = ctypes.c_size_t
+                    dll.vspw_peer_inbox_bytes.argtypes = [_c_int, _c_int, _c_int]
                     dll.vspw_tcb_pool_workspace_floats.restype = ctypes.c_size_t
                     dll.vspw_tcb_pool_workspace_floats.argtypes = [_c_int, _c_int, _c_int, _c_int, _c_vp, _c_int]
                     self._dll = dll

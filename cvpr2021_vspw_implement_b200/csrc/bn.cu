@@ -172,7 +172,7 @@ inline dim3 ew_grid(size_t pixels, int c4) {
   const int PL = kEwThreads / G;
   const unsigned gy = (unsigned)((c4 + G - 1) / G);
   size_t bx = (pixels + (size_t)PL * kUnroll - 1) / ((size_t)PL * kUnroll);
-  size_t cap = (size_t)kNumSMs * 12 / gy;
+  size_t cap = (size_t)num_sms() * 12 / gy;
   if (cap < 1) cap = 1;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
@@ -361,7 +361,7 @@ inline dim3 red_grid(size_t pixels, int c4, int& red_pix) {
   const int PL = kEwThreads / G;
   const unsigned gy = (unsigned)((c4 + G - 1) / G);
   // pixels per thread: a multiple of kUnroll, sized for ~6 blocks per SM (more blocks = more fp64 atomics, fewer = idle SMs)
-  size_t want_blocks = (size_t)kNumSMs * 6 / gy;
+  size_t want_blocks = (size_t)num_sms() * 6 / gy;
   if (want_blocks < 1) want_blocks = 1;
   size_t rp = (pixels + want_blocks * PL - 1) / (want_blocks * PL);
   rp = (rp + kUnroll - 1) / kUnroll * kUnroll;
@@ -379,15 +379,19 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(
     const float4* __restrict__ gamma, const float4* __restrict__ chan_scale, int relu, const double* __restrict__ dbeta,
     const double* __restrict__ dgamma, float4* __restrict__ dy, uint2* __restrict__ dy_hi, uint2* __restrict__ dy_lo,
     float4* __restrict__ dres, float4* __restrict__ dgamma_f, float4* __restrict__ dbeta_f, size_t pixels, int c4,
-    size_t pix_per_img, double inv_count, int eval_mode) {
+    size_t pix_per_img, double inv_count, int eval_mode, double pgrad_scale) {
   const EwMap m = ew_map(c4);
   if (m.cg < 0) return;
   if (blockIdx.x == 0 && threadIdx.x < (c4 < kEwThreads ? c4 : kEwThreads) && dbeta && dgamma) {
-    // the fp64 sums become the fp32 parameter gradients here (one thread per channel group; no extra launch)
+    // the fp64 sums become the fp32 parameter gradients here (one thread per channel group; no extra launch).
+    // pgrad_scale = 1/world under SyncBN: the sums were reduced over all ranks, every rank holds the same total, and the
+    // gradient all-reduce that follows AVERAGES the ranks' parameter gradients (DataParallel's mean of replica losses)
     const double* db = dbeta + (size_t)m.cg * 4;
     const double* dg = dgamma + (size_t)m.cg * 4;
-    if (dgamma_f) dgamma_f[m.cg] = make_float4((float)dg[0], (float)dg[1], (float)dg[2], (float)dg[3]);
-    if (dbeta_f) dbeta_f[m.cg] = make_float4((float)db[0], (float)db[1], (float)db[2], (float)db[3]);
+    if (dgamma_f) dgamma_f[m.cg] = make_float4((float)(dg[0] * pgrad_scale), (float)(dg[1] * pgrad_scale),
+                                               (float)(dg[2] * pgrad_scale), (float)(dg[3] * pgrad_scale));
+    if (dbeta_f) dbeta_f[m.cg] = make_float4((float)(db[0] * pgrad_scale), (float)(db[1] * pgrad_scale),
+                                             (float)(db[2] * pgrad_scale), (float)(db[3] * pgrad_scale));
   }
   // dy = ka*g - kb - kc*(y - mean)
   const float4 is = __ldg(invstd + m.cg);
@@ -542,7 +546,8 @@ extern "C" int vspw_bn_bwd_apply(const float* dout, const float* out, const uint
                                  const float* mean, const float* invstd, const float* gamma, const float* chan_scale,
                                  int32_t relu, const double* dbeta, const double* dgamma, float* dy, uint16_t* dy_hi,
                                  uint16_t* dy_lo, float* dres, float* dgamma_f, float* dbeta_f, size_t pixels, int32_t c,
-                                 size_t pixels_per_image, int32_t eval_mode, double count, void* stream) {
+                                 size_t pixels_per_image, int32_t eval_mode, double count, double pgrad_scale,
+                                 void* stream) {
   VSPW_REQUIRE(dout && invstd && (dy || dy_hi), "vspw_bn_bwd_apply: null pointer");
   VSPW_REQUIRE(!relu || out || out_hi, "vspw_bn_bwd_apply: relu mask needs the forward output (fp32 or bf16 hi plane)");
   VSPW_REQUIRE(!dy_lo || dy_hi, "vspw_bn_bwd_apply: dy_lo without dy_hi");
@@ -554,7 +559,7 @@ extern "C" int vspw_bn_bwd_apply(const float* dout, const float* out, const uint
       (const float4*)dout, (const float4*)out, (const uint2*)out_hi, (const float4*)y, (const float4*)mean,
       (const float4*)invstd, (const float4*)gamma, (const float4*)chan_scale, relu, dbeta, dgamma, (float4*)dy,
       (uint2*)dy_hi, (uint2*)dy_lo, (float4*)dres, (float4*)dgamma_f, (float4*)dbeta_f, pixels, c / 4, pixels_per_image,
-      1.0 / count, eval_mode);
+      1.0 / count, eval_mode, pgrad_scale);
   int rc = check_launch("vspw_bn_bwd_apply");
   return rc;
 }

@@ -22,11 +22,22 @@ inline int check_launch(const char* what) {
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
-constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+// SM count of the CURRENT device (B200: 148 = 2 dies x 74), queried once per device: grids are sized from it
+inline int num_sms() {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cache[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev] = n;
+  }
+  return cache[dev];
+}
 
 inline unsigned grid_for(size_t work_items, int threads, int per_sm = 8) {
   size_t blocks = (work_items + threads - 1) / threads;
-  size_t cap = (size_t)kNumSMs * per_sm;
+  size_t cap = (size_t)num_sms() * per_sm;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (unsigned)blocks;

@@ -537,7 +537,7 @@ StemParams stem_params(const vspw_conv_desc* d) {
 
 unsigned stem_grid(const StemParams& p) {
   const long long tiles = (long long)p.N * p.Ho * p.tiles_x;
-  const long long cap = kNumSMs * 3;  // 80 registers x 256 threads: 3 resident blocks per SM
+  const long long cap = num_sms() * 3;  // 80 registers x 256 threads: 3 resident blocks per SM
   return (unsigned)(tiles < cap ? tiles : cap);
 }
 
@@ -663,7 +663,7 @@ extern "C" int vspw_conv2d_wgrad(const vspw_conv_desc* d, const float* x, const 
   p.M = d->n * d->ho * d->wo;
   p.NW = d->kh * d->kw * d->cin;
   int tiles = ((p.Cout + BM - 1) / BM) * ((p.NW + BN - 1) / BN);
-  int want = (2 * kNumSMs + tiles - 1) / tiles;             // ~2 waves of CTAs
+  int want = (2 * num_sms() + tiles - 1) / tiles;             // ~2 waves of CTAs
   int max_split = (p.M + 8 * BK - 1) / (8 * BK);            // at least 8 k-steps per slice
   int split = want < 1 ? 1 : (want > max_split ? max_split : want);
   if (split > 65535) split = 65535;
@@ -684,7 +684,7 @@ extern "C" int vspw_conv2d_wgrad(const vspw_conv_desc* d, const float* x, const 
   }
   if (p.NW <= kSmallNW && p.Cout <= 256 && 256 % p.Cout == 0 && (p.NW + 256 / p.Cout - 1) / (256 / p.Cout) <= kSmallCols &&
       p.M >= 4096) {
-    wgrad_small_kernel<<<kNumSMs * 4, 256, 0, as_stream(stream)>>>(p);
+    wgrad_small_kernel<<<num_sms() * 4, 256, 0, as_stream(stream)>>>(p);
     return check_launch("vspw_conv2d_wgrad(small)");
   }
   dim3 grid((p.Cout + BM - 1) / BM, (p.NW + BN - 1) / BN, split);

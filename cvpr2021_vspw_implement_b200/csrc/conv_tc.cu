@@ -828,7 +828,7 @@ int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int ta
     if (attr_err2 != cudaSuccess) { set_error("%s: cudaFuncSetAttribute(pair): %s", who, cudaGetErrorString(attr_err2)); return VSPW_ERR_CUDA; }
     const long long tiles_m = (long long)n * p.tiles_y * p.tiles_x;
     const long long pair_tiles = ((tiles_m + 1) / 2) * p.tiles_n;
-    const int pairs = (int)(pair_tiles < kNumSMs / 2 ? pair_tiles : kNumSMs / 2);
+    const int pairs = (int)(pair_tiles < num_sms() / 2 ? pair_tiles : num_sms() / 2);
     conv_tc2_kernel<kStages><<<2 * pairs, kConvThreads, S2::kBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
     return check_launch(who);
   }
@@ -847,7 +847,7 @@ int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int ta
     });
     if (attr_err6 != cudaSuccess) { set_error("%s: cudaFuncSetAttribute(narrow): %s", who, cudaGetErrorString(attr_err6)); return VSPW_ERR_CUDA; }
     const long long tiles6 = (long long)n * p.tiles_y * p.tiles_x;
-    const int grid6 = (int)(tiles6 < kNumSMs ? tiles6 : kNumSMs);
+    const int grid6 = (int)(tiles6 < num_sms() ? tiles6 : num_sms());
     conv_tc_kernel<64, 4><<<grid6, kConvThreads, S6::kBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
     return check_launch(who);
   }
@@ -859,7 +859,7 @@ int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int ta
   });
   if (attr_err != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(attr_err)); return VSPW_ERR_CUDA; }
   long long tiles = (long long)n * p.tiles_y * p.tiles_x * p.tiles_n;
-  int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+  int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   conv_tc_kernel<kBN, kStages><<<grid, kConvThreads, S::kBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   return check_launch(who);
 }
@@ -1209,7 +1209,7 @@ extern "C" int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_h
   if (pair) { p.tiles_co = d->cout / 256; p.tiles_ci = d->cin / 256; }
   const long long tiles = (long long)p.tiles_co * p.tiles_ci * taps;
   const int total_patches = p.N * p.tiles_y * p.tiles_x;
-  int splits = (int)(((pair ? 1 : 2) * kNumSMs) / tiles);  // ~2 CTAs per SM's worth of work items; one resident at a time
+  int splits = (int)(((pair ? 1 : 2) * num_sms()) / tiles);  // ~2 CTAs per SM's worth of work items; one resident at a time
   if (splits < 1) splits = 1;
   if (splits > total_patches) splits = total_patches;
   p.chunk = (total_patches + splits - 1) / splits;

@@ -237,8 +237,8 @@ extern "C" int vspw_bgemm(const float* a, const float* b, float* c, int32_t batc
   p.c_bs = c_bs; p.c_rs = c_rs; p.c_cs = c_cs; p.alpha = alpha; p.beta = beta;
   int tiles = ((m + 63) / 64) * ((n + 63) / 64) * batch;
   int ksplit = 1;
-  if (tiles < 2 * kNumSMs && k >= 512) {
-    ksplit = (2 * kNumSMs + tiles - 1) / tiles;
+  if (tiles < 2 * num_sms() && k >= 512) {
+    ksplit = (2 * num_sms() + tiles - 1) / tiles;
     int maxsplit = k / 128;
     if (ksplit > maxsplit) ksplit = maxsplit;
     if (ksplit < 1) ksplit = 1;

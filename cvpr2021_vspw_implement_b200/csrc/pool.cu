@@ -493,7 +493,7 @@ extern "C" int vspw_upsample_bilinear_bwd(const float* ddst, int32_t dh, int32_t
     int ysplit = 1;
     int threads = c < 128 ? ((c + 31) / 32 * 32) : 128;
     size_t blocks = cells * ((c + threads - 1) / threads);
-    while (blocks * ysplit < 2 * kNumSMs && ysplit * 2 <= dh && ysplit < 32) ysplit *= 2;
+    while (blocks * ysplit < 2 * num_sms() && ysplit * 2 <= dh && ysplit < 32) ysplit *= 2;
     if (ysplit > 1) {
       cudaError_t e = cudaMemsetAsync(dsrc, 0, cells * c * sizeof(float), as_stream(stream));
       if (e != cudaSuccess) { set_error("vspw_upsample_bilinear_bwd: memset: %s", cudaGetErrorString(e)); return VSPW_ERR_CUDA; }

@@ -23,6 +23,22 @@ def synthetic_frame(gen, h, w, num_class, block=32, ignore_frac=0.05, ignore_ind
     return img, lab
 
 
+def synthetic_clip(T, n, H, W, num_class=124, seed=304, block=32, ignore_frac=0.05, ignore_index=255):
+    """The benchmark / parity workload of SURVEY.md section 8d: T image tensors (n,3,H,W) ~ N(0,1) and T label tensors
+    (n,1,H,W) float, piece-wise constant `block` x `block` tiles of uniform classes with `ignore_frac` of the tiles set to
+    ignore_index.  (Same recipe, same bits as the test infrastructure's oracle/tcb_oracle.py::synthetic_clip.)"""
+    g = torch.Generator().manual_seed(seed)
+    imgs = [torch.randn(n, 3, H, W, generator=g) for _ in range(T)]
+    labs = []
+    bh, bw = (H + block - 1) // block, (W + block - 1) // block
+    for _ in range(T):
+        tiles = torch.randint(0, num_class, (n, 1, bh, bw), generator=g).float()
+        drop = torch.rand(n, 1, bh, bw, generator=g) < ignore_frac
+        tiles[drop] = float(ignore_index)
+        labs.append(tiles.repeat_interleave(block, dim=2).repeat_interleave(block, dim=3)[:, :, :H, :W].contiguous())
+    return imgs, labs
+
+
 class SyntheticClipTrain(Dataset):
     """`length` random clips of `clip_num` frames at (height, width); deterministic per index."""
 

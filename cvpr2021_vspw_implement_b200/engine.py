@@ -12,6 +12,7 @@ import contextlib
 import ctypes
 import math
 import os
+import threading
 import weakref
 from contextlib import contextmanager
 
@@ -106,24 +107,37 @@ class _ConvTimer:
         return False
 
 
-def set_syncbn(on, clamp=None):
+class TorchDistGroup:
+    """SyncBN statistics exchange through torch.distributed's default group (NCCL on GPUs)."""
+
+    def size(self):
+        import torch.distributed as dist
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def all_reduce_sums(self, t):
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+
+def set_syncbn(on, clamp=None, group=None):
     """Cross-rank BN statistics (reference multi-GPU semantics, sync_batchnorm/batchnorm.py:110-150): the per-channel
-    sum / sum-of-squares (and the two backward sums) are all-reduced over torch.distributed's default group."""
+    sum / sum-of-squares (and the two backward sums) are summed over the ranks of `group` -- any object with
+    ``size()`` and ``all_reduce_sums(fp64 tensor)`` (in place, on the current stream): `parallel.PeerSums` (one-shot
+    exchange over NVLink peer memory, the default of the entry points), `TorchDistGroup` (torch.distributed's default
+    group; used when none is given), or a test double."""
     _state["syncbn"] = bool(on)
+    _state["syncbn_group"] = group if on else None
     if clamp is not None:
         _state["syncbn_clamp"] = bool(clamp)
 
 
-def _syncbn_world():
+def _syncbn_group():
     if not _state.get("syncbn"):
-        return 1
-    import torch.distributed as dist
-    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-
-
-def _allreduce_sums(t):
-    import torch.distributed as dist
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return None
+    g = _state.get("syncbn_group")
+    if g is None:
+        g = _state["syncbn_group"] = TorchDistGroup()
+    return g if g.size() > 1 else None
 
 
 @contextmanager
@@ -190,15 +204,39 @@ class Var:
         lib.call("vspw_axpby", _p(g), _p(dst), 1.0, 1.0, g.numel(), _stream())
 
 
+_grad_sink = None  # object with destination(param) -> tensor | None and mark(param): parallel.GradBucket
+
+
+def set_grad_sink(sink):
+    """Register where parameter gradients go: `sink.destination(param)` returns the fp32 tensor (the parameter's slice of
+    a flat gradient bucket, pre-zeroed, aliased by ``param.grad``) that the backward kernels write the FIRST contribution
+    into directly; later contributions of the same tape are accumulated into it.  None = hand the gradients to autograd."""
+    global _grad_sink
+    _grad_sink = sink
+
+
 class PVar:
     """A parameter seen by the tape: reference-layout data plus per-step derived layouts."""
 
-    __slots__ = ("param", "grad", "cache")
+    __slots__ = ("param", "grad", "cache", "sunk")
 
     def __init__(self, param):
         self.param = param
         self.grad = None
         self.cache = {}
+        self.sunk = False  # the gradient lives in the sink's tensor (== param.grad's storage): autograd gets None for it
+
+    def first_dst(self):
+        """Destination for a kernel that OVERWRITES its output with this parameter's first gradient contribution: the sink's
+        slice (contiguous, parameter-shaped) or None (then the caller allocates and calls add_grad)."""
+        if self.grad is not None or _grad_sink is None:
+            return None
+        t = _grad_sink.destination(self.param)
+        if t is None or not t.is_contiguous() or t.dtype != torch.float32:
+            return None
+        self.grad = t
+        self.sunk = True
+        return t
 
     @property
     def data(self):
@@ -241,17 +279,18 @@ class Tape:
             n *= int(d)
         n_al = (n + 15) // 16 * 16
         if self._arena is None:
-            slot = _arenas.get(device)
-            if slot is None:
-                slot = _arenas[device] = [torch.empty(_ARENA_BYTES // 8, device=device, dtype=torch.float64), None]
-            owner = slot[1]() if slot[1] is not None else None
-            if owner is None or owner._done:
-                slot[1] = weakref.ref(self)
-                self._arena = slot[0]
-                # fp64 zeros are zero words: one fill of the whole arena per step
-                lib.call("vspw_fill", _p(self._arena), 0.0, self._arena.numel() * 2, _stream())
-            else:
-                self._arena = False  # another tape is still between its forward and backward on this device
+            with _host_lock:
+                slot = _arenas.get(device)
+                if slot is None:
+                    slot = _arenas[device] = [torch.empty(_ARENA_BYTES // 8, device=device, dtype=torch.float64), None]
+                owner = slot[1]() if slot[1] is not None else None
+                if owner is None or owner._done:
+                    slot[1] = weakref.ref(self)
+                    self._arena = slot[0]
+                    # fp64 zeros are zero words: one fill of the whole arena per step
+                    lib.call("vspw_fill", _p(self._arena), 0.0, self._arena.numel() * 2, _stream())
+                else:
+                    self._arena = False  # another tape is still between its forward and backward on this device
         if self._arena is False or self._arena_off + n_al > self._arena.numel():
             return torch.zeros(shape, device=device, dtype=torch.float64)
         out = self._arena[self._arena_off:self._arena_off + n].view(shape)
@@ -445,6 +484,7 @@ class _WeightPrepPlan:
 
 
 _wprep_plans = {}  # (device, precision) -> _WeightPrepPlan
+_host_lock = threading.RLock()  # host-side registries (weight-prep plans, accumulator arenas) are shared by the threads of a process
 
 
 def _tc_weight_planes(tape, wv):
@@ -456,10 +496,11 @@ def _tc_weight_planes(tape, wv):
     if pl is None:
         w = wv.data
         if w.is_contiguous() and _state["wprep_multi"]:
-            plan = _wprep_plans.get((w.device, prec))
-            if plan is None:
-                plan = _wprep_plans[(w.device, prec)] = _WeightPrepPlan(w.device, prec == "bf16x3")
-            pl = plan.planes(tape, wv)
+            with _host_lock:
+                plan = _wprep_plans.get((w.device, prec))
+                if plan is None:
+                    plan = _wprep_plans[(w.device, prec)] = _WeightPrepPlan(w.device, prec == "bf16x3")
+                pl = plan.planes(tape, wv)
         else:
             pl = _tc_weight_planes_once(w if w.is_contiguous() else w.contiguous(), prec == "bf16x3")
         wv.cache[pk] = pl
@@ -527,7 +568,9 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1, want_stats=False)
                 tape._keepalive.append((dyp, xh, xl))
             with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
                 sw = _stream()
-                dw = torch.empty((co, kh, kw, ci), device=dev, dtype=torch.float32)
+                dst = wv.first_dst()  # the parameter's slice of the gradient bucket (OIHW), or None
+                one = kh == 1 and kw == 1
+                dw = dst.view(co, kh, kw, ci) if (dst is not None and one) else torch.empty((co, kh, kw, ci), device=dev, dtype=torch.float32)
                 if wgrad_tc:
                     xh, xl = _var_planes(x)
                     with _ConvTimer(flops, True):
@@ -535,16 +578,22 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1, want_stats=False)
                 else:
                     with _ConvTimer(flops, False, "wgrad " + geom):
                         lib.call("vspw_conv2d_wgrad", ctypes.byref(desc), _p(x.data), _p(dy), _p(dw), sw)
-                if kh == 1 and kw == 1:
-                    wv.add_grad(dw.view(co, ci, 1, 1))
+                if one:
+                    if dst is None:
+                        wv.add_grad(dw.view(wv.data.shape))
                 else:
-                    dw_oihw = torch.empty((co, ci, kh, kw), device=dev, dtype=torch.float32)
+                    dw_oihw = dst.view(co, ci, kh, kw) if dst is not None else torch.empty((co, ci, kh, kw), device=dev, dtype=torch.float32)
                     permute4d(dw, dw_oihw, (co, kh, kw, ci), (0, 3, 1, 2))
-                    wv.add_grad(dw_oihw)
+                    if dst is None:
+                        wv.add_grad(dw_oihw)
         if bv is not None and bv.needs_grad:
             sums = tape.zeros_f64((co,), dev)
             lib.call("vspw_bn_stats", _p(dy), n * ho * wo, co, _p(sums), None, st)
-            bv.add_grad(_double_to_float(sums))
+            bdst = bv.first_dst()
+            if bdst is not None:
+                _double_to_float(sums, out=bdst)
+            else:
+                bv.add_grad(_double_to_float(sums))
         if x.needs_grad:
             # gradient fan-in: when another consumer of x already deposited its share, the tcgen05 epilogue adds into it
             fan_in = use_tc and x.grad is not None and x.grad.is_contiguous() and tuple(x.grad.shape) == (n, h, w, cin)
@@ -586,9 +635,9 @@ def conv_will_use_tc(x_shape, weight_shape, stride, pad, dil):
     return bool(lib.tc_supported(ConvDesc(n, h, w, cin, co, kh, kw, stride, pad, dil, ho, wo, prec)))
 
 
-def _double_to_float(d):
+def _double_to_float(d, out=None):
     """fp64 -> fp32 of a tiny per-channel vector (no ATen compute kernel in the path)."""
-    f = torch.empty(d.shape, device=d.device, dtype=torch.float32)
+    f = out if out is not None else torch.empty(d.shape, device=d.device, dtype=torch.float32)
     lib.call("vspw_cast_f64_f32", _p(d), _p(f), d.numel(), _stream())
     return f
 
@@ -617,9 +666,10 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
         if sums is None:
             sums = tape.zeros_f64((2, c), dev)
             lib.call("vspw_bn_stats", _p(y.data), pixels, c, _p(sums[0]), _p(sums[1]), st)
-        world = _syncbn_world()
-        if world > 1:
-            _allreduce_sums(sums)
+        group = _syncbn_group()
+        world = group.size() if group is not None else 1
+        if group is not None:
+            group.all_reduce_sums(sums)
         count = float(pixels * world)
         mean = torch.empty(c, device=dev, dtype=torch.float32)
         invstd = torch.empty(c, device=dev, dtype=torch.float32)
@@ -670,16 +720,20 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
             dsum = tape.zeros_f64((2, c), dev)
             lib.call("vspw_bn_bwd_reduce", _p(dout), _p(mask_o), _p(mask_hi), _p(y.data), _p(mean), _p(invstd), _p(chan_scale),
                      1 if relu else 0, pixels, c, h * w, _p(dsum[0]), _p(dsum[1]), st)
-            if world > 1:
-                _allreduce_sums(dsum)
-            dgam = torch.empty(c, device=dev, dtype=torch.float32)
-            dbet = torch.empty(c, device=dev, dtype=torch.float32)
+            if group is not None:
+                # dx needs the all-rank sums; gamma/beta gradients leave as sums/world because the gradient all-reduce that
+                # follows AVERAGES the ranks' parameter gradients and every rank holds the same all-rank total here
+                group.all_reduce_sums(dsum)
+            gdst = gv.first_dst() if gv.needs_grad else None
+            bdst = bv.first_dst() if bv.needs_grad else None
+            dgam = gdst if gdst is not None else torch.empty(c, device=dev, dtype=torch.float32)
+            dbet = bdst if bdst is not None else torch.empty(c, device=dev, dtype=torch.float32)
             lib.call("vspw_bn_bwd_apply", _p(dout), _p(mask_o), _p(mask_hi), _p(y.data), _p(mean), _p(invstd), _p(gv.data),
                      _p(chan_scale), 1 if relu else 0, _p(dsum[0]), _p(dsum[1]), _p(dy), _p(dy_hi), _p(dy_lo), _p(dres), _p(dgam),
-                     _p(dbet), pixels, c, h * w, 0, float(pixels * world), st)
-            if gv.needs_grad:
+                     _p(dbet), pixels, c, h * w, 0, float(pixels * world), 1.0 / world, st)
+            if gv.needs_grad and gdst is None:
                 gv.add_grad(dgam)
-            if bv.needs_grad:
+            if bv.needs_grad and bdst is None:
                 bv.add_grad(dbet)
         else:
             # frozen statistics (cfg.TRAIN.fix_bn): dy = g * gamma/sqrt(var+eps) = g * scale; gamma/beta still learn:
@@ -693,7 +747,7 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
                 dbet = torch.empty(c, device=dev, dtype=torch.float32)
             lib.call("vspw_bn_bwd_apply", _p(dout), _p(mask_o), _p(mask_hi), None, None, _p(scale), None, _p(chan_scale),
                      1 if relu else 0, _p(dsum[0]) if dsum is not None else None, _p(dsum[1]) if dsum is not None else None,
-                     _p(dy), _p(dy_hi), _p(dy_lo), _p(dres), _p(dgam), _p(dbet), pixels, c, h * w, 1, float(pixels), st)
+                     _p(dy), _p(dy_hi), _p(dy_lo), _p(dres), _p(dgam), _p(dbet), pixels, c, h * w, 1, float(pixels), 1.0, st)
             if dsum is not None:
                 if gv.needs_grad:
                     gv.add_grad(dgam)
@@ -1264,6 +1318,10 @@ class _GraphFunction(torch.autograd.Function):
         for p in params:
             pv = tape._params.get(id(p))
             g = pv.grad if pv is not None else None
+            if g is not None and _grad_sink is not None:
+                _grad_sink.mark(p)
+            if g is not None and pv.sunk:
+                g = None  # already in param.grad's storage (the gradient bucket): nothing for autograd to accumulate
             if g is not None and g.shape != p.shape:
                 g = g.view(p.shape)
             grads.append(g)

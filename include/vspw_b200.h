@@ -168,13 +168,32 @@ int vspw_bn_bwd_reduce(const float* dout, const float* out, const uint16_t* out_
 /* backward pass 2: dy = gamma*invstd*(g - dbeta/P - xhat*dgamma/P); dres = g (if non-null);
  * also converts the double sums to float dgamma_f/dbeta_f.  eval_mode!=0: dy = g*scale.
  * P = `count` = number of values per channel the statistics were taken over (pixels, or the
- * all-rank total when the sums were all-reduced for SyncBN).  dy goes out as fp32 (`dy`) and/or as the bf16
+ * all-rank total when the sums were all-reduced for SyncBN); dgamma_f/dbeta_f = pgrad_scale * the sums (1 on one
+ * device; 1/world under SyncBN, where every rank holds the all-rank sums and the gradient all-reduce that follows
+ * averages over ranks).  dy goes out as fp32 (`dy`) and/or as the bf16
  * (hi, lo) planes the tcgen05 dgrad/wgrad kernels read (`dy_hi`, `dy_lo`; any of the three may be null). */
 int vspw_bn_bwd_apply(const float* dout, const float* out, const uint16_t* out_hi, const float* y,
                       const float* mean, const float* invstd, const float* gamma, const float* chan_scale,
                       int32_t relu, const double* dbeta, const double* dgamma, float* dy, uint16_t* dy_hi,
                       uint16_t* dy_lo, float* dres, float* dgamma_f, float* dbeta_f, size_t pixels, int32_t c,
-                      size_t pixels_per_image, int32_t eval_mode, double count, void* stream);
+                      size_t pixels_per_image, int32_t eval_mode, double count, double pgrad_scale,
+                      void* stream);
+
+/* ---- SyncBN statistics exchange over NVLink peer memory (replaces the per-layer master/slave rendez-vous of
+ *      models/sync_batchnorm/batchnorm.py:110-131 + comm.py:96-137; one call per BN layer forward and backward) ----
+ * Every rank owns one "inbox" (vspw_peer_inbox_bytes bytes, from vspw_peer_alloc), exports it as a 64-byte CUDA IPC handle,
+ * and opens the handles of its peers (vspw_peer_open); `inbox_bases_host[r]` = rank r's inbox as mapped in this process
+ * (host array of `world` device addresses, this rank's own allocation at index `rank`).
+ * vspw_peer_allreduce_f64: vec[0..n) (device, fp64) <- sum over ranks, in rank order (bit-identical on every rank), in ONE
+ * single-block launch: push to every peer's inbox slot, flag, wait for the peers' flags, add.  `seq` = 1, 2, 3, ... must
+ * advance by one per call and be the same on every rank for the same exchange; n <= max_elems; ring >= 2 slots. */
+size_t vspw_peer_inbox_bytes(int32_t world, int32_t ring, int32_t max_elems);
+int vspw_peer_alloc(size_t bytes, void** dev_ptr, uint8_t* handle64);
+int vspw_peer_open(const uint8_t* handle64, void** dev_ptr);
+int vspw_peer_close(void* dev_ptr);
+int vspw_peer_free(void* dev_ptr);
+int vspw_peer_allreduce_f64(double* vec, int32_t n, const uint64_t* inbox_bases_host, int32_t world, int32_t rank,
+                            uint64_t seq, int32_t ring, int32_t max_elems, void* stream);
 
 /* ---- pooling -------------------------------------------------------------------------- */
 /* nn.MaxPool2d(3, 2, 1) (models/resnet.py:109); idx saves the winning tap (0..8) per output */

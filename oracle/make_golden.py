@@ -36,6 +36,12 @@ CASES = {
     "segmodule_r18": ("SegmentationModule", "resnet18dilated", 1, 2, 49, 65, 14, 307),
     "non_local3d": ("Non_local3d", "resnet50dilated", 3, 2, 49, 65, 15, 308),
 }
+# mid-size, well-conditioned train-mode fixtures for the GRADIENT gates (the 49x65 cases above put everything below
+# layer2 on 7x9 maps, where a single ReLU mask flip is 4e-3 of a gradient norm: oracle/NOISE_FLOOR.md)
+MID_CASES = {
+    "clip_psp_mid": ("Clip_PSP", "resnet50dilated", 3, 4, 97, 129, 16, 309),
+    "clip_ocr_mid": ("ClipOCRNet", "resnet50dilated", 3, 4, 97, 129, 17, 310),
+}
 NUM_CLASS = 124
 
 
@@ -211,6 +217,47 @@ def run_case(ref, name, spec):
           f"-> {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def run_mid_case(ref, name, spec):
+    """Train step only: loss, acc, logits, and for EVERY parameter the gradient norm plus a seeded 2048-element sample of the
+    gradient tensor (tcb_oracle.grad_sample_indices).  Also the reference's own fp32 floor: the same step with 1 oneDNN
+    thread instead of 8 (summation order only) — stored so the test can print it next to the CUDA path's distance."""
+    kind, arch, T, n, H, W, mseed, dseed = spec
+    imgs, labs = O.synthetic_clip(T, n, H, W, NUM_CLASS, seed=dseed, block=16)
+    rec = {"meta": np.array([T, n, H, W, mseed, dseed])}
+    grads = {}
+    for threads in (8, 1):
+        torch.set_num_threads(threads)
+        m = build(ref, kind, arch, mseed)
+        m.train()
+        no_dropout(m)
+        captured = {}
+        head = m.ppm_conv if kind.startswith("Clip_PSP") else m.head
+        h = head.register_forward_hook(lambda mod, i, o: captured.__setitem__("logits", o.detach()))
+        loss, acc = m(feed(imgs, labs, True))
+        loss.backward()
+        h.remove()
+        grads[threads] = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+        if threads == 8:
+            rec["train/loss"] = np.float64(loss.item())
+            rec["train/acc"] = np.float64(acc.item())
+            rec["train/logits"] = captured["logits"].numpy().copy()
+    torch.set_num_threads(8)
+    floor = {}
+    for k, g in grads[8].items():
+        g = g.float().reshape(-1)
+        idx = O.grad_sample_indices(g.numel())
+        rec["train/gnorm/" + k] = np.float64(g.double().norm().item())
+        rec["train/gsample/" + k] = g[idx].numpy().copy()
+        gn = g.double().norm().item()
+        floor[k] = float((grads[1][k].reshape(-1).double() - g.double()).norm().item() / gn) if gn > 1e-7 else 0.0
+        rec["train/gfloor/" + k] = np.float64(floor[k])
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **rec)
+    worst = max(floor.items(), key=lambda kv: kv[1])
+    print(f"{name}: loss={rec['train/loss']:.6f} acc={rec['train/acc']:.6f}; reference fp32 floor (1 vs 8 threads) worst rel-L2 "
+          f"{worst[1]:.2e} ({worst[0]}), median {float(np.median(list(floor.values()))):.2e} -> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def bn_formula_pin():
     """The one numeric pin the reference's own tests hold for this path
     (lib/nn/modules/tests/test_numeric_batchnorm.py:29-52): train-mode BN = (x-mean)/sqrt(var_biased+eps),
@@ -238,6 +285,10 @@ def main():
         if only and name not in only:
             continue
         run_case(ref, name, spec)
+    for name, spec in MID_CASES.items():
+        if only and name not in only:
+            continue
+        run_mid_case(ref, name, spec)
     bn_formula_pin()
 
 

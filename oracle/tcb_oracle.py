@@ -373,6 +373,15 @@ def synthetic_clip(T, n, H, W, num_class=124, seed=304, block=32, ignore_frac=0.
     return imgs, labs
 
 
+def grad_sample_indices(numel, k=2048, seed=99):
+    """Seeded sample of `k` flat indices of a tensor with `numel` elements (all of them when numel <= k): the mid-size
+    golden fixtures pin gradient tensors on such samples (rel-L2 over a uniform sample estimates rel-L2 of the tensor)."""
+    if numel <= k:
+        return torch.arange(numel)
+    g = torch.Generator().manual_seed(seed + numel % 9973)
+    return torch.randint(0, numel, (k,), generator=g)
+
+
 def condition_nonlocal(sd, seed=8):
     """NLBlockND's output BN is initialised to weight = bias = 0 (the block is the identity at init, non_local.py:62-63),
     which would hide the whole affinity path from a parity fixture: give it live values.  In place; returns sd."""

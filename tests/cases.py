@@ -18,6 +18,12 @@ CASES = {
     "non_local3d": ("Non_local3d", "resnet50dilated", 3, 2, 49, 65, 15, 308),
 }
 
+# mid-size train-mode fixtures for the gradient gates (oracle/make_golden.py MID_CASES)
+MID_CASES = {
+    "clip_psp_mid": ("Clip_PSP", "resnet50dilated", 3, 4, 97, 129, 16, 309),
+    "clip_ocr_mid": ("ClipOCRNet", "resnet50dilated", 3, 4, 97, 129, 17, 310),
+}
+
 # cases driven through the img_data / clipimgs_data feed (Non_local3d has its own: every frame is supervised)
 CLIP_CASES = [k for k in CASES if k != "non_local3d"]
 

@@ -1,0 +1,167 @@
+"""GPU: SyncBN (cross-rank BN statistics) and the data-parallel step against the single-device global batch.
+
+Reference semantics: `_SynchronizedBatchNorm.forward` under DataParallel (models/sync_batchnorm/batchnorm.py:75-131) sums
+sum(x), sum(x^2) over all replicas, normalises every replica with the global statistics and back-propagates through them;
+the loss is the mean of the per-replica mean losses (train_clip2.py:98).  So a 2-rank step on clips [0,1] | [2,3] must equal
+ONE device running all four clips: loss, logits, every parameter gradient (after the all-rank average), running statistics.
+
+Two ways to get two ranks:
+  * `test_two_emulated_ranks_*`: two host threads on ONE GPU, each with its own replica and tape, joined by a test double
+    of the statistics exchange (`engine.set_syncbn(group=...)`).  Runs in the ordinary 1-GPU `-m gpu` tier and exercises
+    all of the engine's SyncBN arithmetic (global count, all-rank sums in dx, 1/world on the gamma/beta gradients).
+  * `test_two_nccl_ranks_*`: two real processes over NCCL + the peer-memory exchange (`parallel.PeerSums`), launched with
+    torchrun; skipped when the box has one GPU.
+"""
+import os
+import subprocess
+import sys
+import threading
+
+import pytest
+import torch
+
+import cases as C
+import tcb_oracle as O
+
+pytestmark = pytest.mark.gpu
+T, H, W = 3, 65, 97
+
+
+@pytest.fixture(scope="module")
+def E():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from cvpr2021_vspw_implement_b200 import engine
+    return engine
+
+
+class ThreadGroup:
+    """Test double of the statistics exchange: `n` host threads meet at a barrier and sum their tensors."""
+
+    def __init__(self, n):
+        self.n = n
+        self.barrier = threading.Barrier(n)
+        self.slots = [None] * n
+        self.tls = threading.local()
+        self.calls = 0
+
+    def size(self):
+        return self.n
+
+    def all_reduce_sums(self, t):
+        r = self.tls.rank
+        torch.cuda.synchronize()
+        self.slots[r] = t.clone()
+        self.barrier.wait()
+        total = self.slots[0].clone()
+        for s in self.slots[1:]:
+            total += s
+        torch.cuda.synchronize()
+        self.barrier.wait()
+        t.copy_(total)
+        if r == 0:
+            self.calls += 1
+
+
+def _global_clip(n_clips, seed=41):
+    # no ignore labels: every rank then has the same number of valid pixels and the mean of the rank means IS the global mean
+    return O.synthetic_clip(T, n_clips, H, W, C.NUM_CLASS, seed=seed, block=16, ignore_frac=0.0)
+
+
+def _run_single(E, kind, prec, clamp, imgs, labs):
+    m = C.no_dropout(C.build(kind, "resnet50dilated", 31).cuda().train())
+    E.set_syncbn(False, clamp=clamp)
+    with E.precision(prec), E.capturing() as cap:
+        loss, acc = m(C.feed(imgs, labs, True, "cuda"))
+        loss.backward()
+    torch.cuda.synchronize()
+    return m, loss.item(), cap["logits"].clone()
+
+
+@pytest.mark.parametrize("kind,prec,clamp", [("Clip_PSP", "fp32", False), ("Clip_PSP", "bf16x3", True), ("ClipOCRNet", "bf16x3", False)])
+def test_two_emulated_ranks_equal_the_single_device_global_batch(E, kind, prec, clamp):
+    world, n_loc = 2, 2
+    imgs, labs = _global_clip(world * n_loc)
+    ref_m, ref_loss, ref_logits = _run_single(E, kind, prec, clamp, imgs, labs)
+    group = ThreadGroup(world)
+    reps = [C.no_dropout(C.build(kind, "resnet50dilated", 31).cuda().train()) for _ in range(world)]
+    out = [None] * world
+    errs = []
+
+    def rank_main(r):
+        try:
+            group.tls.rank = r
+            torch.cuda.set_device(0)
+            sl = slice(r * n_loc, (r + 1) * n_loc)
+            feed = C.feed([i[sl] for i in imgs], [l[sl] for l in labs], True, "cuda")
+            loss, acc = reps[r](feed)
+            # the tape's backward in THIS thread (torch's autograd engine would run both ranks on one worker thread)
+            grads = loss.grad_fn.apply(torch.ones_like(loss), torch.zeros_like(acc))[3:]
+            torch.cuda.synchronize()
+            out[r] = (loss.item(), grads)
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+            group.barrier.abort()
+
+    E.set_syncbn(True, clamp=clamp, group=group)
+    try:
+        with E.precision(prec):
+            ths = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+    finally:
+        E.set_syncbn(False, clamp=False)
+    if errs:
+        raise errs[0]
+    assert group.calls >= 2 * 50, "every train-mode BN layer exchanges its sums forward and backward"
+    loss2 = sum(o[0] for o in out) / world
+    assert abs(loss2 - ref_loss) <= 2e-5 * abs(ref_loss), (loss2, ref_loss)
+    params = [p for p in reps[0].parameters()]
+    worst = (0.0, "")
+    checked = 0
+    for i, (name, p_ref) in enumerate(ref_m.named_parameters()):
+        g_ref = p_ref.grad
+        gs = [o[1][i] for o in out]
+        if g_ref is None:
+            assert all(g is None for g in gs), name
+            continue
+        g = sum(x.double() for x in gs) / world  # GradBucket.all_reduce_mean
+        rn = float(g_ref.double().norm())
+        if rn < 1e-7:
+            continue
+        e = float((g - g_ref.double()).norm() / rn)
+        checked += 1
+        if e > worst[0]:
+            worst = (e, name)
+        if name.endswith(("bn1.weight", "bn1.bias", "bn3.weight", "bn3.bias", ".1.weight", ".1.bias")):
+            # BN affine parameters: the advisor's round-1 finding was a factor `world` here
+            assert e <= 2e-2, (name, e)
+    print(f"{kind}/{prec}/clamp={clamp}: loss {loss2:.6f} vs {ref_loss:.6f}; {checked} gradient tensors, worst rel-L2 {worst[0]:.2e} ({worst[1]})")
+    assert checked > 100 and worst[0] <= (3e-3 if prec == "fp32" else 1e-2), worst
+    # running statistics: global mean / unbiased global variance on every rank
+    sd_ref = ref_m.state_dict()
+    for r in range(world):
+        sd = reps[r].state_dict()
+        w = max(C.rel_err(sd[k].cpu(), sd_ref[k].cpu()) for k in sd if k.endswith(("running_mean", "running_var")))
+        assert w <= 1e-4, (r, w)
+    del params
+
+
+def test_two_nccl_ranks_equal_the_single_device_global_batch(E, tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "dist_syncbn.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tests", "dist_syncbn_worker.py"), str(out)]
+    r = subprocess.run(cmd, cwd=root, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    print(r.stdout[-4000:])
+    assert r.returncode == 0
+    import json
+    res = json.load(open(out))
+    for mode, v in res.items():
+        print(mode, v)
+        assert v["loss_rel"] <= 2e-5 and v["worst_grad_rel_l2"] <= 1e-2 and v["worst_running"] <= 1e-4, (mode, v)
+        assert v["bn_affine_worst"] <= 2e-2, (mode, v)

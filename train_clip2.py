@@ -54,7 +54,7 @@ def train(segmentation_module, data_loader, optimizer, bucket, history, epoch, c
     for i, (clip_imgs, clip_gts) in enumerate(DevicePrefetcher(data_loader, device)):
         batch_data = build_batch(clip_imgs, clip_gts, i + 1, args.method)
         data_time.update(time.time() - tic)
-        segmentation_module.zero_grad()
+        bucket.zero_grad()  # one memset; every p.grad is a slice of the flat gradient bucket the backward kernels write into
         adjust_learning_rate(optimizer, i + (epoch - 1) * epoch_iters, cfg, max_iters, args)
         loss, acc = segmentation_module(batch_data)
         loss, acc = loss.mean(), acc.mean()
@@ -162,13 +162,14 @@ def make_loader(args, world, rank):
 
 
 def main(cfg, args):
-    world, rank, local = P.init_from_env()
+    world, rank, local = P.init_from_env(device_offset=args.start_gpu)  # the NCCL communicator is bound to the compute device
     if args.gpu_num != world:
         raise ValueError(f"--gpu_num {args.gpu_num} but WORLD_SIZE={world}: launch one process per GPU with torchrun")
     device = torch.device("cuda", args.start_gpu + local)
     torch.cuda.set_device(device)
     E.set_precision(args.precision)
-    E.set_syncbn(args.syncbn and world > 1, clamp=args.syncbn_clamp)
+    syncbn = args.syncbn and world > 1
+    E.set_syncbn(syncbn, clamp=args.syncbn_clamp, group=P.make_syncbn_group(args.syncbn_exchange) if syncbn else None)
     torch.manual_seed(cfg.TRAIN.seed)
     segmentation_module = build_module(cfg, args)
     loader_train = make_loader(args, world, rank)
@@ -232,6 +233,7 @@ def make_parser():
     # ---- flags of this engine (not in the reference) ----
     parser.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32"])
     parser.add_argument("--syncbn", type=str2bool, default=True, help="all-reduce BN statistics over ranks (reference multi-GPU semantics)")
+    parser.add_argument("--syncbn_exchange", default="peer", choices=["peer", "nccl"], help="peer = one-shot exchange over NVLink peer memory per BN layer (csrc/peer.cu); nccl = one library all-reduce per layer")
     parser.add_argument("--syncbn_clamp", type=str2bool, default=False, help="clamp(var,eps)^-1/2 as the reference's DataParallel SyncBN (quirk Q4)")
     parser.add_argument("--synthetic", type=str2bool, default=False)
     parser.add_argument("--synthetic_size", type=str, default="480x854")
