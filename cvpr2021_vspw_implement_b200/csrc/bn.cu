@@ -167,12 +167,22 @@ __device__ __forceinline__ EwMap ew_map(int c4) {
   m.dp = (size_t)gridDim.x * PL;
   return m;
 }
-inline dim3 ew_grid(size_t pixels, int c4) {
+// Resident blocks per SM of a kernel (queried once): the element-wise kernels run ONE wave of blocks that walk the pixel axis
+// with a grid stride.  ncu on the 256-channel layer3 tensors (r2c) showed why: with 4-6 waves of short blocks every block paid
+// its per-channel prologue for ~9 pixels of work and the backward reduction serialised 803 fp64 atomics per channel address
+// (bn_act_fwd 34.6 us at 27 % DRAM, bn_bwd_reduce 52 us at 39 %), while the 1024-channel tensors already ran at 70-90 %.
+template <typename K>
+inline int blocks_per_sm(K kernel, int threads) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) != cudaSuccess || n < 1) n = 1;
+  return n;
+}
+inline dim3 ew_grid(size_t pixels, int c4, int occ) {
   const int G = c4 < kEwThreads ? c4 : kEwThreads;
   const int PL = kEwThreads / G;
   const unsigned gy = (unsigned)((c4 + G - 1) / G);
   size_t bx = (pixels + (size_t)PL * kUnroll - 1) / ((size_t)PL * kUnroll);
-  size_t cap = (size_t)num_sms() * 12 / gy;
+  size_t cap = (size_t)num_sms() * occ / gy;
   if (cap < 1) cap = 1;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
@@ -186,6 +196,7 @@ struct BnTrainStats {  // non-null `sum` = train mode with the finalize step fus
   const double* sum;
   const double* sqsum;
   double count;
+  double inv_count;
   const float* gamma;
   const float* beta;
   float eps, momentum;
@@ -199,6 +210,7 @@ struct BnTrainStats {  // non-null `sum` = train mode with the finalize step fus
 __global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(
     const float4* __restrict__ y, const float4* __restrict__ scale, const float4* __restrict__ shift,
     const float4* __restrict__ mean, const float4* __restrict__ beta, const float4* __restrict__ residual,
+    const uint2* __restrict__ res_hi, const uint2* __restrict__ res_lo,
     const float4* __restrict__ chan_scale, int relu, float4* __restrict__ out, uint2* __restrict__ out_hi,
     uint2* __restrict__ out_lo, size_t pixels, int c4, size_t pix_per_img, BnTrainStats ts) {
   const EwMap m = ew_map(c4);
@@ -211,12 +223,15 @@ __global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int ch = m.cg * 4 + j;
-      const double mm = ts.sum[ch] / ts.count;
-      double var = ts.sqsum[ch] / ts.count - mm * mm;
+      // mean / biased variance from the fp64 sums with two fp64 multiply-adds (E[x^2] - E[x]^2 needs the fp64 product); the
+      // inverse standard deviation in fp32 with IEEE sqrt and divide, as F.batch_norm does (fp64 divide / sqrt cost hundreds
+      // of cycles per channel on this part and EVERY thread of EVERY block runs this prologue)
+      const double mm = ts.sum[ch] * ts.inv_count;
+      double var = fma(ts.sqsum[ch], ts.inv_count, -mm * mm);
       if (var < 0) var = 0;
-      const double is = ts.clamp_mode ? 1.0 / sqrt(var < (double)ts.eps ? (double)ts.eps : var) : 1.0 / sqrt(var + (double)ts.eps);
+      const float vf = (float)var;
       mf[j] = (float)mm;
-      isf[j] = (float)is;
+      isf[j] = ts.clamp_mode ? 1.0f / sqrtf(vf < ts.eps ? ts.eps : vf) : 1.0f / sqrtf(vf + ts.eps);
       const float gm = ts.gamma ? ts.gamma[ch] : 1.f;
       bt[j] = ts.beta ? ts.beta[ch] : 0.f;
       scf[j] = gm * isf[j];
@@ -247,6 +262,19 @@ __global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(
       if (q < pixels) {
         v[u] = ld_stream(y + q * c4 + m.cg);
         if (residual) r[u] = ld_stream(residual + q * c4 + m.cg);
+        else if (res_hi) {
+          // the residual branch exists as bf16 (hi, lo) planes only (an interior block output, never stored in fp32)
+          const uint2 h = ld_stream(res_hi + q * c4 + m.cg);
+          const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h.x));
+          const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h.y));
+          r[u] = make_float4(h0.x, h0.y, h1.x, h1.y);
+          if (res_lo) {
+            const uint2 l = ld_stream(res_lo + q * c4 + m.cg);
+            const float2 l0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&l.x));
+            const float2 l1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&l.y));
+            r[u].x += l0.x; r[u].y += l0.y; r[u].z += l1.x; r[u].w += l1.y;
+          }
+        }
       }
     }
 #pragma unroll
@@ -257,7 +285,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(
       float4 t = v[u];
       t.x = fmaf(t.x - mu.x, sc.x, add.x); t.y = fmaf(t.y - mu.y, sc.y, add.y);
       t.z = fmaf(t.z - mu.z, sc.z, add.z); t.w = fmaf(t.w - mu.w, sc.w, add.w);
-      if (residual) { t.x += r[u].x; t.y += r[u].y; t.z += r[u].z; t.w += r[u].w; }
+      if (residual || res_hi) { t.x += r[u].x; t.y += r[u].y; t.z += r[u].z; t.w += r[u].w; }
       if (relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
       if (chan_scale) {
         const float4 cs = __ldg(chan_scale + (q / pix_per_img) * c4 + m.cg);
@@ -292,7 +320,7 @@ __device__ __forceinline__ float4 apply_mask(float4 g, bool has_o, float4 o, boo
 
 // backward pass 1: per-channel dbeta = sum g, dgamma = sum g * xhat.  fp32 partials over `red_pix` pixels per
 // thread (kUnroll independent streams), lanes meet in shared memory, one fp64 atomic per channel per block.
-// red_pix is chosen on the host so that the grid is ~6 blocks per SM whatever the channel count.
+// red_pix is chosen on the host so that the grid is one wave of resident blocks whatever the channel count.
 __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(
     const float4* __restrict__ dout, const float4* __restrict__ out, const uint2* __restrict__ out_hi,
     const float4* __restrict__ y, const float4* __restrict__ mean, const float4* __restrict__ invstd,
@@ -356,17 +384,18 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(
     atomicAdd(dgamma + cg * 4 + 2, v2); atomicAdd(dgamma + cg * 4 + 3, v3);
   }
 }
-inline dim3 red_grid(size_t pixels, int c4, int& red_pix) {
+inline dim3 red_grid(size_t pixels, int c4, int& red_pix, int occ) {
   const int G = c4 < kEwThreads ? c4 : kEwThreads;
   const int PL = kEwThreads / G;
   const unsigned gy = (unsigned)((c4 + G - 1) / G);
-  // pixels per thread: a multiple of kUnroll, sized for ~6 blocks per SM (more blocks = more fp64 atomics, fewer = idle SMs)
-  size_t want_blocks = (size_t)num_sms() * 6 / gy;
+  // pixels per thread: a multiple of kUnroll, sized for ONE wave of resident blocks (every extra block adds one fp64 atomic
+  // per channel onto the same 2*C addresses, which serialise in L2)
+  size_t want_blocks = (size_t)num_sms() * occ / gy;
   if (want_blocks < 1) want_blocks = 1;
   size_t rp = (pixels + want_blocks * PL - 1) / (want_blocks * PL);
   rp = (rp + kUnroll - 1) / kUnroll * kUnroll;
   if (rp < (size_t)kUnroll) rp = kUnroll;
-  if (rp > 256) rp = 256;
+  if (rp > 1024) rp = 1024;  // fp32 partial sums stay short; beyond this the grid grows instead
   red_pix = (int)rp;
   const size_t per_block = (size_t)PL * rp;
   return dim3((unsigned)((pixels + per_block - 1) / per_block), gy, 1);
@@ -495,33 +524,38 @@ extern "C" int vspw_bn_fold_eval(const float* gamma, const float* beta, const fl
 }
 
 extern "C" int vspw_bn_act_fwd(const float* y, const float* scale, const float* shift, const float* mean,
-                               const float* beta, const float* residual,
+                               const float* beta, const float* residual, const uint16_t* residual_hi, const uint16_t* residual_lo,
                                const float* chan_scale, int32_t relu, float* out, uint16_t* out_hi, uint16_t* out_lo,
                                size_t pixels, int32_t c, size_t pixels_per_image, void* stream) {
   VSPW_REQUIRE(y && scale && (shift || mean) && (out || out_hi), "vspw_bn_act_fwd: null pointer");
+  VSPW_REQUIRE(!(residual && residual_hi) && (!residual_lo || residual_hi), "vspw_bn_act_fwd: residual as fp32 OR as planes");
   VSPW_REQUIRE(c > 0 && c % 4 == 0, "vspw_bn_act_fwd: channels must be a multiple of 4 (got %d)", c);
   VSPW_REQUIRE(pixels_per_image > 0, "vspw_bn_act_fwd: pixels_per_image must be positive");
   if (pixels == 0) return VSPW_OK;
-  bn_act_fwd_kernel<<<ew_grid(pixels, c / 4), kEwThreads, 0, as_stream(stream)>>>(
+  static const int occ = blocks_per_sm(bn_act_fwd_kernel, kEwThreads);
+  bn_act_fwd_kernel<<<ew_grid(pixels, c / 4, occ), kEwThreads, 0, as_stream(stream)>>>(
       (const float4*)y, (const float4*)scale, (const float4*)shift, (const float4*)mean, (const float4*)beta,
-      (const float4*)residual, (const float4*)chan_scale,
+      (const float4*)residual, (const uint2*)residual_hi, (const uint2*)residual_lo, (const float4*)chan_scale,
       relu, (float4*)out, (uint2*)out_hi, (uint2*)out_lo, pixels, c / 4, pixels_per_image, BnTrainStats{});
   return check_launch("vspw_bn_act_fwd");
 }
 
 extern "C" int vspw_bn_train_fwd(const float* y, const double* sum, const double* sqsum, double count, const float* gamma,
                                  const float* beta, float eps, float momentum, float* running_mean, float* running_var,
-                                 float* mean, float* invstd, int32_t clamp_mode, const float* residual, const float* chan_scale,
-                                 int32_t relu, float* out, uint16_t* out_hi, uint16_t* out_lo, size_t pixels, int32_t c,
+                                 float* mean, float* invstd, int32_t clamp_mode, const float* residual, const uint16_t* residual_hi,
+                                 const uint16_t* residual_lo, const float* chan_scale, int32_t relu, float* out, uint16_t* out_hi, uint16_t* out_lo, size_t pixels, int32_t c,
                                  size_t pixels_per_image, void* stream) {
   VSPW_REQUIRE(y && sum && sqsum && mean && invstd && (out || out_hi), "vspw_bn_train_fwd: null pointer");
+  VSPW_REQUIRE(!(residual && residual_hi) && (!residual_lo || residual_hi), "vspw_bn_train_fwd: residual as fp32 OR as planes");
   VSPW_REQUIRE(count >= 1, "vspw_bn_train_fwd: empty batch");
   VSPW_REQUIRE(c > 0 && c % 4 == 0, "vspw_bn_train_fwd: channels must be a multiple of 4 (got %d)", c);
   VSPW_REQUIRE(pixels_per_image > 0, "vspw_bn_train_fwd: pixels_per_image must be positive");
   if (pixels == 0) return VSPW_OK;
-  BnTrainStats ts{sum, sqsum, count, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, clamp_mode};
-  bn_act_fwd_kernel<<<ew_grid(pixels, c / 4), kEwThreads, 0, as_stream(stream)>>>(
-      (const float4*)y, nullptr, nullptr, nullptr, nullptr, (const float4*)residual, (const float4*)chan_scale, relu,
+  BnTrainStats ts{sum, sqsum, count, 1.0 / count, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, clamp_mode};
+  static const int occ = blocks_per_sm(bn_act_fwd_kernel, kEwThreads);
+  bn_act_fwd_kernel<<<ew_grid(pixels, c / 4, occ), kEwThreads, 0, as_stream(stream)>>>(
+      (const float4*)y, nullptr, nullptr, nullptr, nullptr, (const float4*)residual, (const uint2*)residual_hi,
+      (const uint2*)residual_lo, (const float4*)chan_scale, relu,
       (float4*)out, (uint2*)out_hi, (uint2*)out_lo, pixels, c / 4, pixels_per_image, ts);
   return check_launch("vspw_bn_train_fwd");
 }
@@ -535,7 +569,8 @@ extern "C" int vspw_bn_bwd_reduce(const float* dout, const float* out, const uin
   VSPW_REQUIRE(c > 0 && c % 4 == 0, "vspw_bn_bwd_reduce: channels must be a multiple of 4 (got %d)", c);
   if (pixels == 0) return VSPW_OK;
   int red_pix = kUnroll;
-  const dim3 rg = red_grid(pixels, c / 4, red_pix);
+  static const int occ = blocks_per_sm(bn_bwd_reduce_kernel, kEwThreads);
+  const dim3 rg = red_grid(pixels, c / 4, red_pix, occ);
   bn_bwd_reduce_kernel<<<rg, kEwThreads, 0, as_stream(stream)>>>(
       (const float4*)dout, (const float4*)out, (const uint2*)out_hi, (const float4*)y, (const float4*)mean,
       (const float4*)invstd, (const float4*)chan_scale, relu, pixels, c / 4, pixels_per_image, dbeta, dgamma, red_pix);
@@ -555,7 +590,8 @@ extern "C" int vspw_bn_bwd_apply(const float* dout, const float* out, const uint
   VSPW_REQUIRE(eval_mode || (y && mean && dbeta && dgamma), "vspw_bn_bwd_apply: train mode needs y/mean/sums");
   VSPW_REQUIRE(c > 0 && c % 4 == 0, "vspw_bn_bwd_apply: channels must be a multiple of 4 (got %d)", c);
   if (pixels == 0) return VSPW_OK;
-  bn_bwd_apply_kernel<<<ew_grid(pixels, c / 4), kEwThreads, 0, as_stream(stream)>>>(
+  static const int occ = blocks_per_sm(bn_bwd_apply_kernel, kEwThreads);
+  bn_bwd_apply_kernel<<<ew_grid(pixels, c / 4, occ), kEwThreads, 0, as_stream(stream)>>>(
       (const float4*)dout, (const float4*)out, (const uint2*)out_hi, (const float4*)y, (const float4*)mean,
       (const float4*)invstd, (const float4*)gamma, (const float4*)chan_scale, relu, dbeta, dgamma, (float4*)dy,
       (uint2*)dy_hi, (uint2*)dy_lo, (float4*)dres, (float4*)dgamma_f, (float4*)dbeta_f, pixels, c / 4, pixels_per_image,

@@ -188,6 +188,7 @@ struct ConvTcParams {
   int Nout;
   int taps_h, taps_w;
   int off0, step;      // tap offset = off0 + tap*step (both axes)
+  int b_tap_pitch;     // K distance between two taps in the B matrix (= C, or the weight's wider channel pitch)
   int bw, bh;          // pixel patch, bw*bh == 128
   int tiles_x, tiles_y, tiles_n;
   int x3;              // 1: hi/lo planes, 3 MMAs per k-step
@@ -438,7 +439,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             uint8_t* st = smem + stage * S::kStage;
             mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
             const int cx = x0 * p.stride + p.off0 + s * p.step, cy = y0 * p.stride + p.off0 + r * p.step;
-            const int kcol = ((r * p.taps_w + s) * kblocks_per_tap + kb) * BK;
+            const int kcol = (r * p.taps_w + s) * p.b_tap_pitch + kb * BK;
             tma_load_4d(st, &map_a_hi, &full_bar[stage], kb * BK, cx, cy, img);
             tma_load_2d(st + 2 * S::kATile, &map_b_hi, &full_bar[stage], kcol, n0);
             if (p.x3) {
@@ -624,7 +625,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
             const int cx = x0 * p.stride + p.off0 + s * p.step, cy = y0 * p.stride + p.off0 + r * p.step;
-            const int kcol = ((r * p.taps_w + s) * kblocks_per_tap + kb) * BK;
+            const int kcol = (r * p.taps_w + s) * p.b_tap_pitch + kb * BK;
             tma_load_4d_2sm(st, &map_a_hi, fb, kb * BK, cx, cy, img);
             tma_load_2d_2sm(st + 2 * S::kATile, &map_b_hi, fb, kcol, n0);
             if (p.x3) {
@@ -783,7 +784,7 @@ bool use_narrow_kernel() {
   return v == 1;
 }
 
-int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int taps, int off0, int step, int stride,
+int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int taps, int off0, int step, int stride, int b_pitch,
                    const uint16_t* a_hi,
                    const uint16_t* a_lo, const uint16_t* b_hi, const uint16_t* b_lo, const float* bias, float* out, int x3,
                    double* ch_sum, double* ch_sqsum, int accumulate, cudaStream_t stream) {
@@ -802,6 +803,9 @@ int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int ta
   ConvTcParams p;
   p.out = out; p.bias = bias; p.N = n; p.H = h; p.W = w; p.C = c; p.Nout = nout; p.stride = stride;
   p.taps_h = taps; p.taps_w = taps; p.off0 = off0; p.step = step; p.x3 = x3;
+  if (b_pitch <= 0) b_pitch = c;
+  VSPW_REQUIRE(b_pitch >= c && b_pitch % 8 == 0, "%s: weight channel pitch %d must be >= %d and a multiple of 8", who, b_pitch, c);
+  p.b_tap_pitch = b_pitch;
   VSPW_REQUIRE((ch_sum == nullptr) == (ch_sqsum == nullptr), "%s: ch_sum and ch_sqsum go together", who);
   p.ch_sum = ch_sum; p.ch_sqsum = ch_sqsum; p.accumulate = accumulate;
   pick_patch(h, w, p.bw, p.bh);
@@ -812,7 +816,7 @@ int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int ta
   int rc;
   if ((rc = make_act_map(&ma_hi, a_hi, n, hin, win, c, p.bw, p.bh, who, stride))) return rc;
   if ((rc = make_act_map(&ma_lo, x3 ? a_lo : a_hi, n, hin, win, c, p.bw, p.bh, who, stride))) return rc;
-  const long long kdim = (long long)taps * taps * c;
+  const long long kdim = (long long)taps * taps * b_pitch;
   if ((rc = make_mat_map(&mb_hi, b_hi, nout, kdim, BK, kBN, who))) return rc;
   if ((rc = make_mat_map(&mb_lo, x3 ? b_lo : b_hi, nout, kdim, BK, kBN, who))) return rc;
   if (nout % BN2 == 0 && use_pair_kernel()) {
@@ -878,7 +882,8 @@ constexpr int WG_STAGE_BYTES = 8 * WG_BLK;   // dy: 2 ch-blocks x (hi,lo); x: 2 
 constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
 
 struct WgradTcParams {
-  float* dw;          // [Cout][taps][Cin] fp32, zero-initialised
+  float* dw;          // [Cout][taps][dw_pitch] fp32, zero-initialised (dw_pitch = Cin, or the weight's wider channel pitch)
+  int dw_pitch;
   int N, H, W, Cin, Cout;
   int taps_w, off0, step;   // x pixel = dy pixel * stride + off0 + tap*step
   int stride;
@@ -992,7 +997,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy_hi, const __grid_cons
     tcgen05_fence_after();
     const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
     const int taps = p.taps_w * p.taps_w;
-    float* dst = p.dw + ((size_t)co * taps + tap) * p.Cin + tci * 128;
+    float* dst = p.dw + ((size_t)co * taps + tap) * p.dw_pitch + tci * 128;
 #pragma unroll 1
     for (int c0 = 0; c0 < (p.n64 ? 64 : 128); c0 += 32) {
       uint32_t v[32];
@@ -1127,7 +1132,7 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap map_dy_hi, const __grid_con
     tcgen05_fence_after();
     const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
     const int taps = p.taps_w * p.taps_w;
-    float* dst = p.dw + ((size_t)co * taps + tap) * p.Cin + tci * 256;
+    float* dst = p.dw + ((size_t)co * taps + tap) * p.dw_pitch + tci * 256;
 #pragma unroll 1
     for (int c0 = 0; c0 < 256; c0 += 32) {
       uint32_t v[32];
@@ -1167,7 +1172,7 @@ extern "C" int vspw_conv2d_fwd_tc(const vspw_conv_desc* d, const uint16_t* x_hi,
                                   void* stream) {
   VSPW_REQUIRE(geometry_ok(d), "vspw_conv2d_fwd_tc: geometry not supported by the tcgen05 path");
   VSPW_REQUIRE(d->precision == VSPW_PREC_BF16X3 || d->precision == VSPW_PREC_BF16, "vspw_conv2d_fwd_tc: precision must be BF16X3 or BF16");
-  return launch_conv_tc("vspw_conv2d_fwd_tc", d->n, d->h, d->w, d->cin, d->cout, d->kh, -d->pad, d->dil, d->stride, x_hi, x_lo, w_hi, w_lo,
+  return launch_conv_tc("vspw_conv2d_fwd_tc", d->n, d->h, d->w, d->cin, d->cout, d->kh, -d->pad, d->dil, d->stride, d->cin_pitch, x_hi, x_lo, w_hi, w_lo,
                         bias, y, d->precision == VSPW_PREC_BF16X3, ch_sum, ch_sqsum, 0, as_stream(stream));
 }
 
@@ -1177,7 +1182,8 @@ extern "C" int vspw_conv2d_dgrad_tc(const vspw_conv_desc* d, const uint16_t* dy_
                "(a stride-2 dgrad is a stride-1 dgrad of the zero-inserted dy: vspw_zero_insert2_bf16)");
   VSPW_REQUIRE(d->precision == VSPW_PREC_BF16X3 || d->precision == VSPW_PREC_BF16, "vspw_conv2d_dgrad_tc: precision must be BF16X3 or BF16");
   // dx[p][ci] = sum_{tap,co} dy[p + pad - tap*dil][co] * Wt[ci][tap][co]
-  return launch_conv_tc("vspw_conv2d_dgrad_tc", d->n, d->h, d->w, d->cout, d->cin, d->kh, d->pad, -d->dil, 1, dy_hi, dy_lo, wt_hi,
+  // (a weight with cin_pitch > cin: rows [0, cin) of the [cin_pitch][taps][cout] operand are the ones used — nothing to adjust)
+  return launch_conv_tc("vspw_conv2d_dgrad_tc", d->n, d->h, d->w, d->cout, d->cin, d->kh, d->pad, -d->dil, 1, 0, dy_hi, dy_lo, wt_hi,
                         wt_lo, nullptr, dx, d->precision == VSPW_PREC_BF16X3, nullptr, nullptr, accumulate ? 1 : 0, as_stream(stream));
 }
 
@@ -1192,6 +1198,8 @@ extern "C" int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_h
   WgradTcParams p;
   // p.N x p.H x p.W = the dy (output) pixel grid the K loop walks; x is read at pixel*stride + tap offset
   p.dw = dw_ohwi; p.N = d->n; p.H = d->ho; p.W = d->wo; p.Cin = d->cin; p.Cout = d->cout;
+  p.dw_pitch = d->cin_pitch > 0 ? d->cin_pitch : d->cin;
+  VSPW_REQUIRE(p.dw_pitch >= d->cin && p.dw_pitch % 4 == 0, "%s: weight channel pitch %d must be >= cin and a multiple of 4", who, p.dw_pitch);
   p.taps_w = d->kw; p.off0 = -d->pad; p.step = d->dil; p.x3 = x3; p.stride = d->stride;
   p.n64 = (d->cin == 64 && use_narrow_kernel()) ? 1 : 0;  // stem conv2/conv3, layer1: half of a 128-wide N tile would be zero fill
   int xn = d->n, xh = d->h, xw = d->w;
@@ -1214,7 +1222,7 @@ extern "C" int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_h
   if (splits > total_patches) splits = total_patches;
   p.chunk = (total_patches + splits - 1) / splits;
   p.splits = (total_patches + p.chunk - 1) / p.chunk;
-  cudaError_t e = cudaMemsetAsync(dw_ohwi, 0, (size_t)d->cout * taps * d->cin * sizeof(float), st);
+  cudaError_t e = cudaMemsetAsync(dw_ohwi, 0, (size_t)d->cout * taps * p.dw_pitch * sizeof(float), st);
   if (e != cudaSuccess) { set_error("%s: memset: %s", who, cudaGetErrorString(e)); return VSPW_ERR_CUDA; }
   CUtensorMap mdy_hi, mdy_lo, mx_hi, mx_lo;
   int rc;

@@ -226,9 +226,26 @@ extern "C" int vspw_softmax_strided_bwd(const float* y, const float* dy, float* 
   return check_launch("vspw_softmax_strided_bwd");
 }
 
+static int bgemm_impl(const float* a, const float* b, float* c, int32_t batch, int32_t m, int32_t n, int32_t k,
+                      int64_t a_bs, int64_t a_rs, int64_t a_cs, int64_t b_bs, int64_t b_rs, int64_t b_cs, int64_t c_bs,
+                      int64_t c_rs, int64_t c_cs, float alpha, float beta, bool allow_split_k, void* stream);
+
 extern "C" int vspw_bgemm(const float* a, const float* b, float* c, int32_t batch, int32_t m, int32_t n, int32_t k,
                           int64_t a_bs, int64_t a_rs, int64_t a_cs, int64_t b_bs, int64_t b_rs, int64_t b_cs, int64_t c_bs,
                           int64_t c_rs, int64_t c_cs, float alpha, float beta, void* stream) {
+  return bgemm_impl(a, b, c, batch, m, n, k, a_bs, a_rs, a_cs, b_bs, b_rs, b_cs, c_bs, c_rs, c_cs, alpha, beta, true, stream);
+}
+
+// same product without split-K: no atomics, bit-reproducible (inference paths)
+extern "C" int vspw_bgemm_det(const float* a, const float* b, float* c, int32_t batch, int32_t m, int32_t n, int32_t k,
+                              int64_t a_bs, int64_t a_rs, int64_t a_cs, int64_t b_bs, int64_t b_rs, int64_t b_cs, int64_t c_bs,
+                              int64_t c_rs, int64_t c_cs, float alpha, float beta, void* stream) {
+  return bgemm_impl(a, b, c, batch, m, n, k, a_bs, a_rs, a_cs, b_bs, b_rs, b_cs, c_bs, c_rs, c_cs, alpha, beta, false, stream);
+}
+
+static int bgemm_impl(const float* a, const float* b, float* c, int32_t batch, int32_t m, int32_t n, int32_t k,
+                      int64_t a_bs, int64_t a_rs, int64_t a_cs, int64_t b_bs, int64_t b_rs, int64_t b_cs, int64_t c_bs,
+                      int64_t c_rs, int64_t c_cs, float alpha, float beta, bool allow_split_k, void* stream) {
   VSPW_REQUIRE(a && b && c, "vspw_bgemm: null pointer");
   VSPW_REQUIRE(batch > 0 && m > 0 && n > 0 && k > 0, "vspw_bgemm: bad dims");
   BGemm p;
@@ -237,7 +254,7 @@ extern "C" int vspw_bgemm(const float* a, const float* b, float* c, int32_t batc
   p.c_bs = c_bs; p.c_rs = c_rs; p.c_cs = c_cs; p.alpha = alpha; p.beta = beta;
   int tiles = ((m + 63) / 64) * ((n + 63) / 64) * batch;
   int ksplit = 1;
-  if (tiles < 2 * num_sms() && k >= 512) {
+  if (allow_split_k && tiles < 2 * num_sms() && k >= 512) {
     ksplit = (2 * num_sms() + tiles - 1) / tiles;
     int maxsplit = k / 128;
     if (ksplit > maxsplit) ksplit = maxsplit;

@@ -14,6 +14,7 @@
 // raises inside ITS kernel q-1, i.e. after its kernel q-2 finished reading.  A ring of >= 2 slots is therefore enough;
 // the host side uses 4.
 #include "common.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 using namespace vspw;
@@ -140,7 +141,12 @@ extern "C" int vspw_peer_allreduce_f64(double* vec, int32_t n, const uint64_t* i
   if (n == 0) return VSPW_OK;
   PeerTable tab;
   for (int i = 0; i < 16; ++i) tab.base[i] = i < world ? (unsigned long long)inbox_bases_host[i] : 0ull;
+  static long timeout_s = -1;  // VSPW_PEER_TIMEOUT_S: how long a rank waits for its peers before the kernel traps (default 300 s)
+  if (timeout_s < 0) {
+    const char* e = getenv("VSPW_PEER_TIMEOUT_S");
+    timeout_s = (e && atol(e) > 0) ? atol(e) : 300;
+  }
   peer_allreduce_kernel<<<1, kPeerThreads, 0, as_stream(stream)>>>(vec, n, tab, world, rank, (unsigned long long)seq, ring, max_elems,
-                                                                   300ull * 1000000000ull);
+                                                                   (unsigned long long)timeout_s * 1000000000ull);
   return check_launch("vspw_peer_allreduce_f64");
 }

@@ -642,13 +642,15 @@ def _double_to_float(d, out=None):
     return f
 
 
-def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, training=None, fp32_out=True):
+def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, training=None, fp32_out=True, planes_out=True):
     """BN (train: batch stats, eval: running stats) [+ residual] [+ ReLU] [* Dropout2d mask].
 
     Reference: SynchronizedBatchNorm2d.forward (sync_batchnorm/batchnorm.py:68-73) followed by
     nn.ReLU / `out += residual` (resnet.py:72-92) / nn.Dropout2d (clip_psp.py:39).
-    fp32_out=False: the caller guarantees every consumer is a tcgen05 conv, so only the bf16 planes are written
-    (and the backward ReLU mask is read from the hi plane); ignored when no planes are produced.
+    fp32_out=False: the caller guarantees every consumer is a tcgen05 conv (or the residual add of the next block, which
+    then reads the planes), so only the bf16 planes are written (and the backward ReLU mask is read from the hi plane);
+    ignored when no planes are produced.  planes_out=False: no tensor-core conv reads this output (a downsample branch).
+    `residual` may be a Var that exists as planes only.
     """
     n, h, w, c = y.shape
     pixels = n * h * w
@@ -677,7 +679,13 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
         invstd = torch.empty(c, device=dev, dtype=torch.float32)
         lib.call("vspw_bn_fold_eval", _p(gv.data), _p(bv.data), _p(bn.running_mean), _p(bn.running_var), float(bn.eps),
                  _p(scale), _p(shift), _p(invstd), c, st)
-    want_planes = _state["precision"] != "fp32" and c % 64 == 0
+    want_planes = planes_out and _state["precision"] != "fp32" and c % 64 == 0
+    res_f = res_h = res_l = None
+    if residual is not None:
+        if residual.data is not None:
+            res_f = residual.data
+        else:
+            res_h, res_l = residual.planes
     hi = lo = None
     if want_planes:
         hi = torch.empty(y.shape, device=dev, dtype=torch.bfloat16)
@@ -687,12 +695,11 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
         # finalize (mean / invstd / running statistics from the fp64 sums) + normalise + residual + ReLU + planes: one launch
         lib.call("vspw_bn_train_fwd", _p(y.data), _p(sums[0]), _p(sums[1]), count, _p(gv.data), _p(bv.data), float(bn.eps),
                  float(bn.momentum), _p(bn.running_mean), _p(bn.running_var), _p(mean), _p(invstd),
-                 1 if _state["syncbn_clamp"] else 0, _p(residual.data if residual is not None else None), _p(chan_scale),
+                 1 if _state["syncbn_clamp"] else 0, _p(res_f), _p(res_h), _p(res_l), _p(chan_scale),
                  1 if relu else 0, _p(o), _p(hi), _p(lo), pixels, c, h * w, st)
     else:
         lib.call("vspw_bn_act_fwd", _p(y.data), _p(scale), _p(shift), _p(bn.running_mean), _p(bv.data),
-                 _p(residual.data if residual is not None else None),
-                 _p(chan_scale), 1 if relu else 0, _p(o), _p(hi), _p(lo), pixels, c, h * w, st)
+                 _p(res_f), _p(res_h), _p(res_l), _p(chan_scale), 1 if relu else 0, _p(o), _p(hi), _p(lo), pixels, c, h * w, st)
     needs = tape.grad_enabled and (y.needs_grad or gv.needs_grad or (residual is not None and residual.needs_grad))
     out = Var(o, needs_grad=needs)
     if want_planes:
@@ -932,6 +939,121 @@ def ppm_concat(tape, base, pyramids):
             dp = torch.empty_like(p.data)
             lib.call("vspw_upsample_bilinear_bwd", _p(g), h, w, ctot, o, _p(dp), pn, sh, sw, pc, st)
             p.add_grad(dp)
+
+    tape.record(backward)
+    return out
+
+
+def ppm_fused_supported(base_shape, pyramid_shapes, weight_shape, pad, dil):
+    """True when ppm_conv_fused can take this head in the current precision mode (else: ppm_concat + conv2d)."""
+    prec = _PRECISION[_state["precision"]]
+    if prec == PREC_FP32 or os.environ.get("VSPW_PPM_FUSED", "1") == "0":
+        return False
+    n, h, w, c0 = base_shape
+    co, ctot, kh, kw = weight_shape
+    if kh != kw or kh not in (1, 3) or pad != dil * (kh - 1) // 2 or co % 4:
+        return False
+    cps = {s[3] for s in pyramid_shapes}
+    if len(cps) != 1 or c0 + len(pyramid_shapes) * next(iter(cps)) != ctot or len(pyramid_shapes) > 8:
+        return False
+    if any(s[1] != s[2] or s[0] != n for s in pyramid_shapes):
+        return False
+    return bool(lib.tc_supported(ConvDesc(n, h, w, c0, co, kh, kw, 1, pad, dil, h, w, prec, ctot)))
+
+
+def ppm_conv_fused(tape, base, pyramids, weight, pad=1, dil=1, want_stats=False):
+    """conv(cat([base] + [bilinear_up(p) for p in pyramids], channels), weight) WITHOUT the up-sampled maps and the concat
+    (PPM_conv.forward, clip_psp.py:45-56; PPMDeepsup.forward, models/models.py:975-990; bias-free conv).
+
+    Linearity: the `base` channels run on the tcgen05 conv kernel straight from base's operand planes against the first C0
+    input channels of the weight (ConvDesc.cin_pitch); every pyramid branch is evaluated in bin space — Z_s = P_s . W_s^T
+    (a (n s^2) x Cp x (9 Cout) GEMM), then y[p] += sum_tap sum_bins B_s[p + off(tap), bin] Z_s[bin, tap] (csrc/ppm.cu).
+    At 480p: 242 instead of 485 GFLOP forward, no 210 MB concat (+ its planes and gradient)."""
+    wv = tape.param(weight)
+    n, h, w, c0 = base.shape
+    co, ctot, kh, kw = wv.data.shape
+    S = len(pyramids)
+    cp = pyramids[0].shape[3]
+    scales = [p.shape[1] for p in pyramids]
+    taps = kh * kw
+    dev = base.planes[0].device if base.data is None else base.data.device
+    prec = _PRECISION[_state["precision"]]
+    desc = ConvDesc(n, h, w, c0, co, kh, kw, 1, pad, dil, h, w, prec, ctot)
+    st = _stream()
+    xh, xl = _var_planes(base)
+    wplanes = _tc_weight_planes(tape, wv)
+    wh, wl = wplanes["ohwi"]
+    y = torch.empty((n, h, w, co), device=dev, dtype=torch.float32)
+    flops_base = 2.0 * n * h * w * co * taps * c0
+    flops_pyr = 2.0 * n * h * w * co * taps * cp * S   # algorithmic (reference) count of the part evaluated in bin space
+    with _ConvTimer(flops_base, True):
+        lib.call("vspw_conv2d_fwd_tc", ctypes.byref(desc), _p(xh), _p(xl), _p(wh), _p(wl), None, _p(y), None, None, st)
+    sc = (ctypes.c_int32 * S)(*scales)
+    with _ConvTimer(flops_pyr, False, f"ppm pyramid (bin space) fwd {n}x{h}x{w} {S}x{cp}->{co}"):
+        wp = torch.empty((S, taps, co, cp), device=dev, dtype=torch.float32)
+        lib.call("vspw_ppm_weight_slices", _p(wv.data), _p(wp), co, ctot, kh, kw, c0, cp, S, st)
+        zs = []
+        for i, pv in enumerate(pyramids):
+            m = n * scales[i] * scales[i]
+            z = torch.empty((m, taps * co), device=dev, dtype=torch.float32)
+            # Z[bin][j=(tap,co)] = sum_c P[bin][c] * Wp[i][j][c]
+            # (no split-K: the inference path stays free of atomics, i.e. bit-reproducible)
+            lib.call("vspw_bgemm_det", _p(pv.data), _p(wp[i]), _p(z), 1, m, taps * co, cp, 0, cp, 1, 0, 1, cp, 0, taps * co, 1, 1.0, 0.0, st)
+            zs.append(z)
+        stats = tape.zeros_f64((2, co), dev) if want_stats else None
+        zp = (ctypes.c_void_p * S)(*[z.data_ptr() for z in zs])
+        lib.call("vspw_ppm_pyramid_fwd", _p(y), zp, sc, S, n, h, w, co, kh, pad, dil, _p(stats[0]) if stats is not None else None,
+                 _p(stats[1]) if stats is not None else None, st)
+    del zs
+    out = Var(y, needs_grad=tape.grad_enabled and (base.needs_grad or wv.needs_grad or any(p.needs_grad for p in pyramids)))
+    out.stats = stats
+    out.wants_grad_planes = True
+    out.wants_grad_fp32 = True  # the bin-space gather reads the fp32 gradient
+
+    def backward():
+        dy, dyp = out.grad, out.grad_planes
+        out.grad = out.grad_planes = None
+        if dy is None:
+            return
+        st = _stream()
+        if dyp is None:
+            dyp = _planes_of(dy)
+        # ---- pyramid part: dZ (transposed gather), then dP_s and dW_s as small GEMMs ---------------------------------
+        dzs = [torch.empty((n * s * s, taps * co), device=dev, dtype=torch.float32) for s in scales]
+        with _ConvTimer(2 * flops_pyr, False, f"ppm pyramid (bin space) bwd {n}x{h}x{w} {S}x{cp}->{co}"):
+            dzp = (ctypes.c_void_p * S)(*[z.data_ptr() for z in dzs])
+            lib.call("vspw_ppm_pyramid_bwd", _p(dy), dzp, sc, S, n, h, w, co, kh, pad, dil, st)
+            for i, pv in enumerate(pyramids):
+                if not pv.needs_grad:
+                    continue
+                m = n * scales[i] * scales[i]
+                dp = torch.empty((m, cp), device=dev, dtype=torch.float32)
+                # dP[bin][c] = sum_j dZ[bin][j] * Wp[i][j][c]
+                lib.call("vspw_bgemm", _p(dzs[i]), _p(wp[i]), _p(dp), 1, m, cp, taps * co, 0, taps * co, 1, 0, cp, 1, 0, cp, 1, 1.0, 0.0, st)
+                pv.add_grad(dp.view(pv.shape))
+        if wv.needs_grad:
+            dw = torch.empty((co, kh, kw, ctot), device=dev, dtype=torch.float32)
+            with _ConvTimer(flops_base, True):
+                lib.call("vspw_conv2d_wgrad_tc", ctypes.byref(desc), _p(xh), _p(xl), _p(dyp[0]), _p(dyp[1]), _p(dw), st)
+            for i, pv in enumerate(pyramids):
+                m = n * scales[i] * scales[i]
+                # dW[co][tap][c0 + i*cp + c] = sum_bin dZ[bin][tap][co] * P[bin][c]  (batch = tap)
+                lib.call("vspw_bgemm", _p(dzs[i]), _p(pv.data), _p(dw.view(-1)[c0 + i * cp:]), taps, co, cp, m, co, 1, taps * co, 0, cp, 1,
+                         ctot, taps * ctot, 1, 1.0, 0.0, st)
+            dst = wv.first_dst()
+            dw_oihw = dst.view(co, ctot, kh, kw) if dst is not None else torch.empty((co, ctot, kh, kw), device=dev, dtype=torch.float32)
+            permute4d(dw, dw_oihw, (co, kh, kw, ctot), (0, 3, 1, 2))
+            if dst is None:
+                wv.add_grad(dw_oihw)
+        if base.needs_grad:
+            th, tl = wplanes["ihwo"]  # [ctot][kh][kw][co]: rows [0, c0) are the base channels
+            fan_in = base.grad is not None and base.grad.is_contiguous() and tuple(base.grad.shape) == (n, h, w, c0)
+            dx = base.grad if fan_in else torch.empty((n, h, w, c0), device=dev, dtype=torch.float32)
+            d1 = ConvDesc(n, h, w, c0, co, kh, kw, 1, pad, dil, h, w, prec)
+            with _ConvTimer(flops_base, True):
+                lib.call("vspw_conv2d_dgrad_tc", ctypes.byref(d1), _p(dyp[0]), _p(dyp[1]), _p(th), _p(tl), _p(dx), 1 if fan_in else 0, st)
+            if not fan_in:
+                base.add_grad(dx)
 
     tape.record(backward)
     return out

@@ -100,6 +100,7 @@ class ClipOCRNet(nn.Module):
 
             def runner(tape):
                 logits, _ = self._logits(tape, frames, training, memory)
+                E.publish("logits", logits)
                 return (E.up_softmax(logits, int(segSize[0]), int(segSize[1])),), None
 
             (pred,) = E.run_graph(self, runner)

@@ -33,8 +33,14 @@ class PPM_conv(nn.Module):
         """x: current-frame layer4 map (n,h,w,2048); pooled: per-scale temporal means (n,s,s,2048)."""
         pyr = [E.batchnorm_act(tape, conv_op(tape, br[0], p, br[1]), br[1], relu=True, training=training)
                for br, p in zip(self.ppm, pooled)]
-        cat = E.ppm_concat(tape, x, pyr)
-        y = conv_op(tape, self.conv_last_[0], cat, self.conv_last_[1])
+        conv = self.conv_last_[0]
+        want_stats = self.conv_last_[1].training if training is None else bool(training)
+        if E.ppm_fused_supported(x.shape, [p.shape for p in pyr], conv.weight.shape, conv.padding[0], conv.dilation[0]):
+            # no up-sampled maps, no 4096-channel concat: the pyramid branches are evaluated in bin space (csrc/ppm.cu)
+            y = E.ppm_conv_fused(tape, x, pyr, conv.weight, conv.padding[0], conv.dilation[0], want_stats=want_stats)
+        else:
+            cat = E.ppm_concat(tape, x, pyr)
+            y = conv_op(tape, conv, cat, self.conv_last_[1])
         mask = E.dropout2d_mask(self.conv_last_[3].p, y.shape[0], y.shape[3], y.data.device, training and self.conv_last_[3].training)
         z = E.batchnorm_act(tape, y, self.conv_last_[1], relu=True, chan_scale=mask, training=training)
         return conv_op(tape, self.conv_last_[4], z)
@@ -120,6 +126,7 @@ class Clip_PSP(nn.Module):
         if segSize is not None:
             def runner(tape):
                 logits, _ = self._logits(tape, frames, training=False if not training else training)
+                E.publish("logits", logits)
                 return (E.up_softmax(logits, int(segSize[0]), int(segSize[1])),), None
 
             (pred,) = E.run_graph(self, runner)

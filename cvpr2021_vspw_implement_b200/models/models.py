@@ -171,8 +171,12 @@ class PPMDeepsup(nn.Module):
         pyr = []
         for branch, p in zip(self.ppm, pooled):
             pyr.append(E.batchnorm_act(tape, conv_op(tape, branch[1], p, branch[2]), branch[2], relu=True, training=training))
-        cat = E.ppm_concat(tape, conv5, pyr)
-        y = conv_op(tape, self.conv_last_[0], cat, self.conv_last_[1])
+        conv = self.conv_last_[0]
+        if E.ppm_fused_supported(conv5.shape, [p.shape for p in pyr], conv.weight.shape, conv.padding[0], conv.dilation[0]):
+            y = E.ppm_conv_fused(tape, conv5, pyr, conv.weight, conv.padding[0], conv.dilation[0], want_stats=bool(training))
+        else:
+            cat = E.ppm_concat(tape, conv5, pyr)
+            y = conv_op(tape, conv, cat, self.conv_last_[1])
         mask = E.dropout2d_mask(self.conv_last_[3].p, n, y.shape[3], y.data.device, training and self.conv_last_[3].training)
         x = E.batchnorm_act(tape, y, self.conv_last_[1], relu=True, chan_scale=mask, training=training)
         logits = conv_op(tape, self.conv_last_[4], x)

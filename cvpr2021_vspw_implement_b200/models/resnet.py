@@ -49,14 +49,15 @@ class BasicBlock(nn.Module):
         self.downsample = downsample
         self.stride = stride
 
-    def graph(self, tape, x):
+    def graph(self, tape, x, out_fp32=True):
         y1 = conv_op(tape, self.conv1, x, self.bn1)
         out = E.batchnorm_act(tape, y1, self.bn1, relu=True, fp32_out=not _planes_only_ok(self.conv2, y1.shape))
         y2 = conv_op(tape, self.conv2, out, self.bn2)
         res = x
         if self.downsample is not None:
-            res = E.batchnorm_act(tape, conv_op(tape, self.downsample[0], x, self.downsample[1]), self.downsample[1], relu=False)
-        return E.batchnorm_act(tape, y2, self.bn2, relu=True, residual=res)
+            res = E.batchnorm_act(tape, conv_op(tape, self.downsample[0], x, self.downsample[1]), self.downsample[1], relu=False,
+                                  planes_out=False)
+        return E.batchnorm_act(tape, y2, self.bn2, relu=True, residual=res, fp32_out=out_fp32)
 
 
 class Bottleneck(nn.Module):
@@ -74,7 +75,7 @@ class Bottleneck(nn.Module):
         self.downsample = downsample
         self.stride = stride
 
-    def graph(self, tape, x):
+    def graph(self, tape, x, out_fp32=True):
         # the outputs of bn1 and bn2 are read by the next conv only: bf16 planes suffice when that conv is a tcgen05 one
         y1 = conv_op(tape, self.conv1, x, self.bn1)
         out = E.batchnorm_act(tape, y1, self.bn1, relu=True, fp32_out=not _planes_only_ok(self.conv2, y1.shape))
@@ -83,9 +84,10 @@ class Bottleneck(nn.Module):
         y3 = conv_op(tape, self.conv3, out, self.bn3)
         res = x
         if self.downsample is not None:
-            res = E.batchnorm_act(tape, conv_op(tape, self.downsample[0], x, self.downsample[1]), self.downsample[1], relu=False)
+            res = E.batchnorm_act(tape, conv_op(tape, self.downsample[0], x, self.downsample[1]), self.downsample[1], relu=False,
+                                  planes_out=False)  # read by the residual add only: no operand planes
         # bn3 -> (+residual) -> relu fused in one pass
-        return E.batchnorm_act(tape, y3, self.bn3, relu=True, residual=res)
+        return E.batchnorm_act(tape, y3, self.bn3, relu=True, residual=res, fp32_out=out_fp32)
 
 
 class ResNet(nn.Module):
@@ -138,21 +140,31 @@ def stem_and_layers_graph(tape, net, x):
     x = E.batchnorm_act(tape, conv_op(tape, net.conv3, x, net.bn3), net.bn3, relu=True)
     x = E.maxpool3x3s2(tape, x)
     outs = []
-    prev_droppable = False
     for layer in (net.layer1, net.layer2, net.layer3, net.layer4):
-        for blk in layer:
-            y = blk.graph(tape, x)
-            # x, the previous block's output, has now been read by everything that reads it in the forward pass (conv1,
-            # the downsample conv and the residual add of `blk`).  When those convs are tcgen05 ones the backward pass only
-            # touches its bf16 planes, so the fp32 copy goes back to the allocator now instead of after the backward
-            # (12 % of the activation footprint: 186.8 -> 156 GB at T=9, 720p).  Stage outputs are kept: callers get them.
-            if prev_droppable and x.planes is not None and _planes_only_ok(blk.conv1, x.shape) and (
-                    blk.downsample is None or _planes_only_ok(blk.downsample[0], x.shape)):
-                x.data = None
-            x, prev_droppable = y, True
+        blocks = list(layer)
+        for i, blk in enumerate(blocks):
+            # An interior block output is read by the NEXT block only: its conv1, its downsample conv (none inside a stage) and
+            # its residual add.  When those convs run on tcgen05 they read the bf16 (hi, lo) operand planes, the residual add
+            # reads the same planes (vspw_bn_train_fwd residual_hi/lo) and the backward takes its ReLU mask from the hi plane,
+            # so the fp32 copy is never written: 4 of the 16 bytes per element of every block-output BN pass, and 12 % of the
+            # activation footprint (186.8 -> 156 GB at T=9, 720p).  Stage outputs keep their fp32 copy: callers get them.
+            nxt = blocks[i + 1] if i + 1 < len(blocks) else None
+            planes_only = nxt is not None and _planes_only_next(blk, nxt, x.shape)
+            x = blk.graph(tape, x, out_fp32=not planes_only)
         outs.append(x)
-        prev_droppable = False
     return outs
+
+
+def _planes_only_next(blk, nxt, in_shape):
+    """True when `blk`'s output can exist as operand planes only: the next block of the stage reads it through tcgen05 convs."""
+    if E.get_precision() == "fp32" or nxt.downsample is not None:
+        return False
+    n, h, w, _ = in_shape
+    # the stage's first block may stride; ResnetDilated rewrites strides in place, so read the conv that carries it
+    s = (blk.conv2 if hasattr(blk, "conv3") else blk.conv1).stride[0]
+    ho, wo = (h - 1) // s + 1, (w - 1) // s + 1
+    cout = (blk.conv3 if hasattr(blk, "conv3") else blk.conv2).weight.shape[0]
+    return cout % 64 == 0 and _planes_only_ok(nxt.conv1, (n, ho, wo, cout))
 
 
 def resnet18(pretrained=False, **kw):

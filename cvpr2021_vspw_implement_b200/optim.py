@@ -2,8 +2,10 @@
 as ONE kernel launch per step (vspw_sgd_momentum_step) instead of ~50 multi-tensor ATen launches.
 
 Drop-in for `torch.optim.SGD(params, lr, momentum, weight_decay)`: same `param_groups` (so `adjust_learning_rate` works
-unchanged), same `state[p]['momentum_buffer']` and therefore the same `state_dict()` / `opt_epoch_E.pth` format in both
-directions.  Dampening and Nesterov are not supported (the reference uses neither).
+unchanged), same `state[p]['momentum_buffer']` and therefore the same `state_dict()` layout as `torch.optim.SGD` over the same
+(de-duplicated) parameter groups.  A REFERENCE `opt_epoch_E.pth` repeats every parameter 2-5 times per group (quirk Q10):
+`train_clip2.remap_reference_optimizer_state` maps it onto these groups on resume.  Dampening and Nesterov are not
+supported (the reference uses neither).
 """
 import ctypes
 

@@ -45,6 +45,9 @@ typedef struct vspw_conv_desc {
   int32_t stride, pad, dil;
   int32_t ho, wo;         /* output y[n][ho][wo][cout]                               */
   int32_t precision;      /* VSPW_PREC_*                                             */
+  int32_t cin_pitch;      /* tensor-core entry points only: the weight has cin_pitch >= cin input channels per tap
+                             (w[cout][kh][kw][cin_pitch]) and the conv uses channels [0, cin) of them — the x part of a
+                             conv over a channel concat (PPM head, vspw_ppm_pyramid_fwd).  0 = cin.            */
 } vspw_conv_desc;
 
 const char* vspw_last_error(void);
@@ -126,6 +129,22 @@ int vspw_conv2d_dgrad_tc(const vspw_conv_desc* d, const uint16_t* dy_hi, const u
 int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo,
                          const uint16_t* dy_hi, const uint16_t* dy_lo, float* dw_ohwi, void* stream);
 
+/* ---- PPM head without the concat (PPM_conv.forward clip_psp.py:45-56; PPMDeepsup.forward models/models.py:975-990):
+ *      y = conv(cat([x] + [bilinear_up(P_s)]), W) = conv(x, W[:, :C0])  [vspw_conv2d_fwd_tc with cin_pitch]
+ *                                                   + sum_s sum_tap sum_bin B_s[p + off(tap), bin] Z_s[bin][tap][co]
+ *      with Z_s = P_s . W_s^T formed in bin space by a small GEMM (vspw_bgemm over vspw_ppm_weight_slices' operand). ---- */
+/* wp[s][tap][co][c] = w_oihw[co][c_off + s*cp + c][tap], s < n_slices: the pyramid slices of the conv weight, c contiguous */
+int vspw_ppm_weight_slices(const float* w_oihw, float* wp, int32_t cout, int32_t cin_total, int32_t kh, int32_t kw,
+                           int32_t c_off, int32_t cp, int32_t n_slices, void* stream);
+/* y[n][h][w][cout] += pyramid part; z_host[i] = device pointer of Z_i [n][s_i*s_i][k*k][cout] (host array of n_scales
+ * pointers).  ch_sum / ch_sqsum (nullable, accumulated into): per-channel sum / sum of squares of the FINAL y. */
+int vspw_ppm_pyramid_fwd(float* y, const float* const* z_host, const int32_t* scales_host, int32_t n_scales, int32_t n,
+                         int32_t h, int32_t w, int32_t cout, int32_t k, int32_t pad, int32_t dil, double* ch_sum,
+                         double* ch_sqsum, void* stream);
+/* dz_host[i] (zeroed inside) = dZ_i from dy[n][h][w][cout]: the transposed gather */
+int vspw_ppm_pyramid_bwd(const float* dy, float* const* dz_host, const int32_t* scales_host, int32_t n_scales, int32_t n,
+                         int32_t h, int32_t w, int32_t cout, int32_t k, int32_t pad, int32_t dil, void* stream);
+
 /* ---- batch norm (+ReLU, +residual, +Dropout2d channel mask)
  *      models/sync_batchnorm/batchnorm.py:68-73 (F.batch_norm), :133-150; resnet.py:72-92 ---- */
 /* per-channel sum / sum of squares over `pixels` rows of C channels (double accumulators, caller
@@ -145,10 +164,11 @@ int vspw_bn_fold_eval(const float* gamma, const float* beta, const float* runnin
                       int32_t c, void* stream);
 /* out = relu?(bn(y) + residual?) * chan_scale?[n][c]; bn(y) = (y-mean)*scale + beta when mean is
  * non-null (centred, F.batch_norm's form), else y*scale + shift.  Outputs: fp32 `out` and/or the bf16 (hi, lo)
- * planes the tcgen05 convs consume; `out` may be null when every consumer reads the planes */
+ * planes the tcgen05 convs consume; `out` may be null when every consumer reads the planes.  The residual comes as fp32
+ * (`residual`) or, for a block output that was never stored in fp32, as its planes (`residual_hi` [+ `residual_lo`]). */
 int vspw_bn_act_fwd(const float* y, const float* scale, const float* shift, const float* mean,
-                    const float* beta, const float* residual,
-                    const float* chan_scale, int32_t relu, float* out, uint16_t* out_hi,
+                    const float* beta, const float* residual, const uint16_t* residual_hi,
+                    const uint16_t* residual_lo, const float* chan_scale, int32_t relu, float* out, uint16_t* out_hi,
                     uint16_t* out_lo, size_t pixels, int32_t c, size_t pixels_per_image,
                     void* stream);
 /* train mode in ONE launch: vspw_bn_finalize_train (same arithmetic, same outputs mean/invstd, same running-statistics
@@ -156,7 +176,8 @@ int vspw_bn_act_fwd(const float* y, const float* scale, const float* shift, cons
 int vspw_bn_train_fwd(const float* y, const double* sum, const double* sqsum, double count,
                       const float* gamma, const float* beta, float eps, float momentum,
                       float* running_mean, float* running_var, float* mean, float* invstd,
-                      int32_t clamp_mode, const float* residual, const float* chan_scale, int32_t relu,
+                      int32_t clamp_mode, const float* residual, const uint16_t* residual_hi,
+                      const uint16_t* residual_lo, const float* chan_scale, int32_t relu,
                       float* out, uint16_t* out_hi, uint16_t* out_lo, size_t pixels, int32_t c,
                       size_t pixels_per_image, void* stream);
 /* backward pass 1: g = dout * chan_scale * [out>0]; dbeta = sum g; dgamma = sum g*xhat.  The ReLU mask is read from
@@ -266,6 +287,11 @@ int vspw_bgemm(const float* a, const float* b, float* c, int32_t batch, int32_t 
                int32_t k, int64_t a_bs, int64_t a_rs, int64_t a_cs, int64_t b_bs, int64_t b_rs,
                int64_t b_cs, int64_t c_bs, int64_t c_rs, int64_t c_cs, float alpha, float beta,
                void* stream);
+/* the same product without split-K (no atomics): bit-reproducible, for the inference paths */
+int vspw_bgemm_det(const float* a, const float* b, float* c, int32_t batch, int32_t m, int32_t n,
+                   int32_t k, int64_t a_bs, int64_t a_rs, int64_t a_cs, int64_t b_bs, int64_t b_rs,
+                   int64_t b_cs, int64_t c_bs, int64_t c_rs, int64_t c_cs, float alpha, float beta,
+                   void* stream);
 
 /* ---- optimizer step (train_clip2.py:215-252: torch.optim.SGD, momentum 0.9, per-group lr / weight decay) ----
  * One launch over a DEVICE table of tensors: d = g + wd*p; buf = momentum*buf + d; p -= lr*buf (dampening 0, no Nesterov).

@@ -218,44 +218,47 @@ def run_case(ref, name, spec):
 
 
 def run_mid_case(ref, name, spec):
-    """Train step only: loss, acc, logits, and for EVERY parameter the gradient norm plus a seeded 2048-element sample of the
-    gradient tensor (tcb_oracle.grad_sample_indices).  Also the reference's own fp32 floor: the same step with 1 oneDNN
-    thread instead of 8 (summation order only) — stored so the test can print it next to the CUDA path's distance."""
+    """Train step and frozen-BN step (cfg.TRAIN.fix_bn): loss, acc, logits, and for EVERY parameter the gradient norm plus a
+    seeded 2048-element sample of the gradient tensor (tcb_oracle.grad_sample_indices).  Also the reference's OWN fp32 floor:
+    the same step with 1 oneDNN thread instead of 8 (summation order only) — stored per tensor (`gfloor`) so the test can
+    gate the CUDA path relative to it."""
     kind, arch, T, n, H, W, mseed, dseed = spec
     imgs, labs = O.synthetic_clip(T, n, H, W, NUM_CLASS, seed=dseed, block=16)
     rec = {"meta": np.array([T, n, H, W, mseed, dseed])}
-    grads = {}
-    for threads in (8, 1):
-        torch.set_num_threads(threads)
-        m = build(ref, kind, arch, mseed)
-        m.train()
-        no_dropout(m)
-        captured = {}
-        head = m.ppm_conv if kind.startswith("Clip_PSP") else m.head
-        h = head.register_forward_hook(lambda mod, i, o: captured.__setitem__("logits", o.detach()))
-        loss, acc = m(feed(imgs, labs, True))
-        loss.backward()
-        h.remove()
-        grads[threads] = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
-        if threads == 8:
-            rec["train/loss"] = np.float64(loss.item())
-            rec["train/acc"] = np.float64(acc.item())
-            rec["train/logits"] = captured["logits"].numpy().copy()
-    torch.set_num_threads(8)
-    floor = {}
-    for k, g in grads[8].items():
-        g = g.float().reshape(-1)
-        idx = O.grad_sample_indices(g.numel())
-        rec["train/gnorm/" + k] = np.float64(g.double().norm().item())
-        rec["train/gsample/" + k] = g[idx].numpy().copy()
-        gn = g.double().norm().item()
-        floor[k] = float((grads[1][k].reshape(-1).double() - g.double()).norm().item() / gn) if gn > 1e-7 else 0.0
-        rec["train/gfloor/" + k] = np.float64(floor[k])
+    for mode in ("train", "fixbn"):
+        grads = {}
+        for threads in (8, 1):
+            torch.set_num_threads(threads)
+            m = build(ref, kind, arch, mseed)
+            m.train(mode == "train")
+            no_dropout(m)
+            captured = {}
+            head = m.ppm_conv if kind.startswith("Clip_PSP") else m.head
+            h = head.register_forward_hook(lambda mod, i, o: captured.__setitem__("logits", o.detach()))
+            loss, acc = m(feed(imgs, labs, True))
+            loss.backward()
+            h.remove()
+            grads[threads] = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+            if threads == 8:
+                rec[mode + "/loss"] = np.float64(loss.item())
+                rec[mode + "/acc"] = np.float64(acc.item())
+                rec[mode + "/logits"] = captured["logits"].numpy().copy()
+        torch.set_num_threads(8)
+        floor = {}
+        for k, g in grads[8].items():
+            g = g.float().reshape(-1)
+            idx = O.grad_sample_indices(g.numel())
+            rec[mode + "/gnorm/" + k] = np.float64(g.double().norm().item())
+            rec[mode + "/gsample/" + k] = g[idx].numpy().copy()
+            gn = g.double().norm().item()
+            floor[k] = float((grads[1][k].reshape(-1).double() - g.double()).norm().item() / gn) if gn > 1e-7 else 0.0
+            rec[mode + "/gfloor/" + k] = np.float64(floor[k])
+        worst = max(floor.items(), key=lambda kv: kv[1])
+        print(f"{name}/{mode}: loss={rec[mode + '/loss']:.6f}; reference fp32 floor (1 vs 8 threads) worst rel-L2 "
+              f"{worst[1]:.2e} ({worst[0]}), median {float(np.median(list(floor.values()))):.2e}")
     path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, **rec)
-    worst = max(floor.items(), key=lambda kv: kv[1])
-    print(f"{name}: loss={rec['train/loss']:.6f} acc={rec['train/acc']:.6f}; reference fp32 floor (1 vs 8 threads) worst rel-L2 "
-          f"{worst[1]:.2e} ({worst[0]}), median {float(np.median(list(floor.values()))):.2e} -> {os.path.getsize(path) / 1024:.0f} KiB")
+    print(f"{name} -> {os.path.getsize(path) / 1024:.0f} KiB")
 
 
 def bn_formula_pin():

@@ -214,3 +214,25 @@ def test_shard_clips_errors():
     assert P.shard_clips(16, 8, 3) == (6, 8)
     with pytest.raises(ValueError):
         P.shard_clips(10, 4, 0)
+
+
+def test_reference_optimizer_checkpoint_with_duplicate_params_is_remapped():
+    """a reference opt_epoch_E.pth repeats every parameter per group (quirk Q10); resume must map its
+    momentum buffers onto the de-duplicated groups instead of failing on the group-size mismatch."""
+    import train_clip2 as T
+    torch.manual_seed(0)
+    a, b, c = (torch.nn.Parameter(torch.randn(3)) for _ in range(3))
+    opt = torch.optim.SGD([{"params": [a, b], "lr": 0.1}, {"params": [c], "lr": 1.0}], lr=0.1, momentum=0.9)
+    # what torch writes for the reference's groups [a, b, a, b] and [c, c, c]: positions counted with repeats
+    bufs = {0: torch.full((3,), 1.0), 1: torch.full((3,), 2.0), 4: torch.full((3,), 3.0)}
+    ref = {"state": {k: {"momentum_buffer": v} for k, v in bufs.items()},
+           "param_groups": [dict(opt.state_dict()["param_groups"][0], params=[0, 1, 0, 1]),
+                            dict(opt.state_dict()["param_groups"][1], params=[4, 4, 4])]}
+    opt.load_state_dict(T.remap_reference_optimizer_state(ref, opt))
+    assert torch.equal(opt.state[a]["momentum_buffer"], bufs[0]) and torch.equal(opt.state[b]["momentum_buffer"], bufs[1])
+    assert torch.equal(opt.state[c]["momentum_buffer"], bufs[4])
+    own = opt.state_dict()
+    assert T.remap_reference_optimizer_state(own, opt) is own  # our own checkpoints pass through untouched
+    bad = {"state": {}, "param_groups": [dict(own["param_groups"][0], params=[0, 1, 2, 0]), own["param_groups"][1]]}
+    with pytest.raises(ValueError, match="distinct parameters"):
+        T.remap_reference_optimizer_state(bad, opt)

@@ -473,3 +473,47 @@ def test_fused_sgd_matches_torch_sgd(E):
     od.load_state_dict(ob.state_dict())
     with pytest.raises(NotImplementedError):
         FusedSGD(pb, lr=0.1, momentum=0.9, nesterov=True)
+
+
+@pytest.mark.parametrize("n,h,w,c0,cp,co,k", [(2, 13, 17, 128, 64, 64, 3), (3, 11, 23, 64, 128, 192, 3), (2, 60, 107, 2048, 512, 512, 3),
+                                              (2, 16, 16, 128, 64, 128, 1)])
+def test_ppm_conv_fused_matches_concat_conv(E, n, h, w, c0, cp, co, k):
+    """conv(cat([x] + [bilinear_up(P_s)]), W) without the concat (csrc/ppm.cu, PPM_conv.forward clip_psp.py:45-56): forward,
+    BN statistics of the output, and the gradients of x, every P_s and W against torch in fp64 (F.interpolate + cat + conv2d).
+    (2, 60, 107, 2048, 512 -> 512) is the head of BASELINE configs[1]."""
+    scales = (1, 2, 3, 6)
+    pad = (k - 1) // 2
+    g = torch.Generator(device="cuda").manual_seed(n * 1000 + h)
+    x = torch.randn(n, c0, h, w, generator=g, device="cuda")
+    ps = [torch.randn(n, cp, s, s, generator=g, device="cuda") for s in scales]
+    ctot = c0 + len(scales) * cp
+    wt = torch.randn(co, ctot, k, k, generator=g, device="cuda") / (ctot * k * k) ** 0.5
+    xr = x.double().requires_grad_(True)
+    pr = [p.double().requires_grad_(True) for p in ps]
+    wr = wt.double().requires_grad_(True)
+    cat = torch.cat([xr] + [F.interpolate(p, size=(h, w), mode="bilinear", align_corners=False) for p in pr], 1)
+    yr = F.conv2d(cat, wr, None, 1, pad, 1)
+    gy = torch.randn(n, co, h, w, generator=g, device="cuda")
+    yr.backward(gy.double())
+
+    with E.precision("bf16x3"):
+        assert E.ppm_fused_supported((n, h, w, c0), [(n, s, s, cp) for s in scales], (co, ctot, k, k), pad, 1)
+        tape = E.Tape(True)
+        wp = torch.nn.Parameter(wt.clone())
+        xv = E.Var(nhwc(x), needs_grad=True)
+        pv = [E.Var(nhwc(p), needs_grad=True) for p in ps]
+        yv = E.ppm_conv_fused(tape, xv, pv, wp, pad, 1, want_stats=True)
+        yv.grad = nhwc(gy)
+        tape.backward()
+    torch.cuda.synchronize()
+    assert C.rel_err(nchw(yv.data).cpu(), yr.detach().cpu()) <= 1e-4
+    yd = yv.data.double().reshape(-1, co)
+    assert C.rel_err(yv.stats[0].cpu(), yd.sum(0).cpu()) <= 1e-5 and C.rel_err(yv.stats[1].cpu(), (yd * yd).sum(0).cpu()) <= 1e-5
+    assert C.rel_err(nchw(xv.grad).cpu(), xr.grad.cpu()) <= 1e-4
+    for a, b, s in zip(pv, pr, scales):
+        assert C.rel_err(nchw(a.grad).cpu(), b.grad.cpu()) <= 1e-4, s
+    dw = tape.param(wp).grad
+    e_base = C.rel_err(dw[:, :c0].cpu(), wr.grad[:, :c0].cpu())
+    e_pyr = C.rel_err(dw[:, c0:].cpu(), wr.grad[:, c0:].cpu())
+    print(f"ppm fused {n}x{h}x{w} {c0}+4x{cp}->{co} k{k}: dW base {e_base:.2e} pyramid {e_pyr:.2e}")
+    assert e_base <= 1e-4 and e_pyr <= 1e-4

@@ -63,6 +63,42 @@ class ThreadGroup:
             self.calls += 1
 
 
+def test_peer_exchange_kernel_three_ranks_on_one_device(E):
+    """csrc/peer.cu on ONE GPU: three 'ranks' = three inboxes of this process, one stream each (the kernels of one exchange
+    must be co-resident, as they are on three GPUs).  Integer-valued fp64 vectors: the totals are exact and must be identical
+    on every rank; 12 exchanges wrap the 4-slot ring three times."""
+    import ctypes
+    from cvpr2021_vspw_implement_b200._lib import lib
+    os.environ.setdefault("VSPW_PEER_TIMEOUT_S", "20")
+    world, ring, max_elems, n = 3, 4, 4096, 3000
+    dll = lib.dll()
+    nbytes = int(dll.vspw_peer_inbox_bytes(world, ring, max_elems))
+    ptrs = []
+    for _ in range(world):
+        p, h = ctypes.c_void_p(), (ctypes.c_uint8 * 64)()
+        lib.call("vspw_peer_alloc", nbytes, ctypes.byref(p), h)
+        ptrs.append(p)
+    bases = (ctypes.c_uint64 * world)(*[p.value for p in ptrs])
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    base = torch.arange(n, device="cuda", dtype=torch.float64) + 1
+    vecs = [base * (r + 1) for r in range(world)]
+    torch.cuda.synchronize()
+    try:
+        for seq in range(1, 13):
+            for r in range(world):
+                lib.call("vspw_peer_allreduce_f64", ctypes.c_void_p(vecs[r].data_ptr()), n, bases, world, r, ctypes.c_uint64(seq), ring,
+                         max_elems, ctypes.c_void_p(streams[r].cuda_stream))
+        torch.cuda.synchronize()
+        # after the first exchange every rank holds 6*base; each further exchange multiplies by 3
+        want = base * 6 * 3 ** 11
+        for r in range(world):
+            assert torch.equal(vecs[r], want), r
+    finally:
+        torch.cuda.synchronize()
+        for p in ptrs:
+            lib.call("vspw_peer_free", p)
+
+
 def _global_clip(n_clips, seed=41):
     # no ignore labels: every rank then has the same number of valid pixels and the mean of the rank means IS the global mean
     return O.synthetic_clip(T, n_clips, H, W, C.NUM_CLASS, seed=seed, block=16, ignore_frac=0.0)
@@ -129,17 +165,21 @@ def test_two_emulated_ranks_equal_the_single_device_global_batch(E, kind, prec, 
             continue
         g = sum(x.double() for x in gs) / world  # GradBucket.all_reduce_mean
         rn = float(g_ref.double().norm())
-        if rn < 1e-7:
-            continue
+        if rn < 1e-7 or (name.endswith(".0.bias") or name.endswith(".3.bias")) and "f_" in name or name in ("conv_3x3.0.bias", "dsn_head.0.bias",
+                                                                                                   "spatial_ocr_head.conv_bn_dropout.0.bias"):
+            continue  # conv biases in front of a train-mode BN: the true gradient is exactly zero, both sides hold rounding noise
         e = float((g - g_ref.double()).norm() / rn)
         checked += 1
         if e > worst[0]:
             worst = (e, name)
         if name.endswith(("bn1.weight", "bn1.bias", "bn3.weight", "bn3.bias", ".1.weight", ".1.bias")):
             # BN affine parameters: the advisor's round-1 finding was a factor `world` here
-            assert e <= 2e-2, (name, e)
+            assert e <= (1e-4 if prec == "fp32" else 5e-2), (name, e)
     print(f"{kind}/{prec}/clamp={clamp}: loss {loss2:.6f} vs {ref_loss:.6f}; {checked} gradient tensors, worst rel-L2 {worst[0]:.2e} ({worst[1]})")
-    assert checked > 100 and worst[0] <= (3e-3 if prec == "fp32" else 1e-2), worst
+    # fp32 arm: the two runs differ by summation order only.  bf16x3: the hi/lo split of an activation depends on the last bit of
+    # the BN statistics, so the two runs differ by 1e-6 in the forward and by the ReLU-flip floor in the gradients (see
+    # test_gpu_models.py::test_mid_size_gradients_match_reference_per_tensor); a wrong world-size factor would show as >= 0.5
+    assert checked > 100 and worst[0] <= (1e-4 if prec == "fp32" else 5e-2), worst
     # running statistics: global mean / unbiased global variance on every rank
     sd_ref = ref_m.state_dict()
     for r in range(world):

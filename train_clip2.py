@@ -102,8 +102,12 @@ def _params(gen, seen, keep_duplicates):
 
 def create_optimizers(model, cfg, args):
     """SGD with the reference's four parameter groups (train_clip2.py:215-236).  The reference's generators yield
-    every parameter 2-5 times (quirk Q10); by default the duplicates are dropped (one update per step), and
-    ``--keep_duplicate_params True`` passes them through unchanged for trajectory parity with the reference."""
+    every parameter 2-5 times (quirk Q10).  By default the duplicates are dropped: ONE update per parameter per step.  That is
+    a deliberate difference in the training trajectory — under torch 1.3 (no duplicate check) the reference applies the SGD
+    update k times per step to a parameter yielded k times, i.e. an effective learning rate of ~k x lr with compounding
+    momentum; torch >= 2 refuses such groups in its fused/foreach paths.  ``--keep_duplicate_params True`` passes the repeats
+    through unchanged (torch.optim.SGD, the reference's trajectory and optimizer-checkpoint layout); without it a reference
+    ``opt_epoch_E.pth`` is remapped onto the de-duplicated groups on resume (`remap_reference_optimizer_state`)."""
     seen, kd = set(), args.keep_duplicate_params
     wd = cfg.TRAIN.weight_decay
     if args.fix:
@@ -118,6 +122,35 @@ def create_optimizers(model, cfg, args):
         from cvpr2021_vspw_implement_b200.optim import FusedSGD  # same update rule and state_dict, one launch per step
         return FusedSGD(groups, lr=args.lr, momentum=cfg.TRAIN.beta1, weight_decay=wd)
     return torch.optim.SGD(groups, lr=args.lr, momentum=cfg.TRAIN.beta1, weight_decay=wd)
+
+
+def remap_reference_optimizer_state(state, optimizer):
+    """Make an ``opt_epoch_E.pth`` written by the REFERENCE loadable into this entry point's de-duplicated optimizer.
+
+    The reference's parameter groups repeat every parameter 2-5 times (quirk Q10), and torch's `Optimizer.state_dict()` keeps
+    those repeats in ``param_groups[i]['params']`` (positions are counted WITH the repeats: [0, 1, 0, 1] then the next group
+    starts at 4; torch 1.3 stored `id(p)` values instead of positions — any hashable key works here).  The momentum buffers
+    are keyed by the first key of each parameter.  Mapping: the k-th DISTINCT key of reference group g <-> the k-th parameter
+    of our group g.  A state dict without repeats (one written by this entry point) is returned unchanged."""
+    groups = state["param_groups"]
+    ours = optimizer.state_dict()["param_groups"]
+    if len(groups) != len(ours):
+        raise ValueError(f"optimizer checkpoint has {len(groups)} parameter groups, this run has {len(ours)} "
+                         f"(was it written with a different --fix setting?)")
+    if all(len(set(g["params"])) == len(g["params"]) for g in groups) and [len(g["params"]) for g in groups] == [len(g["params"]) for g in ours]:
+        return state
+    key_map, new_groups = {}, []
+    for g_ref, g_our in zip(groups, ours):
+        distinct = list(dict.fromkeys(g_ref["params"]))
+        if len(distinct) != len(g_our["params"]):
+            raise ValueError(f"optimizer checkpoint group holds {len(distinct)} distinct parameters, this run's group {len(g_our['params'])}: "
+                             f"not the same model / --method; with --keep_duplicate_params True the file is loaded as it is")
+        key_map.update(dict(zip(distinct, g_our["params"])))
+        ng = dict(g_ref)
+        ng["params"] = list(g_our["params"])
+        new_groups.append(ng)
+    new_state = {key_map[k]: v for k, v in state["state"].items() if k in key_map}
+    return {"state": new_state, "param_groups": new_groups}
 
 
 def adjust_learning_rate(optimizer, cur_iter, cfg, max_iters, args):
@@ -181,7 +214,10 @@ def main(cfg, args):
         to_load = torch.load(os.path.join('./resume', 'model_epoch_{}.pth'.format(args.resume_epoch)), map_location=device)
         segmentation_module.load_state_dict(OrderedDict((k[7:], v) for k, v in to_load.items()))  # strip 'module.' (:350-353)
         cfg.TRAIN.start_epoch = args.resume_epoch
-        optimizer.load_state_dict(torch.load(os.path.join('./resume', 'opt_epoch_{}.pth'.format(args.resume_epoch)), map_location=device))
+        opt_state = torch.load(os.path.join('./resume', 'opt_epoch_{}.pth'.format(args.resume_epoch)), map_location=device)
+        if not args.keep_duplicate_params:  # a reference checkpoint repeats every parameter 2-5 times per group (quirk Q10)
+            opt_state = remap_reference_optimizer_state(opt_state, optimizer)
+        optimizer.load_state_dict(opt_state)
         print('resume from epoch {}'.format(args.resume_epoch))
     P.broadcast_parameters(segmentation_module)
     bucket = P.GradBucket(segmentation_module.parameters())
