@@ -29,7 +29,13 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
 
 def test_conv_desc_matches_header_layout():
     from cvpr2021_vspw_implement_b200._lib import ConvDesc
-    assert ctypes.sizeof(ConvDesc) == 13 * 4
+    # 13 int32 geometry fields + cin_pitch (the weight's channel pitch of a conv over a channel concat, 0 = cin)
+    assert ctypes.sizeof(ConvDesc) == 14 * 4
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "vspw_b200.h")).read()
+    body = hdr[hdr.index("typedef struct vspw_conv_desc {"):hdr.index("} vspw_conv_desc;")]
+    fields = [f.strip() for decl in re.findall(r"int32_t ([^;]+);", body) for f in decl.split(",")]
+    assert fields == [f for f, _ in ConvDesc._fields_]
 
 
 def test_argument_errors_surface_as_exceptions_without_a_gpu():
