@@ -67,6 +67,9 @@ _SIGNATURES = {
     "vspw_softmax_strided_bwd": [_c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_sz, _c_int, _c_sz, _c_f, _c_vp],
     "vspw_bgemm": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int] + [_c_i64] * 9 + [_c_f, _c_f, _c_vp],
     "vspw_bgemm_det": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int] + [_c_i64] * 9 + [_c_f, _c_f, _c_vp],
+    "vspw_ocr_attention_fwd_tc": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_f, _c_vp],
+    "vspw_ocr_gather_tc": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp],
+    "vspw_ocr_region_planes": [_c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_f, _c_vp],
     "vspw_vc_counts": [_c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_vp, _c_vp],
     "vspw_sgd_momentum_step": [_c_vp, _c_vp, _c_vp, _c_int, _c_f, _c_vp],
     "vspw_confusion_add": [_c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_vp],
@@ -81,7 +84,8 @@ _SIGNATURES = {
 }
 
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["vspw_last_error", "vspw_version", "vspw_tcb_pool_workspace_floats", "vspw_sgd_chunk_elems",
-                                                   "vspw_conv_weight_prep_tile", "vspw_peer_inbox_bytes"])
+                                                   "vspw_conv_weight_prep_tile", "vspw_peer_inbox_bytes",
+                                                   "vspw_ocr_attention_workspace_bytes"])
 
 
 class VspwError(RuntimeError):
@@ -115,6 +119,8 @@ class _Lib:
                     dll.vspw_sgd_chunk_elems.argtypes = []
                     dll.vspw_conv_weight_prep_tile.restype = ctypes.c_int32
                     dll.vspw_conv_weight_prep_tile.argtypes = [_c_int] * 4
+                    dll.vspw_ocr_attention_workspace_bytes.restype = ctypes.c_size_t
+                    dll.vspw_ocr_attention_workspace_bytes.argtypes = [_c_int]
                     dll.vspw_peer_inbox_bytes.restype = ctypes.c_size_t
                     dll.vspw_peer_inbox_bytes.argtypes = [_c_int, _c_int, _c_int]
                     dll.vspw_tcb_pool_workspace_floats.restype = ctypes.c_size_t

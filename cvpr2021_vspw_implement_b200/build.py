@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libvspw_b200.so")
-SOURCES = ["layout.cu", "conv_simt.cu", "conv_tc.cu", "bn.cu", "pool.cu", "loss.cu", "ocr.cu", "optim.cu", "peer.cu", "ppm.cu"]
+SOURCES = ["layout.cu", "conv_simt.cu", "conv_tc.cu", "bn.cu", "pool.cu", "loss.cu", "ocr.cu", "ocr_tc.cu", "optim.cu", "peer.cu", "ppm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

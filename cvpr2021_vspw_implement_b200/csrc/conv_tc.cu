@@ -20,165 +20,16 @@
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA), tmem full/empty mbarriers (MMA <-> epilogue).
 // Reference call sites replaced: the stride-1 nn.Conv2d of models/resnet.py:61-66 (layer1..4), the PPM / deepsup /
 // OCR head convs (clip_psp.py:35-41,74-79; clip_ocr.py:43,56-62) and their autograd backward.
-#include "common.cuh"
-#include <cuda.h>
-#include <mutex>
+#include "tc_common.cuh"
 #include <stdlib.h>
 
 using namespace vspw;
+using namespace vspw::tc;
 
 namespace {
 
 constexpr int BM = 128;        // pixels per tile (UMMA M)
-constexpr int BK = 64;         // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int UMMA_K = 16;
 constexpr int kThreads = 192;  // 6 warps
-constexpr uint32_t kSpinLimit = 1u << 27;
-
-// ---------------------------------------------------------------------------------------------------------
-// PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// 1024-byte alignment (SWIZZLE_128B atoms) by OFFSET on the __shared__ array: rounding the pointer up through uintptr_t makes
-// the compiler forget the address space, and every staging access of the epilogue becomes a generic LD.E/ST.E that cannot be
-// reordered across the global stores (ncu source page, r1c: LD.E -> STG.E chains, generic ATOM with a run-time space check).
-__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* smem_raw) {
-  return smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-}
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  for (uint32_t spin = 0; !done; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (spin > kSpinLimit) __trap();  // a protocol bug must fail loudly instead of hanging the GPU
-  }
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// ---- thread-block-cluster helpers (cta_group::2 pair) ----
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta_rank) {  // same offset in CTA `cta_rank`'s smem
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-template <int COLS>
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-template <int COLS>
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
-}
-
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_bf16(uint64_t desc_a, uint64_t desc_b, uint32_t tmem_d, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory operand descriptor (cute::UMMA::SmemDescriptor):
-//   [0,14) start address >> 4, [16,30) LBO >> 4 (=1, unused for swizzled K-major), [32,46) SBO >> 4 (8 rows x 128 B
-//   = 1024 B), [46,48) version = 1 (Blackwell), [61,64) layout type = 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// MN-major, SWIZZLE_128B: rows of 64 MN-elements (128 B), 8 K-rows per 1024-B atom.
-//   LBO = byte distance between 64-element MN blocks, SBO = byte distance between 8-row K groups (1024 B).
-__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
-// cute::UMMA::InstrDescriptor for kind::f16: c_format F32 (1) @4, a/b format BF16 (1) @7/@10, a/b major @15/@16
-// (0 = K-major, 1 = MN-major), N>>3 @17, M>>4 @24.
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-
 // ---------------------------------------------------------------------------------------------------------
 struct ConvTcParams {
   float* out;          // [N][H][W][Nout] fp32
@@ -692,55 +543,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// host side: tensor maps through the driver entry point (no link-time dependency on libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  });
-  return fn;
-}
-
-// bf16 NHWC activation planes: dims (C, W, H, N), box (64, bw, bh, 1), 128-byte swizzle, zero OOB fill
-int make_act_map(CUtensorMap* m, const void* base, int n, int h, int w, int c, int bw, int bh, const char* who, int stride = 1) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) { set_error("%s: cuTensorMapEncodeTiled entry point unavailable", who); return VSPW_ERR_CUDA; }
-  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
-  // stride 2: the box spans (b-1)*2+1 input pixels per axis and TMA keeps every second one -> bw x bh pixels land densely
-  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)((bw - 1) * stride + 1), (cuuint32_t)((bh - 1) * stride + 1), 1};
-  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(activation) failed with %d", who, (int)r); return VSPW_ERR_CUDA; }
-  return VSPW_OK;
-}
-
-// bf16 row-major matrix [rows][cols] (cols contiguous): dims (cols, rows), box (box_cols, box_rows)
-int make_mat_map(CUtensorMap* m, const void* base, long long rows, long long cols, int box_cols, int box_rows, const char* who) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) { set_error("%s: cuTensorMapEncodeTiled entry point unavailable", who); return VSPW_ERR_CUDA; }
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(matrix) failed with %d", who, (int)r); return VSPW_ERR_CUDA; }
-  return VSPW_OK;
-}
-
 // pixel patch bw x bh (bw*bh == 128) with the least padding waste on an h x w map
 void pick_patch(int h, int w, int& bw, int& bh) {
   const int cand[8][2] = {{16, 8}, {8, 16}, {32, 4}, {4, 32}, {64, 2}, {2, 64}, {128, 1}, {1, 128}};
@@ -1246,4 +1048,52 @@ extern "C" int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_h
   }
   wgrad_tc_kernel<<<(unsigned)grid, kThreads, WG_SMEM, st>>>(mdy_hi, mdy_lo, mx_hi, mx_lo, p);
   return check_launch(who);
+}
+
+// Region gather of TCB-OCR on the weight-gradient kernel (SpatialTemporalGather_Module.forward, spatial_ocr_block.py:97-109):
+//   ctx[b][k][c] = sum_t sum_p P[t*n + b][p][k] * F[t*n + b][p][c]      (P already carries the 1/T of the temporal mean)
+// = the "dW" of a 1x1 conv whose dy is P (classes padded to 128 channels) and whose x is F, accumulated over the T frames of
+// clip b: image stride n in both tensor maps.  One launch per clip; split-K over the T*hw pixels with red.global.add.
+extern "C" int vspw_ocr_gather_tc(const uint16_t* p_hi, const uint16_t* p_lo, const uint16_t* f_hi, const uint16_t* f_lo, float* ctx,
+                                  int32_t t_frames, int32_t n_clips, int32_t hw, int32_t classes, int32_t c, void* stream) {
+  const char* who = "vspw_ocr_gather_tc";
+  VSPW_REQUIRE(p_hi && f_hi && ctx, "%s: null pointer", who);
+  VSPW_REQUIRE((p_lo == nullptr) == (f_lo == nullptr), "%s: lo planes go together", who);
+  VSPW_REQUIRE(classes >= 1 && classes <= 128 && c % 128 == 0 && t_frames > 0 && n_clips > 0 && hw > 0, "%s: bad dims", who);
+  const int x3 = p_lo != nullptr;
+  cudaStream_t st = as_stream(stream);
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM); });
+  if (attr_err != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(attr_err)); return VSPW_ERR_CUDA; }
+  cudaError_t e = cudaMemsetAsync(ctx, 0, (size_t)n_clips * classes * c * sizeof(float), st);
+  if (e != cudaSuccess) { set_error("%s: memset: %s", who, cudaGetErrorString(e)); return VSPW_ERR_CUDA; }
+  for (int b = 0; b < n_clips; ++b) {
+    WgradTcParams p;
+    p.dw = ctx + (size_t)b * classes * c; p.dw_pitch = c;
+    p.N = t_frames; p.H = 1; p.W = hw; p.Cin = c; p.Cout = classes;
+    p.taps_w = 1; p.off0 = 0; p.step = 1; p.stride = 1; p.x3 = x3; p.n64 = 0;
+    pick_patch64(p.H, p.W, p.bw, p.bh);
+    p.tiles_x = (p.W + p.bw - 1) / p.bw;
+    p.tiles_y = (p.H + p.bh - 1) / p.bh;
+    p.tiles_co = 1;
+    p.tiles_ci = c / 128;
+    const long long tiles = p.tiles_ci;
+    const int total_patches = p.N * p.tiles_y * p.tiles_x;
+    int splits = (int)((2 * num_sms()) / (tiles * n_clips));
+    if (splits < 1) splits = 1;
+    if (splits > total_patches) splits = total_patches;
+    p.chunk = (total_patches + splits - 1) / splits;
+    p.splits = (total_patches + p.chunk - 1) / p.chunk;
+    CUtensorMap mp_hi, mp_lo, mf_hi, mf_lo;
+    int rc;
+    const long long ps = (long long)n_clips * hw * 128, fs = (long long)n_clips * hw * c;
+    if ((rc = make_act_map(&mp_hi, p_hi + (size_t)b * hw * 128, p.N, 1, hw, 128, p.bw, p.bh, who, 1, ps))) return rc;
+    if ((rc = make_act_map(&mp_lo, (x3 ? p_lo : p_hi) + (size_t)b * hw * 128, p.N, 1, hw, 128, p.bw, p.bh, who, 1, ps))) return rc;
+    if ((rc = make_act_map(&mf_hi, f_hi + (size_t)b * hw * c, p.N, 1, hw, c, p.bw, p.bh, who, 1, fs))) return rc;
+    if ((rc = make_act_map(&mf_lo, (x3 ? f_lo : f_hi) + (size_t)b * hw * c, p.N, 1, hw, c, p.bw, p.bh, who, 1, fs))) return rc;
+    wgrad_tc_kernel<<<(unsigned)(tiles * p.splits), kThreads, WG_SMEM, st>>>(mp_hi, mp_lo, mf_hi, mf_lo, p);
+    if ((rc = check_launch(who))) return rc;
+  }
+  return VSPW_OK;
 }

@@ -1276,6 +1276,12 @@ def up_softmax(logits, H, W, want_pred=False):
 
 # ------------------------------------------------------------------------------------------------
 # OCR ops
+def _ocr_tc_ok():
+    """The tcgen05 OCR kernels (csrc/ocr_tc.cu) run in the tensor-core precision modes; VSPW_OCR_TC=0 keeps the CUDA-core
+    fp32 GEMMs (A/B timing)."""
+    return _state["precision"] != "fp32" and os.environ.get("VSPW_OCR_TC", "1") != "0"
+
+
 def region_gather(tape, feats, dsn, t_frames, n_clips):
     """SpatialTemporalGather_Module (spatial_ocr_block.py:97-109): per frame softmax over hw of the dsn
     logits, probs[K x hw] . feats[hw x C], mean over the T frames -> context Var (n_clips, K, 1, C)."""
@@ -1288,12 +1294,24 @@ def region_gather(tape, feats, dsn, t_frames, n_clips):
     lib.call("vspw_softmax_strided_fwd", _p(dsn.data), _p(probs), N * k, hw, 1, k, k, hw * k, 1.0, st)
     ctx = torch.empty((n_clips, k, 1, c), device=dev, dtype=torch.float32)
     inv_t = 1.0 / t_frames
-    for t in range(t_frames):
-        pr = probs[t * n_clips:(t + 1) * n_clips]
-        ft = feats.data[t * n_clips:(t + 1) * n_clips]
-        # C[b][i=class][j=ch] = sum_p probs[b][p][i] * feats[b][p][j]
-        lib.call("vspw_bgemm", _p(pr), _p(ft), _p(ctx), n_clips, k, c, hw, hw * k, 1, k, hw * c, c, 1, k * c, c, 1, inv_t,
-                 0.0 if t == 0 else 1.0, st)
+    if _ocr_tc_ok() and k <= 128 and c % 128 == 0:
+        # tcgen05: the gather is the weight-gradient kernel's GEMM (K axis = pixels, both operands channel-contiguous) over
+        # the probability planes (classes padded to 128, 1/T folded in) and the operand planes of feats
+        x3 = _state["precision"] == "bf16x3"
+        ph = torch.empty((N, hw, 128), device=dev, dtype=torch.bfloat16)
+        pl = torch.empty((N, hw, 128), device=dev, dtype=torch.bfloat16) if x3 else None
+        lib.call("vspw_ocr_region_planes", _p(probs), _p(ph), _p(pl), N * hw, k, inv_t, st)
+        fh, fl = _var_planes(feats)
+        with _ConvTimer(2.0 * N * hw * k * c, True):
+            lib.call("vspw_ocr_gather_tc", _p(ph), _p(pl), _p(fh), _p(fl), _p(ctx), t_frames, n_clips, hw, k, c, st)
+        del ph, pl
+    else:
+        for t in range(t_frames):
+            pr = probs[t * n_clips:(t + 1) * n_clips]
+            ft = feats.data[t * n_clips:(t + 1) * n_clips]
+            # C[b][i=class][j=ch] = sum_p probs[b][p][i] * feats[b][p][j]
+            lib.call("vspw_bgemm", _p(pr), _p(ft), _p(ctx), n_clips, k, c, hw, hw * k, 1, k, hw * c, c, 1, k * c, c, 1, inv_t,
+                     0.0 if t == 0 else 1.0, st)
     out = Var(ctx, needs_grad=tape.grad_enabled and (feats.needs_grad or dsn.needs_grad))
 
     def backward():
@@ -1333,17 +1351,35 @@ def object_attention(tape, query, key, value, key_channels):
     hw = h * w
     dev = query.data.device
     st = _stream()
-    raw = torch.empty((n, hw, K), device=dev, dtype=torch.float32)
-    # raw[b][p][i] = sum_c Q[b][p][c] * Key[b][i][c]
-    lib.call("vspw_bgemm", _p(query.data), _p(key.data), _p(raw), n, hw, K, kc, hw * kc, kc, 1, K * kc, 1, kc, hw * K, K, 1, 1.0,
-             0.0, st)
-    sim = torch.empty_like(raw)
     scale = float(key_channels) ** -0.5
-    lib.call("vspw_softmax_strided_fwd", _p(raw), _p(sim), n * hw, K, K, 1, n * hw, 0, scale, st)
+    needs = tape.grad_enabled and (query.needs_grad or key.needs_grad or value.needs_grad)
     ctx = torch.empty((n, h, w, kc), device=dev, dtype=torch.float32)
-    lib.call("vspw_bgemm", _p(sim), _p(value.data), _p(ctx), n, hw, kc, K, hw * K, K, 1, K * kc, kc, 1, hw * kc, kc, 1, 1.0, 0.0,
-             st)
-    out = Var(ctx, needs_grad=tape.grad_enabled and (query.needs_grad or key.needs_grad or value.needs_grad))
+    planes = None
+    if _ocr_tc_ok() and kc == 256 and K <= 128:
+        # ONE tcgen05 kernel: Q.K^T into TMEM, softmax in registers, P as an smem operand, P.V into TMEM; the scores never
+        # touch HBM and `sim` is written only when a backward will read it
+        x3 = _state["precision"] == "bf16x3"
+        qh, ql = _var_planes(query)
+        ws = torch.empty(int(lib.dll().vspw_ocr_attention_workspace_bytes(n)), device=dev, dtype=torch.uint8)
+        sim = torch.empty((n, hw, K), device=dev, dtype=torch.float32) if needs else None
+        chi = torch.empty((n, h, w, kc), device=dev, dtype=torch.bfloat16)
+        clo = torch.empty((n, h, w, kc), device=dev, dtype=torch.bfloat16) if x3 else None
+        with _ConvTimer(4.0 * n * hw * K * kc, True):
+            lib.call("vspw_ocr_attention_fwd_tc", _p(qh), _p(ql), _p(key.data), _p(value.data), _p(ctx), _p(chi), _p(clo), _p(sim), _p(ws),
+                     n, hw, K, kc, scale, st)
+        planes = (chi, clo)
+    else:
+        raw = torch.empty((n, hw, K), device=dev, dtype=torch.float32)
+        # raw[b][p][i] = sum_c Q[b][p][c] * Key[b][i][c]
+        lib.call("vspw_bgemm", _p(query.data), _p(key.data), _p(raw), n, hw, K, kc, hw * kc, kc, 1, K * kc, 1, kc, hw * K, K, 1, 1.0,
+                 0.0, st)
+        sim = torch.empty_like(raw)
+        lib.call("vspw_softmax_strided_fwd", _p(raw), _p(sim), n * hw, K, K, 1, n * hw, 0, scale, st)
+        del raw
+        lib.call("vspw_bgemm", _p(sim), _p(value.data), _p(ctx), n, hw, kc, K, hw * K, K, 1, K * kc, kc, 1, hw * kc, kc, 1, 1.0, 0.0,
+                 st)
+    out = Var(ctx, needs_grad=needs)
+    out.planes = planes
 
     def backward():
         g = out.grad

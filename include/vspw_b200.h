@@ -293,6 +293,25 @@ int vspw_bgemm_det(const float* a, const float* b, float* c, int32_t batch, int3
                    int64_t b_cs, int64_t c_bs, int64_t c_rs, int64_t c_cs, float alpha, float beta,
                    void* stream);
 
+/* tensor-core OCR kernels (csrc/ocr_tc.cu).
+ * vspw_ocr_attention_fwd_tc: the whole pixel->region attention of _ObjectAttentionBlock.forward (spatial_ocr_block.py:258-275)
+ * in ONE kernel: ctx[n][hw][kc] = softmax_regions(scale * Q . K^T) . V with Q given as bf16 (hi, lo) planes [n][hw][kc] (q_lo
+ * null = single-pass bf16), key / value fp32 [n][regions][kc], kc == 256, regions <= 128.  Scores and probabilities stay in
+ * TMEM / shared memory; `sim` (nullable, [n][hw][regions] fp32) is written only when the caller's backward needs it.  ctx goes
+ * out as fp32 and/or as operand planes.  `workspace`: vspw_ocr_attention_workspace_bytes(n) bytes (K/V operand planes). */
+size_t vspw_ocr_attention_workspace_bytes(int32_t n);
+int vspw_ocr_attention_fwd_tc(const uint16_t* q_hi, const uint16_t* q_lo, const float* key, const float* value, float* ctx,
+                              uint16_t* ctx_hi, uint16_t* ctx_lo, float* sim, void* workspace, int32_t n, int32_t hw,
+                              int32_t regions, int32_t kc, float scale, void* stream);
+/* Region gather (SpatialTemporalGather_Module.forward, spatial_ocr_block.py:97-109) on the tcgen05 weight-gradient kernel:
+ * ctx[b][k][ch] = sum_t sum_p P[t*n_clips + b][p][k] * F[t*n_clips + b][p][ch], P = region planes [T*n][hw][128] from
+ * vspw_ocr_region_planes (1/T folded in), F = operand planes of feats [T*n][hw][c]; ctx [n_clips][classes][c] fp32 (zeroed
+ * inside).  lo planes null = single-pass bf16. */
+int vspw_ocr_gather_tc(const uint16_t* p_hi, const uint16_t* p_lo, const uint16_t* f_hi, const uint16_t* f_lo, float* ctx,
+                       int32_t t_frames, int32_t n_clips, int32_t hw, int32_t classes, int32_t c, void* stream);
+/* probs [rows][k] fp32 -> bf16 (hi, lo) planes [rows][128] * scale, columns >= k zero: the A operand of the region gather */
+int vspw_ocr_region_planes(const float* probs, uint16_t* hi, uint16_t* lo, size_t rows, int32_t k, float scale, void* stream);
+
 /* ---- optimizer step (train_clip2.py:215-252: torch.optim.SGD, momentum 0.9, per-group lr / weight decay) ----
  * One launch over a DEVICE table of tensors: d = g + wd*p; buf = momentum*buf + d; p -= lr*buf (dampening 0, no Nesterov).
  * block b works on elements [block_chunk[b]*vspw_sgd_chunk_elems(), +vspw_sgd_chunk_elems()) of tensor block_tensor[b]. */

@@ -33,8 +33,8 @@ def main(out_path):
     peer.all_reduce_sums(t)
     want = (torch.arange(5000, device=dev, dtype=torch.float64) + 1) * sum(r + 1 for r in range(world))
     assert torch.equal(t, want), "PeerSums total differs"
-    for mode, group in (("peer", peer), ("nccl", E.TorchDistGroup())):
-        E.set_precision("bf16x3")
+    for mode, group, prec in (("peer/fp32", peer, "fp32"), ("peer/bf16x3", peer, "bf16x3"), ("nccl/bf16x3", E.TorchDistGroup(), "bf16x3")):
+        E.set_precision(prec)
         # ---- data-parallel step -----------------------------------------------------------------------------------
         m = C.no_dropout(C.build("Clip_PSP", "resnet50dilated", 31).to(dev).train())
         P.broadcast_parameters(m)

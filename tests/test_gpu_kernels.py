@@ -517,3 +517,60 @@ def test_ppm_conv_fused_matches_concat_conv(E, n, h, w, c0, cp, co, k):
     e_pyr = C.rel_err(dw[:, c0:].cpu(), wr.grad[:, c0:].cpu())
     print(f"ppm fused {n}x{h}x{w} {c0}+4x{cp}->{co} k{k}: dW base {e_base:.2e} pyramid {e_pyr:.2e}")
     assert e_base <= 1e-4 and e_pyr <= 1e-4
+
+
+@pytest.mark.parametrize("T,n,h,w,K", [(5, 2, 60, 107, 124), (3, 2, 13, 21, 124), (2, 3, 16, 24, 97)])
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 1e-4), ("bf16", 2e-2)])
+def test_ocr_tensor_core_gather_and_fused_attention(E, T, n, h, w, K, prec, tol):
+    """csrc/ocr_tc.cu at the TCB-OCR geometry (K = 124 regions, 512 feature channels, 256 key channels; 60x107 = BASELINE
+    configs[2]): the region gather on the tcgen05 weight-gradient kernel and the single-kernel pixel->region attention
+    (Q.K^T -> softmax -> .V with scores and probabilities on chip), against torch in fp64; backward through the recorded tape."""
+    c, kc = 512, 256
+    g = torch.Generator(device="cuda").manual_seed(T * 100 + h)
+    feats = torch.randn(T * n, c, h, w, generator=g, device="cuda")
+    dsn = torch.randn(T * n, K, h, w, generator=g, device="cuda") * 2
+    fr, dr = feats.double().requires_grad_(True), dsn.double().requires_grad_(True)
+    ctx = O.region_gather(fr, dr, T)  # (n, c, K, 1)
+    gc = torch.randn(ctx.shape, generator=g, device="cuda")
+    ctx.backward(gc.double())
+    with E.precision(prec):
+        tape = E.Tape(True)
+        fv, dv = E.Var(nhwc(feats), needs_grad=True), E.Var(nhwc(dsn), needs_grad=True)
+        E.conv_profile_begin()
+        cv = E.region_gather(tape, fv, dv, T, n)
+        assert E.conv_profile_end()["tc_launches"] == 1, "the gather must run on tcgen05"
+        e_ctx = C.rel_err(nchw(cv.data).cpu(), ctx.detach().cpu())
+        cv.grad = nhwc(gc)
+        tape.backward()
+    e_df, e_dd = C.rel_err(nchw(fv.grad).cpu(), fr.grad.cpu()), C.rel_err(nchw(dv.grad).cpu(), dr.grad.cpu())
+
+    q = torch.randn(n, kc, h, w, generator=g, device="cuda")
+    key = torch.randn(n, kc, K, 1, generator=g, device="cuda")
+    val = torch.randn(n, kc, K, 1, generator=g, device="cuda")
+    qr, kr, vr = (t.double().requires_grad_(True) for t in (q, key, val))
+    sim = F.softmax(kc ** -0.5 * torch.matmul(qr.reshape(n, kc, -1).permute(0, 2, 1), kr.reshape(n, kc, -1)), dim=-1)
+    out = torch.matmul(sim, vr.reshape(n, kc, -1).permute(0, 2, 1)).permute(0, 2, 1).reshape(n, kc, h, w)
+    go = torch.randn(out.shape, generator=g, device="cuda")
+    out.backward(go.double())
+    with E.precision(prec):
+        tape = E.Tape(True)
+        qv, kv, vv = (E.Var(nhwc(t), needs_grad=True) for t in (q, key, val))
+        E.conv_profile_begin()
+        ov = E.object_attention(tape, qv, kv, vv, kc)
+        assert E.conv_profile_end()["tc_launches"] == 1, "the attention must run as the fused tcgen05 kernel"
+        e_out = C.rel_err(nchw(ov.data).cpu(), out.detach().cpu())
+        # the operand planes the kernel wrote for the f_up conv reproduce its fp32 output
+        hi, lo = ov.planes
+        rec = hi.float() + (lo.float() if lo is not None else 0)
+        assert C.rel_err(rec.cpu(), ov.data.cpu()) <= (2e-5 if lo is not None else 8e-3)
+        ov.grad = nhwc(go)
+        tape.backward()
+    errs = [C.rel_err(nchw(a.grad).cpu(), b.grad.cpu()) for a, b in ((qv, qr), (kv, kr), (vv, vr))]
+    print(f"{prec} T={T} n={n} {h}x{w} K={K}: gather {e_ctx:.2e} (dF {e_df:.2e}, ddsn {e_dd:.2e}); attention {e_out:.2e} (dQ {errs[0]:.2e}, dK {errs[1]:.2e}, dV {errs[2]:.2e})")
+    assert e_ctx <= tol and e_out <= tol
+    assert e_df <= max(tol, 5e-5) and e_dd <= max(tol, 5e-5) and max(errs) <= max(tol, 5e-5)
+    # without gradients (inference) no probability tensor is produced and the result is the same
+    with E.precision(prec), torch.no_grad():
+        tape = E.Tape(False)
+        ov2 = E.object_attention(tape, E.Var(nhwc(q)), E.Var(nhwc(key)), E.Var(nhwc(val)), kc)
+    assert torch.equal(ov2.data, ov.data)

@@ -203,5 +203,7 @@ def test_two_nccl_ranks_equal_the_single_device_global_batch(E, tmp_path):
     res = json.load(open(out))
     for mode, v in res.items():
         print(mode, v)
-        assert v["loss_rel"] <= 2e-5 and v["worst_grad_rel_l2"] <= 1e-2 and v["worst_running"] <= 1e-4, (mode, v)
-        assert v["bn_affine_worst"] <= 2e-2, (mode, v)
+        # fp32 arm: summation order only; bf16x3: the ReLU-flip floor (see test_two_emulated_ranks_*); a world-size factor is >= 0.5
+        gate = 1e-4 if mode.endswith("fp32") else 5e-2
+        assert v["loss_rel"] <= 2e-5 and v["worst_grad_rel_l2"] <= gate and v["worst_running"] <= 1e-4, (mode, v)
+        assert v["bn_affine_worst"] <= gate, (mode, v)
