@@ -1059,6 +1059,30 @@ def ppm_conv_fused(tape, base, pyramids, weight, pad=1, dil=1, want_stats=False)
     return out
 
 
+def upsample_bilinear(tape, x, H, W):
+    """F.interpolate(x, size=(H, W), mode='bilinear', align_corners=False) on an NHWC Var (UPerNet's top-down and fusion
+    branches, models/models.py:1138-1164)."""
+    n, h, w, c = x.shape
+    if (h, w) == (H, W):
+        return x
+    dev = x.data.device
+    y = torch.empty((n, H, W, c), device=dev, dtype=torch.float32)
+    lib.call("vspw_upsample_bilinear_fwd", _p(x.data), n, h, w, c, _p(y), H, W, c, 0, _stream())
+    out = Var(y, needs_grad=tape.grad_enabled and x.needs_grad)
+
+    def backward():
+        g = out.grad
+        out.grad = None
+        if g is None or not x.needs_grad:
+            return
+        dx = torch.empty_like(x.data)
+        lib.call("vspw_upsample_bilinear_bwd", _p(g), H, W, c, 0, _p(dx), n, h, w, c, _stream())
+        x.add_grad(dx)
+
+    tape.record(backward)
+    return out
+
+
 def concat_channels(tape, parts):
     """torch.cat(parts, dim=1) in NHWC (spatial_ocr_block.py:375)."""
     n, h, w, _ = parts[0].shape

@@ -189,8 +189,129 @@ class PPMDeepsup(nn.Module):
         return logits, conv_op(tape, self.conv_last_deepsup_, d)
 
 
-_OUT_OF_SCOPE_DECODERS = ("c1_deepsup", "c1", "ppm", "ppm_deepsup_clip", "ppm_clip", "upernet_lite", "upernet", "deeplab",
-                          "nonlocal2d", "ocrnet_deepsup")
+def conv3x3_bn_relu(in_planes, out_planes, stride=1):
+    """3x3 convolution + BN + relu (reference models.py:658-666)."""
+    return nn.Sequential(nn.Conv2d(in_planes, out_planes, kernel_size=3, stride=stride, padding=1, bias=False),
+                         BatchNorm2d(out_planes), nn.ReLU(inplace=True))
+
+
+def _cbr_graph(tape, seq, x, training, chan_scale=None):
+    """conv -> BN -> ReLU of a `conv3x3_bn_relu`-style Sequential (conv at [0], BN at [1])."""
+    return E.batchnorm_act(tape, conv_op(tape, seq[0], x, seq[1]), seq[1], relu=True, chan_scale=chan_scale, training=training)
+
+
+class C1(nn.Module):
+    """Single 3x3 conv head (reference models.py:862-886)."""
+
+    def __init__(self, num_class=150, fc_dim=2048, use_softmax=False):
+        super().__init__()
+        self.use_softmax = use_softmax
+        self.cbr = conv3x3_bn_relu(fc_dim, fc_dim // 4, 1)
+        self.conv_last_1 = nn.Conv2d(fc_dim // 4, num_class, 1, 1, 0)
+
+    def graph(self, tape, conv_out, training, want_deepsup):
+        if want_deepsup:
+            raise ValueError("the 'c1' decoder returns one prediction: build the SegmentationModule with deep_sup_scale=None")
+        return conv_op(tape, self.conv_last_1, _cbr_graph(tape, self.cbr, conv_out[-1], training)), None
+
+
+class C1DeepSup(nn.Module):
+    """C1 head with deep supervision on the layer3 map (reference models.py:826-858)."""
+
+    def __init__(self, num_class=150, fc_dim=2048, use_softmax=False):
+        super().__init__()
+        self.use_softmax = use_softmax
+        self.cbr = conv3x3_bn_relu(fc_dim, fc_dim // 4, 1)
+        self.cbr_deepsup = conv3x3_bn_relu(fc_dim // 2, fc_dim // 4, 1)
+        self.conv_last_ = nn.Conv2d(fc_dim // 4, num_class, 1, 1, 0)
+        self.conv_last_deepsup_ = nn.Conv2d(fc_dim // 4, num_class, 1, 1, 0)
+
+    def graph(self, tape, conv_out, training, want_deepsup):
+        logits = conv_op(tape, self.conv_last_, _cbr_graph(tape, self.cbr, conv_out[-1], training))
+        if not want_deepsup:
+            return logits, None
+        return logits, conv_op(tape, self.conv_last_deepsup_, _cbr_graph(tape, self.cbr_deepsup, conv_out[-2], training))
+
+
+def _ppm_head(tape, branches, conv_idx, conv5, pool_scales, conv_last, bn_last, training):
+    """Pyramid pooling -> per-scale 1x1 conv + BN + ReLU -> (up-sample, concat, 3x3 conv) as ONE fused op when the tensor-core
+    path can take it (engine.ppm_conv_fused: no up-sampled maps, no concat), else the explicit concat."""
+    n = conv5.shape[0]
+    pooled = E.tcb_pool(tape, conv5, 1, n, pool_scales)  # AdaptiveAvgPool2d(s) of single images = temporal pooling with T=1
+    pyr = [E.batchnorm_act(tape, conv_op(tape, br[conv_idx], p, br[conv_idx + 1]), br[conv_idx + 1], relu=True, training=training)
+           for br, p in zip(branches, pooled)]
+    if E.ppm_fused_supported(conv5.shape, [p.shape for p in pyr], conv_last.weight.shape, conv_last.padding[0], conv_last.dilation[0]):
+        return E.ppm_conv_fused(tape, conv5, pyr, conv_last.weight, conv_last.padding[0], conv_last.dilation[0], want_stats=bool(training))
+    return conv_op(tape, conv_last, E.ppm_concat(tape, conv5, pyr), bn_last)
+
+
+class PPM(nn.Module):
+    """Pyramid pooling decoder without deep supervision (reference models.py:889-935)."""
+
+    def __init__(self, num_class=150, fc_dim=4096, use_softmax=False, pool_scales=(1, 2, 3, 6)):
+        super().__init__()
+        self.use_softmax = use_softmax
+        self.pool_scales = tuple(pool_scales)
+        self.ppm = nn.ModuleList([
+            nn.Sequential(nn.AdaptiveAvgPool2d(s), nn.Conv2d(fc_dim, 512, kernel_size=1, bias=False), BatchNorm2d(512),
+                          nn.ReLU(inplace=True)) for s in pool_scales])
+        self.conv_last = nn.Sequential(
+            nn.Conv2d(fc_dim + len(pool_scales) * 512, 512, kernel_size=3, padding=1, bias=False), BatchNorm2d(512),
+            nn.ReLU(inplace=True), nn.Dropout2d(0.1), nn.Conv2d(512, num_class, kernel_size=1))
+
+    def graph(self, tape, conv_out, training, want_deepsup):
+        if want_deepsup:
+            raise ValueError("the 'ppm' decoder returns one prediction: build the SegmentationModule with deep_sup_scale=None")
+        conv5 = conv_out[-1]
+        y = _ppm_head(tape, self.ppm, 1, conv5, self.pool_scales, self.conv_last[0], self.conv_last[1], training)
+        mask = E.dropout2d_mask(self.conv_last[3].p, y.shape[0], y.shape[3], y.data.device, training and self.conv_last[3].training)
+        x = E.batchnorm_act(tape, y, self.conv_last[1], relu=True, chan_scale=mask, training=training)
+        return conv_op(tape, self.conv_last[4], x), None
+
+
+class UPerNet(nn.Module):
+    """PPM on the top stage + FPN over the four stages (reference models.py:1085-1175)."""
+
+    def __init__(self, num_class=150, fc_dim=4096, use_softmax=False, pool_scales=(1, 2, 3, 6),
+                 fpn_inplanes=(256, 512, 1024, 2048), fpn_dim=256):
+        super().__init__()
+        self.use_softmax = use_softmax
+        self.pool_scales = tuple(pool_scales)
+        self.ppm_pooling = nn.ModuleList([nn.AdaptiveAvgPool2d(s) for s in pool_scales])
+        self.ppm_conv = nn.ModuleList([
+            nn.Sequential(nn.Conv2d(fc_dim, 512, kernel_size=1, bias=False), BatchNorm2d(512), nn.ReLU(inplace=True))
+            for _ in pool_scales])
+        self.ppm_last_conv = conv3x3_bn_relu(fc_dim + len(pool_scales) * 512, fpn_dim, 1)
+        self.fpn_in = nn.ModuleList([
+            nn.Sequential(nn.Conv2d(c, fpn_dim, kernel_size=1, bias=False), BatchNorm2d(fpn_dim), nn.ReLU(inplace=True))
+            for c in fpn_inplanes[:-1]])
+        self.fpn_out = nn.ModuleList([nn.Sequential(conv3x3_bn_relu(fpn_dim, fpn_dim, 1)) for _ in range(len(fpn_inplanes) - 1)])
+        self.conv_last_ = nn.Sequential(conv3x3_bn_relu(len(fpn_inplanes) * fpn_dim, fpn_dim, 1),
+                                        nn.Conv2d(fpn_dim, num_class, kernel_size=1))
+
+    def graph(self, tape, conv_out, training, want_deepsup):
+        if want_deepsup:
+            raise ValueError("the 'upernet' decoders return one prediction: build the SegmentationModule with deep_sup_scale=None")
+        conv5 = conv_out[-1]
+        n, h, w, _ = conv5.shape
+        # NB UPerNet applies the 1x1 conv + BN AFTER the up-sampling (:1131-1134), so its BN statistics are taken over the h x w
+        # map: the branches cannot be evaluated in bin space, the up-sampled maps are materialised as in the reference
+        pooled = E.tcb_pool(tape, conv5, 1, n, self.pool_scales)
+        parts = [conv5] + [_cbr_graph(tape, br, E.upsample_bilinear(tape, p, h, w), training) for br, p in zip(self.ppm_conv, pooled)]
+        f = _cbr_graph(tape, self.ppm_last_conv, E.concat_channels(tape, parts), training)
+        feats = [f]
+        for i in reversed(range(len(conv_out) - 1)):
+            lat = _cbr_graph(tape, self.fpn_in[i], conv_out[i], training)
+            f = E.add_vars(tape, lat, E.upsample_bilinear(tape, f, lat.shape[1], lat.shape[2]))
+            feats.append(_cbr_graph(tape, self.fpn_out[i][0], f, training))
+        feats.reverse()
+        H, W = feats[0].shape[1], feats[0].shape[2]
+        fusion = E.concat_channels(tape, [feats[0]] + [E.upsample_bilinear(tape, t, H, W) for t in feats[1:]])
+        x = _cbr_graph(tape, self.conv_last_[0], fusion, training)
+        return conv_op(tape, self.conv_last_[1], x), None
+
+
+_OUT_OF_SCOPE_DECODERS = ("ppm_deepsup_clip", "ppm_clip", "deeplab", "nonlocal2d")
 _OUT_OF_SCOPE_ENCODERS = ("mobilenetv2dilated", "resnext101", "hrnetv2", "hrnetv2_clip", "hrnetv2_clip2")
 
 
@@ -233,6 +354,19 @@ class ModelBuilder:
         arch = arch.lower()
         if arch == "ppm_deepsup":
             net_decoder = PPMDeepsup(num_class=num_class, fc_dim=fc_dim, use_softmax=use_softmax)
+        elif arch == "c1_deepsup":
+            net_decoder = C1DeepSup(num_class=num_class, fc_dim=fc_dim, use_softmax=use_softmax)
+        elif arch == "c1":
+            net_decoder = C1(num_class=num_class, fc_dim=fc_dim, use_softmax=use_softmax)
+        elif arch == "ppm":
+            net_decoder = PPM(num_class=num_class, fc_dim=fc_dim, use_softmax=use_softmax)
+        elif arch == "upernet_lite":
+            net_decoder = UPerNet(num_class=num_class, fc_dim=fc_dim, use_softmax=use_softmax, fpn_dim=256)
+        elif arch == "upernet":
+            net_decoder = UPerNet(num_class=num_class, fc_dim=fc_dim, use_softmax=use_softmax, fpn_dim=512)
+        elif arch == "ocrnet_deepsup":
+            from .ocrnet import SpatialOCRNet  # image-level OCR head (reference models/ocrnet.py:22-72)
+            net_decoder = SpatialOCRNet(num_class=num_class)
         elif arch in _OUT_OF_SCOPE_DECODERS:
             raise NotImplementedError(f"decoder '{arch}' is outside the VSPW TCB hot path this engine implements")
         else:

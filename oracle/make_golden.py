@@ -35,6 +35,11 @@ CASES = {
     "clip_ocr": ("ClipOCRNet", "resnet50dilated", 3, 2, 49, 65, 13, 306),
     "segmodule_r18": ("SegmentationModule", "resnet18dilated", 1, 2, 49, 65, 14, 307),
     "non_local3d": ("Non_local3d", "resnet50dilated", 3, 2, 49, 65, 15, 308),
+    # image-model family on the same kernels: "Seg/<decoder>/<fc_dim>/<deep_sup_scale or none>"
+    "seg_ocrnet_r50": ("Seg/ocrnet_deepsup/2048/0.4", "resnet50dilated", 1, 2, 49, 65, 21, 311),
+    "seg_upernet_r50": ("Seg/upernet_lite/2048/none", "resnet50", 1, 2, 65, 97, 22, 312),
+    "seg_c1ds_r18": ("Seg/c1_deepsup/512/0.4", "resnet18dilated", 1, 2, 49, 65, 23, 313),
+    "seg_ppm_r18": ("Seg/ppm/512/none", "resnet18dilated", 1, 2, 49, 65, 24, 314),
 }
 # mid-size, well-conditioned train-mode fixtures for the GRADIENT gates (the 49x65 cases above put everything below
 # layer2 on 7x9 maps, where a single ReLU mask flip is 4e-3 of a gradient norm: oracle/NOISE_FLOOR.md)
@@ -63,6 +68,10 @@ def build(ref, kind, arch, seed, **kw):
         m = ref.ClipOCRNet(enc, crit, ns(**kw), deep_sup_scale=0.4)
     elif kind == "Non_local3d":
         m = ref.Non_local3d(ns(**kw), enc, crit)
+    elif kind.startswith("Seg/"):
+        _, dec_arch, fc, ds = kind.split("/")
+        dec = ref.ModelBuilder.build_decoder(dec_arch, fc_dim=int(fc), num_class=NUM_CLASS)
+        m = ref.SegmentationModule(enc, dec, crit, deep_sup_scale=None if ds == "none" else float(ds))
     else:
         dec = ref.ModelBuilder.build_decoder("ppm_deepsup", fc_dim=512, num_class=NUM_CLASS)
         m = ref.SegmentationModule(enc, dec, crit, deep_sup_scale=0.4)
@@ -151,9 +160,14 @@ def run_case(ref, name, spec):
         hooks.append(m.head.register_forward_hook(lambda mod, i, o: captured.__setitem__("logits", o.detach())))
         hooks.append(m.dsn_head.register_forward_hook(lambda mod, i, o: captured.__setitem__("logits_deepsup", o.detach())))
         hooks.append(m.spatial_context_head.register_forward_hook(lambda mod, i, o: captured.__setitem__("context", o.detach())))
+    elif kind.startswith("Seg/"):
+        last = {"ocrnet_deepsup": "head", "upernet_lite": "conv_last_", "upernet": "conv_last_", "c1_deepsup": "conv_last_", "c1": "conv_last_1",
+                "ppm": "conv_last"}[kind.split("/")[1]]
+        hooks.append(getattr(m.decoder, last).register_forward_hook(lambda mod, i, o: captured.__setitem__("logits", o.detach())))
     else:
         hooks.append(m.decoder.conv_last_.register_forward_hook(lambda mod, i, o: captured.__setitem__("logits", o.detach())))
-    loss, acc = m(feed(imgs, labs, True)) if kind != "SegmentationModule" else m({"img_data": imgs[0], "seg_label": labs[0]})
+    single = kind == "SegmentationModule" or kind.startswith("Seg/")
+    loss, acc = m(feed(imgs, labs, True)) if not single else m({"img_data": imgs[0], "seg_label": labs[0]})
     loss.backward()
     for h in hooks:
         h.remove()
@@ -170,7 +184,7 @@ def run_case(ref, name, spec):
     #      running statistics; the network is not chaotic in this mode, so gradients pin tightly ----------
     m = build(ref, kind, arch, mseed)
     m.eval()
-    loss, acc = m(feed(imgs, labs, True)) if kind != "SegmentationModule" else m({"img_data": imgs[0], "seg_label": labs[0]})
+    loss, acc = m(feed(imgs, labs, True)) if not single else m({"img_data": imgs[0], "seg_label": labs[0]})
     loss.backward()
     rec["fixbn/loss"] = np.float64(loss.item())
     rec["fixbn/acc"] = np.float64(acc.item())
@@ -179,7 +193,9 @@ def run_case(ref, name, spec):
     m = build(ref, kind, arch, mseed)
     m.eval()
     with torch.no_grad():
-        if kind == "SegmentationModule":
+        if single:
+            if kind.startswith("Seg/"):
+                m.decoder.use_softmax = True  # test.py builds the decoder with use_softmax=True for inference
             probs = m({"img_data": imgs[0], "seg_label": labs[0]}, segSize=(H, W))
         else:
             probs = m(feed(imgs, labs, False), segSize=(H, W))

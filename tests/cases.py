@@ -16,6 +16,11 @@ CASES = {
     "clip_ocr": ("ClipOCRNet", "resnet50dilated", 3, 2, 49, 65, 13, 306),
     "segmodule_r18": ("SegmentationModule", "resnet18dilated", 1, 2, 49, 65, 14, 307),
     "non_local3d": ("Non_local3d", "resnet50dilated", 3, 2, 49, 65, 15, 308),
+    # image-model family on the same kernels: "Seg/<decoder>/<fc_dim>/<deep_sup_scale or none>"
+    "seg_ocrnet_r50": ("Seg/ocrnet_deepsup/2048/0.4", "resnet50dilated", 1, 2, 49, 65, 21, 311),
+    "seg_upernet_r50": ("Seg/upernet_lite/2048/none", "resnet50", 1, 2, 65, 97, 22, 312),
+    "seg_c1ds_r18": ("Seg/c1_deepsup/512/0.4", "resnet18dilated", 1, 2, 49, 65, 23, 313),
+    "seg_ppm_r18": ("Seg/ppm/512/none", "resnet18dilated", 1, 2, 49, 65, 24, 314),
 }
 
 # mid-size train-mode fixtures for the gradient gates (oracle/make_golden.py MID_CASES)
@@ -25,7 +30,8 @@ MID_CASES = {
 }
 
 # cases driven through the img_data / clipimgs_data feed (Non_local3d has its own: every frame is supervised)
-CLIP_CASES = [k for k in CASES if k != "non_local3d"]
+CLIP_CASES = [k for k in CASES if k != "non_local3d" and not k.startswith("seg_")]
+SEG_CASES = [k for k in CASES if k.startswith("seg_")]
 
 
 def ns(**kw):
@@ -47,6 +53,10 @@ def build(kind, arch, seed, conditioned=True, **kw):
         m = M.ClipOCRNet(enc, crit, ns(**kw), deep_sup_scale=0.4)
     elif kind == "Non_local3d":
         m = M.Non_local3d(ns(**kw), enc, crit)
+    elif kind.startswith("Seg/"):
+        _, dec_arch, fc, ds = kind.split("/")
+        dec = M.ModelBuilder.build_decoder(dec_arch, fc_dim=int(fc), num_class=NUM_CLASS)
+        m = M.SegmentationModule(enc, dec, crit, deep_sup_scale=None if ds == "none" else float(ds))
     else:
         dec = M.ModelBuilder.build_decoder("ppm_deepsup", fc_dim=512, num_class=NUM_CLASS)
         m = M.SegmentationModule(enc, dec, crit, deep_sup_scale=0.4)

@@ -335,3 +335,61 @@ def test_mid_size_gradients_match_reference_per_tensor(E, name, prec, mode):
     print(f"{name}/{mode}/{prec}: logits {e_log:.2e}; {len(errs)} gradient tensors: median rel-L2 {med:.2e}, worst {worst[1]:.2e} ({worst[0]}); "
           f"median ratio to the reference's own 1-vs-8-thread floor {float(np.median(list(ratios.values()))):.2f}")
     assert len(errs) > 100
+
+
+def _seg_feed(name, with_label=True):
+    imgs, labs = C.clip_inputs(name)
+    d = {"img_data": imgs[0].cuda()}
+    if with_label:
+        d["seg_label"] = labs[0].cuda()
+    return d, labs
+
+
+@pytest.mark.parametrize("name", C.SEG_CASES)
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+def test_image_model_family_matches_reference(E, name, prec):
+    """SURVEY 8f row f4 — the image models that share the TCB kernels, through the reference's builder API
+    (`ModelBuilder.build_decoder(arch)` + `SegmentationModule`): SpatialOCRNet (models/ocrnet.py:22-72; tcgen05 gather +
+    fused attention), UPerNet (models/models.py:1085-1175; FPN with bilinear top-down), C1DeepSup (:826-858), PPM (:889-935;
+    bin-space pyramid head).  Golden outputs of the REFERENCE modules: train step (loss, acc, logits, gradient norms, running
+    statistics), frozen-BN step (gradient norms + element pins), inference (probabilities, argmax)."""
+    kind, arch, T, n, H, W, mseed, dseed = C.CASES[name]
+    g = C.golden(name)
+    for mode in ("train", "fixbn"):
+        m = C.build(kind, arch, mseed).cuda()
+        m = C.no_dropout(m.train()) if mode == "train" else m.eval()
+        feed, _ = _seg_feed(name)
+        with E.precision(prec), E.capturing() as cap:
+            loss, acc = m(feed)
+            loss.backward()
+        torch.cuda.synchronize()
+        assert abs(loss.item() - float(g[mode + "/loss"])) <= TOL * abs(float(g[mode + "/loss"])), mode
+        assert abs(acc.item() - float(g[mode + "/acc"])) <= TOL
+        if mode == "train":
+            assert C.rel_err(nchw(cap["logits"].cpu()), g["train/logits"]) <= TOL
+            sd = m.state_dict()
+            for k in ("encoder.bn1.running_mean", "encoder.bn1.running_var", "encoder.layer4.0.bn2.running_mean",
+                      "encoder.layer4.0.bn2.running_var"):
+                assert C.rel_err(sd[k].cpu(), g["train/after/" + k]) <= TOL, k
+        worst, checked = 0.0, 0
+        for k, p in m.named_parameters():
+            key = mode + "/gnorm/" + k
+            if key not in g or float(g[key]) < (1e-5 if mode == "train" else 1e-9):
+                continue
+            assert p.grad is not None, k
+            ref_norm = float(g[key])
+            en = abs(float(p.grad.double().norm()) - ref_norm) / ref_norm
+            worst = max(worst, en)
+            assert en <= GRAD_GATES[prec][0 if mode == "train" else 1], (mode, k, en)
+            if mode == "fixbn":
+                assert head_err(p.grad, g["fixbn/ghead/" + k], ref_norm) <= GRAD_GATES[prec][2], k
+            checked += 1
+        assert checked > 20
+        print(f"{name}/{prec}/{mode}: worst grad-norm rel err {worst:.2e} over {checked} tensors")
+    m = C.build(kind, arch, mseed).cuda().eval()
+    feed, labs = _seg_feed(name)
+    with torch.no_grad(), E.precision(prec):
+        probs = m(feed, segSize=(H, W))
+    assert tuple(probs.shape) == (n, C.NUM_CLASS, H, W)
+    assert C.rel_err(probs[:, :, ::4, ::4].cpu(), g["eval/probs_sub"]) <= TOL
+    assert (probs.argmax(1).cpu().numpy() == g["eval/pred"]).mean() >= 0.999

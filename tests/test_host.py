@@ -105,6 +105,13 @@ def test_state_dict_and_init_identical_to_reference():
     b = ref.SegmentationModule(ref.ModelBuilder.build_encoder("resnet18dilated"), ref.ModelBuilder.build_decoder("ppm_deepsup", fc_dim=512, num_class=124), crit, 0.4)
     sa, sb = a.state_dict(), b.state_dict()
     assert list(sa) == list(sb) and all(torch.equal(sa[k], sb[k]) for k in sa)
+    # image-model decoder family: same keys, shapes and init RNG consumption as the reference builders
+    for dec, fc in (("c1", 512), ("c1_deepsup", 512), ("ppm", 512), ("upernet", 2048), ("upernet_lite", 2048), ("ocrnet_deepsup", 2048)):
+        torch.manual_seed(3); a = M.ModelBuilder.build_decoder(dec, fc_dim=fc, num_class=124)
+        torch.manual_seed(3); b = ref.ModelBuilder.build_decoder(dec, fc_dim=fc, num_class=124)
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa) == list(sb), dec
+        assert all(torch.equal(sa[k], sb[k]) for k in sa), dec
 
 
 def test_clip_window_and_sublists_follow_the_reference_rule():
