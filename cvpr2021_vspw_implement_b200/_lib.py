@@ -26,6 +26,13 @@ class ConvDesc(ctypes.Structure):
     _fields_ = [(k, _c_int) for k in ("n", "h", "w", "cin", "cout", "kh", "kw", "stride", "pad", "dil", "ho", "wo", "precision", "cin_pitch")]
 
 
+class PeerCtx(ctypes.Structure):
+    """Mirror of ``vspw_peer_ctx`` (include/vspw_b200.h)."""
+
+    _fields_ = [("inbox", ctypes.c_uint64 * 16), ("world", _c_int), ("rank", _c_int), ("ring", _c_int), ("max_elems", _c_int),
+                ("seq", ctypes.c_uint64)]
+
+
 # name -> argtypes; every function returns int (0 = ok)
 _SIGNATURES = {
     "vspw_conv2d_tc_supported": [ctypes.POINTER(ConvDesc)],
@@ -37,6 +44,7 @@ _SIGNATURES = {
     "vspw_zero_insert2_bf16": [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp],
     "vspw_conv_weight_prep": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp],
     "vspw_conv_weight_prep_multi": [_c_vp, _c_int, _c_int, _c_int, _c_vp],
+    "vspw_clip_finish_u8": [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp],
     "vspw_cast_f64_f32": [_c_vp, _c_vp, _c_sz, _c_vp],
     "vspw_copy_channels": [_c_vp, _c_int, _c_int, _c_vp, _c_int, _c_int, _c_int, _c_sz, _c_int, _c_vp],
     "vspw_conv2d_fwd": [ctypes.POINTER(ConvDesc), _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
@@ -48,11 +56,15 @@ _SIGNATURES = {
     "vspw_bn_stats": [_c_vp, _c_sz, _c_int, _c_vp, _c_vp, _c_vp],
     "vspw_bn_finalize_train": [_c_vp, _c_vp, _c_d, _c_vp, _c_vp, _c_f, _c_f, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_vp],
     "vspw_bn_fold_eval": [_c_vp, _c_vp, _c_vp, _c_vp, _c_f, _c_vp, _c_vp, _c_vp, _c_int, _c_vp],
-    "vspw_bn_act_fwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_vp],
+    "vspw_bn_act_fwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_vp],
     "vspw_bn_train_fwd": [_c_vp, _c_vp, _c_vp, _c_d, _c_vp, _c_vp, _c_f, _c_f, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_int,
-                          _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_vp],
-    "vspw_bn_bwd_reduce": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_sz, _c_vp, _c_vp, _c_vp],
-    "vspw_bn_bwd_apply": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_int, _c_d, _c_d, _c_vp],
+                          _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_vp],
+    "vspw_bn_train_fwd_sync": [_c_vp, _c_vp, _c_d, _c_vp, _c_vp, _c_f, _c_f, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_int,
+                               _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, ctypes.POINTER(PeerCtx), _c_vp],
+    "vspw_bn_bwd_apply_sync": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp,
+                               _c_vp, _c_sz, _c_int, _c_sz, _c_d, _c_d, ctypes.POINTER(PeerCtx), _c_vp],
+    "vspw_bn_bwd_reduce": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_sz, _c_int, _c_sz, _c_vp, _c_vp, _c_vp],
+    "vspw_bn_bwd_apply": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_sz, _c_int, _c_d, _c_d, _c_vp],
     "vspw_maxpool3x3s2_fwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp],
     "vspw_maxpool3x3s2_bwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp],
     "vspw_tcb_pool_fwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_int, _c_vp],
@@ -69,6 +81,8 @@ _SIGNATURES = {
     "vspw_bgemm_det": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int] + [_c_i64] * 9 + [_c_f, _c_f, _c_vp],
     "vspw_ocr_attention_fwd_tc": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_f, _c_vp],
     "vspw_ocr_gather_tc": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp],
+    "vspw_ocr_region_softmax_fwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_f, _c_vp],
+    "vspw_ocr_region_softmax_bwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp],
     "vspw_ocr_region_planes": [_c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_f, _c_vp],
     "vspw_vc_counts": [_c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_vp, _c_vp],
     "vspw_sgd_momentum_step": [_c_vp, _c_vp, _c_vp, _c_int, _c_f, _c_vp],
@@ -85,7 +99,7 @@ _SIGNATURES = {
 
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["vspw_last_error", "vspw_version", "vspw_tcb_pool_workspace_floats", "vspw_sgd_chunk_elems",
                                                    "vspw_conv_weight_prep_tile", "vspw_peer_inbox_bytes",
-                                                   "vspw_ocr_attention_workspace_bytes"])
+                                                   "vspw_ocr_attention_workspace_bytes", "vspw_ocr_region_softmax_workspace_bytes"])
 
 
 class VspwError(RuntimeError):
@@ -119,6 +133,8 @@ class _Lib:
                     dll.vspw_sgd_chunk_elems.argtypes = []
                     dll.vspw_conv_weight_prep_tile.restype = ctypes.c_int32
                     dll.vspw_conv_weight_prep_tile.argtypes = [_c_int] * 4
+                    dll.vspw_ocr_region_softmax_workspace_bytes.restype = ctypes.c_size_t
+                    dll.vspw_ocr_region_softmax_workspace_bytes.argtypes = [_c_int, _c_int]
                     dll.vspw_ocr_attention_workspace_bytes.restype = ctypes.c_size_t
                     dll.vspw_ocr_attention_workspace_bytes.argtypes = [_c_int]
                     dll.vspw_peer_inbox_bytes.restype = ctypes.c_size_t

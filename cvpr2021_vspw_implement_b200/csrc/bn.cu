@@ -3,7 +3,8 @@
 // Reference: SynchronizedBatchNorm2d.forward -> F.batch_norm (models/sync_batchnorm/batchnorm.py:68-73),
 // _compute_mean_std (:133-150), Bottleneck.forward residual/ReLU order (models/resnet.py:72-92).
 // All kernels are HBM-bound: float4 accesses along the channel axis, grids sized from the SM count.
-#include "common.cuh"
+#include "peer_common.cuh"
+#include <stdlib.h>
 
 using namespace vspw;
 
@@ -212,7 +213,11 @@ __global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(
     const float4* __restrict__ mean, const float4* __restrict__ beta, const float4* __restrict__ residual,
     const uint2* __restrict__ res_hi, const uint2* __restrict__ res_lo,
     const float4* __restrict__ chan_scale, int relu, float4* __restrict__ out, uint2* __restrict__ out_hi,
-    uint2* __restrict__ out_lo, size_t pixels, int c4, size_t pix_per_img, BnTrainStats ts) {
+    uint2* __restrict__ out_lo, uint4* __restrict__ relu_bits, size_t pixels, int c4, size_t pix_per_img, BnTrainStats ts,
+    peer::PeerArgs pa, int rev) {
+  // SyncBN: the cross-rank sum of the statistics runs HERE (block 0 exchanges over NVLink peer memory, the other blocks of
+  // this one-wave grid wait for its "totals ready" flag) instead of as a separate launch between the conv and this kernel
+  if (pa.world > 1) peer::grid_allreduce(const_cast<double*>(ts.sum), 2 * c4 * 4, pa);
   const EwMap m = ew_map(c4);
   if (m.cg < 0) return;
   float4 sc, mu, add;
@@ -226,8 +231,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(
       // mean / biased variance from the fp64 sums with two fp64 multiply-adds (E[x^2] - E[x]^2 needs the fp64 product); the
       // inverse standard deviation in fp32 with IEEE sqrt and divide, as F.batch_norm does (fp64 divide / sqrt cost hundreds
       // of cycles per channel on this part and EVERY thread of EVERY block runs this prologue)
-      const double mm = ts.sum[ch] * ts.inv_count;
-      double var = fma(ts.sqsum[ch], ts.inv_count, -mm * mm);
+      const double mm = __ldcg(ts.sum + ch) * ts.inv_count;
+      double var = fma(__ldcg(ts.sqsum + ch), ts.inv_count, -mm * mm);
       if (var < 0) var = 0;
       const float vf = (float)var;
       mf[j] = (float)mm;
@@ -254,7 +259,18 @@ __global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(
     mu = mean ? __ldg(mean + m.cg) : make_float4(0.f, 0.f, 0.f, 0.f);
     add = mean ? (beta ? __ldg(beta + m.cg) : make_float4(0.f, 0.f, 0.f, 0.f)) : __ldg(shift + m.cg);
   }
-  for (size_t p = m.p0; p < pixels; p += m.dp * kUnroll) {
+  // relu_bits: the backward passes need only [out != 0] per element; one BIT instead of re-reading the bf16 hi plane (2 B).
+  // Warp w of this launch covers 32 consecutive float4 groups e = q * c4 + cg (host-checked: c4 == 16 or c4 % 32 == 0), so four
+  // ballots (one per component) give the four 32-bit words of those 128 elements: word (e >> 5) * 4 + component, bit e & 31.
+  // With c4 == 16 a warp holds two adjacent pixels; the loop runs on the even one so that all 32 lanes stay together.
+  const size_t poff = (relu_bits && c4 < 32) ? (m.p0 & 1) : 0;
+  // rev (experiment, off by default): walk this thread's grid-stride sequence from the LAST pixel group down, to start on what
+  // the producing conv left in the 126 MB L2 and end on what the consuming conv wants first.
+  const size_t pstep = m.dp * kUnroll, pfirst = m.p0 - poff;
+  const size_t iters = pfirst < pixels ? (pixels - pfirst + pstep - 1) / pstep : 0;
+  for (size_t it = 0; it < iters; ++it) {
+    const size_t pb = pfirst + (rev ? iters - 1 - it : it) * pstep;
+    const size_t p = pb + poff;
     float4 v[kUnroll], r[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
@@ -280,16 +296,27 @@ __global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const size_t q = p + u * m.dp;
-      if (q >= pixels) break;
+      if (relu_bits) {
+        if (pb + u * m.dp >= pixels) break;  // warp-uniform: every lane of the warp leaves together
+      } else if (q >= pixels) {
+        break;
+      }
+      const bool valid = q < pixels;
       const size_t i = q * c4 + m.cg;
-      float4 t = v[u];
+      float4 t = valid ? v[u] : make_float4(0.f, 0.f, 0.f, 0.f);
       t.x = fmaf(t.x - mu.x, sc.x, add.x); t.y = fmaf(t.y - mu.y, sc.y, add.y);
       t.z = fmaf(t.z - mu.z, sc.z, add.z); t.w = fmaf(t.w - mu.w, sc.w, add.w);
       if (residual || res_hi) { t.x += r[u].x; t.y += r[u].y; t.z += r[u].z; t.w += r[u].w; }
       if (relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
-      if (chan_scale) {
+      if (chan_scale && valid) {
         const float4 cs = __ldg(chan_scale + (q / pix_per_img) * c4 + m.cg);
         t.x *= cs.x; t.y *= cs.y; t.z *= cs.z; t.w *= cs.w;
+      }
+      if (relu_bits) {
+        const unsigned bx = __ballot_sync(0xffffffffu, valid && t.x != 0.f), by = __ballot_sync(0xffffffffu, valid && t.y != 0.f);
+        const unsigned bz = __ballot_sync(0xffffffffu, valid && t.z != 0.f), bw = __ballot_sync(0xffffffffu, valid && t.w != 0.f);
+        if ((threadIdx.x & 31) == 0) relu_bits[i >> 5] = make_uint4(bx, by, bz, bw);
+        if (!valid) continue;
       }
       if (out) out[i] = t;
       if (out_hi) {
@@ -307,6 +334,11 @@ __global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(
 
 // g = dout * chan_scale * [out > 0]; the ReLU mask comes from the fp32 output or from its bf16 hi plane
 // (bf16_rn(x) is non-zero exactly when the normal fp32 x is); a dropped channel (scale 0) already has g == 0.
+__device__ __forceinline__ float4 apply_bits(float4 g, uint4 w, unsigned bit) {
+  g.x = ((w.x >> bit) & 1u) ? g.x : 0.f; g.y = ((w.y >> bit) & 1u) ? g.y : 0.f;
+  g.z = ((w.z >> bit) & 1u) ? g.z : 0.f; g.w = ((w.w >> bit) & 1u) ? g.w : 0.f;
+  return g;
+}
 __device__ __forceinline__ float4 apply_mask(float4 g, bool has_o, float4 o, bool has_h, uint2 h) {
   if (has_o) {
     g.x = o.x != 0.f ? g.x : 0.f; g.y = o.y != 0.f ? g.y : 0.f;
@@ -324,8 +356,8 @@ __device__ __forceinline__ float4 apply_mask(float4 g, bool has_o, float4 o, boo
 __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(
     const float4* __restrict__ dout, const float4* __restrict__ out, const uint2* __restrict__ out_hi,
     const float4* __restrict__ y, const float4* __restrict__ mean, const float4* __restrict__ invstd,
-    const float4* __restrict__ chan_scale, int relu, size_t pixels, int c4, size_t pix_per_img, double* dbeta,
-    double* dgamma, int red_pix) {
+    const float4* __restrict__ chan_scale, int relu, const uint4* __restrict__ relu_bits, size_t pixels, int c4,
+    size_t pix_per_img, double* dbeta, double* dgamma, int red_pix) {
   __shared__ float4 sh[2][kEwThreads];
   const int G = c4 < kEwThreads ? c4 : kEwThreads;
   const int PL = kEwThreads / G;
@@ -335,19 +367,21 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
   if (active) {
     const float4 mu = __ldg(mean + cg), is = __ldg(invstd + cg);
-    const bool has_o = relu && out, has_h = relu && !out;
+    const bool has_b = relu && relu_bits, has_o = relu && !has_b && out, has_h = relu && !has_b && !out;
     const size_t pbeg = (size_t)blockIdx.x * PL * red_pix + pl;
     const size_t pend = min(pixels, (size_t)(blockIdx.x + 1) * PL * red_pix);
     for (size_t p = pbeg; p < pend; p += (size_t)PL * kUnroll) {
       float4 d[kUnroll], yv[kUnroll], o[kUnroll];
       uint2 h[kUnroll];
+      uint4 bw[kUnroll];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         const size_t q = p + (size_t)u * PL;
         if (q < pend) {
           const size_t i = q * c4 + cg;
-          d[u] = ld_stream(dout + i);
+          d[u] = __ldg(dout + i);  // (no evict-first hint: the apply pass that follows re-reads these lines, highest pixels first)
           yv[u] = __ldg(y + i);
+          if (has_b) bw[u] = __ldg(relu_bits + (i >> 5));
           if (has_o) o[u] = __ldg(out + i);
           if (has_h) h[u] = __ldg(out_hi + i);
         }
@@ -361,7 +395,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(
           const float4 cs = __ldg(chan_scale + (q / pix_per_img) * c4 + cg);
           gg.x *= cs.x; gg.y *= cs.y; gg.z *= cs.z; gg.w *= cs.w;
         }
-        gg = apply_mask(gg, has_o, o[u], has_h, h[u]);
+        if (has_b) gg = apply_bits(gg, bw[u], (unsigned)((q * c4 + cg) & 31));
+        else gg = apply_mask(gg, has_o, o[u], has_h, h[u]);
         a.x += gg.x; a.y += gg.y; a.z += gg.z; a.w += gg.w;
         b.x = fmaf(gg.x, (yv[u].x - mu.x) * is.x, b.x); b.y = fmaf(gg.y, (yv[u].y - mu.y) * is.y, b.y);
         b.z = fmaf(gg.z, (yv[u].z - mu.z) * is.z, b.z); b.w = fmaf(gg.w, (yv[u].w - mu.w) * is.w, b.w);
@@ -407,8 +442,9 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(
     const float4* __restrict__ y, const float4* __restrict__ mean, const float4* __restrict__ invstd,
     const float4* __restrict__ gamma, const float4* __restrict__ chan_scale, int relu, const double* __restrict__ dbeta,
     const double* __restrict__ dgamma, float4* __restrict__ dy, uint2* __restrict__ dy_hi, uint2* __restrict__ dy_lo,
-    float4* __restrict__ dres, float4* __restrict__ dgamma_f, float4* __restrict__ dbeta_f, size_t pixels, int c4,
-    size_t pix_per_img, double inv_count, int eval_mode, double pgrad_scale) {
+    float4* __restrict__ dres, float4* __restrict__ dgamma_f, float4* __restrict__ dbeta_f, const uint4* __restrict__ relu_bits,
+    size_t pixels, int c4, size_t pix_per_img, double inv_count, int eval_mode, double pgrad_scale, peer::PeerArgs pa, int rev) {
+  if (pa.world > 1) peer::grid_allreduce(const_cast<double*>(dbeta), 2 * c4 * 4, pa);  // (dbeta, dgamma) are one (2, C) buffer
   const EwMap m = ew_map(c4);
   if (m.cg < 0) return;
   if (blockIdx.x == 0 && threadIdx.x < (c4 < kEwThreads ? c4 : kEwThreads) && dbeta && dgamma) {
@@ -417,10 +453,10 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(
     // gradient all-reduce that follows AVERAGES the ranks' parameter gradients (DataParallel's mean of replica losses)
     const double* db = dbeta + (size_t)m.cg * 4;
     const double* dg = dgamma + (size_t)m.cg * 4;
-    if (dgamma_f) dgamma_f[m.cg] = make_float4((float)(dg[0] * pgrad_scale), (float)(dg[1] * pgrad_scale),
-                                               (float)(dg[2] * pgrad_scale), (float)(dg[3] * pgrad_scale));
-    if (dbeta_f) dbeta_f[m.cg] = make_float4((float)(db[0] * pgrad_scale), (float)(db[1] * pgrad_scale),
-                                             (float)(db[2] * pgrad_scale), (float)(db[3] * pgrad_scale));
+    if (dgamma_f) dgamma_f[m.cg] = make_float4((float)(__ldcg(dg) * pgrad_scale), (float)(__ldcg(dg + 1) * pgrad_scale),
+                                               (float)(__ldcg(dg + 2) * pgrad_scale), (float)(__ldcg(dg + 3) * pgrad_scale));
+    if (dbeta_f) dbeta_f[m.cg] = make_float4((float)(__ldcg(db) * pgrad_scale), (float)(__ldcg(db + 1) * pgrad_scale),
+                                             (float)(__ldcg(db + 2) * pgrad_scale), (float)(__ldcg(db + 3) * pgrad_scale));
   }
   // dy = ka*g - kb - kc*(y - mean)
   const float4 is = __ldg(invstd + m.cg);
@@ -431,15 +467,19 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(
     mu = __ldg(mean + m.cg);
     const double* db = dbeta + (size_t)m.cg * 4;
     const double* dg = dgamma + (size_t)m.cg * 4;
-    kb = make_float4(ka.x * (float)(db[0] * inv_count), ka.y * (float)(db[1] * inv_count), ka.z * (float)(db[2] * inv_count),
-                     ka.w * (float)(db[3] * inv_count));
-    kc = make_float4(ka.x * is.x * (float)(dg[0] * inv_count), ka.y * is.y * (float)(dg[1] * inv_count),
-                     ka.z * is.z * (float)(dg[2] * inv_count), ka.w * is.w * (float)(dg[3] * inv_count));
+    kb = make_float4(ka.x * (float)(__ldcg(db) * inv_count), ka.y * (float)(__ldcg(db + 1) * inv_count),
+                     ka.z * (float)(__ldcg(db + 2) * inv_count), ka.w * (float)(__ldcg(db + 3) * inv_count));
+    kc = make_float4(ka.x * is.x * (float)(__ldcg(dg) * inv_count), ka.y * is.y * (float)(__ldcg(dg + 1) * inv_count),
+                     ka.z * is.z * (float)(__ldcg(dg + 2) * inv_count), ka.w * is.w * (float)(__ldcg(dg + 3) * inv_count));
   }
-  const bool has_o = relu && out, has_h = relu && !out;
-  for (size_t p = m.p0; p < pixels; p += m.dp * kUnroll) {
+  const bool has_b = relu && relu_bits, has_o = relu && !has_b && out, has_h = relu && !has_b && !out;
+  const size_t pstep = m.dp * kUnroll;
+  const size_t iters = m.p0 < pixels ? (pixels - m.p0 + pstep - 1) / pstep : 0;
+  for (size_t it = 0; it < iters; ++it) {
+    const size_t p = m.p0 + (rev ? iters - 1 - it : it) * pstep;  // rev: see bn_act_fwd_kernel
     float4 d[kUnroll], yv[kUnroll], o[kUnroll];
     uint2 h[kUnroll];
+    uint4 bw[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const size_t q = p + u * m.dp;
@@ -447,6 +487,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(
         const size_t i = q * c4 + m.cg;
         d[u] = ld_stream(dout + i);
         if (!eval_mode) yv[u] = ld_stream(y + i);
+        if (has_b) bw[u] = __ldg(relu_bits + (i >> 5));
         if (has_o) o[u] = ld_stream(out + i);
         if (has_h) h[u] = ld_stream(out_hi + i);
       }
@@ -461,7 +502,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(
         const float4 cs = __ldg(chan_scale + (q / pix_per_img) * c4 + m.cg);
         g.x *= cs.x; g.y *= cs.y; g.z *= cs.z; g.w *= cs.w;
       }
-      g = apply_mask(g, has_o, o[u], has_h, h[u]);
+      if (has_b) g = apply_bits(g, bw[u], (unsigned)(i & 31));
+      else g = apply_mask(g, has_o, o[u], has_h, h[u]);
       if (dres) dres[i] = g;
       float4 r;
       if (eval_mode) {
@@ -486,6 +528,37 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(
   }
 }
 
+
+// VSPW_BN_ORDER=down: the element-wise forward and the second backward pass walk the pixel axis downwards, hoping for L2 reuse
+// across the kernel boundary (see bn_act_fwd_kernel).  Measured on B200 inside one box (tools/ab.sh, 2 x 10 steps each):
+// 92.60 ms/step down vs 92.38 up — no gain (what the producer leaves in L2 is dirty write-back traffic either way), so
+// ascending stays the default and the switch stays for the record.
+int bn_reverse() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VSPW_BN_ORDER");
+    v = (e && e[0] == 'd') ? 1 : 0;
+  }
+  return v;
+}
+
+peer::PeerArgs no_peer() {
+  peer::PeerArgs pa{};
+  pa.world = 0;
+  return pa;
+}
+
+int peer_args(const vspw_peer_ctx* ctx, int n_elems, peer::PeerArgs& pa, const char* who) {
+  pa = no_peer();
+  if (!ctx || ctx->world <= 1) return VSPW_OK;
+  VSPW_REQUIRE(ctx->world <= 16 && ctx->rank >= 0 && ctx->rank < ctx->world, "%s: peer world %d / rank %d out of range", who, ctx->world, ctx->rank);
+  VSPW_REQUIRE(ctx->ring >= 2 && ctx->seq > 0, "%s: peer ring must be >= 2 and seq > 0", who);
+  VSPW_REQUIRE(n_elems <= ctx->max_elems, "%s: %d statistics exceed the inbox slot (%d)", who, n_elems, ctx->max_elems);
+  for (int i = 0; i < ctx->world; ++i) pa.base[i] = (unsigned long long)ctx->inbox[i];
+  pa.world = ctx->world; pa.rank = ctx->rank; pa.ring = ctx->ring; pa.max_elems = ctx->max_elems; pa.seq = ctx->seq;
+  pa.timeout_ns = peer::timeout_ns_from_env();
+  return VSPW_OK;
+}
 
 }  // namespace
 
@@ -526,46 +599,82 @@ extern "C" int vspw_bn_fold_eval(const float* gamma, const float* beta, const fl
 extern "C" int vspw_bn_act_fwd(const float* y, const float* scale, const float* shift, const float* mean,
                                const float* beta, const float* residual, const uint16_t* residual_hi, const uint16_t* residual_lo,
                                const float* chan_scale, int32_t relu, float* out, uint16_t* out_hi, uint16_t* out_lo,
-                               size_t pixels, int32_t c, size_t pixels_per_image, void* stream) {
+                               uint32_t* relu_bits, size_t pixels, int32_t c, size_t pixels_per_image, void* stream) {
   VSPW_REQUIRE(y && scale && (shift || mean) && (out || out_hi), "vspw_bn_act_fwd: null pointer");
   VSPW_REQUIRE(!(residual && residual_hi) && (!residual_lo || residual_hi), "vspw_bn_act_fwd: residual as fp32 OR as planes");
   VSPW_REQUIRE(c > 0 && c % 4 == 0, "vspw_bn_act_fwd: channels must be a multiple of 4 (got %d)", c);
   VSPW_REQUIRE(pixels_per_image > 0, "vspw_bn_act_fwd: pixels_per_image must be positive");
+  VSPW_REQUIRE(!relu_bits || (relu && (c == 64 || c % 128 == 0)), "vspw_bn_act_fwd: relu_bits needs relu and 64 or a multiple of 128 channels");
   if (pixels == 0) return VSPW_OK;
   static const int occ = blocks_per_sm(bn_act_fwd_kernel, kEwThreads);
   bn_act_fwd_kernel<<<ew_grid(pixels, c / 4, occ), kEwThreads, 0, as_stream(stream)>>>(
       (const float4*)y, (const float4*)scale, (const float4*)shift, (const float4*)mean, (const float4*)beta,
       (const float4*)residual, (const uint2*)residual_hi, (const uint2*)residual_lo, (const float4*)chan_scale,
-      relu, (float4*)out, (uint2*)out_hi, (uint2*)out_lo, pixels, c / 4, pixels_per_image, BnTrainStats{});
+      relu, (float4*)out, (uint2*)out_hi, (uint2*)out_lo, (uint4*)relu_bits, pixels, c / 4, pixels_per_image, BnTrainStats{}, no_peer(), bn_reverse());
   return check_launch("vspw_bn_act_fwd");
 }
+
+static int bn_train_fwd_impl(const float* y, const double* sum, const double* sqsum, double count, const float* gamma,
+                             const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                             float* mean, float* invstd, int32_t clamp_mode, const float* residual, const uint16_t* residual_hi,
+                             const uint16_t* residual_lo, const float* chan_scale, int32_t relu, float* out, uint16_t* out_hi,
+                             uint16_t* out_lo, uint32_t* relu_bits, size_t pixels, int32_t c, size_t pixels_per_image,
+                             const vspw_peer_ctx* peer_ctx, void* stream);
 
 extern "C" int vspw_bn_train_fwd(const float* y, const double* sum, const double* sqsum, double count, const float* gamma,
                                  const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                                  float* mean, float* invstd, int32_t clamp_mode, const float* residual, const uint16_t* residual_hi,
-                                 const uint16_t* residual_lo, const float* chan_scale, int32_t relu, float* out, uint16_t* out_hi, uint16_t* out_lo, size_t pixels, int32_t c,
-                                 size_t pixels_per_image, void* stream) {
+                                 const uint16_t* residual_lo, const float* chan_scale, int32_t relu, float* out, uint16_t* out_hi,
+                                 uint16_t* out_lo, uint32_t* relu_bits, size_t pixels, int32_t c, size_t pixels_per_image, void* stream) {
+  return bn_train_fwd_impl(y, sum, sqsum, count, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, clamp_mode, residual,
+                           residual_hi, residual_lo, chan_scale, relu, out, out_hi, out_lo, relu_bits, pixels, c, pixels_per_image, nullptr,
+                           stream);
+}
+
+extern "C" int vspw_bn_train_fwd_sync(const float* y, double* sums, double count, const float* gamma, const float* beta, float eps,
+                                      float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
+                                      int32_t clamp_mode, const float* residual, const uint16_t* residual_hi, const uint16_t* residual_lo,
+                                      const float* chan_scale, int32_t relu, float* out, uint16_t* out_hi, uint16_t* out_lo,
+                                      uint32_t* relu_bits, size_t pixels, int32_t c, size_t pixels_per_image,
+                                      const vspw_peer_ctx* peer_ctx, void* stream) {
+  VSPW_REQUIRE(sums && peer_ctx, "vspw_bn_train_fwd_sync: null pointer");
+  return bn_train_fwd_impl(y, sums, sums + c, count, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, clamp_mode, residual,
+                           residual_hi, residual_lo, chan_scale, relu, out, out_hi, out_lo, relu_bits, pixels, c, pixels_per_image, peer_ctx,
+                           stream);
+}
+
+static int bn_train_fwd_impl(const float* y, const double* sum, const double* sqsum, double count, const float* gamma,
+                             const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                             float* mean, float* invstd, int32_t clamp_mode, const float* residual, const uint16_t* residual_hi,
+                             const uint16_t* residual_lo, const float* chan_scale, int32_t relu, float* out, uint16_t* out_hi,
+                             uint16_t* out_lo, uint32_t* relu_bits, size_t pixels, int32_t c, size_t pixels_per_image,
+                             const vspw_peer_ctx* peer_ctx, void* stream) {
   VSPW_REQUIRE(y && sum && sqsum && mean && invstd && (out || out_hi), "vspw_bn_train_fwd: null pointer");
   VSPW_REQUIRE(!(residual && residual_hi) && (!residual_lo || residual_hi), "vspw_bn_train_fwd: residual as fp32 OR as planes");
   VSPW_REQUIRE(count >= 1, "vspw_bn_train_fwd: empty batch");
   VSPW_REQUIRE(c > 0 && c % 4 == 0, "vspw_bn_train_fwd: channels must be a multiple of 4 (got %d)", c);
   VSPW_REQUIRE(pixels_per_image > 0, "vspw_bn_train_fwd: pixels_per_image must be positive");
+  VSPW_REQUIRE(!relu_bits || (relu && (c == 64 || c % 128 == 0)), "vspw_bn_train_fwd: relu_bits needs relu and 64 or a multiple of 128 channels");
+  peer::PeerArgs pa;
+  int rc = peer_args(peer_ctx, 2 * c, pa, "vspw_bn_train_fwd_sync");
+  if (rc) return rc;
+  VSPW_REQUIRE(pa.world <= 1 || pixels > 0, "vspw_bn_train_fwd_sync: every rank must take part in the exchange (empty local batch)");
   if (pixels == 0) return VSPW_OK;
   BnTrainStats ts{sum, sqsum, count, 1.0 / count, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, clamp_mode};
   static const int occ = blocks_per_sm(bn_act_fwd_kernel, kEwThreads);
   bn_act_fwd_kernel<<<ew_grid(pixels, c / 4, occ), kEwThreads, 0, as_stream(stream)>>>(
       (const float4*)y, nullptr, nullptr, nullptr, nullptr, (const float4*)residual, (const uint2*)residual_hi,
       (const uint2*)residual_lo, (const float4*)chan_scale, relu,
-      (float4*)out, (uint2*)out_hi, (uint2*)out_lo, pixels, c / 4, pixels_per_image, ts);
+      (float4*)out, (uint2*)out_hi, (uint2*)out_lo, (uint4*)relu_bits, pixels, c / 4, pixels_per_image, ts, pa, bn_reverse());
   return check_launch("vspw_bn_train_fwd");
 }
 
 extern "C" int vspw_bn_bwd_reduce(const float* dout, const float* out, const uint16_t* out_hi, const float* y,
                                   const float* mean, const float* invstd, const float* chan_scale, int32_t relu,
-                                  size_t pixels, int32_t c, size_t pixels_per_image, double* dbeta, double* dgamma,
-                                  void* stream) {
+                                  const uint32_t* relu_bits, size_t pixels, int32_t c, size_t pixels_per_image, double* dbeta,
+                                  double* dgamma, void* stream) {
   VSPW_REQUIRE(dout && y && mean && invstd && dbeta && dgamma, "vspw_bn_bwd_reduce: null pointer");
-  VSPW_REQUIRE(!relu || out || out_hi, "vspw_bn_bwd_reduce: relu mask needs the forward output (fp32 or bf16 hi plane)");
+  VSPW_REQUIRE(!relu || out || out_hi || relu_bits, "vspw_bn_bwd_reduce: relu mask needs the forward output (fp32, bf16 hi plane or bits)");
   VSPW_REQUIRE(c > 0 && c % 4 == 0, "vspw_bn_bwd_reduce: channels must be a multiple of 4 (got %d)", c);
   if (pixels == 0) return VSPW_OK;
   int red_pix = kUnroll;
@@ -573,29 +682,59 @@ extern "C" int vspw_bn_bwd_reduce(const float* dout, const float* out, const uin
   const dim3 rg = red_grid(pixels, c / 4, red_pix, occ);
   bn_bwd_reduce_kernel<<<rg, kEwThreads, 0, as_stream(stream)>>>(
       (const float4*)dout, (const float4*)out, (const uint2*)out_hi, (const float4*)y, (const float4*)mean,
-      (const float4*)invstd, (const float4*)chan_scale, relu, pixels, c / 4, pixels_per_image, dbeta, dgamma, red_pix);
+      (const float4*)invstd, (const float4*)chan_scale, relu, (const uint4*)relu_bits, pixels, c / 4, pixels_per_image, dbeta, dgamma,
+      red_pix);
   return check_launch("vspw_bn_bwd_reduce");
 }
+
+static int bn_bwd_apply_impl(const float* dout, const float* out, const uint16_t* out_hi, const float* y, const float* mean,
+                             const float* invstd, const float* gamma, const float* chan_scale, int32_t relu, const double* dbeta,
+                             const double* dgamma, float* dy, uint16_t* dy_hi, uint16_t* dy_lo, float* dres, float* dgamma_f,
+                             float* dbeta_f, const uint32_t* relu_bits, size_t pixels, int32_t c, size_t pixels_per_image,
+                             int32_t eval_mode, double count, double pgrad_scale, const vspw_peer_ctx* peer_ctx, void* stream);
 
 extern "C" int vspw_bn_bwd_apply(const float* dout, const float* out, const uint16_t* out_hi, const float* y,
                                  const float* mean, const float* invstd, const float* gamma, const float* chan_scale,
                                  int32_t relu, const double* dbeta, const double* dgamma, float* dy, uint16_t* dy_hi,
-                                 uint16_t* dy_lo, float* dres, float* dgamma_f, float* dbeta_f, size_t pixels, int32_t c,
-                                 size_t pixels_per_image, int32_t eval_mode, double count, double pgrad_scale,
-                                 void* stream) {
+                                 uint16_t* dy_lo, float* dres, float* dgamma_f, float* dbeta_f, const uint32_t* relu_bits,
+                                 size_t pixels, int32_t c, size_t pixels_per_image, int32_t eval_mode, double count,
+                                 double pgrad_scale, void* stream) {
+  return bn_bwd_apply_impl(dout, out, out_hi, y, mean, invstd, gamma, chan_scale, relu, dbeta, dgamma, dy, dy_hi, dy_lo, dres, dgamma_f,
+                           dbeta_f, relu_bits, pixels, c, pixels_per_image, eval_mode, count, pgrad_scale, nullptr, stream);
+}
+
+extern "C" int vspw_bn_bwd_apply_sync(const float* dout, const float* out, const uint16_t* out_hi, const float* y, const float* mean,
+                                      const float* invstd, const float* gamma, const float* chan_scale, int32_t relu, double* dsums,
+                                      float* dy, uint16_t* dy_hi, uint16_t* dy_lo, float* dres, float* dgamma_f, float* dbeta_f,
+                                      const uint32_t* relu_bits, size_t pixels, int32_t c, size_t pixels_per_image, double count,
+                                      double pgrad_scale, const vspw_peer_ctx* peer_ctx, void* stream) {
+  VSPW_REQUIRE(dsums && peer_ctx, "vspw_bn_bwd_apply_sync: null pointer");
+  return bn_bwd_apply_impl(dout, out, out_hi, y, mean, invstd, gamma, chan_scale, relu, dsums, dsums + c, dy, dy_hi, dy_lo, dres, dgamma_f,
+                           dbeta_f, relu_bits, pixels, c, pixels_per_image, 0, count, pgrad_scale, peer_ctx, stream);
+}
+
+static int bn_bwd_apply_impl(const float* dout, const float* out, const uint16_t* out_hi, const float* y, const float* mean,
+                             const float* invstd, const float* gamma, const float* chan_scale, int32_t relu, const double* dbeta,
+                             const double* dgamma, float* dy, uint16_t* dy_hi, uint16_t* dy_lo, float* dres, float* dgamma_f,
+                             float* dbeta_f, const uint32_t* relu_bits, size_t pixels, int32_t c, size_t pixels_per_image,
+                             int32_t eval_mode, double count, double pgrad_scale, const vspw_peer_ctx* peer_ctx, void* stream) {
   VSPW_REQUIRE(dout && invstd && (dy || dy_hi), "vspw_bn_bwd_apply: null pointer");
-  VSPW_REQUIRE(!relu || out || out_hi, "vspw_bn_bwd_apply: relu mask needs the forward output (fp32 or bf16 hi plane)");
+  VSPW_REQUIRE(!relu || out || out_hi || relu_bits, "vspw_bn_bwd_apply: relu mask needs the forward output (fp32, bf16 hi plane or bits)");
   VSPW_REQUIRE(!dy_lo || dy_hi, "vspw_bn_bwd_apply: dy_lo without dy_hi");
   VSPW_REQUIRE(count >= 1.0, "vspw_bn_bwd_apply: count must be >= 1");
   VSPW_REQUIRE(eval_mode || (y && mean && dbeta && dgamma), "vspw_bn_bwd_apply: train mode needs y/mean/sums");
   VSPW_REQUIRE(c > 0 && c % 4 == 0, "vspw_bn_bwd_apply: channels must be a multiple of 4 (got %d)", c);
+  peer::PeerArgs pa;
+  int rc0 = peer_args(peer_ctx, 2 * c, pa, "vspw_bn_bwd_apply_sync");
+  if (rc0) return rc0;
+  VSPW_REQUIRE(pa.world <= 1 || (pixels > 0 && dgamma == dbeta + c), "vspw_bn_bwd_apply_sync: (dbeta, dgamma) must be one (2, C) buffer");
   if (pixels == 0) return VSPW_OK;
   static const int occ = blocks_per_sm(bn_bwd_apply_kernel, kEwThreads);
   bn_bwd_apply_kernel<<<ew_grid(pixels, c / 4, occ), kEwThreads, 0, as_stream(stream)>>>(
       (const float4*)dout, (const float4*)out, (const uint2*)out_hi, (const float4*)y, (const float4*)mean,
       (const float4*)invstd, (const float4*)gamma, (const float4*)chan_scale, relu, dbeta, dgamma, (float4*)dy,
-      (uint2*)dy_hi, (uint2*)dy_lo, (float4*)dres, (float4*)dgamma_f, (float4*)dbeta_f, pixels, c / 4, pixels_per_image,
-      1.0 / count, eval_mode, pgrad_scale);
+      (uint2*)dy_hi, (uint2*)dy_lo, (float4*)dres, (float4*)dgamma_f, (float4*)dbeta_f, (const uint4*)relu_bits, pixels, c / 4,
+      pixels_per_image, 1.0 / count, eval_mode, pgrad_scale, pa, bn_reverse());
   int rc = check_launch("vspw_bn_bwd_apply");
   return rc;
 }

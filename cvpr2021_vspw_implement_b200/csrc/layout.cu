@@ -207,6 +207,39 @@ extern "C" int vspw_cast_f64_f32(const double* x, float* y, size_t n, void* stre
 }
 
 // ---------------------------------------------------------------------------------------------
+// Device-side end of the data path (dataset2.py:962-977 img_transform / segm_transform): uint8 HWC crops and raw uint8 masks,
+// copied to the device as bytes, become the tensors the reference's loader hands to the model — ImageNet-normalised fp32 NCHW
+// and float labels with raw 0 -> 255 (ignore), raw k -> k - 1.  Same IEEE operations in the same order as the host code
+// (u / 255, - mean, / std in fp32 with correctly rounded division), so the result is bit-identical to it.
+__global__ void clip_finish_u8_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ lab, float* __restrict__ out,
+                                      float* __restrict__ lab_out, int n, int h, int w) {
+  const size_t hw = (size_t)h * w, total = (size_t)n * hw;
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t im = i / hw, px = i - im * hw;
+    const uint8_t* src = img + i * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = __fdiv_rn((float)src[c], 255.f);
+      out[(im * 3 + c) * hw + px] = __fdiv_rn(__fsub_rn(v, mean[c]), stdv[c]);
+    }
+    if (lab) {
+      const uint8_t r = lab[i];
+      lab_out[i] = (r == 0 || r == 255) ? 255.f : (float)(r - 1);  // (raw 255 -> 254 -> 255 in the host code)
+    }
+  }
+}
+
+extern "C" int vspw_clip_finish_u8(const uint8_t* img_hwc, const uint8_t* lab, float* img_nchw, float* lab_out, int32_t n, int32_t h,
+                                   int32_t w, void* stream) {
+  VSPW_REQUIRE(img_hwc && img_nchw && ((lab == nullptr) == (lab_out == nullptr)), "vspw_clip_finish_u8: null pointer");
+  const size_t total = (size_t)n * h * w;
+  if (!total) return VSPW_OK;
+  clip_finish_u8_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(img_hwc, lab, img_nchw, lab_out, n, h, w);
+  return check_launch("vspw_clip_finish_u8");
+}
+
+// ---------------------------------------------------------------------------------------------
 // dst[n][h][w][c] = src[n][y/2][x/2][c] at even (y, x), zero elsewhere: the gradient of a stride-2 conv's output laid on
 // the input grid, so that its dgrad is the stride-1 tcgen05 dgrad of the same filter.  One thread = 8 bf16 channels.
 __global__ void zero_insert2_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n, int ho, int wo, int c8,

@@ -275,7 +275,122 @@ __global__ void ocr_region_planes_kernel(const float* __restrict__ probs, uint16
   }
 }
 
+// ---- soft object regions: softmax over the hw axis of the dsn logits (spatial_ocr_block.py:104), column-wise on [hw][K] ----
+// Two passes, `kRsChunks` row chunks per image so that 10 images fill the machine: (1) per (image, chunk, class) running max and
+// sum of exponentials; (2) merge the chunk partials, normalise, write the fp32 probabilities (the backward reads them) AND the
+// bf16 (hi, lo) operand planes of the tensor-core gather (classes padded to 128, 1/T folded in) in the same sweep.
+constexpr int kRsChunks = 32;
+
+__global__ void __launch_bounds__(128) region_softmax_stats_kernel(const float* __restrict__ x, float2* __restrict__ part, int hw, int k) {
+  const int cls = threadIdx.x, img = blockIdx.y, chunk = blockIdx.x;
+  if (cls >= k) return;
+  const int rows = (hw + kRsChunks - 1) / kRsChunks, r0 = chunk * rows, r1 = min(hw, r0 + rows);
+  const float* src = x + (size_t)img * hw * k + cls;
+  float m = -INFINITY, s = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const float v = __ldg(src + (size_t)r * k);
+    if (v > m) { s = s * expf(m - v); m = v; }
+    s += expf(v - m);
+  }
+  part[((size_t)img * kRsChunks + chunk) * k + cls] = make_float2(m, s);
+}
+
+__global__ void __launch_bounds__(128) region_softmax_write_kernel(const float* __restrict__ x, const float2* __restrict__ part,
+                                                                    float* __restrict__ probs, uint16_t* __restrict__ hi,
+                                                                    uint16_t* __restrict__ lo, int hw, int k, float plane_scale) {
+  const int cls = threadIdx.x, img = blockIdx.y, chunk = blockIdx.x;
+  const int rows = (hw + kRsChunks - 1) / kRsChunks, r0 = chunk * rows, r1 = min(hw, r0 + rows);
+  float m = -INFINITY, inv = 0.f;
+  if (cls < k) {
+    const float2* pp = part + (size_t)img * kRsChunks * k + cls;
+    for (int c = 0; c < kRsChunks; ++c) m = fmaxf(m, pp[(size_t)c * k].x);
+    float s = 0.f;
+    for (int c = 0; c < kRsChunks; ++c) {
+      const float2 t = pp[(size_t)c * k];
+      if (t.y > 0.f) s += t.y * expf(t.x - m);
+    }
+    inv = 1.f / s;
+  }
+  for (int r = r0; r < r1; ++r) {
+    const size_t row = (size_t)img * hw + r;
+    float pv = 0.f;
+    if (cls < k) {
+      pv = expf(__ldg(x + row * k + cls) - m) * inv;
+      if (probs) probs[row * k + cls] = pv;
+    }
+    if (hi) {
+      const float ps = pv * plane_scale;
+      const __nv_bfloat16 h = __float2bfloat16_rn(ps);
+      hi[row * AT_REG + cls] = *reinterpret_cast<const uint16_t*>(&h);
+      if (lo) {
+        const __nv_bfloat16 l = __float2bfloat16_rn(ps - __bfloat162float(h));
+        lo[row * AT_REG + cls] = *reinterpret_cast<const uint16_t*>(&l);
+      }
+    }
+  }
+}
+
+// backward: dx = p * (dp - sum_rows p * dp), column-wise
+__global__ void __launch_bounds__(128) region_softmax_bwd_dot_kernel(const float* __restrict__ p, const float* __restrict__ dp,
+                                                                      float* __restrict__ part, int hw, int k) {
+  const int cls = threadIdx.x, img = blockIdx.y, chunk = blockIdx.x;
+  if (cls >= k) return;
+  const int rows = (hw + kRsChunks - 1) / kRsChunks, r0 = chunk * rows, r1 = min(hw, r0 + rows);
+  const size_t base = (size_t)img * hw * k + cls;
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) s = fmaf(__ldg(p + base + (size_t)r * k), __ldg(dp + base + (size_t)r * k), s);
+  part[((size_t)img * kRsChunks + chunk) * k + cls] = s;
+}
+
+__global__ void __launch_bounds__(128) region_softmax_bwd_write_kernel(const float* __restrict__ p, const float* __restrict__ dp,
+                                                                        const float* __restrict__ part, float* __restrict__ dx, int hw,
+                                                                        int k) {
+  const int cls = threadIdx.x, img = blockIdx.y, chunk = blockIdx.x;
+  if (cls >= k) return;
+  const int rows = (hw + kRsChunks - 1) / kRsChunks, r0 = chunk * rows, r1 = min(hw, r0 + rows);
+  float dot = 0.f;
+  for (int c = 0; c < kRsChunks; ++c) dot += part[((size_t)img * kRsChunks + c) * k + cls];
+  const size_t base = (size_t)img * hw * k + cls;
+  for (int r = r0; r < r1; ++r) {
+    const size_t i = base + (size_t)r * k;
+    dx[i] = __ldg(p + i) * (__ldg(dp + i) - dot);
+  }
+}
+
 }  // namespace
+
+extern "C" size_t vspw_ocr_region_softmax_workspace_bytes(int32_t n_images, int32_t k) { return (size_t)n_images * kRsChunks * k * sizeof(float2); }
+
+extern "C" int vspw_ocr_region_softmax_fwd(const float* dsn, float* probs, uint16_t* p_hi, uint16_t* p_lo, void* workspace,
+                                           int32_t n_images, int32_t hw, int32_t k, float plane_scale, void* stream) {
+  const char* who = "vspw_ocr_region_softmax_fwd";
+  VSPW_REQUIRE(dsn && workspace && (probs || p_hi), "%s: null pointer", who);
+  VSPW_REQUIRE(k >= 1 && k <= AT_REG && (!p_lo || p_hi), "%s: 1..%d classes", who, AT_REG);
+  VSPW_REQUIRE(n_images <= 65535, "%s: grid limit", who);
+  if (!n_images || !hw) return VSPW_OK;
+  cudaStream_t st = as_stream(stream);
+  dim3 grid(kRsChunks, n_images);
+  region_softmax_stats_kernel<<<grid, 128, 0, st>>>(dsn, (float2*)workspace, hw, k);
+  int rc = check_launch("vspw_ocr_region_softmax_fwd(stats)");
+  if (rc) return rc;
+  region_softmax_write_kernel<<<grid, 128, 0, st>>>(dsn, (const float2*)workspace, probs, p_hi, p_lo, hw, k, plane_scale);
+  return check_launch(who);
+}
+
+extern "C" int vspw_ocr_region_softmax_bwd(const float* probs, const float* dprobs, float* ddsn, void* workspace, int32_t n_images,
+                                           int32_t hw, int32_t k, void* stream) {
+  const char* who = "vspw_ocr_region_softmax_bwd";
+  VSPW_REQUIRE(probs && dprobs && ddsn && workspace, "%s: null pointer", who);
+  VSPW_REQUIRE(k >= 1 && k <= AT_REG && n_images <= 65535, "%s: bad dims", who);
+  if (!n_images || !hw) return VSPW_OK;
+  cudaStream_t st = as_stream(stream);
+  dim3 grid(kRsChunks, n_images);
+  region_softmax_bwd_dot_kernel<<<grid, 128, 0, st>>>(probs, dprobs, (float*)workspace, hw, k);
+  int rc = check_launch("vspw_ocr_region_softmax_bwd(dot)");
+  if (rc) return rc;
+  region_softmax_bwd_write_kernel<<<grid, 128, 0, st>>>(probs, dprobs, (const float*)workspace, ddsn, hw, k);
+  return check_launch(who);
+}
 
 extern "C" size_t vspw_ocr_attention_workspace_bytes(int32_t n) { return (size_t)4 * n * AT_REG * AT_KC * sizeof(uint16_t); }
 

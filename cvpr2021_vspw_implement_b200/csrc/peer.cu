@@ -9,11 +9,13 @@
 //
 // Memory (per rank, one cudaMalloc exported with cudaIpcGetMemHandle and opened by the peers):
 //   flags : [ring][world] uint64  — flags[s][r] = sequence number of the last exchange rank r completed into slot s
+//   ready : [ring] uint64         — "the totals of slot s are in place" for the BN kernels that run the exchange in their own
+//                                   prologue (peer_common.cuh grid_allreduce: block 0 exchanges, the other blocks wait here)
 //   data  : [ring][world][max_elems] double
 // Slot reuse: rank A starts exchange q only after it finished q-1, which needed every peer's flag of q-1, which a peer
 // raises inside ITS kernel q-1, i.e. after its kernel q-2 finished reading.  A ring of >= 2 slots is therefore enough;
 // the host side uses 4.
-#include "common.cuh"
+#include "peer_common.cuh"
 #include <stdlib.h>
 #include <string.h>
 
@@ -21,70 +23,16 @@ using namespace vspw;
 
 namespace {
 
-struct PeerTable {
-  unsigned long long base[16];  // inbox base address of every rank, as mapped in THIS process
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
 constexpr int kPeerThreads = 1024;
 
-__global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(double* __restrict__ vec, int n, PeerTable tab, int world,
-                                                                       int rank, unsigned long long seq, int ring, int max_elems,
-                                                                       unsigned long long timeout_ns) {
-  const int slot = (int)(seq % (unsigned long long)ring);
-  const size_t flag_bytes = ((size_t)ring * world * sizeof(unsigned long long) + 255) & ~(size_t)255;
-  // 1. push my vector into inbox[slot][rank] of every rank (my own included)
-  for (int i = threadIdx.x; i < n; i += kPeerThreads) {
-    const double v = vec[i];
-    for (int p = 0; p < world; ++p) {
-      double* dst = reinterpret_cast<double*>(tab.base[p] + flag_bytes) + ((size_t)slot * world + rank) * max_elems + i;
-      *dst = v;
-    }
-  }
-  __threadfence_system();
-  __syncthreads();
-  // 2. raise my flag on every rank
-  if ((int)threadIdx.x < world) {
-    unsigned long long* f = reinterpret_cast<unsigned long long*>(tab.base[threadIdx.x]) + (size_t)slot * world + rank;
-    st_release_sys(f, seq);
-  }
-  // 3. wait for every rank's flag in MY memory
-  if ((int)threadIdx.x < world) {
-    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(tab.base[rank]) + (size_t)slot * world + threadIdx.x;
-    const unsigned long long t0 = globaltimer_ns();
-    while (ld_acquire_sys(f) < seq) {
-      if (globaltimer_ns() - t0 > timeout_ns) __trap();  // a rank that never arrives must fail loudly, not hang the box
-      __nanosleep(200);
-    }
-  }
-  __syncthreads();
-  // 4. total in rank order: identical bits on every rank
-  const double* inbox = reinterpret_cast<const double*>(tab.base[rank] + flag_bytes) + (size_t)slot * world * max_elems;
-  for (int i = threadIdx.x; i < n; i += kPeerThreads) {
-    double s = 0.0;
-    for (int p = 0; p < world; ++p) s += __ldcv(inbox + (size_t)p * max_elems + i);
-    vec[i] = s;
-  }
+__global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(double* __restrict__ vec, int n, peer::PeerArgs pa) {
+  peer::block_allreduce(vec, n, pa);
 }
 
 }  // namespace
 
 extern "C" size_t vspw_peer_inbox_bytes(int32_t world, int32_t ring, int32_t max_elems) {
-  const size_t flag_bytes = ((size_t)ring * world * sizeof(unsigned long long) + 255) & ~(size_t)255;
-  return flag_bytes + (size_t)ring * world * max_elems * sizeof(double);
+  return peer::flag_bytes(ring, world) + (size_t)ring * world * max_elems * sizeof(double);
 }
 
 extern "C" int vspw_peer_alloc(size_t bytes, void** dev_ptr, uint8_t* handle64) {
@@ -139,14 +87,10 @@ extern "C" int vspw_peer_allreduce_f64(double* vec, int32_t n, const uint64_t* i
   VSPW_REQUIRE(n >= 0 && n <= max_elems, "vspw_peer_allreduce_f64: %d elements exceed the inbox slot (%d)", n, max_elems);
   VSPW_REQUIRE(ring >= 2 && seq > 0, "vspw_peer_allreduce_f64: ring must be >= 2 and seq > 0");
   if (n == 0) return VSPW_OK;
-  PeerTable tab;
-  for (int i = 0; i < 16; ++i) tab.base[i] = i < world ? (unsigned long long)inbox_bases_host[i] : 0ull;
-  static long timeout_s = -1;  // VSPW_PEER_TIMEOUT_S: how long a rank waits for its peers before the kernel traps (default 300 s)
-  if (timeout_s < 0) {
-    const char* e = getenv("VSPW_PEER_TIMEOUT_S");
-    timeout_s = (e && atol(e) > 0) ? atol(e) : 300;
-  }
-  peer_allreduce_kernel<<<1, kPeerThreads, 0, as_stream(stream)>>>(vec, n, tab, world, rank, (unsigned long long)seq, ring, max_elems,
-                                                                   (unsigned long long)timeout_s * 1000000000ull);
+  peer::PeerArgs pa;
+  for (int i = 0; i < 16; ++i) pa.base[i] = i < world ? (unsigned long long)inbox_bases_host[i] : 0ull;
+  pa.world = world; pa.rank = rank; pa.ring = ring; pa.max_elems = max_elems; pa.seq = seq;
+  pa.timeout_ns = peer::timeout_ns_from_env();
+  peer_allreduce_kernel<<<1, kPeerThreads, 0, as_stream(stream)>>>(vec, n, pa);
   return check_launch("vspw_peer_allreduce_f64");
 }

@@ -125,9 +125,13 @@ class DevicePrefetcher:
     (clip_imgs, clip_gts) lists of pinned host tensors; iteration yields the same lists on `device`, valid until the next
     item is requested."""
 
-    def __init__(self, source, device):
+    def __init__(self, source, device, finish_u8=False):
+        """finish_u8=True: `source` yields uint8 batches — images (n, h, w, 3), raw masks (n, h, w) — as
+        `vspw_data.VSPWClipTrain(device_finish=True)` produces them; they are copied as bytes and turned into the model's
+        float tensors on the copy stream by vspw_clip_finish_u8."""
         self.it = iter(source)
         self.device = device
+        self.finish_u8 = bool(finish_u8)
         # one copy stream per device for the life of the process: the caching allocator keeps a pool per stream, so a fresh
         # stream per prefetcher would cudaMalloc its input buffers again every epoch
         key = torch.device(device)
@@ -146,7 +150,27 @@ class DevicePrefetcher:
         with torch.cuda.stream(self.stream):
             d_imgs = [t.to(self.device, non_blocking=True) for t in imgs]
             d_gts = [t.to(self.device, non_blocking=True) for t in gts]
+            if self.finish_u8:
+                d_imgs, d_gts = self._finish(d_imgs, d_gts)
         self.next = (d_imgs, d_gts)
+
+    def _finish(self, imgs_u8, gts_u8):
+        import ctypes
+        from ._lib import lib
+        st = ctypes.c_void_p(self.stream.cuda_stream)
+        out_i, out_l = [], []
+        for im, lb in zip(imgs_u8, gts_u8):
+            if im.dtype != torch.uint8 or lb.dtype != torch.uint8 or im.dim() != 4 or im.shape[3] != 3:
+                raise ValueError("finish_u8 expects uint8 (n, h, w, 3) images and uint8 (n, h, w) masks")
+            n, h, w, _ = im.shape
+            fi = torch.empty((n, 3, h, w), device=self.device, dtype=torch.float32)
+            fl = torch.empty((n, 1, h, w), device=self.device, dtype=torch.float32)
+            lib.call("vspw_clip_finish_u8", ctypes.c_void_p(im.data_ptr()), ctypes.c_void_p(lb.data_ptr()), ctypes.c_void_p(fi.data_ptr()),
+                     ctypes.c_void_p(fl.data_ptr()), n, h, w, st)
+            out_i.append(fi)
+            out_l.append(fl)
+        self._keep = (imgs_u8, gts_u8)  # the byte buffers stay alive until the next preload (same stream: ordering is implicit)
+        return out_i, out_l
 
     def __iter__(self):
         return self

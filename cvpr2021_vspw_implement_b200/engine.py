@@ -670,7 +670,10 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
             lib.call("vspw_bn_stats", _p(y.data), pixels, c, _p(sums[0]), _p(sums[1]), st)
         group = _syncbn_group()
         world = group.size() if group is not None else 1
-        if group is not None:
+        # the statistics exchange: inside the BN kernel's prologue when the group offers it (parallel.PeerSums), else a call of
+        # its own (torch.distributed all-reduce, test doubles)
+        peer_ctx = group.next_ctx(2 * c) if (group is not None and hasattr(group, "next_ctx") and sums.is_contiguous()) else None
+        if group is not None and peer_ctx is None:
             group.all_reduce_sums(sums)
         count = float(pixels * world)
         mean = torch.empty(c, device=dev, dtype=torch.float32)
@@ -691,16 +694,27 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
         hi = torch.empty(y.shape, device=dev, dtype=torch.bfloat16)
         lo = torch.empty(y.shape, device=dev, dtype=torch.bfloat16) if _state["precision"] == "bf16x3" else None
     o = torch.empty_like(y.data) if (fp32_out or not want_planes) else None
+    needs = tape.grad_enabled and (y.needs_grad or gv.needs_grad or (residual is not None and residual.needs_grad))
+    # the backward needs [out != 0] only: one bit per element (written by the forward kernel with warp ballots) instead of
+    # re-reading the bf16 hi plane (2 B) or the fp32 output (4 B) in both backward passes
+    bits = None
+    if relu and needs and (c == 64 or c % 128 == 0) and os.environ.get("VSPW_RELU_BITS", "1") != "0":
+        bits = torch.empty(((pixels * c // 4 + 31) // 32) * 4, device=dev, dtype=torch.int32)
     if training:
         # finalize (mean / invstd / running statistics from the fp64 sums) + normalise + residual + ReLU + planes: one launch
-        lib.call("vspw_bn_train_fwd", _p(y.data), _p(sums[0]), _p(sums[1]), count, _p(gv.data), _p(bv.data), float(bn.eps),
-                 float(bn.momentum), _p(bn.running_mean), _p(bn.running_var), _p(mean), _p(invstd),
-                 1 if _state["syncbn_clamp"] else 0, _p(res_f), _p(res_h), _p(res_l), _p(chan_scale),
-                 1 if relu else 0, _p(o), _p(hi), _p(lo), pixels, c, h * w, st)
+        if peer_ctx is not None:
+            lib.call("vspw_bn_train_fwd_sync", _p(y.data), _p(sums), count, _p(gv.data), _p(bv.data), float(bn.eps),
+                     float(bn.momentum), _p(bn.running_mean), _p(bn.running_var), _p(mean), _p(invstd),
+                     1 if _state["syncbn_clamp"] else 0, _p(res_f), _p(res_h), _p(res_l), _p(chan_scale),
+                     1 if relu else 0, _p(o), _p(hi), _p(lo), _p(bits), pixels, c, h * w, ctypes.byref(peer_ctx), st)
+        else:
+            lib.call("vspw_bn_train_fwd", _p(y.data), _p(sums[0]), _p(sums[1]), count, _p(gv.data), _p(bv.data), float(bn.eps),
+                     float(bn.momentum), _p(bn.running_mean), _p(bn.running_var), _p(mean), _p(invstd),
+                     1 if _state["syncbn_clamp"] else 0, _p(res_f), _p(res_h), _p(res_l), _p(chan_scale),
+                     1 if relu else 0, _p(o), _p(hi), _p(lo), _p(bits), pixels, c, h * w, st)
     else:
         lib.call("vspw_bn_act_fwd", _p(y.data), _p(scale), _p(shift), _p(bn.running_mean), _p(bv.data),
-                 _p(res_f), _p(res_h), _p(res_l), _p(chan_scale), 1 if relu else 0, _p(o), _p(hi), _p(lo), pixels, c, h * w, st)
-    needs = tape.grad_enabled and (y.needs_grad or gv.needs_grad or (residual is not None and residual.needs_grad))
+                 _p(res_f), _p(res_h), _p(res_l), _p(chan_scale), 1 if relu else 0, _p(o), _p(hi), _p(lo), _p(bits), pixels, c, h * w, st)
     out = Var(o, needs_grad=needs)
     if want_planes:
         out.planes = (hi, lo)
@@ -726,8 +740,9 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
         if training:
             dsum = tape.zeros_f64((2, c), dev)
             lib.call("vspw_bn_bwd_reduce", _p(dout), _p(mask_o), _p(mask_hi), _p(y.data), _p(mean), _p(invstd), _p(chan_scale),
-                     1 if relu else 0, pixels, c, h * w, _p(dsum[0]), _p(dsum[1]), st)
-            if group is not None:
+                     1 if relu else 0, _p(bits), pixels, c, h * w, _p(dsum[0]), _p(dsum[1]), st)
+            bctx = group.next_ctx(2 * c) if (group is not None and hasattr(group, "next_ctx")) else None
+            if group is not None and bctx is None:
                 # dx needs the all-rank sums; gamma/beta gradients leave as sums/world because the gradient all-reduce that
                 # follows AVERAGES the ranks' parameter gradients and every rank holds the same all-rank total here
                 group.all_reduce_sums(dsum)
@@ -735,9 +750,14 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
             bdst = bv.first_dst() if bv.needs_grad else None
             dgam = gdst if gdst is not None else torch.empty(c, device=dev, dtype=torch.float32)
             dbet = bdst if bdst is not None else torch.empty(c, device=dev, dtype=torch.float32)
-            lib.call("vspw_bn_bwd_apply", _p(dout), _p(mask_o), _p(mask_hi), _p(y.data), _p(mean), _p(invstd), _p(gv.data),
-                     _p(chan_scale), 1 if relu else 0, _p(dsum[0]), _p(dsum[1]), _p(dy), _p(dy_hi), _p(dy_lo), _p(dres), _p(dgam),
-                     _p(dbet), pixels, c, h * w, 0, float(pixels * world), 1.0 / world, st)
+            if bctx is not None:
+                lib.call("vspw_bn_bwd_apply_sync", _p(dout), _p(mask_o), _p(mask_hi), _p(y.data), _p(mean), _p(invstd), _p(gv.data),
+                         _p(chan_scale), 1 if relu else 0, _p(dsum), _p(dy), _p(dy_hi), _p(dy_lo), _p(dres), _p(dgam), _p(dbet),
+                         _p(bits), pixels, c, h * w, float(pixels * world), 1.0 / world, ctypes.byref(bctx), st)
+            else:
+                lib.call("vspw_bn_bwd_apply", _p(dout), _p(mask_o), _p(mask_hi), _p(y.data), _p(mean), _p(invstd), _p(gv.data),
+                         _p(chan_scale), 1 if relu else 0, _p(dsum[0]), _p(dsum[1]), _p(dy), _p(dy_hi), _p(dy_lo), _p(dres), _p(dgam),
+                         _p(dbet), _p(bits), pixels, c, h * w, 0, float(pixels * world), 1.0 / world, st)
             if gv.needs_grad and gdst is None:
                 gv.add_grad(dgam)
             if bv.needs_grad and bdst is None:
@@ -749,12 +769,12 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
             if gv.needs_grad or bv.needs_grad:
                 dsum = tape.zeros_f64((2, c), dev)
                 lib.call("vspw_bn_bwd_reduce", _p(dout), _p(mask_o), _p(mask_hi), _p(y.data), _p(bn.running_mean), _p(invstd),
-                         _p(chan_scale), 1 if relu else 0, pixels, c, h * w, _p(dsum[0]), _p(dsum[1]), st)
+                         _p(chan_scale), 1 if relu else 0, _p(bits), pixels, c, h * w, _p(dsum[0]), _p(dsum[1]), st)
                 dgam = torch.empty(c, device=dev, dtype=torch.float32)
                 dbet = torch.empty(c, device=dev, dtype=torch.float32)
             lib.call("vspw_bn_bwd_apply", _p(dout), _p(mask_o), _p(mask_hi), None, None, _p(scale), None, _p(chan_scale),
                      1 if relu else 0, _p(dsum[0]) if dsum is not None else None, _p(dsum[1]) if dsum is not None else None,
-                     _p(dy), _p(dy_hi), _p(dy_lo), _p(dres), _p(dgam), _p(dbet), pixels, c, h * w, 1, float(pixels), 1.0, st)
+                     _p(dy), _p(dy_hi), _p(dy_lo), _p(dres), _p(dgam), _p(dbet), _p(bits), pixels, c, h * w, 1, float(pixels), 1.0, st)
             if dsum is not None:
                 if gv.needs_grad:
                     gv.add_grad(dgam)
@@ -1315,21 +1335,27 @@ def region_gather(tape, feats, dsn, t_frames, n_clips):
     dev = feats.data.device
     st = _stream()
     probs = torch.empty_like(dsn.data)  # [N][hw][K]
-    lib.call("vspw_softmax_strided_fwd", _p(dsn.data), _p(probs), N * k, hw, 1, k, k, hw * k, 1.0, st)
     ctx = torch.empty((n_clips, k, 1, c), device=dev, dtype=torch.float32)
     inv_t = 1.0 / t_frames
-    if _ocr_tc_ok() and k <= 128 and c % 128 == 0:
+    use_tc = _ocr_tc_ok() and k <= 128 and c % 128 == 0
+    sm_ws = torch.empty(int(lib.dll().vspw_ocr_region_softmax_workspace_bytes(N, k)), device=dev, dtype=torch.uint8) if k <= 128 else None
+    if use_tc:
         # tcgen05: the gather is the weight-gradient kernel's GEMM (K axis = pixels, both operands channel-contiguous) over
-        # the probability planes (classes padded to 128, 1/T folded in) and the operand planes of feats
+        # the probability planes (classes padded to 128, 1/T folded in; written by the softmax sweep itself) and the operand
+        # planes of feats
         x3 = _state["precision"] == "bf16x3"
         ph = torch.empty((N, hw, 128), device=dev, dtype=torch.bfloat16)
         pl = torch.empty((N, hw, 128), device=dev, dtype=torch.bfloat16) if x3 else None
-        lib.call("vspw_ocr_region_planes", _p(probs), _p(ph), _p(pl), N * hw, k, inv_t, st)
+        lib.call("vspw_ocr_region_softmax_fwd", _p(dsn.data), _p(probs), _p(ph), _p(pl), _p(sm_ws), N, hw, k, inv_t, st)
         fh, fl = _var_planes(feats)
         with _ConvTimer(2.0 * N * hw * k * c, True):
             lib.call("vspw_ocr_gather_tc", _p(ph), _p(pl), _p(fh), _p(fl), _p(ctx), t_frames, n_clips, hw, k, c, st)
         del ph, pl
     else:
+        if sm_ws is not None:
+            lib.call("vspw_ocr_region_softmax_fwd", _p(dsn.data), _p(probs), None, None, _p(sm_ws), N, hw, k, 1.0, st)
+        else:
+            lib.call("vspw_softmax_strided_fwd", _p(dsn.data), _p(probs), N * k, hw, 1, k, k, hw * k, 1.0, st)
         for t in range(t_frames):
             pr = probs[t * n_clips:(t + 1) * n_clips]
             ft = feats.data[t * n_clips:(t + 1) * n_clips]
@@ -1360,7 +1386,10 @@ def region_gather(tape, feats, dsn, t_frames, n_clips):
                 lib.call("vspw_bgemm", _p(ft), _p(g), _p(dprobs[t * n_clips:(t + 1) * n_clips]), n_clips, hw, k, c, hw * c, c, 1,
                          k * c, 1, c, hw * k, k, 1, inv_t, 0.0, st)
             dd = torch.empty_like(dsn.data)
-            lib.call("vspw_softmax_strided_bwd", _p(probs), _p(dprobs), _p(dd), N * k, hw, 1, k, k, hw * k, 1.0, st)
+            if sm_ws is not None:
+                lib.call("vspw_ocr_region_softmax_bwd", _p(probs), _p(dprobs), _p(dd), _p(sm_ws), N, hw, k, st)
+            else:
+                lib.call("vspw_softmax_strided_bwd", _p(probs), _p(dprobs), _p(dd), N * k, hw, 1, k, k, hw * k, 1.0, st)
             dsn.add_grad(dd)
 
     tape.record(backward)

@@ -6,6 +6,7 @@ beta=0) follow the reference so the same torch seed yields the same state_dict; 
 through ``engine`` (implicit-GEMM convs, fused BN/ReLU/residual kernels).
 """
 import math
+import os
 
 import torch.nn as nn
 
@@ -143,21 +144,24 @@ def stem_and_layers_graph(tape, net, x):
     for layer in (net.layer1, net.layer2, net.layer3, net.layer4):
         blocks = list(layer)
         for i, blk in enumerate(blocks):
-            # An interior block output is read by the NEXT block only: its conv1, its downsample conv (none inside a stage) and
-            # its residual add.  When those convs run on tcgen05 they read the bf16 (hi, lo) operand planes, the residual add
-            # reads the same planes (vspw_bn_train_fwd residual_hi/lo) and the backward takes its ReLU mask from the hi plane,
-            # so the fp32 copy is never written: 4 of the 16 bytes per element of every block-output BN pass, and 12 % of the
-            # activation footprint (186.8 -> 156 GB at T=9, 720p).  Stage outputs keep their fp32 copy: callers get them.
+            # An interior block output is read by the NEXT block only: its conv1 and its residual add.  With
+            # VSPW_PLANES_ONLY_OUT=1 it exists as bf16 (hi, lo) operand planes only (the residual add reads the planes:
+            # vspw_bn_train_fwd residual_hi/lo): 4 fewer bytes written per element.  Measured inside one box (tools/ab.sh):
+            # 92.60 ms/step with it, 91.91 without — two 8-byte plane loads cost the latency-bound BN kernel more than the
+            # 16-byte fp32 store saves — so the default keeps the fp32 copy and releases it right after the next block has read it.
             nxt = blocks[i + 1] if i + 1 < len(blocks) else None
             planes_only = nxt is not None and _planes_only_next(blk, nxt, x.shape)
-            x = blk.graph(tape, x, out_fp32=not planes_only)
+            y = blk.graph(tape, x, out_fp32=not planes_only)
+            if i > 0 and x.planes is not None and x.data is not None and _planes_only_ok(blk.conv1, x.shape) and blk.downsample is None:
+                x.data = None  # backward reads only the planes: the fp32 copy goes back to the allocator now (12 % of the footprint)
+            x = y
         outs.append(x)
     return outs
 
 
 def _planes_only_next(blk, nxt, in_shape):
     """True when `blk`'s output can exist as operand planes only: the next block of the stage reads it through tcgen05 convs."""
-    if E.get_precision() == "fp32" or nxt.downsample is not None:
+    if E.get_precision() == "fp32" or nxt.downsample is not None or os.environ.get("VSPW_PLANES_ONLY_OUT", "0") != "1":
         return False
     n, h, w, _ = in_shape
     # the stage's first block may stride; ResnetDilated rewrites strides in place, so read the conv that carries it

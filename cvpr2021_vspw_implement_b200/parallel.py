@@ -202,10 +202,25 @@ class PeerSums:
             bases.append(ptr.value)
         self._bases = (ctypes.c_uint64 * self.world)(*bases)
         self.seq = 0
+        # VSPW_SYNCBN_FUSED=0: one stand-alone exchange launch per BN layer instead of the exchange in the BN kernels' prologue
+        self.fused = os.environ.get("VSPW_SYNCBN_FUSED", "1") != "0"
         dist.barrier()  # every inbox is mapped everywhere before the first exchange
 
     def size(self):
         return self.world
+
+    def next_ctx(self, n_elems):
+        """The `vspw_peer_ctx` of the NEXT exchange, for the BN kernels that run it in their own prologue
+        (vspw_bn_train_fwd_sync / vspw_bn_bwd_apply_sync); None when the vector does not fit one inbox slot."""
+        from ._lib import PeerCtx
+        if not self.fused or n_elems > self.max_elems:
+            return None
+        self.seq += 1
+        ctx = PeerCtx()
+        for i in range(self.world):
+            ctx.inbox[i] = self._bases[i]
+        ctx.world, ctx.rank, ctx.ring, ctx.max_elems, ctx.seq = self.world, self.rank, self.RING, self.max_elems, self.seq
+        return ctx
 
     def all_reduce_sums(self, t):
         if t.dtype != torch.float64 or not t.is_contiguous():

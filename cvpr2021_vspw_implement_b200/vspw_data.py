@@ -55,8 +55,13 @@ class VSPWClipTrain(torch.utils.data.Dataset):
 
     SCALES = [0.8, 1., 1.5, 2.0]
 
-    def __init__(self, args, split="train"):
+    def __init__(self, args, split="train", device_finish=False):
+        """device_finish=True: items are uint8 — (h, w, 3) image crops and (h, w) RAW masks — and the float conversion,
+        normalisation, HWC->CHW and label remap run on the GPU (`data.DevicePrefetcher(..., finish_u8=True)` ->
+        vspw_clip_finish_u8), bit-identical to the host transform: the workers skip three fp32 passes per frame and the H2D copy
+        moves a quarter of the bytes."""
         self.args = args
+        self.device_finish = bool(device_finish)
         self.split = split
         self.crop = (int(args.cropsize), int(args.cropsize))
         self.dataroot = args.dataroot
@@ -76,7 +81,8 @@ class VSPWClipTrain(torch.utils.data.Dataset):
         y = random.randint(0, H - self.crop[0])
         out_i, out_l = [], []
         for im, lb in zip(images, labels):
-            lb = np.pad(lb, ((ph, ph), (pw, pw)), "constant", constant_values=(255, 255))
+            # raw masks (device_finish) are padded with the RAW ignore value 0, which the device remaps to 255
+            lb = np.pad(lb, ((ph, ph), (pw, pw)), "constant", constant_values=(0, 0) if self.device_finish else (255, 255))
             im = np.pad(im, ((ph, ph), (pw, pw), (0, 0)), "constant")
             out_i.append(im[y:y + self.crop[0], x:x + self.crop[1]])
             out_l.append(lb[y:y + self.crop[0], x:x + self.crop[1]])
@@ -109,10 +115,15 @@ class VSPWClipTrain(torch.utils.data.Dataset):
                     size = (int(w * scale), int(h * scale))
                     img = img.resize(size, Image.BILINEAR)
                     seg = seg.resize(size, Image.NEAREST)
-            images.append(np.float32(np.array(img)) / 255.)
+            images.append(np.array(img) if self.device_finish else np.float32(np.array(img)) / 255.)
             labels.append(np.array(seg))
         if self.split == "train":
             images, labels = self._pad_and_crop(images, labels)
+        if self.device_finish:
+            # (padding: image 0 = 0/255 exactly as the float path pads 0.0; mask padding 255 is the remapped ignore value, so
+            # the raw value that maps to it is 0)
+            return ([torch.from_numpy(np.ascontiguousarray(i)) for i in images],
+                    [torch.from_numpy(np.ascontiguousarray(l)) for l in labels])
         return [image_to_tensor(i) for i in images], [labels_to_tensor(l) for l in labels]
 
 

@@ -101,6 +101,12 @@ int vspw_cast_f64_f32(const double* x, float* y, size_t n, void* stream);
 int vspw_copy_channels(const float* src, int32_t src_c, int32_t src_off, float* dst, int32_t dst_c,
                        int32_t dst_off, int32_t cc, size_t pixels, int32_t accumulate, void* stream);
 
+/* Device-side end of the loader (dataset2.py:962-977 img_transform + segm_transform): uint8 HWC images [n][h][w][3] and raw
+ * uint8 masks [n][h][w] (nullable, together with lab_out) -> ImageNet-normalised fp32 NCHW + float labels (raw 0 -> 255, raw k ->
+ * k - 1), bit-identical to the host transform; the host then ships bytes instead of floats (4x less H2D, no float pass on the CPU) */
+int vspw_clip_finish_u8(const uint8_t* img_hwc, const uint8_t* lab, float* img_nchw, float* lab_out, int32_t n, int32_t h,
+                        int32_t w, void* stream);
+
 /* ---- convolution = implicit GEMM (nn.Conv2d, models/resnet.py:61-66,100-106,130;
  *      clip_psp.py:28,35-41,74-79; clip_ocr.py:43,56-62; spatial_ocr_block.py:208-245,351) ---- */
 /* y = conv(x, w_ohwi) (+ bias[cout] if non-null).  For VSPW_PREC_BF16X3/BF16 the caller passes
@@ -169,7 +175,7 @@ int vspw_bn_fold_eval(const float* gamma, const float* beta, const float* runnin
 int vspw_bn_act_fwd(const float* y, const float* scale, const float* shift, const float* mean,
                     const float* beta, const float* residual, const uint16_t* residual_hi,
                     const uint16_t* residual_lo, const float* chan_scale, int32_t relu, float* out, uint16_t* out_hi,
-                    uint16_t* out_lo, size_t pixels, int32_t c, size_t pixels_per_image,
+                    uint16_t* out_lo, uint32_t* relu_bits, size_t pixels, int32_t c, size_t pixels_per_image,
                     void* stream);
 /* train mode in ONE launch: vspw_bn_finalize_train (same arithmetic, same outputs mean/invstd, same running-statistics
  * update) fused into vspw_bn_act_fwd's centred form; `sum`/`sqsum` come from vspw_bn_stats or from the conv epilogue */
@@ -178,14 +184,17 @@ int vspw_bn_train_fwd(const float* y, const double* sum, const double* sqsum, do
                       float* running_mean, float* running_var, float* mean, float* invstd,
                       int32_t clamp_mode, const float* residual, const uint16_t* residual_hi,
                       const uint16_t* residual_lo, const float* chan_scale, int32_t relu,
-                      float* out, uint16_t* out_hi, uint16_t* out_lo, size_t pixels, int32_t c,
+                      float* out, uint16_t* out_hi, uint16_t* out_lo, uint32_t* relu_bits, size_t pixels, int32_t c,
                       size_t pixels_per_image, void* stream);
+/* `relu_bits` (nullable; needs relu and c == 64 or c % 128 == 0): one bit per output element, [out != 0], as ceil(pixels*c/128)
+ * uint4 words — word (e >> 5) holds, per component, bit (e & 31) of float4 group e = pixel * c/4 + channel/4.  The backward
+ * passes read it instead of the fp32 output or the bf16 hi plane (1/16 of the bytes). */
 /* backward pass 1: g = dout * chan_scale * [out>0]; dbeta = sum g; dgamma = sum g*xhat.  The ReLU mask is read from
- * the fp32 output `out` or, when that is null, from its bf16 hi plane `out_hi` */
+ * `relu_bits`, else from the fp32 output `out`, else from its bf16 hi plane `out_hi` */
 int vspw_bn_bwd_reduce(const float* dout, const float* out, const uint16_t* out_hi, const float* y,
                        const float* mean, const float* invstd, const float* chan_scale, int32_t relu,
-                       size_t pixels, int32_t c, size_t pixels_per_image, double* dbeta, double* dgamma,
-                       void* stream);
+                       const uint32_t* relu_bits, size_t pixels, int32_t c, size_t pixels_per_image, double* dbeta,
+                       double* dgamma, void* stream);
 /* backward pass 2: dy = gamma*invstd*(g - dbeta/P - xhat*dgamma/P); dres = g (if non-null);
  * also converts the double sums to float dgamma_f/dbeta_f.  eval_mode!=0: dy = g*scale.
  * P = `count` = number of values per channel the statistics were taken over (pixels, or the
@@ -196,9 +205,9 @@ int vspw_bn_bwd_reduce(const float* dout, const float* out, const uint16_t* out_
 int vspw_bn_bwd_apply(const float* dout, const float* out, const uint16_t* out_hi, const float* y,
                       const float* mean, const float* invstd, const float* gamma, const float* chan_scale,
                       int32_t relu, const double* dbeta, const double* dgamma, float* dy, uint16_t* dy_hi,
-                      uint16_t* dy_lo, float* dres, float* dgamma_f, float* dbeta_f, size_t pixels, int32_t c,
-                      size_t pixels_per_image, int32_t eval_mode, double count, double pgrad_scale,
-                      void* stream);
+                      uint16_t* dy_lo, float* dres, float* dgamma_f, float* dbeta_f, const uint32_t* relu_bits,
+                      size_t pixels, int32_t c, size_t pixels_per_image, int32_t eval_mode, double count,
+                      double pgrad_scale, void* stream);
 
 /* ---- SyncBN statistics exchange over NVLink peer memory (replaces the per-layer master/slave rendez-vous of
  *      models/sync_batchnorm/batchnorm.py:110-131 + comm.py:96-137; one call per BN layer forward and backward) ----
@@ -208,6 +217,26 @@ int vspw_bn_bwd_apply(const float* dout, const float* out, const uint16_t* out_h
  * vspw_peer_allreduce_f64: vec[0..n) (device, fp64) <- sum over ranks, in rank order (bit-identical on every rank), in ONE
  * single-block launch: push to every peer's inbox slot, flag, wait for the peers' flags, add.  `seq` = 1, 2, 3, ... must
  * advance by one per call and be the same on every rank for the same exchange; n <= max_elems; ring >= 2 slots. */
+typedef struct vspw_peer_ctx {
+  uint64_t inbox[16];                     /* inbox base of every rank as mapped in this process */
+  int32_t world, rank, ring, max_elems;
+  uint64_t seq;                           /* sequence number of THIS exchange (1, 2, 3, ...; the same on every rank) */
+} vspw_peer_ctx;
+/* The SyncBN forms of the two BN passes that need all-rank sums: the exchange (as vspw_peer_allreduce_f64, same inboxes, same
+ * sequence numbering) runs in the prologue of the kernel itself — block 0 exchanges, the other blocks of the one-wave grid
+ * wait — so a BN layer costs no extra launch for it.  `sums` / `dsums`: ONE (2, C) fp64 buffer [sum | sum of squares] /
+ * [dbeta | dgamma] holding this rank's sums on entry and the all-rank totals on return; `count` = all-rank value count. */
+int vspw_bn_train_fwd_sync(const float* y, double* sums, double count, const float* gamma, const float* beta, float eps,
+                           float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
+                           int32_t clamp_mode, const float* residual, const uint16_t* residual_hi,
+                           const uint16_t* residual_lo, const float* chan_scale, int32_t relu, float* out,
+                           uint16_t* out_hi, uint16_t* out_lo, uint32_t* relu_bits, size_t pixels, int32_t c,
+                           size_t pixels_per_image, const vspw_peer_ctx* peer_ctx, void* stream);
+int vspw_bn_bwd_apply_sync(const float* dout, const float* out, const uint16_t* out_hi, const float* y, const float* mean,
+                           const float* invstd, const float* gamma, const float* chan_scale, int32_t relu, double* dsums,
+                           float* dy, uint16_t* dy_hi, uint16_t* dy_lo, float* dres, float* dgamma_f, float* dbeta_f,
+                           const uint32_t* relu_bits, size_t pixels, int32_t c, size_t pixels_per_image, double count,
+                           double pgrad_scale, const vspw_peer_ctx* peer_ctx, void* stream);
 size_t vspw_peer_inbox_bytes(int32_t world, int32_t ring, int32_t max_elems);
 int vspw_peer_alloc(size_t bytes, void** dev_ptr, uint8_t* handle64);
 int vspw_peer_open(const uint8_t* handle64, void** dev_ptr);
@@ -309,6 +338,15 @@ int vspw_ocr_attention_fwd_tc(const uint16_t* q_hi, const uint16_t* q_lo, const 
  * inside).  lo planes null = single-pass bf16. */
 int vspw_ocr_gather_tc(const uint16_t* p_hi, const uint16_t* p_lo, const uint16_t* f_hi, const uint16_t* f_lo, float* ctx,
                        int32_t t_frames, int32_t n_clips, int32_t hw, int32_t classes, int32_t c, void* stream);
+/* Soft object regions (spatial_ocr_block.py:104): probs[img][p][k] = softmax over the hw pixels p of dsn[img][p][k], column-wise
+ * on the NHWC logits, in two sweeps; the second one also writes the operand planes of the tensor-core gather (p_hi / p_lo
+ * [n_images*hw][128], classes padded with zeros, scaled by plane_scale = 1/T).  probs or the planes may be null.
+ * workspace: vspw_ocr_region_softmax_workspace_bytes(n_images, k).  _bwd: ddsn = probs * (dprobs - sum_p probs * dprobs). */
+size_t vspw_ocr_region_softmax_workspace_bytes(int32_t n_images, int32_t k);
+int vspw_ocr_region_softmax_fwd(const float* dsn, float* probs, uint16_t* p_hi, uint16_t* p_lo, void* workspace,
+                                int32_t n_images, int32_t hw, int32_t k, float plane_scale, void* stream);
+int vspw_ocr_region_softmax_bwd(const float* probs, const float* dprobs, float* ddsn, void* workspace, int32_t n_images,
+                                int32_t hw, int32_t k, void* stream);
 /* probs [rows][k] fp32 -> bf16 (hi, lo) planes [rows][128] * scale, columns >= k zero: the A operand of the region gather */
 int vspw_ocr_region_planes(const float* probs, uint16_t* hi, uint16_t* lo, size_t rows, int32_t k, float scale, void* stream);
 

@@ -112,8 +112,8 @@ def test_clips_of_a_batch_do_not_mix_in_eval_mode(E, kind):
         q = m(_feed(mixed), segSize=(H, W))
     if kind == "psp":
         assert torch.equal(p[0], q[0])
-    else:
-        assert float((p[0] - q[0]).abs().max()) <= 1e-5
+    else:  # (split-K atomics in the region gather: summation order varies; this calibrated random-init fixture amplifies it 1e4 x)
+        assert float((p[0] - q[0]).abs().max()) <= 5e-5
     assert float((p[1] - q[1]).abs().max()) > 1e-3
 
 

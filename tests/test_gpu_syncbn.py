@@ -99,6 +99,94 @@ def test_peer_exchange_kernel_three_ranks_on_one_device(E):
             lib.call("vspw_peer_free", p)
 
 
+def test_bn_kernels_with_the_exchange_in_their_prologue_two_ranks_on_one_device(E):
+    """vspw_bn_train_fwd_sync / vspw_bn_bwd_apply_sync: two 'ranks' = two inboxes + two streams of this process, tensors small
+    enough that both one-wave grids are co-resident (on two GPUs each has a device to itself).  Every rank must produce
+    exactly what the plain kernels produce from the pre-summed statistics."""
+    import ctypes
+    from cvpr2021_vspw_implement_b200._lib import PeerCtx, lib
+    os.environ.setdefault("VSPW_PEER_TIMEOUT_S", "20")
+    world, ring, max_elems, c, pixels = 2, 4, 1024, 64, 1500
+    dll = lib.dll()
+    nbytes = int(dll.vspw_peer_inbox_bytes(world, ring, max_elems))
+    ptrs = []
+    for _ in range(world):
+        p, h = ctypes.c_void_p(), (ctypes.c_uint8 * 64)()
+        lib.call("vspw_peer_alloc", nbytes, ctypes.byref(p), h)
+        ptrs.append(p)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ys = [torch.randn(pixels, c, generator=g, device="cuda") * (r + 1) + r for r in range(world)]
+    douts = [torch.randn(pixels, c, generator=g, device="cuda") for _ in range(world)]
+    gamma = torch.rand(c, generator=g, device="cuda") + 0.5
+    beta = torch.randn(c, generator=g, device="cuda")
+    vp = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    streams = [torch.cuda.Stream() for _ in range(world)]
+
+    def ctx_for(rank, seq):
+        ctx = PeerCtx()
+        for i in range(world):
+            ctx.inbox[i] = ptrs[i].value
+        ctx.world, ctx.rank, ctx.ring, ctx.max_elems, ctx.seq = world, rank, ring, max_elems, seq
+        return ctx
+
+    def local_sums(y):
+        d = y.double()
+        return torch.stack([d.sum(0), (d * d).sum(0)]).contiguous()
+
+    try:
+        count = float(world * pixels)
+        total = sum(local_sums(y) for y in ys)
+        outs, means, invstds = [], [], []
+        sums_after = [local_sums(ys[r]) for r in range(world)]
+        for r in range(world):
+            outs.append(torch.empty_like(ys[r])); means.append(torch.empty(c, device="cuda")); invstds.append(torch.empty(c, device="cuda"))
+        torch.cuda.synchronize()  # (no host synchronisation between the two launches: rank 0's kernel waits for rank 1's)
+        for r in range(world):
+            sums, o, mean, invstd = sums_after[r], outs[r], means[r], invstds[r]
+            ctx = ctx_for(r, 1)
+            lib.call("vspw_bn_train_fwd_sync", vp(ys[r]), vp(sums), count, vp(gamma), vp(beta), 1e-5, 0.1, None, None, vp(mean), vp(invstd), 0,
+                     None, None, None, None, 1, vp(o), None, None, None, pixels, c, pixels, ctypes.byref(ctx), ctypes.c_void_p(streams[r].cuda_stream))
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert torch.equal(sums_after[r], sums_after[0]) and C.rel_err(sums_after[r].cpu(), total.cpu()) <= 1e-14
+            ref_o = torch.empty_like(ys[r]); rm = torch.empty(c, device="cuda"); ri = torch.empty(c, device="cuda")
+            t = sums_after[r]
+            lib.call("vspw_bn_train_fwd", vp(ys[r]), vp(t[0]), vp(t[1]), count, vp(gamma), vp(beta), 1e-5, 0.1, None, None, vp(rm), vp(ri), 0,
+                     None, None, None, None, 1, vp(ref_o), None, None, None, pixels, c, pixels, None)
+            torch.cuda.synchronize()
+            assert torch.equal(outs[r], ref_o) and torch.equal(means[r], rm) and torch.equal(invstds[r], ri)
+        # backward: (dbeta, dgamma) exchanged in the prologue of the apply pass
+        dys, dsums = [], []
+        for r in range(world):
+            ds = torch.zeros(2, c, device="cuda", dtype=torch.float64)
+            lib.call("vspw_bn_bwd_reduce", vp(douts[r]), vp(outs[r]), None, vp(ys[r]), vp(means[r]), vp(invstds[r]), None, 1, None, pixels, c, pixels,
+                     vp(ds[0]), vp(ds[1]), None)
+            dsums.append(ds)
+        torch.cuda.synchronize()
+        dtotal = dsums[0] + dsums[1]
+        bufs = [(torch.empty_like(ys[r]), torch.empty(c, device="cuda"), torch.empty(c, device="cuda")) for r in range(world)]
+        torch.cuda.synchronize()
+        for r in range(world):
+            dy, dg, db = bufs[r]
+            ctx = ctx_for(r, 2)
+            lib.call("vspw_bn_bwd_apply_sync", vp(douts[r]), vp(outs[r]), None, vp(ys[r]), vp(means[r]), vp(invstds[r]), vp(gamma), None, 1,
+                     vp(dsums[r]), vp(dy), None, None, None, vp(dg), vp(db), None, pixels, c, pixels, count, 1.0 / world, ctypes.byref(ctx),
+                     ctypes.c_void_p(streams[r].cuda_stream))
+            dys.append((dy, dg, db))
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert torch.equal(dsums[r], dtotal)
+            ry = torch.empty_like(ys[r]); rg = torch.empty(c, device="cuda"); rb = torch.empty(c, device="cuda")
+            lib.call("vspw_bn_bwd_apply", vp(douts[r]), vp(outs[r]), None, vp(ys[r]), vp(means[r]), vp(invstds[r]), vp(gamma), None, 1,
+                     vp(dtotal[0]), vp(dtotal[1]), vp(ry), None, None, None, vp(rg), vp(rb), None, pixels, c, pixels, 0, count, 1.0 / world, None)
+            torch.cuda.synchronize()
+            assert torch.equal(dys[r][0], ry) and torch.equal(dys[r][1], rg) and torch.equal(dys[r][2], rb)
+    finally:
+        torch.cuda.synchronize()
+        for p in ptrs:
+            lib.call("vspw_peer_free", p)
+
+
 def _global_clip(n_clips, seed=41):
     # no ignore labels: every rank then has the same number of valid pixels and the mean of the rank means IS the global mean
     return O.synthetic_clip(T, n_clips, H, W, C.NUM_CLASS, seed=seed, block=16, ignore_frac=0.0)

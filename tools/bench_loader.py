@@ -44,12 +44,12 @@ def make_tree(root, videos, frames, h, w, seed=0):
             fh.write("".join(f"vid_{v:03d}\n" for v in range(videos)))
 
 
-def measure(ds, workers, batch, iters, device):
+def measure(ds, workers, batch, iters, device, finish_u8=False):
     dl = torch.utils.data.DataLoader(ds, batch_size=batch, shuffle=True, num_workers=workers, drop_last=True, pin_memory=True,
                                      persistent_workers=workers > 0, prefetch_factor=4 if workers > 0 else None)
     done, t0, frames = 0, None, 0
     while done < iters + 2:
-        it = DevicePrefetcher(dl, device) if device is not None else iter(dl)
+        it = DevicePrefetcher(dl, device, finish_u8=finish_u8) if device is not None else iter(dl)
         for imgs, labs in it:
             if done == 2:  # two untimed batches: worker start-up, first decode
                 if device is not None:
@@ -80,19 +80,21 @@ def main():
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--iters", type=int, default=24)
     ap.add_argument("--multi-scale", action="store_true")
+    ap.add_argument("--device-finish", action="store_true", help="uint8 items, float conversion / normalisation / label remap on the GPU")
     a = ap.parse_args()
     h, w = (int(x) for x in a.size.lower().split("x"))
     device = torch.device("cuda", 0) if torch.cuda.is_available() else None
     out = {"what": "VSPWClipTrain (= dataset2.BaseDataset_longclip) -> DataLoader(pin_memory) -> DevicePrefetcher", "frame_size": [h, w],
            "cropsize": a.cropsize, "clip_num": a.clip_num, "multi_scale": bool(a.multi_scale), "host_cpus": os.cpu_count(),
-           "h2d": device is not None, "clip_frames_per_s": {}}
+           "h2d": device is not None, "device_finish": bool(a.device_finish and device is not None), "clip_frames_per_s": {}}
     with tempfile.TemporaryDirectory() as root:
         make_tree(root, a.videos, a.frames, h, w)
         args = argparse.Namespace(cropsize=a.cropsize, dataroot=root, trainfps=1, clip_num=a.clip_num,
                                   dilation2=",".join(str(i + 1) for i in range(a.clip_num - 1)), multi_scale=a.multi_scale, lesslabel=False)
-        ds = VSPWClipTrain(args, "train")
+        fin = bool(a.device_finish and device is not None)
+        ds = VSPWClipTrain(args, "train", device_finish=fin)
         for wk in [int(x) for x in a.workers.split(",")]:
-            out["clip_frames_per_s"][str(wk)] = round(measure(ds, wk, a.batch, a.iters, device), 1)
+            out["clip_frames_per_s"][str(wk)] = round(measure(ds, wk, a.batch, a.iters, device, fin), 1)
     print(json.dumps(out), flush=True)
 
 
