@@ -82,7 +82,9 @@ _SIGNATURES = {
     "vspw_ocr_attention_fwd_tc": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_f, _c_vp],
     "vspw_ocr_gather_tc": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp],
     "vspw_ocr_region_softmax_fwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_f, _c_vp],
-    "vspw_ocr_region_softmax_bwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp],
+    "vspw_ocr_region_softmax_bwd": [_c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp],
+    "vspw_ocr_attn_softmax_bwd_planes": [_c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_f, _c_vp],
+    "vspw_ocr_operand_planes": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _c_vp],
     "vspw_ocr_region_planes": [_c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_f, _c_vp],
     "vspw_vc_counts": [_c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_vp, _c_vp],
     "vspw_sgd_momentum_step": [_c_vp, _c_vp, _c_vp, _c_int, _c_f, _c_vp],

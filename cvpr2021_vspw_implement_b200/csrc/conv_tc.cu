@@ -46,6 +46,7 @@ struct ConvTcParams {
   int accumulate;      // 1: out += result (gradient fan-in: the residual branch already wrote its share)
   double* ch_sum;      // [Nout] per-channel sum of the outputs (train-mode BN statistics), or null
   double* ch_sqsum;    // [Nout] per-channel sum of squares
+  int tma_store;       // 1: the epilogue leaves through TMA (cp.async.bulk.tensor store / cp.reduce .add for the fan-in)
 };
 
 // Epilogue geometry of the conv kernels.  The accumulator drain (TMEM -> registers -> smem transpose -> global) is a chain
@@ -66,6 +67,9 @@ constexpr int kChunk = kEpiWarps == 8 ? 16 : 32;   // accumulator columns per ep
 constexpr int kStgPitch = kChunk + 4;  // floats per staged row (36 / 20): 16-byte row writes, column reads and the 16-byte
                                        // reads of the store phase are all bank-conflict-free (row pairs r, r + 4 for pitch 20)
 constexpr int kStoreIters = kChunk / 4;  // float4 stores per lane per step: 32 rows x kChunk columns / (32 lanes x 4)
+// staging block of one epilogue warp: 32 rows x kStgPitch floats (padded transpose path) or 32 rows x 128 B with the 128-byte
+// swizzle (TMA-store path: needs 1024-byte alignment), whichever is larger, rounded up to 1 KB
+constexpr int kStgWarpBytes = ((32 * kStgPitch * 4 + 1023) / 1024) * 1024;
 
 template <int BN, int STAGES>
 struct ConvSmem {
@@ -73,8 +77,8 @@ struct ConvSmem {
   static constexpr int kBTile = BN * BK * 2;
   static constexpr int kStage = 2 * kATile + 2 * kBTile;  // hi+lo of A and B
   static constexpr int kStatBytes = 4 /*lane quadrants*/ * 2 /*sum, sqsum*/ * BN * 4;
-  static constexpr int kStgBytes = kEpiWarps * 32 * kStgPitch * 4;
-  static constexpr int kBytes = STAGES * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/ + kStatBytes + kStgBytes;
+  static constexpr int kStgBytes = kEpiWarps * kStgWarpBytes;
+  static constexpr int kBytes = STAGES * kStage + 1024 /*alignment slack*/ + kStgBytes + 256 /*barriers*/ + kStatBytes;
 };
 
 __device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld_32x32b_x32(taddr, v); }
@@ -97,10 +101,125 @@ __device__ __forceinline__ int store_row(int i, int lane) {
 // One output tile of the epilogue: wait for the accumulator, TMEM -> registers -> per-warp smem transpose -> coalesced NHWC
 // stores (+bias, +fan-in), fused BN statistics, release the accumulator.  Called by the epilogue warps (warp 2 ..).
 // empty_remote != 0: the accumulator-empty barrier lives in the peer (leader) CTA of a cta_group::2 pair.
+// ---- TMA store side (output tiles leave shared memory through cp.async.bulk.tensor; the gradient fan-in through cp.reduce .add) ----
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// One output tile, TMA-store form: TMEM -> registers -> (+bias) -> this warp's 32-row x 128-byte staging block in the
+// SWIZZLE_128B layout -> ONE bulk tensor store (or reduce-add) per 32-column chunk issued by lane 0.  Out-of-range rows and
+// columns are clipped by the tensor map, the fan-in add happens in the memory system (no read-modify-write through the SM),
+// and the per-lane address arithmetic, predicates, 8 LDS.128 and 8 STG.128 per chunk of the transpose form are gone.
+// The BN column sums read the staged block with the same swizzle (conflict-free: a row is one 128-byte line of 32 banks).
 template <int BN>
-__device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, float* stg, float* stat_s, int acc, uint32_t acc_phase,
-                                              uint32_t tmem_base, uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar,
+__device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const CUtensorMap* map_out, float* stg, float* stat_s, int acc,
+                                                  uint32_t acc_phase, uint32_t tmem_base, uint64_t* tmem_full_bar,
+                                                  uint64_t* tmem_empty_bar, uint32_t empty_remote, int img, int ty, int tx, int n0,
+                                                  int warp, int lane) {
+  const int q = warp & 3;
+  const int row = q * 32 + lane;
+  const int px = tx * p.bw + row % p.bw, py = ty * p.bh + row / p.bw;
+  const bool ok = img < p.N && px < p.W && py < p.H;
+  const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
+  // pixel coordinates of this warp's 32 rows as a box: one row segment of the patch (bw >= 32) or 32 / bw whole patch rows
+  int bx, by;
+  if (p.bw >= 32) { bx = tx * p.bw + (q * 32) % p.bw; by = ty * p.bh + (q * 32) / p.bw; }
+  else { bx = tx * p.bw; by = ty * p.bh + q * (32 / p.bw); }
+  mbar_wait(tmem_full_bar, acc_phase);
+  tcgen05_fence_after();
+  const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+  int c_end = BN;
+  if (c_end > p.Nout - n0) c_end = p.Nout - n0;  // Nout % 64 == 0: whole chunks
+  float* stat_row = stat_s + q * 2 * BN;
+  uint8_t* stb = reinterpret_cast<uint8_t*>(stg);
+  const uint32_t sw = (uint32_t)(lane & 7);
+  uint32_t v[32];
+  if (c_end > 0) tmem_ld_32x32b_x32(taddr, v);
+#pragma unroll 1
+  for (int c0 = 0; c0 < c_end; c0 += 32) {
+    if (lane == 0) bulk_wait_read_all();  // the previous chunk's store has finished reading the staging block
+    __syncwarp();
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                             __uint_as_float(v[4 * j + 3]));
+      if (p.bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + 4 * j));
+        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+      }
+      *reinterpret_cast<float4*>(stb + lane * 128 + (((uint32_t)j ^ sw) << 4)) = o;
+    }
+    if (c0 + 32 < c_end) tmem_ld_32x32b_x32(taddr + c0 + 32, v);  // the next chunk travels out of TMEM meanwhile
+    fence_proxy_async();  // generic-proxy writes -> visible to the bulk copy engine
+    __syncwarp();
+    if (lane == 0 && img < p.N) {
+      if (p.accumulate) tma_reduce_add_4d(map_out, stb, n0 + c0, bx, by, img);
+      else tma_store_4d(map_out, stb, n0 + c0, bx, by, img);
+      bulk_commit();
+    }
+    if (p.ch_sum) {
+      // lane = column; element (r, lane) sits in chunk (lane >> 2) ^ (r & 7) of row r
+      float sa = 0.f, sb = 0.f, sa2 = 0.f, sb2 = 0.f;
+      const uint32_t cj = (uint32_t)lane >> 2, cw = ((uint32_t)lane & 3) * 4;
+      if (okmask == 0xffffffffu) {
+#pragma unroll
+        for (int r = 0; r < 32; r += 2) {
+          const float x = *reinterpret_cast<const float*>(stb + r * 128 + ((cj ^ (uint32_t)(r & 7)) << 4) + cw);
+          const float x2 = *reinterpret_cast<const float*>(stb + (r + 1) * 128 + ((cj ^ (uint32_t)((r + 1) & 7)) << 4) + cw);
+          sa += x; sb = fmaf(x, x, sb);
+          sa2 += x2; sb2 = fmaf(x2, x2, sb2);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          const float x = ((okmask >> r) & 1u) ? *reinterpret_cast<const float*>(stb + r * 128 + ((cj ^ (uint32_t)(r & 7)) << 4) + cw) : 0.f;
+          sa += x;
+          sb = fmaf(x, x, sb);
+        }
+      }
+      stat_row[c0 + lane] = sa + sa2;
+      stat_row[BN + c0 + lane] = sb + sb2;
+    }
+  }
+  tcgen05_fence_before();
+  __syncwarp();
+  if (lane == 0) { if (empty_remote) mbar_arrive_cluster(empty_remote); else mbar_arrive(tmem_empty_bar); }
+  if (p.ch_sum) {
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+#pragma unroll
+    for (int col = (warp - 2) * 32 + lane; col < BN; col += 32 * kEpiWarps) {
+      if (n0 + col < p.Nout) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { s1 += stat_s[w * 2 * BN + col]; s2 += stat_s[(w * 2 + 1) * BN + col]; }
+        atomicAdd(p.ch_sum + n0 + col, (double)s1);
+        atomicAdd(p.ch_sqsum + n0 + col, (double)s2);
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+  }
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const CUtensorMap* map_out, float* stg, float* stat_s, int acc,
+                                              uint32_t acc_phase, uint32_t tmem_base, uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar,
                                               uint32_t empty_remote, int img, int ty, int tx, int n0, int warp, int lane) {
+  if constexpr (kEpiWarps == 4) {
+    if (p.tma_store) {
+      epilogue_tile_tma<BN>(p, map_out, stg, stat_s, acc, acc_phase, tmem_base, tmem_full_bar, tmem_empty_bar, empty_remote, img, ty, tx,
+                            n0, warp, lane);
+      return;
+    }
+  }
   constexpr int kColsPerWarp = BN / (kEpiWarps / 4);  // warps w and w + 4 split the columns
   const int q = warp & 3;
   const int row = q * 32 + lane;
@@ -237,18 +356,19 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, float* stg,
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, ConvTcParams p) {
+               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+               const __grid_constant__ CUtensorMap map_out, ConvTcParams p) {
   using S = ConvSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStage);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStage + S::kStgBytes);
   uint64_t* full_bar = bars;                    // [STAGES]
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* stat_s = reinterpret_cast<float*>(smem + STAGES * S::kStage + 256);  // [4 epilogue warps][sum | sqsum][BN]
-  float* stg = stat_s + 8 * BN + (threadIdx.x >= 64 ? ((threadIdx.x >> 5) - 2) * 32 * kStgPitch : 0);  // per epilogue warp
+  float* stg = reinterpret_cast<float*>(smem + STAGES * S::kStage + (threadIdx.x >= 64 ? ((threadIdx.x >> 5) - 2) * kStgWarpBytes : 0));  // per epilogue warp
+  float* stat_s = reinterpret_cast<float*>(smem + STAGES * S::kStage + S::kStgBytes + 256);  // [4 lane quadrants][sum | sqsum][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.N * p.tiles_y * p.tiles_x * p.tiles_n;
@@ -346,11 +466,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       int ty = tm % p.tiles_y;
       int img = tm / p.tiles_y;
       const int n0 = tn * BN;
-      epilogue_tile<BN>(p, stg, stat_s, acc, acc_phase, tmem_base, &tmem_full[acc], &tmem_empty[acc], 0u, img, ty, tx, n0, warp, lane);
+      epilogue_tile<BN>(p, &map_out, stg, stat_s, acc, acc_phase, tmem_base, &tmem_full[acc], &tmem_empty[acc], 0u, img, ty, tx, n0, warp, lane);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
+  if (p.tma_store && warp >= 2 && lane == 0) bulk_wait_all();  // this thread's TMA stores have left shared memory and landed
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -374,8 +495,8 @@ struct Conv2Smem {
   static constexpr int kBTile = (BN2 / 2) * BK * 2;   // 16 KB: this CTA's 128 of the 256 output channels
   static constexpr int kStage = 2 * kATile + 2 * kBTile;
   static constexpr int kStatBytes = 4 * 2 * BN2 * 4;
-  static constexpr int kStgBytes = kEpiWarps * 32 * kStgPitch * 4;
-  static constexpr int kBytes = STAGES * kStage + 1024 + 256 + kStatBytes + kStgBytes;
+  static constexpr int kStgBytes = kEpiWarps * kStgWarpBytes;
+  static constexpr int kBytes = STAGES * kStage + 1024 + kStgBytes + 256 + kStatBytes;
 };
 
 __device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1,
@@ -408,18 +529,19 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 template <int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, ConvTcParams p) {
+                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                const __grid_constant__ CUtensorMap map_out, ConvTcParams p) {
   using S = Conv2Smem<STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStage);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStage + S::kStgBytes);
   uint64_t* full_bar = bars;                    // [STAGES]  used in the leader only
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]  one per CTA (multicast commit)
   uint64_t* tmem_full = bars + 2 * STAGES;      // [2]       one per CTA (multicast commit)
   uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]       leader only, count = epilogue warps x 2 CTAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* stat_s = reinterpret_cast<float*>(smem + STAGES * S::kStage + 256);
-  float* stg = stat_s + 8 * BN2 + (threadIdx.x >= 64 ? ((threadIdx.x >> 5) - 2) * 32 * kStgPitch : 0);
+  float* stg = reinterpret_cast<float*>(smem + STAGES * S::kStage + (threadIdx.x >= 64 ? ((threadIdx.x >> 5) - 2) * kStgWarpBytes : 0));
+  float* stat_s = reinterpret_cast<float*>(smem + STAGES * S::kStage + S::kStgBytes + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -529,12 +651,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       int img, ty, tx, tn;
       decode(tile, img, ty, tx, tn);
       const uint32_t remote = rank == 0 ? 0u : mapa_shared(smem_u32(&tmem_empty[acc]), 0);
-      epilogue_tile<BN2>(p, stg, stat_s, acc, acc_phase, tmem_base, &tmem_full[acc], &tmem_empty[acc], remote, img, ty, tx,
+      epilogue_tile<BN2>(p, &map_out, stg, stat_s, acc, acc_phase, tmem_base, &tmem_full[acc], &tmem_empty[acc], remote, img, ty, tx,
                          tn * BN2, warp, lane);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
+  if (p.tma_store && warp >= 2 && lane == 0) bulk_wait_all();
   tcgen05_fence_before();
   __syncthreads();
   cluster_sync_all();  // the peer may still be reading operands of / committing to this CTA
@@ -574,6 +697,31 @@ bool use_pair_kernel() {
     v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
+}
+
+// VSPW_CONV_TMA_STORE=0: the epilogue goes back to the per-warp transpose + 16-byte STG form (A/B comparisons)
+bool use_tma_store() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VSPW_CONV_TMA_STORE");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1 && kEpiWarps == 4;
+}
+
+// fp32 NHWC output as a 4-D tiled map (C, W, H, N) for bulk tensor STORES: box = 32 channels (128 B, SWIZZLE_128B) x box_w x box_h
+// pixels = the 32 rows one epilogue warp owns
+int make_out_map(CUtensorMap* m, float* base, int n, int h, int w, int c, int box_w, int box_h, const char* who) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("%s: cuTensorMapEncodeTiled entry point unavailable", who); return VSPW_ERR_CUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 4, (cuuint64_t)w * c * 4, (cuuint64_t)h * w * c * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(output) failed with %d", who, (int)r); return VSPW_ERR_CUDA; }
+  return VSPW_OK;
 }
 
 // VSPW_CONV_NARROW=0 sends 64-channel outputs through the 128-wide kernel (A/B comparisons)
@@ -621,6 +769,10 @@ int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int ta
   const long long kdim = (long long)taps * taps * b_pitch;
   if ((rc = make_mat_map(&mb_hi, b_hi, nout, kdim, BK, kBN, who))) return rc;
   if ((rc = make_mat_map(&mb_lo, x3 ? b_lo : b_hi, nout, kdim, BK, kBN, who))) return rc;
+  // output tile map for the TMA-store epilogue: fp32 (Nout, W, H, N), box = 32 channels x one warp's 32 pixel rows
+  CUtensorMap mo;
+  p.tma_store = use_tma_store() ? 1 : 0;
+  if ((rc = make_out_map(&mo, out, n, h, w, nout, p.bw < 32 ? p.bw : 32, p.bw < 32 ? 32 / p.bw : 1, who))) return rc;
   if (nout % BN2 == 0 && use_pair_kernel()) {
     p.tiles_n = nout / BN2;
     if ((rc = make_mat_map(&mb_hi, b_hi, nout, kdim, BK, BN2 / 2, who))) return rc;
@@ -635,7 +787,7 @@ int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int ta
     const long long tiles_m = (long long)n * p.tiles_y * p.tiles_x;
     const long long pair_tiles = ((tiles_m + 1) / 2) * p.tiles_n;
     const int pairs = (int)(pair_tiles < num_sms() / 2 ? pair_tiles : num_sms() / 2);
-    conv_tc2_kernel<kStages><<<2 * pairs, kConvThreads, S2::kBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+    conv_tc2_kernel<kStages><<<2 * pairs, kConvThreads, S2::kBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, p);
     return check_launch(who);
   }
   if (nout == 64 && use_narrow_kernel()) {
@@ -654,7 +806,7 @@ int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int ta
     if (attr_err6 != cudaSuccess) { set_error("%s: cudaFuncSetAttribute(narrow): %s", who, cudaGetErrorString(attr_err6)); return VSPW_ERR_CUDA; }
     const long long tiles6 = (long long)n * p.tiles_y * p.tiles_x;
     const int grid6 = (int)(tiles6 < num_sms() ? tiles6 : num_sms());
-    conv_tc_kernel<64, 4><<<grid6, kConvThreads, S6::kBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+    conv_tc_kernel<64, 4><<<grid6, kConvThreads, S6::kBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, p);
     return check_launch(who);
   }
   using S = ConvSmem<kBN, kStages>;
@@ -666,7 +818,7 @@ int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int ta
   if (attr_err != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(attr_err)); return VSPW_ERR_CUDA; }
   long long tiles = (long long)n * p.tiles_y * p.tiles_x * p.tiles_n;
   int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  conv_tc_kernel<kBN, kStages><<<grid, kConvThreads, S::kBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  conv_tc_kernel<kBN, kStages><<<grid, kConvThreads, S::kBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, p);
   return check_launch(who);
 }
 

@@ -330,30 +330,79 @@ __global__ void __launch_bounds__(128) region_softmax_write_kernel(const float* 
   }
 }
 
-// backward: dx = p * (dp - sum_rows p * dp), column-wise
+// backward: dx = p * (dp - sum_rows p * dp), column-wise; dp rows have pitch `dpp` (k, or 128 when a tensor-core GEMM wrote them)
 __global__ void __launch_bounds__(128) region_softmax_bwd_dot_kernel(const float* __restrict__ p, const float* __restrict__ dp,
-                                                                      float* __restrict__ part, int hw, int k) {
+                                                                      float* __restrict__ part, int hw, int k, int dpp) {
   const int cls = threadIdx.x, img = blockIdx.y, chunk = blockIdx.x;
   if (cls >= k) return;
   const int rows = (hw + kRsChunks - 1) / kRsChunks, r0 = chunk * rows, r1 = min(hw, r0 + rows);
-  const size_t base = (size_t)img * hw * k + cls;
+  const size_t base = (size_t)img * hw * k + cls, dbase = (size_t)img * hw * dpp + cls;
   float s = 0.f;
-  for (int r = r0; r < r1; ++r) s = fmaf(__ldg(p + base + (size_t)r * k), __ldg(dp + base + (size_t)r * k), s);
+  for (int r = r0; r < r1; ++r) s = fmaf(__ldg(p + base + (size_t)r * k), __ldg(dp + dbase + (size_t)r * dpp), s);
   part[((size_t)img * kRsChunks + chunk) * k + cls] = s;
 }
 
 __global__ void __launch_bounds__(128) region_softmax_bwd_write_kernel(const float* __restrict__ p, const float* __restrict__ dp,
                                                                         const float* __restrict__ part, float* __restrict__ dx, int hw,
-                                                                        int k) {
+                                                                        int k, int dpp) {
   const int cls = threadIdx.x, img = blockIdx.y, chunk = blockIdx.x;
   if (cls >= k) return;
   const int rows = (hw + kRsChunks - 1) / kRsChunks, r0 = chunk * rows, r1 = min(hw, r0 + rows);
   float dot = 0.f;
   for (int c = 0; c < kRsChunks; ++c) dot += part[((size_t)img * kRsChunks + c) * k + cls];
-  const size_t base = (size_t)img * hw * k + cls;
+  const size_t base = (size_t)img * hw * k + cls, dbase = (size_t)img * hw * dpp + cls;
   for (int r = r0; r < r1; ++r) {
     const size_t i = base + (size_t)r * k;
-    dx[i] = __ldg(p + i) * (__ldg(dp + i) - dot);
+    dx[i] = __ldg(p + i) * (__ldg(dp + dbase + (size_t)r * dpp) - dot);
+  }
+}
+
+// attention softmax backward, one warp per pixel row: draw = scale * sim * (dsim - sum_k sim * dsim), written straight as the
+// bf16 (hi, lo) operand planes [rows][128] (columns >= k zero) of the two GEMMs that consume it (dQ = draw . K, dK = draw^T . Q)
+__global__ void __launch_bounds__(256) attn_softmax_bwd_planes_kernel(const float* __restrict__ sim, const float* __restrict__ dsim,
+                                                                       uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, size_t rows,
+                                                                       int k, float scale) {
+  const int lane = threadIdx.x & 31;
+  const size_t warps = (size_t)gridDim.x * (blockDim.x >> 5);
+  for (size_t r = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
+    float sv[4], dv[4], dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = lane + 32 * j;
+      sv[j] = c < k ? __ldg(sim + r * k + c) : 0.f;
+      dv[j] = c < k ? __ldg(dsim + r * AT_REG + c) : 0.f;
+      dot = fmaf(sv[j], dv[j], dot);
+    }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = lane + 32 * j;
+      const float v = scale * sv[j] * (dv[j] - dot);
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      hi[r * AT_REG + c] = *reinterpret_cast<const uint16_t*>(&h);
+      if (lo) {
+        const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+        lo[r * AT_REG + c] = *reinterpret_cast<const uint16_t*>(&l);
+      }
+    }
+  }
+}
+
+// small per-image GEMM operands: src [n][rows][cols] fp32 -> bf16 (hi, lo) planes, scaled; transpose == 0: [n][rows_pad][cols]
+// (rows >= rows zero); transpose == 1: [n][cols][rows_pad] (dst[c][r] = src[r][c])
+__global__ void operand_planes_kernel(const float* __restrict__ src, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int n, int rows,
+                                      int cols, int rows_pad, int transpose, float scale, size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int r, c, img;
+    if (transpose) { r = (int)(i % rows_pad); c = (int)((i / rows_pad) % cols); img = (int)(i / ((size_t)rows_pad * cols)); }
+    else { c = (int)(i % cols); r = (int)((i / cols) % rows_pad); img = (int)(i / ((size_t)rows_pad * cols)); }
+    const float v = r < rows ? scale * __ldg(src + ((size_t)img * rows + r) * cols + c) : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = *reinterpret_cast<const uint16_t*>(&h);
+    if (lo) {
+      const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+      lo[i] = *reinterpret_cast<const uint16_t*>(&l);
+    }
   }
 }
 
@@ -377,18 +426,36 @@ extern "C" int vspw_ocr_region_softmax_fwd(const float* dsn, float* probs, uint1
   return check_launch(who);
 }
 
-extern "C" int vspw_ocr_region_softmax_bwd(const float* probs, const float* dprobs, float* ddsn, void* workspace, int32_t n_images,
-                                           int32_t hw, int32_t k, void* stream) {
+extern "C" int vspw_ocr_attn_softmax_bwd_planes(const float* sim, const float* dsim, uint16_t* draw_hi, uint16_t* draw_lo, size_t rows,
+                                                int32_t k, float scale, void* stream) {
+  VSPW_REQUIRE(sim && dsim && draw_hi, "vspw_ocr_attn_softmax_bwd_planes: null pointer");
+  VSPW_REQUIRE(k >= 1 && k <= AT_REG, "vspw_ocr_attn_softmax_bwd_planes: 1..%d regions", AT_REG);
+  if (!rows) return VSPW_OK;
+  attn_softmax_bwd_planes_kernel<<<grid_for(rows * 32, 256), 256, 0, as_stream(stream)>>>(sim, dsim, draw_hi, draw_lo, rows, k, scale);
+  return check_launch("vspw_ocr_attn_softmax_bwd_planes");
+}
+
+extern "C" int vspw_ocr_operand_planes(const float* src, uint16_t* hi, uint16_t* lo, int32_t n, int32_t rows, int32_t cols,
+                                       int32_t rows_pad, int32_t transpose, float scale, void* stream) {
+  VSPW_REQUIRE(src && hi, "vspw_ocr_operand_planes: null pointer");
+  VSPW_REQUIRE(n > 0 && rows > 0 && cols > 0 && rows_pad >= rows, "vspw_ocr_operand_planes: bad dims");
+  const size_t total = (size_t)n * rows_pad * cols;
+  operand_planes_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(src, hi, lo, n, rows, cols, rows_pad, transpose, scale, total);
+  return check_launch("vspw_ocr_operand_planes");
+}
+
+extern "C" int vspw_ocr_region_softmax_bwd(const float* probs, const float* dprobs, int32_t dprobs_pitch, float* ddsn, void* workspace,
+                                           int32_t n_images, int32_t hw, int32_t k, void* stream) {
   const char* who = "vspw_ocr_region_softmax_bwd";
   VSPW_REQUIRE(probs && dprobs && ddsn && workspace, "%s: null pointer", who);
-  VSPW_REQUIRE(k >= 1 && k <= AT_REG && n_images <= 65535, "%s: bad dims", who);
+  VSPW_REQUIRE(k >= 1 && k <= AT_REG && n_images <= 65535 && dprobs_pitch >= k, "%s: bad dims", who);
   if (!n_images || !hw) return VSPW_OK;
   cudaStream_t st = as_stream(stream);
   dim3 grid(kRsChunks, n_images);
-  region_softmax_bwd_dot_kernel<<<grid, 128, 0, st>>>(probs, dprobs, (float*)workspace, hw, k);
+  region_softmax_bwd_dot_kernel<<<grid, 128, 0, st>>>(probs, dprobs, (float*)workspace, hw, k, dprobs_pitch);
   int rc = check_launch("vspw_ocr_region_softmax_bwd(dot)");
   if (rc) return rc;
-  region_softmax_bwd_write_kernel<<<grid, 128, 0, st>>>(probs, dprobs, (const float*)workspace, ddsn, hw, k);
+  region_softmax_bwd_write_kernel<<<grid, 128, 0, st>>>(probs, dprobs, (const float*)workspace, ddsn, hw, k, dprobs_pitch);
   return check_launch(who);
 }
 

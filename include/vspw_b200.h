@@ -345,8 +345,15 @@ int vspw_ocr_gather_tc(const uint16_t* p_hi, const uint16_t* p_lo, const uint16_
 size_t vspw_ocr_region_softmax_workspace_bytes(int32_t n_images, int32_t k);
 int vspw_ocr_region_softmax_fwd(const float* dsn, float* probs, uint16_t* p_hi, uint16_t* p_lo, void* workspace,
                                 int32_t n_images, int32_t hw, int32_t k, float plane_scale, void* stream);
-int vspw_ocr_region_softmax_bwd(const float* probs, const float* dprobs, float* ddsn, void* workspace, int32_t n_images,
-                                int32_t hw, int32_t k, void* stream);
+int vspw_ocr_region_softmax_bwd(const float* probs, const float* dprobs, int32_t dprobs_pitch, float* ddsn, void* workspace,
+                                int32_t n_images, int32_t hw, int32_t k, void* stream);
+/* backward helpers of the tensor-core OCR path: the attention softmax backward written as operand planes
+ * (draw = scale * sim * (dsim - sum_k sim*dsim); dsim rows have pitch 128), and the small per-image GEMM operands
+ * (key / value / context gradients: [n][rows][cols] fp32 -> planes, rows padded to rows_pad, optionally transposed, scaled) */
+int vspw_ocr_attn_softmax_bwd_planes(const float* sim, const float* dsim, uint16_t* draw_hi, uint16_t* draw_lo, size_t rows,
+                                     int32_t k, float scale, void* stream);
+int vspw_ocr_operand_planes(const float* src, uint16_t* hi, uint16_t* lo, int32_t n, int32_t rows, int32_t cols,
+                            int32_t rows_pad, int32_t transpose, float scale, void* stream);
 /* probs [rows][k] fp32 -> bf16 (hi, lo) planes [rows][128] * scale, columns >= k zero: the A operand of the region gather */
 int vspw_ocr_region_planes(const float* probs, uint16_t* hi, uint16_t* lo, size_t rows, int32_t k, float scale, void* stream);
 
