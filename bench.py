@@ -313,6 +313,26 @@ def run_ours(args):
                     "steps": k_loc, "note": "same step with per-rank BN statistics (syncbn off), no L2 flush between steps"}
         E.set_syncbn(True, group=sync_group)
 
+    # ---- reported option (NOT the parity mode): single-pass bf16 weight gradients, forward / dgrad still bf16x3 ------------------
+    fast_wgrad = None
+    if world == 1 and not args.profile_run and args.precision == "bf16x3":
+        E._state["wgrad_single"] = True
+        for _ in range(2):
+            step(imgs_d, labs_d)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        k_opt = max(3, min(args.steps, 5))
+        for _ in range(k_opt):
+            step(imgs_d, labs_d)
+        e1.record()
+        barrier()
+        ms_opt = e0.elapsed_time(e1) / k_opt
+        fast_wgrad = {"value": round(frames_per_step / (ms_opt / 1e3), 3), "unit": UNIT, "ms_per_step": round(ms_opt, 3), "steps": k_opt,
+                      "note": "VSPW_WGRAD_SINGLE=1: weight gradients with single-pass bf16 operands (1 MMA per product), forward and dgrad bf16x3; "
+                              "weight-gradient error ~2e-3 rel-L2, below the fp32-vs-fp32 floor of these gradients but not parity mode; no L2 flush between steps"}
+        E._state["wgrad_single"] = False
+
     if args.kernel_profile and rank == 0:
         lib.profile_begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -387,6 +407,8 @@ def run_ours(args):
            "roofline": roof}
     if local_bn is not None:
         out["local_bn"] = local_bn
+    if fast_wgrad is not None:
+        out["option_wgrad_single_bf16"] = fast_wgrad
     if rank == 0 and not args.profile_run and world == 1 and not args.no_gpu_library_baseline:
         del model, opt, bucket
         out["gpu_library_baseline"] = gpu_library_baseline(dev, imgs_d, labs_d, args)

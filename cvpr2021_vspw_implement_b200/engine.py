@@ -86,7 +86,8 @@ def conv_profile_end():
     torch.cuda.synchronize()
     ms = sum(r[0].elapsed_time(r[1]) for r in rec)
     tc = sum(1 for r in rec if r[3])
-    kern = "conv_tc_kernel (tcgen05 implicit GEMM)" if tc * 2 > len(rec) else "igemm_kernel/wgrad_kernel (fp32 FFMA implicit GEMM)"
+    kern = ("conv_tc2_kernel / conv_tc_kernel / wgrad_tc2_kernel (tcgen05 implicit-GEMM family)" if tc * 2 > len(rec)
+            else "igemm_kernel/wgrad_kernel (fp32 FFMA implicit GEMM)")
     return {"launches": len(rec), "ms": ms, "tflop": sum(r[2] for r in rec) / 1e12, "kernel": kern, "tc_launches": tc,
             # the launches that stayed on the CUDA-core arm, with their geometry: what is left to move
             "fp32_arm": [(r[4], r[0].elapsed_time(r[1])) for r in rec if not r[3]]}
@@ -1397,7 +1398,7 @@ def region_gather(tape, feats, dsn, t_frames, n_clips):
         if g is None:
             return
         st = _stream()
-        if use_tc:
+        if use_tc and hw >= 256:  # (a per-image 1x1 GEMM needs >= 256 pixels on the conv kernel; tiny maps keep the fp32 GEMMs)
             # tcgen05 backward: dF = P . g and dP = F . g^T / T as per-image 1x1 GEMMs on the conv kernel (the context gradient of
             # the image's clip is the weight), then the column softmax backward on the 128-pitch dP
             gc = g.view(n_clips, k, c)
@@ -1492,7 +1493,7 @@ def object_attention(tape, query, key, value, key_channels):
         if g is None:
             return
         st = _stream()
-        if attn_tc is not None:
+        if attn_tc is not None and hw >= 256:
             # tcgen05 backward: dV = sim^T . g and dK = draw^T . Q on the weight-gradient kernel (K axis = pixels), dsim = g . V^T
             # and dQ = draw . K as per-image 1x1 GEMMs on the conv kernel, the softmax backward writing operand planes directly
             qh, ql, ws, x3 = attn_tc
