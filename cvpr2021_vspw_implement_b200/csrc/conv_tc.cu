@@ -152,7 +152,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const C
     for (int j = 0; j < 8; ++j) {
       float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                              __uint_as_float(v[4 * j + 3]));
-      if (p.bias) {
+      if (p.bias && n0 + c0 + 4 * j + 3 < p.Nout) {  // (a 124-class head ends inside the last chunk)
         const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + 4 * j));
         o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
       }
@@ -676,10 +676,20 @@ void pick_patch(int h, int w, int& bw, int& bh) {
   }
 }
 
+bool use_tma_store();
+
+// A 1x1 classifier head whose class count is not a multiple of 64 (the 124-class logits): forward only, and only with the
+// TMA-store epilogue — the weight rows beyond cout are zero-filled by the TMA load, the columns beyond cout clipped by the TMA
+// store, so no padded copy of the logits ever exists.  (Its dgrad / wgrad run on padded operand planes: see the engine.)
+bool head_geometry(const vspw_conv_desc* d) {
+  return d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pad == 0 && d->cout % 64 != 0 && d->cout % 4 == 0 && d->cout < 128 &&
+         d->cin % 128 == 0 && use_tma_store();
+}
+
 bool geometry_ok(const vspw_conv_desc* d) {
   if (!d) return false;
   if (d->stride != 1 && d->stride != 2) return false;
-  if (d->cin % 64 || d->cout % 64) return false;
+  if (d->cin % 64 || (d->cout % 64 && !head_geometry(d))) return false;
   if (d->kh != d->kw || (d->kh != 1 && d->kh != 3)) return false;
   if (d->pad != d->dil * (d->kh - 1) / 2) return false;          // "same" padding only
   if (d->ho != (d->h - 1) / d->stride + 1 || d->wo != (d->w - 1) / d->stride + 1) return false;
@@ -1119,12 +1129,13 @@ void pick_patch64(int h, int w, int& bw, int& bh) {
 }  // namespace
 
 extern "C" int vspw_conv2d_tc_supported(const vspw_conv_desc* d) { return geometry_ok(d) ? 1 : 0; }
-extern "C" int vspw_conv2d_wgrad_tc_supported(const vspw_conv_desc* d) { return geometry_ok(d) ? 1 : 0; }
+extern "C" int vspw_conv2d_wgrad_tc_supported(const vspw_conv_desc* d) { return geometry_ok(d) && d->cout % 64 == 0 ? 1 : 0; }
 
 extern "C" int vspw_conv2d_fwd_tc(const vspw_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi,
                                   const uint16_t* w_lo, const float* bias, float* y, double* ch_sum, double* ch_sqsum,
                                   void* stream) {
   VSPW_REQUIRE(geometry_ok(d), "vspw_conv2d_fwd_tc: geometry not supported by the tcgen05 path");
+  VSPW_REQUIRE(d->cout % 64 == 0 || (!ch_sum && !ch_sqsum), "vspw_conv2d_fwd_tc: no fused statistics on a classifier head");
   VSPW_REQUIRE(d->precision == VSPW_PREC_BF16X3 || d->precision == VSPW_PREC_BF16, "vspw_conv2d_fwd_tc: precision must be BF16X3 or BF16");
   return launch_conv_tc("vspw_conv2d_fwd_tc", d->n, d->h, d->w, d->cin, d->cout, d->kh, -d->pad, d->dil, d->stride, d->cin_pitch, x_hi, x_lo, w_hi, w_lo,
                         bias, y, d->precision == VSPW_PREC_BF16X3, ch_sum, ch_sqsum, 0, as_stream(stream));
@@ -1132,7 +1143,7 @@ extern "C" int vspw_conv2d_fwd_tc(const vspw_conv_desc* d, const uint16_t* x_hi,
 
 extern "C" int vspw_conv2d_dgrad_tc(const vspw_conv_desc* d, const uint16_t* dy_hi, const uint16_t* dy_lo, const uint16_t* wt_hi,
                                     const uint16_t* wt_lo, float* dx, int32_t accumulate, void* stream) {
-  VSPW_REQUIRE(geometry_ok(d) && d->stride == 1, "vspw_conv2d_dgrad_tc: geometry not supported by the tcgen05 path "
+  VSPW_REQUIRE(geometry_ok(d) && d->stride == 1 && d->cout % 64 == 0, "vspw_conv2d_dgrad_tc: geometry not supported by the tcgen05 path "
                "(a stride-2 dgrad is a stride-1 dgrad of the zero-inserted dy: vspw_zero_insert2_bf16)");
   VSPW_REQUIRE(d->precision == VSPW_PREC_BF16X3 || d->precision == VSPW_PREC_BF16, "vspw_conv2d_dgrad_tc: precision must be BF16X3 or BF16");
   // dx[p][ci] = sum_{tap,co} dy[p + pad - tap*dil][co] * Wt[ci][tap][co]
@@ -1144,7 +1155,7 @@ extern "C" int vspw_conv2d_dgrad_tc(const vspw_conv_desc* d, const uint16_t* dy_
 extern "C" int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* dy_hi,
                                     const uint16_t* dy_lo, float* dw_ohwi, void* stream) {
   const char* who = "vspw_conv2d_wgrad_tc";
-  VSPW_REQUIRE(geometry_ok(d), "%s: geometry not supported by the tcgen05 path", who);
+  VSPW_REQUIRE(geometry_ok(d) && d->cout % 64 == 0, "%s: geometry not supported by the tcgen05 path", who);
   VSPW_REQUIRE(d->precision == VSPW_PREC_BF16X3 || d->precision == VSPW_PREC_BF16, "%s: precision must be BF16X3 or BF16", who);
   const int x3 = d->precision == VSPW_PREC_BF16X3;
   VSPW_REQUIRE(x_hi && dy_hi && dw_ohwi && (!x3 || (x_lo && dy_lo)), "%s: null pointer", who);
@@ -1173,6 +1184,12 @@ extern "C" int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_h
   const int total_patches = p.N * p.tiles_y * p.tiles_x;
   int splits = (int)(((pair ? 1 : 2) * num_sms()) / tiles);  // ~2 CTAs per SM's worth of work items; one resident at a time
   if (splits < 1) splits = 1;
+  // tcgen05 adds into the fp32 accumulator with truncation: -1.6e-8 relative per MMA accumulated (tests/test_gpu_conv_multiwave.py).
+  // A CTA that walks all 64 200 pixels of a layer3 map alone (12 000 MMAs) returns a weight gradient 2.8e-4 low; at most
+  // kMaxChunk 64-pixel patches per CTA (1 536 MMAs in bf16x3) keeps the bias below 3e-5.  The partial sums meet in fp32 red.add.
+  constexpr int kMaxChunk = 128;
+  const int min_splits = (total_patches + kMaxChunk - 1) / kMaxChunk;
+  if (splits < min_splits) splits = min_splits;
   if (splits > total_patches) splits = total_patches;
   p.chunk = (total_patches + splits - 1) / splits;
   p.splits = (total_patches + p.chunk - 1) / p.chunk;

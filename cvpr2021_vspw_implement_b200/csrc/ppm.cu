@@ -43,7 +43,7 @@ __device__ __forceinline__ void bil(int d, int dst_len, int src_len, int& i0, in
   l0 = 1.f - l1;
 }
 
-constexpr int kFwdPix = 32;  // pixels per block
+constexpr int kFwdPix = 8;   // pixels per block (1605 blocks at 480p: the gather is latency-bound, it wants warps, not reuse)
 
 // y[pix][co] += pyramid(pix, co); then per-channel sum / sum of squares of the final y (train-mode BN statistics)
 __global__ void __launch_bounds__(128) ppm_pyramid_fwd_kernel(float4* __restrict__ y, PpmPtrs ptr, PpmGeom g, int n, int h, int w,
@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(128) ppm_pyramid_fwd_kernel(float4* __restrict
 }
 
 constexpr int kBwdRows = 4;   // up-sampled rows (q rows) per block
+constexpr int kBwdCols = 32;  // ... and columns: a scale-1 bin has the whole map as support, one block per 4 x 32 window
 
 // dZ_s[img][bin][tap][co] += sum over the up-sampled positions q in this block's rows of B_s[q, bin] * dy[q - off(tap)][co]
 // grid: x = bin (all scales concatenated), y = row chunk, z = image; block = cout/4 threads (one float4 of channels each)
@@ -123,13 +124,15 @@ __global__ void __launch_bounds__(128) ppm_pyramid_bwd_kernel(const float4* __re
   const int img = blockIdx.z / co4_blocks;
   const int cg = (blockIdx.z % co4_blocks) * blockDim.x + threadIdx.x;
   if (cg >= co4) return;
-  const int q0 = blockIdx.y * kBwdRows, q1 = min(h, q0 + kBwdRows);
+  const int xchunks = (w + kBwdCols - 1) / kBwdCols;
+  const int q0 = (blockIdx.y / xchunks) * kBwdRows, q1 = min(h, q0 + kBwdRows);
+  const int c0x = (blockIdx.y % xchunks) * kBwdCols, c1x = min(w, c0x + kBwdCols);
   // conservative support of bin (by, bx): source coordinate in [b - 1, b + 1)
   const float ry = (float)h / (float)s, rx = (float)w / (float)s;
   int ylo = (int)floorf(((float)by - 0.5f) * ry - 0.5f) - 1, yhi = (int)ceilf(((float)by + 1.5f) * ry - 0.5f) + 1;
   int xlo = (int)floorf(((float)bx - 0.5f) * rx - 0.5f) - 1, xhi = (int)ceilf(((float)bx + 1.5f) * rx - 0.5f) + 1;
   ylo = max(ylo, q0); yhi = min(yhi, q1);
-  xlo = max(xlo, 0); xhi = min(xhi, w);
+  xlo = max(xlo, c0x); xhi = min(xhi, c1x);
   if (ylo >= yhi || xlo >= xhi) return;
   constexpr int taps = taps_w * taps_w;
   float4 acc[taps];
@@ -254,8 +257,9 @@ extern "C" int vspw_ppm_pyramid_bwd(const float* dy, float* const* dz_host, cons
   const int co4 = cout / 4;
   const int threads = co4 < 128 ? ((co4 + 31) / 32 * 32) : 128;
   const int co4_blocks = (co4 + threads - 1) / threads;
-  VSPW_REQUIRE((long long)n * co4_blocks <= 65535 && (h + kBwdRows - 1) / kBwdRows <= 65535, "%s: grid limit", who);
-  dim3 grid(g.total_bins, (h + kBwdRows - 1) / kBwdRows, n * co4_blocks);
+  const long long chunks = (long long)((h + kBwdRows - 1) / kBwdRows) * ((w + kBwdCols - 1) / kBwdCols);
+  VSPW_REQUIRE((long long)n * co4_blocks <= 65535 && chunks <= 65535, "%s: grid limit", who);
+  dim3 grid(g.total_bins, (unsigned)chunks, n * co4_blocks);
   if (k == 3) ppm_pyramid_bwd_kernel<3><<<grid, threads, 0, st>>>((const float4*)dy, ptr, g, n, h, w, co4, pad, dil, co4_blocks);
   else ppm_pyramid_bwd_kernel<1><<<grid, threads, 0, st>>>((const float4*)dy, ptr, g, n, h, w, co4, pad, dil, co4_blocks);
   return check_launch(who);

@@ -541,7 +541,7 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1, want_stats=False)
     if use_tc:
         xh, xl = _var_planes(x)
         wh, wl = _tc_weight_planes(tape, wv)["ohwi"]
-        if want_stats:
+        if want_stats and co % 64 == 0:
             stats = tape.zeros_f64((2, co), y.device)
         with _ConvTimer(flops, True):
             lib.call("vspw_conv2d_fwd_tc", ctypes.byref(desc), _p(xh), _p(xl), _p(wh), _p(wl), _p(bv.data if bv else None), _p(y),
@@ -553,15 +553,50 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1, want_stats=False)
     out = Var(y, needs_grad=tape.grad_enabled and (x.needs_grad or wv.needs_grad))
     out.stats = stats
     wgrad_tc_ok = use_tc and lib.wgrad_tc_supported(desc)
-    if use_tc:
+    # a classifier head (1x1, 124 classes): forward on the conv kernel with TMA zero-fill / clipping of the missing 4 classes;
+    # backward on 128-pitch operand planes of the logit gradient — wgrad on the weight-gradient kernel, dgrad as a 1x1 GEMM
+    head = use_tc and co % 64 != 0
+    if use_tc and not head:
         out.wants_grad_planes = True
         out.wants_grad_fp32 = (bv is not None and bv.needs_grad) or (wv.needs_grad and not wgrad_tc_ok)
+
+    def head_backward(dy):
+        st = _stream()
+        x3 = prec == PREC_BF16X3
+        pixels = n * h * w
+        ph = torch.empty((pixels, 128), device=dev, dtype=torch.bfloat16)
+        pl = torch.empty((pixels, 128), device=dev, dtype=torch.bfloat16) if x3 else None
+        lib.call("vspw_ocr_region_planes", _p(dy), _p(ph), _p(pl), pixels, co, 1.0, st)
+        if wv.needs_grad:
+            xh, xl = _var_planes(x)
+            dst = wv.first_dst()
+            dw = dst.view(co, ci) if dst is not None else torch.empty((co, ci), device=dev, dtype=torch.float32)
+            with _ConvTimer(flops, True):
+                lib.call("vspw_ocr_gather_tc", _p(ph), _p(pl), _p(xh), _p(xl if x3 else None), _p(dw), n, 1, h * w, co, ci, st)
+            if dst is None:
+                wv.add_grad(dw.view(wv.data.shape))
+        if bv is not None and bv.needs_grad:
+            sums = tape.zeros_f64((co,), dev)
+            lib.call("vspw_bn_stats", _p(dy), pixels, co, _p(sums), None, st)
+            bdst = bv.first_dst()
+            if bdst is not None:
+                _double_to_float(sums, out=bdst)
+            else:
+                bv.add_grad(_double_to_float(sums))
+        if x.needs_grad:
+            wt_h, wt_l = _operand_planes(wv.data.view(1, co, ci), 1, co, ci, 128, True, 1.0, x3, st)  # [1][ci][128] = W^T, classes padded
+            dx = torch.empty((n, h, w, cin), device=dev, dtype=torch.float32)
+            with _ConvTimer(flops, True):
+                _conv1x1_tc_raw(ph, pl, wt_h[0], wt_l[0] if x3 else None, dx, pixels, 128, ci, st)
+            x.add_grad(dx)
 
     def backward():
         dy, dyp = out.grad, out.grad_planes
         out.grad = out.grad_planes = None
         if dy is None and dyp is None:
             return
+        if head:
+            return head_backward(dy)
         st = _stream()
         wgrad_tc = wgrad_tc_ok and wv.needs_grad
         if dyp is None and use_tc and (x.needs_grad or wgrad_tc):

@@ -72,6 +72,8 @@ class ClipOCRNet(nn.Module):
         x_dsn = conv_op(tape, self.dsn_head[4], d)
         feats = E.batchnorm_act(tape, conv_op(tape, self.conv_3x3[0], maps[-1], self.conv_3x3[1]), self.conv_3x3[1], relu=True,
                                 training=training)
+        # (recorded before the gather: the backward then runs the gather's first, which owns the full gradient of `feats`)
+        cur = E.slice_images(tape, feats, (t_frames - 1) * n, t_frames * n)
         if memory is not None:
             context = self.spatial_context_head.graph(tape, feats, x_dsn, t_frames - 1, memory, self.args.memory_num)
         else:
@@ -80,7 +82,6 @@ class ClipOCRNet(nn.Module):
         if self.args.clipocr_all:
             raise NotImplementedError("--clipocr_all True fails inside the reference itself (view of T*n pixels rows "
                                       "against an n-clip context, clip_ocr.py:136-137); the TCB scripts use False")
-        cur = E.slice_images(tape, feats, (t_frames - 1) * n, t_frames * n)
         z = self.spatial_ocr_head.graph(tape, cur, context, training)
         return conv_op(tape, self.head, z), x_dsn
 

@@ -112,8 +112,10 @@ class Clip_PSP(nn.Module):
         maps = self.encoder.graph(tape, x)
         feat = maps[-1]
         fw = self._frame_weights(tape, feat, t_frames, n) if self.args.psp_weight else None
-        pooled = E.tcb_pool(tape, feat, t_frames, n, self.pool_scales, frame_w=fw)
+        # (the slice is recorded BEFORE the pooling so that the backward runs the pooling's first: it then owns the full-size
+        # gradient of `feat` and the current frame's rows are added into it, instead of a 526 MB zero fill + a full add)
         cur = E.slice_images(tape, feat, (t_frames - 1) * n, t_frames * n)
+        pooled = E.tcb_pool(tape, feat, t_frames, n, self.pool_scales, frame_w=fw)
         return self.ppm_conv.graph(tape, cur, pooled, training), maps
 
     def forward(self, feed_dict, segSize=None):

@@ -93,3 +93,33 @@ def test_conv_tc_zero_padding_is_exact(E):
     with E.precision("bf16x3"):
         y = E.conv2d(tape, E.Var(nhwc(x).cuda()), torch.nn.Parameter(wt.cuda()), None, 1, 4, 4)
     assert torch.equal(nchw(y.data.cpu()), ref)
+
+
+@pytest.mark.parametrize("n,cin,h,w,cout", [(10, 512, 60, 107, 124), (2, 512, 60, 107, 124), (3, 256, 13, 21, 124), (2, 128, 20, 30, 100)])
+def test_classifier_head_on_tensor_cores(E, n, cin, h, w, cout):
+    """The 124-class 1x1 heads (clip_psp.py:40,79; clip_ocr.py:56-62): forward on the tcgen05 conv kernel with the missing classes
+    zero-filled by the TMA load and clipped by the TMA store (no padded logits tensor), backward on 128-pitch operand planes of
+    the logit gradient (weight gradient on the weight-gradient kernel, input gradient as a 1x1 GEMM).  Against torch in fp64."""
+    g = torch.Generator(device="cuda").manual_seed(cin + cout + n)
+    x = torch.randn(n, cin, h, w, generator=g, device="cuda")
+    wt = torch.randn(cout, cin, 1, 1, generator=g, device="cuda") / cin ** 0.5
+    b = torch.randn(cout, generator=g, device="cuda")
+    xr, wr, br = x.double().requires_grad_(True), wt.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = F.conv2d(xr, wr, br)
+    gy = torch.randn(yr.shape, generator=g, device="cuda")
+    yr.backward(gy.double())
+    tape = E.Tape(True)
+    wp, bp = torch.nn.Parameter(wt.clone()), torch.nn.Parameter(b.clone())
+    xv = E.Var(nhwc(x), needs_grad=True)
+    with E.precision("bf16x3"):
+        E.conv_profile_begin()
+        yv = E.conv2d(tape, xv, wp, bp, 1, 0, 1)
+        yv.grad = nhwc(gy)
+        tape.backward()
+        prof = E.conv_profile_end()
+    assert prof["tc_launches"] == 3 and not prof["fp32_arm"], "fwd, dgrad and wgrad of the head must run on tcgen05"
+    assert tuple(yv.data.shape) == (n, h, w, cout)
+    e = [C.rel_err(nchw(yv.data).cpu(), yr.detach().cpu()), C.rel_err(nchw(xv.grad).cpu(), xr.grad.cpu()),
+         C.rel_err(tape.param(wp).grad.cpu(), wr.grad.cpu()), C.rel_err(tape.param(bp).grad.cpu(), br.grad.cpu())]
+    print(f"head {n}x{h}x{w} {cin}->{cout}: fwd {e[0]:.2e} dgrad {e[1]:.2e} wgrad {e[2]:.2e} dbias {e[3]:.2e}")
+    assert max(e) <= 1e-4
