@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(
     const uint2* __restrict__ res_hi, const uint2* __restrict__ res_lo,
     const float4* __restrict__ chan_scale, int relu, float4* __restrict__ out, uint2* __restrict__ out_hi,
     uint2* __restrict__ out_lo, uint4* __restrict__ relu_bits, size_t pixels, int c4, size_t pix_per_img, BnTrainStats ts,
-    peer::PeerArgs pa, int rev) {
+    peer::PeerArgs pa) {
   // SyncBN: the cross-rank sum of the statistics runs HERE (block 0 exchanges over NVLink peer memory, the other blocks of
   // this one-wave grid wait for its "totals ready" flag) instead of as a separate launch between the conv and this kernel
   if (pa.world > 1) peer::grid_allreduce(const_cast<double*>(ts.sum), 2 * c4 * 4, pa);
@@ -264,12 +264,9 @@ __global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(
   // ballots (one per component) give the four 32-bit words of those 128 elements: word (e >> 5) * 4 + component, bit e & 31.
   // With c4 == 16 a warp holds two adjacent pixels; the loop runs on the even one so that all 32 lanes stay together.
   const size_t poff = (relu_bits && c4 < 32) ? (m.p0 & 1) : 0;
-  // rev (experiment, off by default): walk this thread's grid-stride sequence from the LAST pixel group down, to start on what
-  // the producing conv left in the 126 MB L2 and end on what the consuming conv wants first.
-  const size_t pstep = m.dp * kUnroll, pfirst = m.p0 - poff;
-  const size_t iters = pfirst < pixels ? (pixels - pfirst + pstep - 1) / pstep : 0;
-  for (size_t it = 0; it < iters; ++it) {
-    const size_t pb = pfirst + (rev ? iters - 1 - it : it) * pstep;
+  // (Walking the pixel axis DOWNWARDS here and in the second backward pass — to start on what the producing conv left in the
+  // 126 MB L2 — was measured inside one box: 92.60 ms/step against 92.38 ascending.  No gain; removed.)
+  for (size_t pb = m.p0 - poff; pb < pixels; pb += m.dp * kUnroll) {
     const size_t p = pb + poff;
     float4 v[kUnroll], r[kUnroll];
 #pragma unroll
@@ -293,6 +290,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(
         }
       }
     }
+    uint4 mybits = make_uint4(0u, 0u, 0u, 0u);  // lane u keeps the ballot words of unroll step u: ONE store for the kUnroll steps
+    size_t mybits_at = ~(size_t)0;
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const size_t q = p + u * m.dp;
@@ -315,7 +314,9 @@ __global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(
       if (relu_bits) {
         const unsigned bx = __ballot_sync(0xffffffffu, valid && t.x != 0.f), by = __ballot_sync(0xffffffffu, valid && t.y != 0.f);
         const unsigned bz = __ballot_sync(0xffffffffu, valid && t.z != 0.f), bw = __ballot_sync(0xffffffffu, valid && t.w != 0.f);
-        if ((threadIdx.x & 31) == 0) relu_bits[i >> 5] = make_uint4(bx, by, bz, bw);
+        // lane 0's float4 group index i is a multiple of 32: word i >> 5; handed to lane u for the merged store below
+        const size_t word = __shfl_sync(0xffffffffu, i, 0) >> 5;
+        if ((threadIdx.x & 31) == u) { mybits = make_uint4(bx, by, bz, bw); mybits_at = word; }
         if (!valid) continue;
       }
       if (out) out[i] = t;
@@ -329,6 +330,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_act_fwd_kernel(
         }
       }
     }
+    if (relu_bits && mybits_at != ~(size_t)0) relu_bits[mybits_at] = mybits;
   }
 }
 
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(
         const size_t q = p + (size_t)u * PL;
         if (q < pend) {
           const size_t i = q * c4 + cg;
-          d[u] = __ldg(dout + i);  // (no evict-first hint: the apply pass that follows re-reads these lines, highest pixels first)
+          d[u] = ld_stream(dout + i);
           yv[u] = __ldg(y + i);
           if (has_b) bw[u] = __ldg(relu_bits + (i >> 5));
           if (has_o) o[u] = __ldg(out + i);
@@ -443,7 +445,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(
     const float4* __restrict__ gamma, const float4* __restrict__ chan_scale, int relu, const double* __restrict__ dbeta,
     const double* __restrict__ dgamma, float4* __restrict__ dy, uint2* __restrict__ dy_hi, uint2* __restrict__ dy_lo,
     float4* __restrict__ dres, float4* __restrict__ dgamma_f, float4* __restrict__ dbeta_f, const uint4* __restrict__ relu_bits,
-    size_t pixels, int c4, size_t pix_per_img, double inv_count, int eval_mode, double pgrad_scale, peer::PeerArgs pa, int rev) {
+    size_t pixels, int c4, size_t pix_per_img, double inv_count, int eval_mode, double pgrad_scale, peer::PeerArgs pa) {
   if (pa.world > 1) peer::grid_allreduce(const_cast<double*>(dbeta), 2 * c4 * 4, pa);  // (dbeta, dgamma) are one (2, C) buffer
   const EwMap m = ew_map(c4);
   if (m.cg < 0) return;
@@ -473,10 +475,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(
                      ka.z * is.z * (float)(__ldcg(dg + 2) * inv_count), ka.w * is.w * (float)(__ldcg(dg + 3) * inv_count));
   }
   const bool has_b = relu && relu_bits, has_o = relu && !has_b && out, has_h = relu && !has_b && !out;
-  const size_t pstep = m.dp * kUnroll;
-  const size_t iters = m.p0 < pixels ? (pixels - m.p0 + pstep - 1) / pstep : 0;
-  for (size_t it = 0; it < iters; ++it) {
-    const size_t p = m.p0 + (rev ? iters - 1 - it : it) * pstep;  // rev: see bn_act_fwd_kernel
+  for (size_t p = m.p0; p < pixels; p += m.dp * kUnroll) {
     float4 d[kUnroll], yv[kUnroll], o[kUnroll];
     uint2 h[kUnroll];
     uint4 bw[kUnroll];
@@ -528,19 +527,6 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(
   }
 }
 
-
-// VSPW_BN_ORDER=down: the element-wise forward and the second backward pass walk the pixel axis downwards, hoping for L2 reuse
-// across the kernel boundary (see bn_act_fwd_kernel).  Measured on B200 inside one box (tools/ab.sh, 2 x 10 steps each):
-// 92.60 ms/step down vs 92.38 up — no gain (what the producer leaves in L2 is dirty write-back traffic either way), so
-// ascending stays the default and the switch stays for the record.
-int bn_reverse() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("VSPW_BN_ORDER");
-    v = (e && e[0] == 'd') ? 1 : 0;
-  }
-  return v;
-}
 
 peer::PeerArgs no_peer() {
   peer::PeerArgs pa{};
@@ -610,7 +596,7 @@ extern "C" int vspw_bn_act_fwd(const float* y, const float* scale, const float* 
   bn_act_fwd_kernel<<<ew_grid(pixels, c / 4, occ), kEwThreads, 0, as_stream(stream)>>>(
       (const float4*)y, (const float4*)scale, (const float4*)shift, (const float4*)mean, (const float4*)beta,
       (const float4*)residual, (const uint2*)residual_hi, (const uint2*)residual_lo, (const float4*)chan_scale,
-      relu, (float4*)out, (uint2*)out_hi, (uint2*)out_lo, (uint4*)relu_bits, pixels, c / 4, pixels_per_image, BnTrainStats{}, no_peer(), bn_reverse());
+      relu, (float4*)out, (uint2*)out_hi, (uint2*)out_lo, (uint4*)relu_bits, pixels, c / 4, pixels_per_image, BnTrainStats{}, no_peer());
   return check_launch("vspw_bn_act_fwd");
 }
 
@@ -665,7 +651,7 @@ static int bn_train_fwd_impl(const float* y, const double* sum, const double* sq
   bn_act_fwd_kernel<<<ew_grid(pixels, c / 4, occ), kEwThreads, 0, as_stream(stream)>>>(
       (const float4*)y, nullptr, nullptr, nullptr, nullptr, (const float4*)residual, (const uint2*)residual_hi,
       (const uint2*)residual_lo, (const float4*)chan_scale, relu,
-      (float4*)out, (uint2*)out_hi, (uint2*)out_lo, (uint4*)relu_bits, pixels, c / 4, pixels_per_image, ts, pa, bn_reverse());
+      (float4*)out, (uint2*)out_hi, (uint2*)out_lo, (uint4*)relu_bits, pixels, c / 4, pixels_per_image, ts, pa);
   return check_launch("vspw_bn_train_fwd");
 }
 
@@ -734,7 +720,7 @@ static int bn_bwd_apply_impl(const float* dout, const float* out, const uint16_t
       (const float4*)dout, (const float4*)out, (const uint2*)out_hi, (const float4*)y, (const float4*)mean,
       (const float4*)invstd, (const float4*)gamma, (const float4*)chan_scale, relu, dbeta, dgamma, (float4*)dy,
       (uint2*)dy_hi, (uint2*)dy_lo, (float4*)dres, (float4*)dgamma_f, (float4*)dbeta_f, (const uint4*)relu_bits, pixels, c / 4,
-      pixels_per_image, 1.0 / count, eval_mode, pgrad_scale, pa, bn_reverse());
+      pixels_per_image, 1.0 / count, eval_mode, pgrad_scale, pa);
   int rc = check_launch("vspw_bn_bwd_apply");
   return rc;
 }

@@ -688,6 +688,9 @@ def _double_to_float(d, out=None):
     return f
 
 
+_RELU_BITS_MIN_ELEMS = int(os.environ.get("VSPW_RELU_BITS_MIN", str(24 << 20)))
+
+
 def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, training=None, fp32_out=True, planes_out=True):
     """BN (train: batch stats, eval: running stats) [+ residual] [+ ReLU] [* Dropout2d mask].
 
@@ -744,7 +747,9 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
     # the backward needs [out != 0] only: one bit per element (written by the forward kernel with warp ballots) instead of
     # re-reading the bf16 hi plane (2 B) or the fp32 output (4 B) in both backward passes
     bits = None
-    if relu and needs and (c == 64 or c % 128 == 0) and os.environ.get("VSPW_RELU_BITS", "1") != "0":
+    # (tools/bench_bn.py: on the 16 M-element interior tensors the forward's ballots cost what the backward saves; from 32 M
+    # elements up — block outputs, stem — the bits win 15-25 us per layer)
+    if relu and needs and (c == 64 or c % 128 == 0) and pixels * c >= _RELU_BITS_MIN_ELEMS and os.environ.get("VSPW_RELU_BITS", "1") != "0":
         bits = torch.empty(((pixels * c // 4 + 31) // 32) * 4, device=dev, dtype=torch.int32)
     if training:
         # finalize (mean / invstd / running statistics from the fp64 sums) + normalise + residual + ReLU + planes: one launch
