@@ -395,7 +395,9 @@ def run_ours(args):
            "data": "synthetic", "impl": "ours",
            "config": {"workload": ("TCB-PSP" if args.model == "psp" else "TCB-OCR") + " ResNet101-dilated train fwd+bwd+SGD, T=5, n=2 clips/GPU, 480x854, K=124 (BASELINE configs[%d])" % (1 if args.model == "psp" else 2),
                       "frames_per_step_per_gpu": T_FRAMES * N_CLIPS, "parallelism": f"dp{world}", "precision_mode": args.precision,
-                      "syncbn": bool(syncbn), "syncbn_exchange": (args.syncbn_exchange if syncbn else None), "l2_flush": "256 MiB write between timed steps",
+                      "syncbn": bool(syncbn), "syncbn_exchange": (args.syncbn_exchange if syncbn else None),
+                      "grad_allreduce": (None if world == 1 else f"NCCL AVG over one flat bucket, {bucket.last_overlapped} of {len(bucket._chunks)} chunks launched during the backward pass"),
+                      "l2_flush": "256 MiB write between timed steps",
                       "optimizer": ("torch.optim.SGD" if args.torch_sgd else "FusedSGD (vspw_sgd_momentum_step)") + ": the reference's update rule and 4 param groups (train_clip2.py:215-236), inside the timed step",
                       "loss": round(final_loss, 5), "wall_s_timed_region": round(wall, 3),
                       "peak_hbm_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 2)},

@@ -211,7 +211,7 @@ class Var:
         lib.call("vspw_axpby", _p(g), _p(dst), 1.0, 1.0, g.numel(), _stream())
 
 
-_grad_sink = None  # object with destination(param) -> tensor | None and mark(param): parallel.GradBucket
+_grad_sink = None  # object with destination(param) -> tensor | None, mark(param), late(param), node_done(): parallel.GradBucket
 
 
 def set_grad_sink(sink):
@@ -259,6 +259,8 @@ class PVar:
         if self.grad is None:
             self.grad = g
         else:
+            if self.sunk and _grad_sink is not None:
+                _grad_sink.late(self.param)  # a weight used twice: its chunk of the bucket is not complete yet
             lib.call("vspw_axpby", _p(g), _p(self.grad), 1.0, 1.0, g.numel(), _stream())
 
 
@@ -319,6 +321,10 @@ class Tape:
     def backward(self):
         for fn in reversed(self._nodes):
             fn()
+            # every kernel of this node is enqueued: the sink may start reducing the gradient chunks it completed (not while
+            # weight gradients run on the side stream — then the sink reduces at the end of the step)
+            if _grad_sink is not None and self._side is None:
+                _grad_sink.node_done()
         if self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)
             self._side = None

@@ -6,8 +6,10 @@ reference's per-step 282 MB parameter broadcast and scatter/gather disappear.  W
 
   * gradient averaging (`GradBucket`): every parameter's ``.grad`` IS a view of one flat buffer that the backward kernels
     write into directly (weight-gradient kernels, BN backward, bias sums: `engine.set_grad_sink`), so there is no pack /
-    unpack pass; one all-reduce (NCCL AVG over NVLink on GPUs, gloo on CPU tests) per step — DataParallel's "mean over
-    replicas of per-replica mean losses" (train_clip2.py:98);
+    unpack pass; the buffer is all-reduced (NCCL AVG over NVLink on GPUs, gloo on CPU tests) — DataParallel's "mean over
+    replicas of per-replica mean losses" (train_clip2.py:98) — in a few contiguous chunks, each launched on a side stream
+    as soon as the backward pass has enqueued the last kernel that writes into it (the pattern is learned in the first
+    step), so only the small chunk of the stem/layer1/layer2 gradients is reduced after the backward pass has ended;
   * SyncBN statistics (`PeerSums`): a one-shot exchange over NVLink peer memory per BN layer (csrc/peer.cu) instead of a
     library all-reduce per layer — the reference's multi-GPU BN semantics (sync_batchnorm/batchnorm.py:110-131);
   * scalar loss/acc averaging for logging.
@@ -64,7 +66,7 @@ class GradBucket:
     The legacy protocol still works: gradients produced without `zero_grad()` (plain tensors, possibly None on some ranks)
     are packed into the buffer by `all_reduce_mean()`, and a parameter nobody touched stays None."""
 
-    def __init__(self, params):
+    def __init__(self, params, overlap=None, chunk_elems=None):
         self.params = [p for p in params if p.requires_grad]
         self.numel = sum(p.numel() for p in self.params)
         self.flat = None
@@ -72,6 +74,43 @@ class GradBucket:
         self._index = {id(p): i for i, p in enumerate(self.params)}
         self._marked = set()   # parameter indices that received a gradient from an engine graph since zero_grad()
         self._armed = False    # zero_grad() was called: p.grad are bucket views
+        # -- overlap of the all-reduce with the backward pass (module docstring) --------------------------------------
+        if overlap is None:
+            overlap = os.environ.get("VSPW_GRAD_OVERLAP", "1") != "0"
+        self.overlap = bool(overlap)
+        self._offsets, off = [], 0
+        for p in self.params:
+            self._offsets.append(off)
+            off += p.numel()
+        self._chunks = self._make_chunks(chunk_elems)   # [(first param, one past the last param, lo, hi)] in PARAMETER order
+        self._chunk_of = [0] * len(self.params)
+        for c, (a, b, _, _) in enumerate(self._chunks):
+            for i in range(a, b):
+                self._chunk_of[i] = c
+        self._pattern = None     # parameter indices whose gradient arrived through destination() in the previous step
+        self._sunk = set()       # ... in this step
+        self._left = None        # per chunk: expected parameters still missing in this step
+        self._ready = []         # chunks complete except for the launch that was about to be issued when they completed
+        self._launched = set()
+        self._side = None
+        self._pg = None
+        self.last_overlapped = 0
+
+    def _make_chunks(self, chunk_elems):
+        """Contiguous parameter ranges.  The backward pass fills the buffer from its END towards its start, so the chunk at
+        the start (stem, layer1, layer2: done last, its reduction is exposed) is small and the later ones grow."""
+        if chunk_elems is None:
+            chunk_elems = [int(x) for x in os.environ.get("VSPW_GRAD_CHUNKS", "2097152,8388608,16777216").split(",")]
+        elif isinstance(chunk_elems, int):
+            chunk_elems = [chunk_elems]
+        chunks, a, lo, k = [], 0, 0, 0
+        for i, p in enumerate(self.params):
+            hi = self._offsets[i] + p.numel()
+            cap = chunk_elems[min(k, len(chunk_elems) - 1)]
+            if hi - lo >= cap or i == len(self.params) - 1:
+                chunks.append((a, i + 1, lo, hi))
+                a, lo, k = i + 1, hi, k + 1
+        return chunks
 
     def _ensure(self, device):
         if self.flat is None or self.flat.device != device:
@@ -94,17 +133,97 @@ class GradBucket:
                 p.grad = v
         self._marked.clear()
         self._armed = True
+        self._begin_overlap()
         from . import engine as E
         E.set_grad_sink(self)
+
+    # -- overlap ----------------------------------------------------------------------------------------------------------
+    def reset_overlap(self):
+        """Forget the learned gradient pattern (call when the graph that produces the gradients changes)."""
+        self._pattern = None
+
+    def _begin_overlap(self):
+        self._sunk = set()
+        self._ready = []
+        self._launched = set()
+        self._left = None
+        if self.overlap and is_parallel() and self._pattern is not None:
+            self._left = [0] * len(self._chunks)
+            for i in self._pattern:
+                self._left[self._chunk_of[i]] += 1
+
+    def _reduce(self, t):
+        if dist.get_backend(self._pg) == "nccl":
+            dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self._pg)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self._pg)
+            t.mul_(1.0 / dist.get_world_size())
+
+    def _launch(self, lo, hi):
+        """All-reduce flat[lo:hi] behind everything enqueued so far on the current stream, without blocking that stream."""
+        t = self.flat[lo:hi]
+        if not t.is_cuda:
+            self._reduce(t)
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=t.device)
+            ctas = int(os.environ.get("VSPW_GRAD_NCCL_CTAS", "0"))
+            if ctas > 0 and dist.get_backend() == "nccl":
+                # its own communicator with few CTAs: the reduction shares the SMs with the persistent backward kernels
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.config.max_ctas = ctas
+                self._pg = dist.new_group(backend="nccl", pg_options=opts)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(t.device))
+        self._side.wait_event(ev)
+        with torch.cuda.stream(self._side):
+            self._reduce(t)
+
+    def _flush_ready(self):
+        for c in self._ready:
+            _, _, lo, hi = self._chunks[c]
+            self._launch(lo, hi)
+            self._launched.add(c)
+        self._ready = []
 
     # -- engine-facing sink protocol ------------------------------------------------------------------------------
     def destination(self, param):
         """The tensor the FIRST gradient contribution of `param` may be written into (overwriting zeros), or None."""
         i = self._index.get(id(param))
         if i is None or not self._armed or i in self._marked or param.grad is not self.views[i]:
+            if i is not None and self._chunk_of[i] in self._launched:
+                raise RuntimeError("GradBucket: a second gradient contribution arrived for a parameter whose chunk is already being "
+                                   "all-reduced; build the bucket with overlap=False for steps with several graphs")
             return None  # (a second graph of the same step accumulates through autograd instead of overwriting)
         self._marked.add(i)
+        self._sunk.add(i)
+        if self._left is not None:
+            c = self._chunk_of[i]
+            if c in self._launched or c in self._ready:
+                raise RuntimeError("GradBucket: the set of parameters that receive gradients changed since the previous step; "
+                                   "call reset_overlap() when switching graphs")
+            if i in self._pattern:
+                self._left[c] -= 1
+                if self._left[c] == 0:
+                    self._ready.append(c)  # launched by node_done(): this parameter's kernel is not enqueued yet
         return self.views[i]
+
+    def node_done(self):
+        """The engine finished enqueueing the backward kernels of one tape node on the current stream."""
+        if self._ready:
+            self._flush_ready()
+
+    def late(self, param):
+        """The engine is about to ACCUMULATE a further contribution into a parameter it already wrote (weight used twice)."""
+        i = self._index.get(id(param))
+        if i is None:
+            return
+        c = self._chunk_of[i]
+        if c in self._ready:
+            self._ready.remove(c)
+            self._left[c] = -1  # reduced at the end of the step
+        elif c in self._launched:
+            raise RuntimeError("GradBucket: gradient accumulated into a chunk that is already being all-reduced")
 
     def mark(self, param):
         i = self._index.get(id(param))
@@ -123,7 +242,7 @@ class GradBucket:
         if not is_parallel():
             self.finish_step()
             return
-        world = dist.get_world_size()
+        armed = self._armed
         self.finish_step()
         have = [p for p in self.params if p.grad is not None]
         if not have:
@@ -133,14 +252,18 @@ class GradBucket:
         else:
             dev = have[0].grad.device
         self._ensure(dev)
+        self._flush_ready()
         stray_v, stray_g = [], []
         missing = []
         for i, (v, p) in enumerate(zip(self.views, self.params)):
             if p.grad is None:
-                v.zero_()  # this rank contributes zero
+                if self._chunk_of[i] not in self._launched:
+                    v.zero_()  # this rank contributes zero (a launched chunk already holds the average of zeros)
                 missing.append(i)
                 continue
             if p.grad is not v and p.grad.data_ptr() != v.data_ptr():
+                if self._chunk_of[i] in self._launched:
+                    raise RuntimeError("GradBucket: a gradient outside the bucket belongs to a chunk that is already all-reduced")
                 stray_v.append(v)
                 stray_g.append(p.grad)
         if stray_v:
@@ -148,11 +271,30 @@ class GradBucket:
         self.tail.fill_(1.0)  # device-side: the host must stay ahead of the stream here
         if missing:
             self.tail[torch.tensor(missing, device=dev)] = 0.0
-        if dist.get_backend() == "nccl":
-            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
+        # what is left: maximal runs of chunks not launched during the backward pass; the flags travel with the last run
+        runs, c = [], len(self._chunks) - 1
+        while c >= 0:
+            if c in self._launched:
+                c -= 1
+                continue
+            hi = self._chunks[c][3]
+            while c - 1 >= 0 and (c - 1) not in self._launched:
+                c -= 1
+            runs.append([self._chunks[c][2], hi])
+            c -= 1
+        if runs and runs[0][1] == self.numel:
+            runs[0][1] = self.flat.numel()
         else:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            self.flat.mul_(1.0 / world)
+            runs.append([self.numel, self.flat.numel()])
+        for lo, hi in runs:
+            self._launch(lo, hi)
+        if self._side is not None and self.flat.is_cuda:
+            torch.cuda.current_stream(dev).wait_stream(self._side)
+        if self.overlap and armed:
+            self._pattern = frozenset(self._sunk)  # the next step reduces each chunk as soon as these have all arrived
+        self.last_overlapped = len(self._launched)  # chunks whose all-reduce was launched during the backward pass
+        self._launched = set()
+        self._left = None
         for v, p in zip(self.views, self.params):
             if p.grad is not None and p.grad is not v:
                 p.grad = v  # adopt the reduced slice: no unpack copy

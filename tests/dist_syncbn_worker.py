@@ -46,6 +46,23 @@ def main(out_path):
         loss.backward()
         bucket.all_reduce_mean()
         loss_dp = float(P.mean_scalar(loss).item())
+        if mode == "peer/fp32":
+            # a second step with the same bucket: now the gradient chunks are all-reduced DURING the backward pass
+            # (GradBucket overlap); same weights and inputs, so the averaged gradients must repeat
+            first = bucket.flat[:bucket.numel].clone()
+            assert bucket.last_overlapped == 0
+            state_first = {k: v.clone() for k, v in m.state_dict().items()}
+            bucket.zero_grad()
+            loss2, _ = m(C.feed([i[sl] for i in imgs], [l[sl] for l in labs], True, dev))
+            loss2.backward()
+            bucket.all_reduce_mean()
+            assert bucket.last_overlapped == len(bucket._chunks), (bucket.last_overlapped, len(bucket._chunks))
+            again = bucket.flat[:bucket.numel]
+            rel = float((again.double() - first.double()).norm() / first.double().norm())
+            assert rel < 1e-5, f"overlapped all-reduce changed the gradients: rel {rel:.3e}"
+            report["overlap_rel"] = rel
+            bucket.flat[:bucket.numel].copy_(first)
+            m.load_state_dict(state_first)  # (running statistics of ONE step are what the single-device run is compared with)
         E.set_syncbn(False)
         # ---- single-device global batch (rank 0) --------------------------------------------------------------------
         if rank == 0:

@@ -209,6 +209,68 @@ def test_two_rank_gradient_all_reduce_matches_single_process(tmp_path):
         assert torch.allclose(g, want, rtol=1e-5, atol=1e-7), i
 
 
+def _overlap_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from cvpr2021_vspw_implement_b200 import parallel as P
+    P.init_from_env(backend="gloo")
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(s)) for s in ((4, 3), (5,), (2, 6), (7,), (3, 3), (2,))]
+    bucket = P.GradBucket(params, overlap=True, chunk_elems=[10, 12])
+    assert [(a, b) for a, b, _, _ in bucket._chunks] == [(0, 1), (1, 3), (3, 5), (5, 6)]
+    unused = 3  # a parameter that never receives a gradient: the optimizer must see grad = None for it
+    record, launches = [], []
+    real_launch = bucket._launch
+    bucket._launch = lambda lo, hi: (launches.append((len(record), lo, hi)), real_launch(lo, hi))[1]
+    for step in range(3):
+        bucket.zero_grad()
+        record.clear()
+        del launches[:]
+        g = torch.Generator().manual_seed(100 * step + rank)
+        for i in reversed(range(len(params))):       # the backward pass: last parameter first, one tape node per parameter
+            if i == unused:
+                continue
+            dst = bucket.destination(params[i])
+            assert dst is not None and dst.data_ptr() == params[i].grad.data_ptr()
+            dst.copy_(torch.randn(params[i].shape, generator=g))
+            record.append(i)
+            bucket.node_done()
+        during = len(launches)
+        bucket.all_reduce_mean()
+        # step 0 learns the pattern (everything reduced at the end: one launch); afterwards every chunk goes out as soon as
+        # its last expected parameter has been written (after 1, 2, 4 and 5 parameters), only the flags at the end
+        assert during == (0 if step == 0 else 4) and len(launches) == (1 if step == 0 else 5), (step, launches)
+        if step:
+            assert [n for n, _, _ in launches[:4]] == [1, 2, 4, 5]
+        assert params[unused].grad is None
+        if rank == 0:
+            torch.save([None if p.grad is None else p.grad.clone() for p in params], out + f".{step}")
+    with pytest.raises(RuntimeError, match="changed since the previous step"):
+        bucket.zero_grad()
+        for i in reversed(range(len(params))):
+            bucket.destination(params[i])   # parameter 3 now receives a gradient after its chunk was scheduled
+            bucket.node_done()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_overlapped_chunked_all_reduce_matches_the_mean(tmp_path):
+    """GradBucket(overlap=True) on gloo, world 2: chunks are reduced during the emulated backward pass from the second step on,
+    the result is the plain mean of the two ranks' gradients, unused parameters stay None."""
+    port = 29500 + (os.getpid() + 7) % 2000
+    out = str(tmp_path / "g")
+    mp.spawn(_overlap_worker, args=(2, port, out), nprocs=2, join=True)
+    shapes = ((4, 3), (5,), (2, 6), (7,), (3, 3), (2,))
+    for step in range(3):
+        got = torch.load(out + f".{step}")
+        gens = [torch.Generator().manual_seed(100 * step + r) for r in range(2)]
+        for i in reversed(range(len(shapes))):
+            if i == 3:
+                assert got[i] is None
+                continue
+            want = sum(torch.randn(shapes[i], generator=g) for g in gens) / 2
+            assert torch.allclose(got[i], want, rtol=1e-6, atol=1e-7), (step, i)
+
+
 def test_shard_clips_errors():
     from cvpr2021_vspw_implement_b200 import parallel as P
     assert P.shard_clips(16, 8, 3) == (6, 8)
