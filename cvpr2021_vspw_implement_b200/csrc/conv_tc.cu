@@ -734,6 +734,18 @@ int make_out_map(CUtensorMap* m, float* base, int n, int h, int w, int c, int bo
   return VSPW_OK;
 }
 
+// Weight gradients of the 3x3 convs with 64 input channels.  VSPW_WGRAD_TAP_GROUPS=0: one filter tap per CTA (as everywhere
+// else); 1: one filter row per CTA, one x box per tap; 2: one filter row per CTA and ONE x box per row.  For A/B comparisons.
+int tap_group_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VSPW_WGRAD_TAP_GROUPS");
+    v = e ? atoi(e) : 2;
+    if (v < 0 || v > 2) v = 2;
+  }
+  return v;
+}
+
 // VSPW_CONV_NARROW=0 sends 64-channel outputs through the 128-wide kernel (A/B comparisons)
 bool use_narrow_kernel() {
   static int v = -1;
@@ -839,6 +851,10 @@ int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int ta
 //   fetched as [64 pixels][64 channels] boxes (128-byte swizzle) -> MN-major SWIZZLE_128B UMMA operands:
 //   LBO = distance between 64-channel blocks (8 KB), SBO = distance between 8-pixel groups (1 KB).
 //   One CTA = one (co tile, ci tile, tap, pixel-range split); partial sums are added with red.global.add.v4.f32.
+//   Tap groups (Cin = 64, 3x3: stem conv2/conv3, layer1): with one tap per CTA the [64 px][128 co] dy boxes are fetched once per
+//   tap, 9 x (dy + x) through L2 -- 6.9 GB for the 1 M-pixel stem map, which is what bounds the kernel (6.7 TB/s of L2
+//   throughput at 1.03 ms).  There one CTA owns a ROW of the filter (tg = 3 taps): the dy boxes are fetched once per 3 taps and
+//   three 128x64 accumulators sit side by side in TMEM (192 columns); stages grow to 80 KB, two of them in flight.
 constexpr int WG_PIX = 64;                   // pixels (GEMM K) per stage
 constexpr int WG_BLK = WG_PIX * 64 * 2;      // one [64 px][64 ch] bf16 box = 8 KB
 constexpr int WG_STAGES = 3;
@@ -856,6 +872,10 @@ struct WgradTcParams {
   int tiles_co, tiles_ci, splits, chunk;  // chunk = patches per split
   int x3;
   int n64;            // Cin == 64: the GEMM's N is one 64-channel block (UMMA 128x64x16), the second x box is not fetched
+  int tg;             // taps per CTA (1, or taps_w with n64: one filter row); blockIdx then enumerates tap GROUPS
+  int shift;          // tg > 1 only. 1: the patch is a 64-pixel row segment and ONE x box of 64 + 2*step pixels serves the three
+                      // taps of the row: tap j's operand starts j*step pixel rows (128 B each) into the box
+  int xbox_bytes;     // shift: bytes of one x box in shared memory, (64 + 2*step) * 128 rounded up to 1 KB
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -867,6 +887,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy_hi, const __grid_cons
                 const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo, WgradTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
+  // stage = [dy_hi c0][dy_hi c1][x_hi ...][dy_lo c0][dy_lo c1][x_lo ...]; x blocks per plane: 2 channel blocks, 1 (n64) or tg taps
+  const int xblocks = p.tg > 1 ? p.tg : (p.n64 ? 1 : 2);
+  const int plane_blocks = 2 + (p.tg > 1 ? p.tg : 2);            // (the one-tap layout keeps its fixed 4-block planes)
+  const int plane_bytes = p.shift ? 2 * WG_BLK + p.xbox_bytes : plane_blocks * WG_BLK;
+  const int stage_size = 2 * plane_bytes;
+  const int n_stages = (p.tg > 1 && !p.shift) ? 2 : WG_STAGES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + WG_STAGES;
@@ -878,14 +904,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy_hi, const __grid_cons
   const int split = t % p.splits; t /= p.splits;
   const int tco = t % p.tiles_co; t /= p.tiles_co;
   const int tci = t % p.tiles_ci; t /= p.tiles_ci;
-  const int tap = t;
-  const int tr = tap / p.taps_w, ts = tap - tr * p.taps_w;
-  const int dxo = p.off0 + ts * p.step, dyo = p.off0 + tr * p.step;
+  const int tap0 = t * p.tg;  // first tap of this CTA's group
   const int total_patches = p.N * p.tiles_y * p.tiles_x;
   const int pbeg = split * p.chunk;
   const int pend = min(total_patches, pbeg + p.chunk);
   const int num_k = pend - pbeg;  // host guarantees >= 1
-  const uint32_t stage_bytes = (uint32_t)((p.n64 ? 3 : 4) * WG_BLK) * (p.x3 ? 2u : 1u);
+  const uint32_t stage_bytes = (uint32_t)(p.shift ? 2 * WG_BLK + (64 + 2 * p.step) * 128 : (2 + xblocks) * WG_BLK) * (p.x3 ? 2u : 1u);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_dy_hi);
@@ -897,7 +921,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy_hi, const __grid_cons
     mbar_init(done_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<128>(tmem_slot);
+  if (warp == 2) { if (p.tg > 1) tmem_alloc<256>(tmem_slot); else tmem_alloc<128>(tmem_slot); }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -913,45 +937,68 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy_hi, const __grid_cons
       const int img = q / p.tiles_y;
       const int x0 = tx * p.bw, y0 = ty * p.bh;
       mbar_wait(&empty_bar[stage], phase ^ 1);
-      uint8_t* st = smem + stage * WG_STAGE_BYTES;
+      uint8_t* st = smem + stage * stage_size;
+      uint8_t* st_lo = st + plane_bytes;
       mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-      // layout of a stage: [dy_hi c0][dy_hi c1][x_hi c0][x_hi c1][dy_lo c0][dy_lo c1][x_lo c0][x_lo c1]
       tma_load_4d(st + 0 * WG_BLK, &map_dy_hi, &full_bar[stage], tco * 128, x0, y0, img);
       tma_load_4d(st + 1 * WG_BLK, &map_dy_hi, &full_bar[stage], tco * 128 + 64, x0, y0, img);
-      const int xx = x0 * p.stride + dxo, xy = y0 * p.stride + dyo;
-      tma_load_4d(st + 2 * WG_BLK, &map_x_hi, &full_bar[stage], tci * 128, xx, xy, img);
-      if (!p.n64) tma_load_4d(st + 3 * WG_BLK, &map_x_hi, &full_bar[stage], tci * 128 + 64, xx, xy, img);
       if (p.x3) {
-        tma_load_4d(st + 4 * WG_BLK, &map_dy_lo, &full_bar[stage], tco * 128, x0, y0, img);
-        tma_load_4d(st + 5 * WG_BLK, &map_dy_lo, &full_bar[stage], tco * 128 + 64, x0, y0, img);
-        tma_load_4d(st + 6 * WG_BLK, &map_x_lo, &full_bar[stage], tci * 128, xx, xy, img);
-        if (!p.n64) tma_load_4d(st + 7 * WG_BLK, &map_x_lo, &full_bar[stage], tci * 128 + 64, xx, xy, img);
+        tma_load_4d(st_lo + 0 * WG_BLK, &map_dy_lo, &full_bar[stage], tco * 128, x0, y0, img);
+        tma_load_4d(st_lo + 1 * WG_BLK, &map_dy_lo, &full_bar[stage], tco * 128 + 64, x0, y0, img);
       }
-      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      if (p.shift) {  // one box: pixels [x0 + off0, x0 + off0 + 64 + 2*step) of row y0 + off0 + tr*step, for the 3 taps of row tr
+        const int xy = y0 + p.off0 + (tap0 / p.taps_w) * p.step;
+        tma_load_4d(st + 2 * WG_BLK, &map_x_hi, &full_bar[stage], 0, x0 + p.off0, xy, img);
+        if (p.x3) tma_load_4d(st_lo + 2 * WG_BLK, &map_x_lo, &full_bar[stage], 0, x0 + p.off0, xy, img);
+      }
+      for (int j = 0; j < (p.shift ? 0 : p.tg); ++j) {
+        const int tap = tap0 + j;
+        const int tr = tap / p.taps_w, ts = tap - tr * p.taps_w;
+        const int xx = x0 * p.stride + p.off0 + ts * p.step, xy = y0 * p.stride + p.off0 + tr * p.step;
+        if (p.tg > 1) {  // one 64-channel x box per tap
+          tma_load_4d(st + (2 + j) * WG_BLK, &map_x_hi, &full_bar[stage], 0, xx, xy, img);
+          if (p.x3) tma_load_4d(st_lo + (2 + j) * WG_BLK, &map_x_lo, &full_bar[stage], 0, xx, xy, img);
+        } else {
+          tma_load_4d(st + 2 * WG_BLK, &map_x_hi, &full_bar[stage], tci * 128, xx, xy, img);
+          if (!p.n64) tma_load_4d(st + 3 * WG_BLK, &map_x_hi, &full_bar[stage], tci * 128 + 64, xx, xy, img);
+          if (p.x3) {
+            tma_load_4d(st_lo + 2 * WG_BLK, &map_x_lo, &full_bar[stage], tci * 128, xx, xy, img);
+            if (!p.n64) tma_load_4d(st_lo + 3 * WG_BLK, &map_x_lo, &full_bar[stage], tci * 128 + 64, xx, xy, img);
+          }
+        }
+      }
+      if (++stage == n_stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1 && lane == 0) {
-    const uint32_t idesc = p.n64 ? make_idesc(128, 64, 1, 1) : make_idesc(128, 128, 1, 1);  // both operands MN-major
+    // both operands MN-major.  A tap group is ONE MMA of N = 64 * tg: the taps' x blocks are "64-element MN blocks" of the B
+    // operand, LBO apart — 8 KB with one box per tap, step * 128 B (= step pixel rows) inside the shared box.  The latter starts
+    // blocks inside a 1024-byte swizzle atom; the tensor core applies the 128-byte swizzle to the absolute shared-memory address
+    // bits, as TMA did when it wrote the box, so the plain start address is right (measured: a descriptor base offset is wrong).
+    const uint32_t idesc = p.tg > 1 ? make_idesc(128, 64 * p.tg, 1, 1) : p.n64 ? make_idesc(128, 64, 1, 1) : make_idesc(128, 128, 1, 1);
+    const uint32_t lo_off = (uint32_t)plane_bytes;
+    const uint32_t b_lbo = p.shift ? (uint32_t)(p.step * 128) : (uint32_t)WG_BLK;
     int stage = 0;
     uint32_t phase = 0;
     for (int k = 0; k < num_k; ++k) {
       mbar_wait(&full_bar[stage], phase);
       tcgen05_fence_after();
-      const uint32_t base = smem_u32(smem + stage * WG_STAGE_BYTES);
+      const uint32_t base = smem_u32(smem + stage * stage_size);
+      const uint32_t xb = base + (uint32_t)(2 * WG_BLK);
 #pragma unroll
       for (int kk = 0; kk < WG_PIX / UMMA_K; ++kk) {
         const uint32_t koff = kk * UMMA_K * 128;  // 16 pixel rows of 128 B
-        const uint64_t a_hi = make_mnmajor_sw128_desc(base + 0 * WG_BLK + koff, WG_BLK);
-        const uint64_t b_hi = make_mnmajor_sw128_desc(base + 2 * WG_BLK + koff, WG_BLK);
+        const uint64_t a_hi = make_mnmajor_sw128_desc(base + koff, WG_BLK);
+        const uint64_t b_hi = make_mnmajor_sw128_desc(xb + koff, b_lbo);
         umma_bf16(a_hi, b_hi, tmem_d, idesc, (k | kk) != 0);
         if (p.x3) {
-          const uint64_t a_lo = make_mnmajor_sw128_desc(base + 4 * WG_BLK + koff, WG_BLK);
-          const uint64_t b_lo = make_mnmajor_sw128_desc(base + 6 * WG_BLK + koff, WG_BLK);
+          const uint64_t a_lo = make_mnmajor_sw128_desc(base + lo_off + koff, WG_BLK);
+          const uint64_t b_lo = make_mnmajor_sw128_desc(xb + lo_off + koff, b_lbo);
           umma_bf16(a_hi, b_lo, tmem_d, idesc, 1);
           umma_bf16(a_lo, b_hi, tmem_d, idesc, 1);
         }
       }
       umma_commit(&empty_bar[stage]);
-      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      if (++stage == n_stages) { stage = 0; phase ^= 1; }
     }
     umma_commit(done_bar);
   } else if (warp >= 2) {
@@ -961,24 +1008,28 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy_hi, const __grid_cons
     tcgen05_fence_after();
     const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
     const int taps = p.taps_w * p.taps_w;
-    float* dst = p.dw + ((size_t)co * taps + tap) * p.dw_pitch + tci * 128;
+    const int ncols = p.n64 ? 64 : 128;
 #pragma unroll 1
-    for (int c0 = 0; c0 < (p.n64 ? 64 : 128); c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(taddr + c0, v);
-      tmem_ld_wait();
-      if (co < p.Cout && tci * 128 + c0 < p.Cin) {
+    for (int j = 0; j < p.tg; ++j) {
+      float* dst = p.dw + ((size_t)co * taps + tap0 + j) * p.dw_pitch + tci * 128;
+#pragma unroll 1
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + j * 64 + c0, v);
+        tmem_ld_wait();
+        if (co < p.Cout && tci * 128 + c0 < p.Cin) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          red_add_v4(dst + c0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                     __uint_as_float(v[j + 3]));
+          for (int jj = 0; jj < 32; jj += 4)
+            red_add_v4(dst + c0 + jj, __uint_as_float(v[jj]), __uint_as_float(v[jj + 1]), __uint_as_float(v[jj + 2]),
+                       __uint_as_float(v[jj + 3]));
+        }
       }
     }
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  if (warp == 2) tmem_dealloc<128>(tmem_d);
+  if (warp == 2) { if (p.tg > 1) tmem_dealloc<256>(tmem_d); else tmem_dealloc<128>(tmem_d); }
 }
 
 // cta_group::2 variant of the wgrad kernel: a CTA pair accumulates a 256 (co) x 256 (ci) block of dW with UMMA 256x256x16.
@@ -1173,6 +1224,14 @@ extern "C" int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_h
     xn = 1; xh = 1; xw = p.W;
   }
   pick_patch64(p.H, p.W, p.bw, p.bh);
+  p.tg = (p.n64 && d->kw == 3 && tap_group_mode() > 0) ? 3 : 1;  // Cin = 64, 3x3: one CTA per filter ROW (dy boxes fetched once per 3 taps)
+  p.shift = 0; p.xbox_bytes = 0;
+  if (p.tg > 1 && d->stride == 1 && tap_group_mode() >= 2 && 64 + 2 * d->dil <= 256) {
+    // ... and one x box per row: the patch becomes a 64-pixel row segment, the taps are row offsets into a (64 + 2 dil)-pixel box
+    p.shift = 1;
+    p.bw = 64; p.bh = 1;
+    p.xbox_bytes = (((64 + 2 * d->dil) * 128 + 1023) / 1024) * 1024;
+  }
   p.tiles_x = (p.W + p.bw - 1) / p.bw;
   p.tiles_y = (p.H + p.bh - 1) / p.bh;
   p.tiles_co = (d->cout + 127) / 128;
@@ -1180,7 +1239,7 @@ extern "C" int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_h
   const int taps = d->kh * d->kw;
   const bool pair = d->cout % 256 == 0 && d->cin % 256 == 0 && use_pair_kernel();
   if (pair) { p.tiles_co = d->cout / 256; p.tiles_ci = d->cin / 256; }
-  const long long tiles = (long long)p.tiles_co * p.tiles_ci * taps;
+  const long long tiles = (long long)p.tiles_co * p.tiles_ci * (taps / p.tg);
   const int total_patches = p.N * p.tiles_y * p.tiles_x;
   int splits = (int)(((pair ? 1 : 2) * num_sms()) / tiles);  // ~2 CTAs per SM's worth of work items; one resident at a time
   if (splits < 1) splits = 1;
@@ -1190,6 +1249,19 @@ extern "C" int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_h
   constexpr int kMaxChunk = 128;
   const int min_splits = (total_patches + kMaxChunk - 1) / kMaxChunk;
   if (splits < min_splits) splits = min_splits;
+  if (p.tg > 1) {
+    // few, long work items (3 tap rows x splits): pick the split count whose CTA count fills whole waves of the SMs
+    const int sms = num_sms();
+    int best = splits;
+    double best_eff = 0.0;
+    for (int s2 = splits; s2 < splits + sms && s2 <= total_patches; ++s2) {
+      const int chunk = (total_patches + s2 - 1) / s2;
+      const long long ctas = tiles * ((total_patches + chunk - 1) / chunk);
+      const double eff = (double)ctas / (double)(((ctas + sms - 1) / sms) * sms);
+      if (eff > best_eff + 0.01) { best_eff = eff; best = s2; }
+    }
+    splits = best;
+  }
   if (splits > total_patches) splits = total_patches;
   p.chunk = (total_patches + splits - 1) / splits;
   p.splits = (total_patches + p.chunk - 1) / p.chunk;
@@ -1199,8 +1271,9 @@ extern "C" int vspw_conv2d_wgrad_tc(const vspw_conv_desc* d, const uint16_t* x_h
   int rc;
   if ((rc = make_act_map(&mdy_hi, dy_hi, p.N, p.H, p.W, d->cout, p.bw, p.bh, who))) return rc;
   if ((rc = make_act_map(&mdy_lo, x3 ? dy_lo : dy_hi, p.N, p.H, p.W, d->cout, p.bw, p.bh, who))) return rc;
-  if ((rc = make_act_map(&mx_hi, x_hi, xn, xh, xw, d->cin, p.bw, p.bh, who, d->stride))) return rc;
-  if ((rc = make_act_map(&mx_lo, x3 ? x_lo : x_hi, xn, xh, xw, d->cin, p.bw, p.bh, who, d->stride))) return rc;
+  const int xbw = p.shift ? 64 + 2 * d->dil : p.bw;
+  if ((rc = make_act_map(&mx_hi, x_hi, xn, xh, xw, d->cin, xbw, p.bh, who, d->stride))) return rc;
+  if ((rc = make_act_map(&mx_lo, x3 ? x_lo : x_hi, xn, xh, xw, d->cin, xbw, p.bh, who, d->stride))) return rc;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] { attr_err = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM); });
@@ -1241,7 +1314,7 @@ extern "C" int vspw_ocr_gather_tc(const uint16_t* p_hi, const uint16_t* p_lo, co
     WgradTcParams p;
     p.dw = ctx + (size_t)b * classes * c; p.dw_pitch = c;
     p.N = t_frames; p.H = 1; p.W = hw; p.Cin = c; p.Cout = classes;
-    p.taps_w = 1; p.off0 = 0; p.step = 1; p.stride = 1; p.x3 = x3; p.n64 = 0;
+    p.taps_w = 1; p.off0 = 0; p.step = 1; p.stride = 1; p.x3 = x3; p.n64 = 0; p.tg = 1; p.shift = 0; p.xbox_bytes = 0;
     pick_patch64(p.H, p.W, p.bw, p.bh);
     p.tiles_x = (p.W + p.bw - 1) / p.bw;
     p.tiles_y = (p.H + p.bh - 1) / p.bh;
