@@ -355,10 +355,20 @@ def run_ours(args):
                 f.write(f"- #{i} `{name}` {ms:.3f}\n")
             E.conv_profile_begin()
             step(imgs_d, labs_d)
-            arm = E.conv_profile_end()["fp32_arm"]
+            cp = E.conv_profile_end()
+            arm = cp["fp32_arm"]
             f.write(f"\nconvs left on the CUDA-core arm ({len(arm)} launches, {sum(m for _, m in arm):.2f} ms/step):\n")
             for tag, ms in sorted(arm, key=lambda r: -r[1]):
                 f.write(f"- {tag}: {ms:.3f} ms\n")
+            geo = {}
+            for tag, ms, fl in cp["tc_arm"]:
+                g = geo.setdefault(tag, [0, 0.0, 0.0])
+                g[0] += 1; g[1] += ms; g[2] += fl
+            mul = 3 if args.precision == "bf16x3" else 1
+            f.write("\ntensor-core convs by geometry, inside one real step (CUDA events around each launch; launches, ms/step, "
+                    "algorithmic and executed tensor TFLOP/s):\n| conv | launches | ms/step | ms each | alg TF/s | tensor TF/s |\n|---|---|---|---|---|---|\n")
+            for tag, (cnt, ms, fl) in sorted(geo.items(), key=lambda kv: -kv[1][1]):
+                f.write(f"| {tag} | {cnt} | {ms:.3f} | {ms / cnt:.3f} | {fl / ms / 1e9:.0f} | {mul * fl / ms / 1e9:.0f} |\n")
 
     gc.enable()
     pk = peaks()

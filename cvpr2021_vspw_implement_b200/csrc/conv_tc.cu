@@ -47,6 +47,7 @@ struct ConvTcParams {
   double* ch_sum;      // [Nout] per-channel sum of the outputs (train-mode BN statistics), or null
   double* ch_sqsum;    // [Nout] per-channel sum of squares
   int tma_store;       // 1: the epilogue leaves through TMA (cp.async.bulk.tensor store / cp.reduce .add for the fan-in)
+  int fuse_hilo;       // 64-wide kernel, bf16x3: a_hi * [b_hi | b_lo] as one 128-column MMA (0: three MMAs, VSPW_CONV_FUSE64=0)
 };
 
 // Epilogue geometry of the conv kernels.  The accumulator drain (TMEM -> registers -> smem transpose -> global) is a chain
@@ -119,7 +120,9 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // columns are clipped by the tensor map, the fan-in add happens in the memory system (no read-modify-write through the SM),
 // and the per-lane address arithmetic, predicates, 8 LDS.128 and 8 STG.128 per chunk of the transpose form are gone.
 // The BN column sums read the staged block with the same swizzle (conflict-free: a row is one 128-byte line of 32 banks).
-template <int BN>
+// ACC = accumulator pitch in TMEM columns.  ACC == 2 * BN (the 64-wide kernel in bf16x3): columns [BN, 2 BN) hold the a_hi * b_lo
+// partial product of the fused hi|lo MMA and are added to columns [0, BN) here.
+template <int BN, int ACC>
 __device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const CUtensorMap* map_out, float* stg, float* stat_s, int acc,
                                                   uint32_t acc_phase, uint32_t tmem_base, uint64_t* tmem_full_bar,
                                                   uint64_t* tmem_empty_bar, uint32_t empty_remote, int img, int ty, int tx, int n0,
@@ -135,19 +138,30 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const C
   else { bx = tx * p.bw; by = ty * p.bh + q * (32 / p.bw); }
   mbar_wait(tmem_full_bar, acc_phase);
   tcgen05_fence_after();
-  const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+  const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC);
+  const bool sum2 = ACC != BN && p.x3 && p.fuse_hilo;
   int c_end = BN;
   if (c_end > p.Nout - n0) c_end = p.Nout - n0;  // Nout % 64 == 0: whole chunks
   float* stat_row = stat_s + q * 2 * BN;
   uint8_t* stb = reinterpret_cast<uint8_t*>(stg);
   const uint32_t sw = (uint32_t)(lane & 7);
   uint32_t v[32];
-  if (c_end > 0) tmem_ld_32x32b_x32(taddr, v);
+  uint32_t v2[ACC != BN ? 32 : 1];
+  if (c_end > 0) {
+    tmem_ld_32x32b_x32(taddr, v);
+    if constexpr (ACC != BN) { if (sum2) tmem_ld_32x32b_x32(taddr + BN, v2); }
+  }
 #pragma unroll 1
   for (int c0 = 0; c0 < c_end; c0 += 32) {
     if (lane == 0) bulk_wait_read_all();  // the previous chunk's store has finished reading the staging block
     __syncwarp();
     tmem_ld_wait();
+    if constexpr (ACC != BN) {
+      if (sum2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
@@ -158,7 +172,10 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const C
       }
       *reinterpret_cast<float4*>(stb + lane * 128 + (((uint32_t)j ^ sw) << 4)) = o;
     }
-    if (c0 + 32 < c_end) tmem_ld_32x32b_x32(taddr + c0 + 32, v);  // the next chunk travels out of TMEM meanwhile
+    if (c0 + 32 < c_end) {  // the next chunk travels out of TMEM meanwhile
+      tmem_ld_32x32b_x32(taddr + c0 + 32, v);
+      if constexpr (ACC != BN) { if (sum2) tmem_ld_32x32b_x32(taddr + BN + c0 + 32, v2); }
+    }
     fence_proxy_async();  // generic-proxy writes -> visible to the bulk copy engine
     __syncwarp();
     if (lane == 0 && img < p.N) {
@@ -209,13 +226,13 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const C
   }
 }
 
-template <int BN>
+template <int BN, int ACC = BN>
 __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const CUtensorMap* map_out, float* stg, float* stat_s, int acc,
                                               uint32_t acc_phase, uint32_t tmem_base, uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar,
                                               uint32_t empty_remote, int img, int ty, int tx, int n0, int warp, int lane) {
   if constexpr (kEpiWarps == 4) {
     if (p.tma_store) {
-      epilogue_tile_tma<BN>(p, map_out, stg, stat_s, acc, acc_phase, tmem_base, tmem_full_bar, tmem_empty_bar, empty_remote, img, ty, tx,
+      epilogue_tile_tma<BN, ACC>(p, map_out, stg, stat_s, acc, acc_phase, tmem_base, tmem_full_bar, tmem_empty_bar, empty_remote, img, ty, tx,
                             n0, warp, lane);
       return;
     }
@@ -234,7 +251,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const CUten
   const int cq = (kChunk == 32 ? (lane & 7) : (lane & 3)) * 4;
   mbar_wait(tmem_full_bar, acc_phase);
   tcgen05_fence_after();
-  const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+  const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC);
+  const bool sum2 = ACC != BN && p.x3 && p.fuse_hilo;
   const int c_begin = ((warp - 2) >> 2) * kColsPerWarp;
   int c_end = c_begin + kColsPerWarp;
   if (c_end > p.Nout - n0) c_end = p.Nout - n0;  // Nout % 64 == 0: whole chunks; may leave this warp without columns
@@ -253,6 +271,15 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const CUten
       }
     }
     tmem_ld_wait();  // v = accumulator columns [c0, c0 + kChunk) of this lane's pixel
+    if constexpr (ACC != BN) {
+      if (sum2) {  // + the a_hi * b_lo half of the fused MMA (fallback path: fetched here, not prefetched)
+        uint32_t v2[kChunk];
+        tmem_ld_chunk(taddr + BN + c0, v2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+      }
+    }
     // TMEM gives one pixel row per lane; a row-per-lane global store would touch 32 different cache lines per
     // instruction.  Transpose through this warp's private, padded staging block so that every store instruction
     // writes whole 64/128-byte row segments, and the BN column sums become conflict-free column reads.
@@ -386,7 +413,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
+  // 64-wide kernel, bf16x3: the b_hi and b_lo tiles are adjacent in the stage, i.e. ONE K-major operand of 128 rows, so
+  // a_hi * [b_hi | b_lo] is a single UMMA 128x128x16 into 128 accumulator columns and a_lo * b_hi a second one into the first 64:
+  // 2 MMA instructions per k-step instead of 3.  At N = 64 an instruction costs what it costs at N = 128 (the 4 KB A operand
+  // fetched from shared memory per instruction sets the pace, profiles/r2_wgrad_tap_rows.md), so this is 1/3 less tensor time;
+  // the epilogue adds the two column halves.
+  constexpr int ACC = BN == 64 ? 128 : BN;
+  if (warp == 2) tmem_alloc<2 * ACC>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -430,7 +463,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tcgen05_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * ACC);
       for (int k = 0; k < num_k; ++k) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
@@ -442,6 +475,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         for (int kk = 0; kk < BK / UMMA_K; ++kk) {
           const uint32_t koff = kk * UMMA_K * 2;  // bytes inside the 128-byte swizzle row
           const uint64_t da_hi = make_kmajor_sw128_desc(a_hi + koff), db_hi = make_kmajor_sw128_desc(b_hi + koff);
+          if constexpr (ACC != BN) {
+            if (p.x3 && p.fuse_hilo) {
+              constexpr uint32_t idesc_w = make_idesc(BM, 2 * BN, 0, 0);
+              umma_bf16(da_hi, db_hi, tmem_d, idesc_w, (k | kk) != 0);                                // a_hi * [b_hi | b_lo]
+              umma_bf16(make_kmajor_sw128_desc(a_lo + koff), db_hi, tmem_d, idesc, 1);               // a_lo * b_hi
+              continue;
+            }
+          }
           umma_bf16(da_hi, db_hi, tmem_d, idesc, (k | kk) != 0);
           if (p.x3) {
             const uint64_t da_lo = make_kmajor_sw128_desc(a_lo + koff), db_lo = make_kmajor_sw128_desc(b_lo + koff);
@@ -466,7 +507,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       int ty = tm % p.tiles_y;
       int img = tm / p.tiles_y;
       const int n0 = tn * BN;
-      epilogue_tile<BN>(p, &map_out, stg, stat_s, acc, acc_phase, tmem_base, &tmem_full[acc], &tmem_empty[acc], 0u, img, ty, tx, n0, warp, lane);
+      epilogue_tile<BN, ACC>(p, &map_out, stg, stat_s, acc, acc_phase, tmem_base, &tmem_full[acc], &tmem_empty[acc], 0u, img, ty, tx, n0, warp, lane);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -475,7 +516,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  if (warp == 2) tmem_dealloc<2 * BN>(tmem_base);
+  if (warp == 2) tmem_dealloc<2 * ACC>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -794,6 +835,11 @@ int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int ta
   // output tile map for the TMA-store epilogue: fp32 (Nout, W, H, N), box = 32 channels x one warp's 32 pixel rows
   CUtensorMap mo;
   p.tma_store = use_tma_store() ? 1 : 0;
+  {
+    static int fuse = -1;
+    if (fuse < 0) { const char* e = getenv("VSPW_CONV_FUSE64"); fuse = (e && e[0] == '0') ? 0 : 1; }
+    p.fuse_hilo = fuse;
+  }
   if ((rc = make_out_map(&mo, out, n, h, w, nout, p.bw < 32 ? p.bw : 32, p.bw < 32 ? 32 / p.bw : 1, who))) return rc;
   if (nout % BN2 == 0 && use_pair_kernel()) {
     p.tiles_n = nout / BN2;
@@ -854,7 +900,7 @@ int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int ta
 //   Tap groups (Cin = 64, 3x3: stem conv2/conv3, layer1): with one tap per CTA the [64 px][128 co] dy boxes are fetched once per
 //   tap, 9 x (dy + x) through L2 -- 6.9 GB for the 1 M-pixel stem map, which is what bounds the kernel (6.7 TB/s of L2
 //   throughput at 1.03 ms).  There one CTA owns a ROW of the filter (tg = 3 taps): the dy boxes are fetched once per 3 taps and
-//   three 128x64 accumulators sit side by side in TMEM (192 columns); stages grow to 80 KB, two of them in flight.
+//   three 128x64 accumulators sit side by side in TMEM (192 columns) — profiles/r2_wgrad_tap_rows.md.
 constexpr int WG_PIX = 64;                   // pixels (GEMM K) per stage
 constexpr int WG_BLK = WG_PIX * 64 * 2;      // one [64 px][64 ch] bf16 box = 8 KB
 constexpr int WG_STAGES = 3;

@@ -90,7 +90,9 @@ def conv_profile_end():
             else "igemm_kernel/wgrad_kernel (fp32 FFMA implicit GEMM)")
     return {"launches": len(rec), "ms": ms, "tflop": sum(r[2] for r in rec) / 1e12, "kernel": kern, "tc_launches": tc,
             # the launches that stayed on the CUDA-core arm, with their geometry: what is left to move
-            "fp32_arm": [(r[4], r[0].elapsed_time(r[1])) for r in rec if not r[3]]}
+            "fp32_arm": [(r[4], r[0].elapsed_time(r[1])) for r in rec if not r[3]],
+            # (tag, ms, flops) of the tensor-core launches that carry a geometry tag: the per-layer table of bench.py --kernel-profile
+            "tc_arm": [(r[4], r[0].elapsed_time(r[1]), r[2]) for r in rec if r[3] and r[4]]}
 
 
 class _ConvTimer:
@@ -549,7 +551,7 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1, want_stats=False)
         wh, wl = _tc_weight_planes(tape, wv)["ohwi"]
         if want_stats and co % 64 == 0:
             stats = tape.zeros_f64((2, co), y.device)
-        with _ConvTimer(flops, True):
+        with _ConvTimer(flops, True, "fwd " + geom):
             lib.call("vspw_conv2d_fwd_tc", ctypes.byref(desc), _p(xh), _p(xl), _p(wh), _p(wl), _p(bv.data if bv else None), _p(y),
                      _p(stats[0]) if stats is not None else None, _p(stats[1]) if stats is not None else None, _stream())
     else:
@@ -625,7 +627,7 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1, want_stats=False)
                     if _state["wgrad_single"] and prec == PREC_BF16X3:
                         wdesc = ConvDesc(n, h, w, cin, co, kh, kw, stride, pad, dil, ho, wo, PREC_BF16)
                         w_xl = w_dl = None
-                    with _ConvTimer(flops, True):
+                    with _ConvTimer(flops, True, "wgrad " + geom):
                         lib.call("vspw_conv2d_wgrad_tc", ctypes.byref(wdesc), _p(xh), _p(w_xl), _p(dyp[0]), _p(w_dl), _p(dw), sw)
                 else:
                     with _ConvTimer(flops, False, "wgrad " + geom):
@@ -661,7 +663,7 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1, want_stats=False)
                     if dyp[1] is not None:
                         g_lo = torch.empty((n, h, w, co), device=dev, dtype=torch.bfloat16)
                         lib.call("vspw_zero_insert2_bf16", _p(dyp[1]), _p(g_lo), n, ho, wo, co, h, w, st)
-                with _ConvTimer(flops, True):
+                with _ConvTimer(flops, True, "dgrad " + geom):
                     lib.call("vspw_conv2d_dgrad_tc", ctypes.byref(d1), _p(g_hi), _p(g_lo), _p(th), _p(tl), _p(dx), 1 if fan_in else 0, st)
             else:
                 w_t = _weight_ihwo(tape, wv)
