@@ -39,7 +39,11 @@ TC_GEOMS = [
     (1, 64, 60, 107, 128, 3, 1, 1, True, 2),   # stride 2 with bias on the real 480p map width
     (2, 64, 33, 47, 64, 3, 1, 1, False),       # layer1 3x3 64->64: the 64-wide (UMMA 128x64x16, 4-stage) kernel, fwd and dgrad
     (2, 256, 24, 40, 64, 1, 0, 1, True),       # layer1 1x1 256->64 with bias: narrow forward, pair-kernel dgrad
-    # row kernel (conv_row_kernel: 128-pixel row segments, one activation box per filter row, taps = row offsets into it)
+    # multi-wave 1x1 maps on the pair kernel with short reductions
+    (8, 128, 60, 80, 512, 1, 0, 1, False),     # K = 128, 2 channel tiles; dgrad is 512 -> 128
+    (6, 64, 60, 107, 256, 1, 0, 1, True),      # K = 64 (one k-block per tile), bias, odd patch count
+    (3, 192, 60, 107, 768, 1, 0, 1, False),    # K = 192, 3 channel tiles
+    # wide few-channel 3x3 maps (wgrad: filter-row CTAs with the shared x box; fwd / dgrad: the fused hi|lo 64-wide kernel)
     (2, 64, 9, 130, 64, 3, 1, 1, True),        # 64->64 with bias, 130 = 128 + 2: second segment almost empty; wgrad: shared x box
     (1, 128, 7, 200, 128, 3, 2, 2, False),     # 128->128 dilation 2, two k-blocks per tap row
     (1, 128, 5, 100, 64, 3, 4, 4, False),      # 128->64 dilation 4 (widest box: 136 pixels); its dgrad is 64->128
