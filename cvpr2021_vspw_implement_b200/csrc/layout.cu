@@ -54,6 +54,23 @@ __global__ void transpose_inner_kernel(const float* __restrict__ src, float* __r
   }
 }
 
+// [A][B][C] -> [A][C][B] with a SHORT middle axis (B <= 16: the 9 filter taps of an OHWI weight gradient going to OIHW).  The
+// 32 x 32 tiles of transpose_inner_kernel would be 72 % empty; here a block moves one [B][256] slab through shared memory with
+// whole-row reads and one contiguous 256 * B run of writes.
+constexpr int kTapsMaxB = 16, kTapsCols = 256;
+__global__ void __launch_bounds__(kTapsCols) transpose_short_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C) {
+  __shared__ float tile[kTapsMaxB][kTapsCols + 1];
+  const size_t a = blockIdx.y;
+  const int c0 = blockIdx.x * kTapsCols;
+  const int cw = min(kTapsCols, C - c0);
+  const float* s = src + a * (size_t)B * C + c0;
+  if ((int)threadIdx.x < cw)
+    for (int b = 0; b < B; ++b) tile[b][threadIdx.x] = s[(size_t)b * C + threadIdx.x];
+  __syncthreads();
+  float* d = dst + (a * (size_t)C + c0) * B;
+  for (int i = threadIdx.x; i < cw * B; i += kTapsCols) d[i] = tile[i % B][i / B];
+}
+
 extern "C" int vspw_permute4d(const float* src, float* dst, const int32_t d[4], const int32_t perm[4], void* stream) {
   VSPW_REQUIRE(src && dst && d && perm, "vspw_permute4d: null argument");
   long long sstride[4];
@@ -83,6 +100,11 @@ extern "C" int vspw_permute4d(const float* src, float* dst, const int32_t d[4], 
   }
   if (perm[0] == 0 && perm[1] == 3 && perm[2] == 1 && perm[3] == 2) {
     int B = d[1] * d[2], C = d[3];
+    if (B <= kTapsMaxB && d[0] <= 65535) {
+      dim3 grid((C + kTapsCols - 1) / kTapsCols, d[0]);
+      transpose_short_kernel<<<grid, kTapsCols, 0, as_stream(stream)>>>(src, dst, B, C);
+      return check_launch("vspw_permute4d(short transpose)");
+    }
     if (d[0] <= 65535 && (B + 31) / 32 <= 65535) {
       dim3 grid((C + 31) / 32, (B + 31) / 32, d[0]);
       transpose_inner_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(src, dst, B, C);

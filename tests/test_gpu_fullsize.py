@@ -203,7 +203,9 @@ def test_config5_shape_720p_T9_ocr_inference(E):
             q = m(_feed(mixed), segSize=(H, W))
         assert tuple(p.shape) == (N_CLIPS, K, H, W)
         assert torch.isfinite(p).all() and float((p.sum(1) - 1.0).abs().max()) <= 1e-5
-        assert float((p[0] - q[0]).abs().max()) <= 1e-5 and float((p[1] - q[1]).abs().max()) > 1e-3
+        # (clip 0 is bit-for-bit the same input in both batches; the region gather's split-K partial sums meet in fp32 atomics
+        # whose order varies run to run: same 5e-5 allowance as the 480p clip-independence test)
+        assert float((p[0] - q[0]).abs().max()) <= 5e-5 and float((p[1] - q[1]).abs().max()) > 1e-3
         assert p.argmax(1).unique().numel() > 1
     finally:
         T, H, W = old

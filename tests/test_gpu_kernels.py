@@ -294,6 +294,12 @@ def test_permute_and_layout(E):
     out2 = torch.empty(11, 3, 7, 5, device="cuda")
     E.permute4d(x.cuda(), out2, (3, 5, 7, 11), (3, 0, 2, 1))
     assert torch.equal(out2.cpu(), x.permute(3, 0, 2, 1))
+    # OHWI -> OIHW of a 3x3 weight gradient: the short-middle-axis transpose (9 taps), ragged last 256-channel slab
+    for co, ci in ((5, 64), (3, 300), (2, 513)):
+        w = torch.randn(co, 3, 3, ci)
+        o = torch.empty(co, ci, 3, 3, device="cuda")
+        E.permute4d(w.cuda(), o, (co, 3, 3, ci), (0, 3, 1, 2))
+        assert torch.equal(o.cpu(), w.permute(0, 3, 1, 2))
 
 
 def test_confusion_matrix_matches_evaluator(E):
