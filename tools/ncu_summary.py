@@ -17,6 +17,7 @@ FULL_METRICS = [
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram % peak"),
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe %"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM %"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %"),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem wavefronts %"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
     ("launch__registers_per_thread", "regs"),
