@@ -603,6 +603,11 @@ def conv2d(tape, x, weight, bias=None, stride=1, pad=0, dil=1, want_stats=False)
         out.grad = out.grad_planes = None
         if dy is None and dyp is None:
             return
+        if dy is not None and dyp is not None and not getattr(out, "wants_grad_fp32", False):
+            # planes = the COMPLETE gradient written by the one consumer (a BN backward); a second consumer's fp32 share
+            # deposited afterwards would be dropped by the tensor-core kernels, which read the planes only
+            raise VspwError("conv2d backward: the output received both gradient planes and an fp32 gradient — a conv output read by "
+                            "a BN and by a second consumer must not take the planes-only path")
         if head:
             return head_backward(dy)
         st = _stream()
