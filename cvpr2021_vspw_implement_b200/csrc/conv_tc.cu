@@ -122,7 +122,9 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // The BN column sums read the staged block with the same swizzle (conflict-free: a row is one 128-byte line of 32 banks).
 // ACC = accumulator pitch in TMEM columns.  ACC == 2 * BN (the 64-wide kernel in bf16x3): columns [BN, 2 BN) hold the a_hi * b_lo
 // partial product of the fused hi|lo MMA and are added to columns [0, BN) here.
-template <int BN, int ACC>
+// EPI = epilogue warps of the calling kernel (4, or 8: warps w and w + 4 share TMEM lane quadrant w % 4 and take one half of
+// the tile's columns each — half as many dependent chunk steps per warp on the tiles whose time IS the epilogue's latency chain).
+template <int BN, int ACC, int EPI = kEpiWarps>
 __device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const CUtensorMap* map_out, float* stg, float* stat_s, int acc,
                                                   uint32_t acc_phase, uint32_t tmem_base, uint64_t* tmem_full_bar,
                                                   uint64_t* tmem_empty_bar, uint32_t empty_remote, int img, int ty, int tx, int n0,
@@ -140,19 +142,21 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const C
   tcgen05_fence_after();
   const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC);
   const bool sum2 = ACC != BN && p.x3 && p.fuse_hilo;
-  int c_end = BN;
-  if (c_end > p.Nout - n0) c_end = p.Nout - n0;  // Nout % 64 == 0: whole chunks
+  constexpr int kCols = BN / (EPI / 4);                 // columns per warp
+  const int c_begin = ((warp - 2) >> 2) * kCols;        // (EPI == 4: warp - 2 < 4, c_begin = 0)
+  int c_end = c_begin + kCols;
+  if (c_end > p.Nout - n0) c_end = p.Nout - n0;  // Nout % 64 == 0: whole chunks; may leave the second warp without columns
   float* stat_row = stat_s + q * 2 * BN;
   uint8_t* stb = reinterpret_cast<uint8_t*>(stg);
   const uint32_t sw = (uint32_t)(lane & 7);
   uint32_t v[32];
   uint32_t v2[ACC != BN ? 32 : 1];
-  if (c_end > 0) {
-    tmem_ld_32x32b_x32(taddr, v);
-    if constexpr (ACC != BN) { if (sum2) tmem_ld_32x32b_x32(taddr + BN, v2); }
+  if (c_begin < c_end) {
+    tmem_ld_32x32b_x32(taddr + c_begin, v);
+    if constexpr (ACC != BN) { if (sum2) tmem_ld_32x32b_x32(taddr + BN + c_begin, v2); }
   }
 #pragma unroll 1
-  for (int c0 = 0; c0 < c_end; c0 += 32) {
+  for (int c0 = c_begin; c0 < c_end; c0 += 32) {
     if (lane == 0) bulk_wait_read_all();  // the previous chunk's store has finished reading the staging block
     __syncwarp();
     tmem_ld_wait();
@@ -211,9 +215,9 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const C
   __syncwarp();
   if (lane == 0) { if (empty_remote) mbar_arrive_cluster(empty_remote); else mbar_arrive(tmem_empty_bar); }
   if (p.ch_sum) {
-    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI) : "memory");
 #pragma unroll
-    for (int col = (warp - 2) * 32 + lane; col < BN; col += 32 * kEpiWarps) {
+    for (int col = (warp - 2) * 32 + lane; col < BN; col += 32 * EPI) {
       if (n0 + col < p.Nout) {
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -222,7 +226,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const C
         atomicAdd(p.ch_sqsum + n0 + col, (double)s2);
       }
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI) : "memory");
   }
 }
 
@@ -530,13 +534,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 //     and arrive on the leader's tmem_empty barrier (count 2 x kEpiWarps).
 constexpr int BN2 = 256;
 
-template <int STAGES>
+template <int STAGES, int EPI = kEpiWarps>
 struct Conv2Smem {
   static constexpr int kATile = BM * BK * 2;          // 16 KB: this CTA's 128 pixels
   static constexpr int kBTile = (BN2 / 2) * BK * 2;   // 16 KB: this CTA's 128 of the 256 output channels
   static constexpr int kStage = 2 * kATile + 2 * kBTile;
   static constexpr int kStatBytes = 4 * 2 * BN2 * 4;
-  static constexpr int kStgBytes = kEpiWarps * kStgWarpBytes;
+  // per-warp staging block: the transpose path's padded block (EPI == kEpiWarps) or one 32-row x 128-byte TMA-store box
+  static constexpr int kStgWarp = EPI == kEpiWarps ? kStgWarpBytes : 4096;
+  static constexpr int kStgBytes = EPI * kStgWarp;
   static constexpr int kBytes = STAGES * kStage + 1024 + kStgBytes + 256 + kStatBytes;
 };
 
@@ -567,12 +573,16 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
                ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
-template <int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+// EPI = 8 (with STAGES = 2, launched for the 1x1 convs with K <= 256 only): those tiles carry 16..48 MMAs of main loop for a
+// 128 x 256 fp32 output tile per CTA, so the kernel's time is the epilogue's chain of dependent latencies (ncu: tensor pipe
+// 56 %, L2 34 %, HBM 42 %: profiles/r2_conv_epilogue_dbuf_experiment.md); two warps per TMEM lane quadrant halve that chain, and
+// the third operand stage such short reductions do not need pays for the 8 staging boxes.  TMA-store path only.
+template <int STAGES, int EPI = kEpiWarps>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                 const __grid_constant__ CUtensorMap map_out, ConvTcParams p) {
-  using S = Conv2Smem<STAGES>;
+  using S = Conv2Smem<STAGES, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStage + S::kStgBytes);
@@ -581,7 +591,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   uint64_t* tmem_full = bars + 2 * STAGES;      // [2]       one per CTA (multicast commit)
   uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]       leader only, count = epilogue warps x 2 CTAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* stg = reinterpret_cast<float*>(smem + STAGES * S::kStage + (threadIdx.x >= 64 ? ((threadIdx.x >> 5) - 2) * kStgWarpBytes : 0));
+  float* stg = reinterpret_cast<float*>(smem + STAGES * S::kStage + (threadIdx.x >= 64 ? ((threadIdx.x >> 5) - 2) * S::kStgWarp : 0));
   float* stat_s = reinterpret_cast<float*>(smem + STAGES * S::kStage + S::kStgBytes + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -601,7 +611,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * EPI); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -692,8 +702,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       int img, ty, tx, tn;
       decode(tile, img, ty, tx, tn);
       const uint32_t remote = rank == 0 ? 0u : mapa_shared(smem_u32(&tmem_empty[acc]), 0);
-      epilogue_tile<BN2>(p, &map_out, stg, stat_s, acc, acc_phase, tmem_base, &tmem_full[acc], &tmem_empty[acc], remote, img, ty, tx,
-                         tn * BN2, warp, lane);
+      if constexpr (EPI == kEpiWarps)
+        epilogue_tile<BN2>(p, &map_out, stg, stat_s, acc, acc_phase, tmem_base, &tmem_full[acc], &tmem_empty[acc], remote, img, ty, tx,
+                           tn * BN2, warp, lane);
+      else
+        epilogue_tile_tma<BN2, BN2, EPI>(p, &map_out, stg, stat_s, acc, acc_phase, tmem_base, &tmem_full[acc], &tmem_empty[acc], remote,
+                                         img, ty, tx, tn * BN2, warp, lane);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -787,6 +801,16 @@ int tap_group_mode() {
   return v;
 }
 
+// VSPW_CONV_EPI8=0: the short-reduction 1x1 convs run the 4-epilogue-warp, 3-stage pair kernel like every other conv (A/B)
+bool use_epi8() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VSPW_CONV_EPI8");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 // VSPW_CONV_NARROW=0 sends 64-channel outputs through the 128-wide kernel (A/B comparisons)
 bool use_narrow_kernel() {
   static int v = -1;
@@ -855,6 +879,18 @@ int launch_conv_tc(const char* who, int n, int h, int w, int c, int nout, int ta
     const long long tiles_m = (long long)n * p.tiles_y * p.tiles_x;
     const long long pair_tiles = ((tiles_m + 1) / 2) * p.tiles_n;
     const int pairs = (int)(pair_tiles < num_sms() / 2 ? pair_tiles : num_sms() / 2);
+    if (taps == 1 && c <= 256 && p.tma_store && kEpiWarps == 4 && use_epi8()) {
+      // short reductions: the 8-epilogue-warp, 2-stage instantiation (see the kernel)
+      using S8 = Conv2Smem<2, 8>;
+      static std::once_flag once8;
+      static cudaError_t attr_err8 = cudaSuccess;
+      std::call_once(once8, [] {
+        attr_err8 = cudaFuncSetAttribute(conv_tc2_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, S8::kBytes);
+      });
+      if (attr_err8 != cudaSuccess) { set_error("%s: cudaFuncSetAttribute(pair, 8 warps): %s", who, cudaGetErrorString(attr_err8)); return VSPW_ERR_CUDA; }
+      conv_tc2_kernel<2, 8><<<2 * pairs, 64 + 32 * 8, S8::kBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, p);
+      return check_launch(who);
+    }
     conv_tc2_kernel<kStages><<<2 * pairs, kConvThreads, S2::kBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, p);
     return check_launch(who);
   }
