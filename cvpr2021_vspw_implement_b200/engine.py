@@ -704,6 +704,13 @@ def _double_to_float(d, out=None):
 _RELU_BITS_MIN_ELEMS = int(os.environ.get("VSPW_RELU_BITS_MIN", str(24 << 20)))
 
 
+def set_relu(on):
+    """Test switch: False turns every ReLU of the graphs into the identity.  A ReLU-free network has no mask flips, so its
+    whole-model gradients can be compared with the reference at kernel-level tolerances (tests/golden/*_norelu.npz,
+    oracle/NOISE_FLOOR.md) instead of the ~sqrt(eps) floor a ReLU network has."""
+    _state["relu"] = bool(on)
+
+
 def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, training=None, fp32_out=True, planes_out=True):
     """BN (train: batch stats, eval: running stats) [+ residual] [+ ReLU] [* Dropout2d mask].
 
@@ -716,6 +723,7 @@ def batchnorm_act(tape, y, bn, relu=True, residual=None, chan_scale=None, traini
     """
     n, h, w, c = y.shape
     pixels = n * h * w
+    relu = relu and _state.get("relu", True)  # (set_relu(False): ReLU-free test graphs)
     training = bn.training if training is None else training
     gv, bv = tape.param(bn.weight), tape.param(bn.bias)
     dev = y.data.device

@@ -35,6 +35,13 @@ BN_MOMENTUM = 0.1
 
 # --------------------------------------------------------------------------------------------------
 # primitive ops (each is the ATen call the reference makes)
+
+RELU = True  # False: every ReLU of the restated graphs is the identity (the *_norelu fixtures: ReLU-free gradient parity)
+
+
+def _act(x):
+    return F.relu(x) if RELU else x
+
 def conv2d(x, w, b=None, stride=1, pad=0, dil=1):
     return F.conv2d(x, w, b, stride=stride, padding=pad, dilation=dil)
 
@@ -84,9 +91,9 @@ def resnet_geometry(layer_i, block_i, dilated, bottleneck):
 def resnet_forward(sd, prefix, x, train, dilated=True):
     """ResnetDilated.forward(x, return_feature_maps=True) (models.py:752-767)."""
     p = prefix
-    x = F.relu(batch_norm(sd, p + "bn1", conv2d(x, sd[p + "conv1.weight"], None, 2, 1, 1), train))
-    x = F.relu(batch_norm(sd, p + "bn2", conv2d(x, sd[p + "conv2.weight"], None, 1, 1, 1), train))
-    x = F.relu(batch_norm(sd, p + "bn3", conv2d(x, sd[p + "conv3.weight"], None, 1, 1, 1), train))
+    x = _act(batch_norm(sd, p + "bn1", conv2d(x, sd[p + "conv1.weight"], None, 2, 1, 1), train))
+    x = _act(batch_norm(sd, p + "bn2", conv2d(x, sd[p + "conv2.weight"], None, 1, 1, 1), train))
+    x = _act(batch_norm(sd, p + "bn3", conv2d(x, sd[p + "conv3.weight"], None, 1, 1, 1), train))
     x = maxpool(x)
     outs = []
     for li in (1, 2, 3, 4):
@@ -97,15 +104,15 @@ def resnet_forward(sd, prefix, x, train, dilated=True):
             strided, other, ds_stride = resnet_geometry(li, bi, dilated, bottleneck)
             res = x
             if bottleneck:  # resnet.py:72-92 (stride lives on the 3x3 conv2)
-                o = F.relu(batch_norm(sd, q + "bn1", conv2d(x, sd[q + "conv1.weight"]), train))
-                o = F.relu(batch_norm(sd, q + "bn2", conv2d(o, sd[q + "conv2.weight"], None, *strided), train))
+                o = _act(batch_norm(sd, q + "bn1", conv2d(x, sd[q + "conv1.weight"]), train))
+                o = _act(batch_norm(sd, q + "bn2", conv2d(o, sd[q + "conv2.weight"], None, *strided), train))
                 o = batch_norm(sd, q + "bn3", conv2d(o, sd[q + "conv3.weight"]), train)
             else:  # BasicBlock resnet.py:37-53 (stride lives on conv1)
-                o = F.relu(batch_norm(sd, q + "bn1", conv2d(x, sd[q + "conv1.weight"], None, *strided), train))
+                o = _act(batch_norm(sd, q + "bn1", conv2d(x, sd[q + "conv1.weight"], None, *strided), train))
                 o = batch_norm(sd, q + "bn2", conv2d(o, sd[q + "conv2.weight"], None, *other), train)
             if (q + "downsample.0.weight") in sd:
                 res = batch_norm(sd, q + "downsample.1", conv2d(x, sd[q + "downsample.0.weight"], None, ds_stride), train)
-            x = F.relu(o + res)
+            x = _act(o + res)
         outs.append(x)
     return outs
 
@@ -162,10 +169,10 @@ def clip_psp_forward(sd, frames, labels=None, args_psp_weight=False, deep_sup_sc
     # PPM_conv.forward (clip_psp.py:45-56)
     ppm_out = [c_tmp]
     for i, pf in enumerate(p_fs):
-        z = F.relu(batch_norm(sd, f"ppm_conv.ppm.{i}.1", conv2d(pf, sd[f"ppm_conv.ppm.{i}.0.weight"]), train))
+        z = _act(batch_norm(sd, f"ppm_conv.ppm.{i}.1", conv2d(pf, sd[f"ppm_conv.ppm.{i}.0.weight"]), train))
         ppm_out.append(bilinear(z, c_tmp.shape[-2:]))
     cat = torch.cat(ppm_out, 1)
-    z = F.relu(batch_norm(sd, "ppm_conv.conv_last_.1", conv2d(cat, sd["ppm_conv.conv_last_.0.weight"], None, 1, 1, 1), train))
+    z = _act(batch_norm(sd, "ppm_conv.conv_last_.1", conv2d(cat, sd["ppm_conv.conv_last_.0.weight"], None, 1, 1, 1), train))
     if dropout_masks and dropout_masks.get("ppm") is not None:
         z = z * dropout_masks["ppm"][:, :, None, None]
     logits = conv2d(z, sd["ppm_conv.conv_last_.4.weight"], sd["ppm_conv.conv_last_.4.bias"])
@@ -174,7 +181,7 @@ def clip_psp_forward(sd, frames, labels=None, args_psp_weight=False, deep_sup_sc
     loss, lp, lab = nll_up(logits, labels[-1], ignore_index)
     out = {"logits": logits, "loss_main": loss}
     if deep_sup_scale is not None:
-        d = F.relu(batch_norm(sd, "deepsup.1", conv2d(maps[-2], sd["deepsup.0.weight"], None, 1, 1, 1), train))
+        d = _act(batch_norm(sd, "deepsup.1", conv2d(maps[-2], sd["deepsup.0.weight"], None, 1, 1, 1), train))
         if dropout_masks and dropout_masks.get("deepsup") is not None:
             d = d * dropout_masks["deepsup"][:, :, None, None]
         lds = conv2d(d, sd["deepsup.4.weight"], sd["deepsup.4.bias"])
@@ -234,7 +241,7 @@ def region_gather(feats, probs, T):
 
 def _cbr(sd, prefix, x, train, idx=0):
     x = conv2d(x, sd[f"{prefix}.{idx}.weight"], sd.get(f"{prefix}.{idx}.bias"))
-    return F.relu(batch_norm(sd, f"{prefix}.{idx + 1}", x, train))
+    return _act(batch_norm(sd, f"{prefix}.{idx + 1}", x, train))
 
 
 def object_attention(sd, prefix, x, proxy, train, key_channels=256):
@@ -258,11 +265,11 @@ def clip_ocr_forward(sd, frames, labels=None, deep_sup_scale=0.4, train=True, se
     T = len(frames)
     n = frames[0].shape[0]
     maps = resnet_forward(sd, "encoder.", torch.cat(frames, dim=0), train)
-    d = F.relu(batch_norm(sd, "dsn_head.1", conv2d(maps[-2], sd["dsn_head.0.weight"], sd["dsn_head.0.bias"], 1, 1, 1), train))
+    d = _act(batch_norm(sd, "dsn_head.1", conv2d(maps[-2], sd["dsn_head.0.weight"], sd["dsn_head.0.bias"], 1, 1, 1), train))
     if dropout_masks and dropout_masks.get("dsn") is not None:
         d = d * dropout_masks["dsn"][:, :, None, None]
     x_dsn = conv2d(d, sd["dsn_head.4.weight"], sd["dsn_head.4.bias"])
-    feats = F.relu(batch_norm(sd, "conv_3x3.1", conv2d(maps[-1], sd["conv_3x3.0.weight"], sd["conv_3x3.0.bias"], 1, 1, 1), train))
+    feats = _act(batch_norm(sd, "conv_3x3.1", conv2d(maps[-1], sd["conv_3x3.0.weight"], sd["conv_3x3.0.bias"], 1, 1, 1), train))
     if memory is None:
         context = region_gather(feats, x_dsn, T)
     else:
@@ -278,7 +285,7 @@ def clip_ocr_forward(sd, frames, labels=None, deep_sup_scale=0.4, train=True, se
     x = torch.split(feats, n, dim=0)[-1]
     ctx = object_attention(sd, "spatial_ocr_head.object_context_block", x, context, train)
     z = conv2d(torch.cat([ctx, x], 1), sd["spatial_ocr_head.conv_bn_dropout.0.weight"], sd["spatial_ocr_head.conv_bn_dropout.0.bias"])
-    z = F.relu(batch_norm(sd, "spatial_ocr_head.conv_bn_dropout.1", z, train))
+    z = _act(batch_norm(sd, "spatial_ocr_head.conv_bn_dropout.1", z, train))
     if dropout_masks and dropout_masks.get("ocr") is not None:
         z = z * dropout_masks["ocr"][:, :, None, None]
     logits = conv2d(z, sd["head.weight"], sd["head.bias"])
@@ -300,9 +307,9 @@ def segmentation_module_forward(sd, img, label=None, deep_sup_scale=0.4, train=T
     ppm_out = [conv5]
     for i, s in enumerate(pool_scales):
         z = conv2d(F.adaptive_avg_pool2d(conv5, s), sd[f"decoder.ppm.{i}.1.weight"])
-        ppm_out.append(bilinear(F.relu(batch_norm(sd, f"decoder.ppm.{i}.2", z, train)), conv5.shape[-2:]))
+        ppm_out.append(bilinear(_act(batch_norm(sd, f"decoder.ppm.{i}.2", z, train)), conv5.shape[-2:]))
     z = conv2d(torch.cat(ppm_out, 1), sd["decoder.conv_last_.0.weight"], None, 1, 1, 1)
-    z = F.relu(batch_norm(sd, "decoder.conv_last_.1", z, train))
+    z = _act(batch_norm(sd, "decoder.conv_last_.1", z, train))
     if dropout_masks and dropout_masks.get("ppm") is not None:
         z = z * dropout_masks["ppm"][:, :, None, None]
     logits = conv2d(z, sd["decoder.conv_last_.4.weight"], sd["decoder.conv_last_.4.bias"])
@@ -311,7 +318,7 @@ def segmentation_module_forward(sd, img, label=None, deep_sup_scale=0.4, train=T
     loss, lp, lab = nll_up(logits, label, ignore_index)
     out = {"logits": logits, "loss_main": loss}
     if deep_sup_scale is not None:
-        d = F.relu(batch_norm(sd, "decoder.cbr_deepsup.1", conv2d(maps[-2], sd["decoder.cbr_deepsup.0.weight"], None, 1, 1, 1), train))
+        d = _act(batch_norm(sd, "decoder.cbr_deepsup.1", conv2d(maps[-2], sd["decoder.cbr_deepsup.0.weight"], None, 1, 1, 1), train))
         if dropout_masks and dropout_masks.get("deepsup") is not None:
             d = d * dropout_masks["deepsup"][:, :, None, None]
         lds = conv2d(d, sd["decoder.conv_last_deepsup_.weight"], sd["decoder.conv_last_deepsup_.bias"])

@@ -25,6 +25,9 @@ CASES = {
 
 # mid-size train-mode fixtures for the gradient gates (oracle/make_golden.py MID_CASES)
 MID_CASES = {
+    # the same two with every ReLU replaced by the identity (no mask flips: gradient parity at kernel-level tolerances)
+    "clip_psp_mid_norelu": ("Clip_PSP", "resnet50dilated", 3, 4, 97, 129, 16, 309),
+    "clip_ocr_mid_norelu": ("ClipOCRNet", "resnet50dilated", 3, 4, 97, 129, 17, 310),
     "clip_psp_mid": ("Clip_PSP", "resnet50dilated", 3, 4, 97, 129, 16, 309),
     "clip_ocr_mid": ("ClipOCRNet", "resnet50dilated", 3, 4, 97, 129, 17, 310),
 }
