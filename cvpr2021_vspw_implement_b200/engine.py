@@ -71,12 +71,21 @@ def precision(mode):
 
 _capture = None
 _prof = None  # live conv-kernel profile: list of (start_event, stop_event, flops, used_tc)
+_prof_on = True
 
 
 def conv_profile_begin():
     """Start timing every implicit-GEMM conv launch (fwd/dgrad/wgrad) with CUDA events on the launching stream."""
-    global _prof
+    global _prof, _prof_on
     _prof = []
+    _prof_on = True
+
+
+def conv_profile_sample(on):
+    """Between conv_profile_begin() and conv_profile_end(): record (True) or skip (False) the launches that follow — bench.py
+    samples every 4th timed step so that the event pairs do not weigh on the step they measure."""
+    global _prof_on
+    _prof_on = bool(on)
 
 
 def conv_profile_end():
@@ -103,7 +112,7 @@ class _ConvTimer:
         self.e0 = None
 
     def __enter__(self):
-        if _prof is not None:
+        if _prof is not None and _prof_on:
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e0.record()
         return self
