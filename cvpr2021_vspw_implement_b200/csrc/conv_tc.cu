@@ -1141,11 +1141,15 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap map_dy_hi, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
 
+  // tap fastest: the pairs that read the same pixel range (the dy boxes, overlapping x boxes) are neighbours in the grid and
+  // run in the same wave, so one HBM read serves the 9 taps through L2 (tap slowest: ncu 270 MB of DRAM reads for the 131 MB of
+  // dy + x planes of layer3's 3x3)
   int t = blockIdx.x >> 1;  // pair index
+  const int n_taps = p.taps_w * p.taps_w;
+  const int tap = t % n_taps; t /= n_taps;
   const int split = t % p.splits; t /= p.splits;
   const int tco = t % p.tiles_co; t /= p.tiles_co;   // 256-wide tiles here
-  const int tci = t % p.tiles_ci; t /= p.tiles_ci;
-  const int tap = t;
+  const int tci = t;
   const int tr = tap / p.taps_w, ts = tap - tr * p.taps_w;
   const int dxo = p.off0 + ts * p.step, dyo = p.off0 + tr * p.step;
   const int total_patches = p.N * p.tiles_y * p.tiles_x;
