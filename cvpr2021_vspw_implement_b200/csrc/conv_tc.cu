@@ -14,9 +14,16 @@
 //                     K-major SWIZZLE_128B operand layout tcgen05.mma reads.
 //   warp 1 / lane 0 : MMA issuer.  UMMA 128 x BN x 16 (bf16 in, fp32 accumulate in TMEM).  In BF16X3 mode every
 //                     k-step issues hi*hi + hi*lo + lo*hi (3 MMAs) for ~16 mantissa bits per operand.
-//   warps 2..5      : epilogue.  tcgen05.ld of the 128 x BN fp32 accumulator (one TMEM lane = one pixel),
-//                     bias add, 16-byte stores to the NHWC fp32 output.  Two TMEM accumulator stages let the
-//                     epilogue of tile i overlap the main loop of tile i+1.
+//   warps 2..5      : epilogue.  tcgen05.ld of the 128 x BN fp32 accumulator (one TMEM lane = one pixel), bias add, the
+//                     warp's 32-row x 128-byte SWIZZLE_128B staging block, ONE cp.async.bulk.tensor store per 32-column
+//                     chunk (cp.reduce.async.bulk.tensor .add for the dgrad fan-in), fused BN statistics from the staged
+//                     block.  Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
+//                     (VSPW_CONV_TMA_STORE=0: padded transpose + 16-byte STG instead of the bulk stores.)
+// Variants: conv_tc2_kernel<3, 4> = cta_group::2 pairs, UMMA 256x256x16 (every Cout % 256 == 0 conv); conv_tc2_kernel<2, 8> =
+// the same with 8 epilogue warps and 2 stages for the 1x1 convs with K <= 256; conv_tc_kernel<128, 3> single CTA;
+// conv_tc_kernel<64, 4> for 64 output channels with a_hi * [b_hi | b_lo] fused into one 128-column MMA; the head path of the
+// same kernels for the 124-class 1x1 convs (TMA-clipped); wgrad_tc2_kernel / wgrad_tc_kernel for the weight gradients
+// (filter-row CTAs with one UMMA 128x192x16 over a shared x box when Cin = 64).
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA), tmem full/empty mbarriers (MMA <-> epilogue).
 // Reference call sites replaced: the stride-1 nn.Conv2d of models/resnet.py:61-66 (layer1..4), the PPM / deepsup /
 // OCR head convs (clip_psp.py:35-41,74-79; clip_ocr.py:43,56-62) and their autograd backward.
