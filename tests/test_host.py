@@ -152,3 +152,23 @@ def test_clip_window_and_sublists_follow_the_reference_rule():
     args.method = "clip_psp"
     ds = SyntheticWindowTest(args, "v", frames=9, height=8, width=8, seed=1)
     assert ds[4][4] == "00000004.png" and len(ds[4][2]) == 3
+
+
+def test_environment_switches_are_documented():
+    """Every VSPW_* environment variable the package, the kernels or the entry points read appears in INTEGRATION.md's table,
+    and the table lists nothing that no longer exists (A/B switches come and go with the experiments: profiles/r2_ab_table.md)."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    doc = set(re.findall(r"`(VSPW_[A-Z0-9_]+)`", open(os.path.join(root, "INTEGRATION.md")).read()))
+    code = set()
+    files = glob.glob(os.path.join(root, "cvpr2021_vspw_implement_b200", "**", "*.py"), recursive=True)
+    files += glob.glob(os.path.join(root, "cvpr2021_vspw_implement_b200", "csrc", "*.cu*"))
+    files += [os.path.join(root, f) for f in ("bench.py", "train_clip2.py", "test_clip2.py")]
+    for f in files:
+        t = open(f).read()
+        code |= set(re.findall(r'getenv\("(VSPW_[A-Z0-9_]+)"\)', t))
+        code |= set(re.findall(r'environ(?:\.get)?[\(\[]"(VSPW_[A-Z0-9_]+)"', t))
+    assert code, "no switches found: the patterns above no longer match the code"
+    assert code - doc == set(), f"undocumented switches: {sorted(code - doc)}"
+    assert doc - code == set(), f"documented switches that no longer exist: {sorted(doc - code)}"
